@@ -1,0 +1,153 @@
+/*
+ * pno_b200.h -- C ABI of libpno_b200.so: the B200 (sm_100a) implementation of pno-physics-bench's probabilistic
+ * spectral-convolution hot path.
+ *
+ * The reference (danieleschmidt/pno-physics-bench) is 100 % Python and exposes no FFI for this path:
+ * the drop-in boundary is the Python class API of src/pno_physics_bench/models.py.  This header is therefore the
+ * builder-defined C ABI that the Python mirror of that API (pno_physics_bench_b200/models.py) binds through ctypes;
+ * each entry point cites the reference lines whose work it replaces (paths relative to src/pno_physics_bench/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch's caching allocator); the library never frees
+ *     caller memory and allocates only the small twiddle tables a plan owns;
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes on it; no hidden synchronisation;
+ *   - every function returns 0 on success, a negative PNO_E_* code otherwise; pno_last_error() gives the message
+ *     (thread-local);
+ *   - activations are fp32 NCHW contiguous; complex numbers are interleaved (re, im) fp32 pairs;
+ *   - spectral parameters use the kernel-native layout  mu[kx][ky][i][o] (complex) / log_var[kx][ky][i][o] (fp32),
+ *     one array per block (weights1 = +kx rows, weights2 = -kx rows).  The Python modules store the reference's
+ *     [Ci,Co,m1,m2] parameters as strided views of exactly this storage, so no repacking happens per call;
+ *   - truncated spectra use the layout  xhat[mode][b][c], mode = kx2*m2 + ky, kx2 in [0, 2*m1): rows [0,m1) are
+ *     kx = kx2 (weights1), rows [m1,2*m1) are kx = H - 2*m1 + kx2 (weights2); real and imaginary planes are
+ *     separate arrays;
+ *   - noise is a counter-based Philox4x32-10 stream keyed by (seed, sample_idx, site, element) -- see
+ *     oracle/philox.py for the normative definition; nothing depends on launch geometry or GPU count.
+ */
+#ifndef PNO_B200_H
+#define PNO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNO_VERSION 100
+
+enum {
+    PNO_OK = 0,
+    PNO_E_INVALID = -1,   /* bad shape / null pointer / misalignment                          */
+    PNO_E_MODES = -2,     /* m1 > H or m2 > W/2+1 (reference: RuntimeError from einsum, models.py:93-94) */
+    PNO_E_CUDA = -3,      /* a CUDA runtime call failed                                        */
+    PNO_E_ARCH = -4,      /* device is not sm_100 (no fallback paths exist)                    */
+    PNO_E_UNSUPPORTED = -5 /* the requested engine does not support this shape                 */
+};
+
+enum { PNO_ACT_NONE = 0, PNO_ACT_GELU = 1, PNO_ACT_RELU = 2 };   /* models.py:224-229 (exact-erf GELU) */
+
+/* arithmetic engines */
+enum {
+    PNO_ENGINE_FP32 = 0,      /* fp32 FMA on CUDA cores: any shape, reference-grade fp32 (rel-L2 <= 1e-5)      */
+    PNO_ENGINE_TC_TF32X3 = 1, /* tcgen05 tensor cores, error-compensated 3xTF32 (rel-L2 <= 1e-5)                */
+    PNO_ENGINE_TC_BF16 = 2    /* tcgen05 tensor cores, bf16 operands / fp32 accumulate (rel-L2 <= 2e-2)         */
+};
+
+typedef struct pno_plan pno_plan_t;
+
+int pno_version(void);
+const char* pno_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x), PNO_E_ARCH otherwise. */
+int pno_check_device(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; bench.py reports deltas) */
+uint64_t pno_launch_count(void);
+
+/* Plan = twiddle tables for one (H, W, m1, m2) on the current device.  Immutable after creation. */
+int pno_plan_create(int H, int W, int m1, int m2, pno_plan_t** plan);
+int pno_plan_destroy(pno_plan_t* plan);
+/* bytes of scratch pno_spectral_fwd / pno_spectral_bwd need for batch B and channel counts Ci, Co */
+size_t pno_spectral_workspace_bytes(const pno_plan_t* plan, int B, int Ci, int Co);
+
+/* ---- noise stream (parity / debugging; the hot path draws the same numbers in-kernel) -------------------------- */
+/* eps[first_elem .. first_elem+n) of an activation-shaped site (replaces torch.randn_like, models.py:272). */
+int pno_philox_normal_activation(uint64_t seed, uint32_t sample_idx, uint32_t site, uint64_t first_elem, uint64_t n,
+                                 float* out, void* stream);
+/* eps_re, eps_im, each [2][Ci][Co][m1][m2] in the reference's logical layout (models.py:67-68, 74, 76). */
+int pno_philox_normal_spectral(uint64_t seed, uint32_t sample_idx, uint32_t site, int Ci, int Co, int m1, int m2,
+                               float* eps_re, float* eps_im, void* stream);
+/* raw Philox4x32-10 output words for quads [q0, q0+nq): out[nq][4] */
+int pno_philox_bits(uint64_t seed, uint32_t sample_idx, uint32_t site, uint64_t q0, uint64_t nq, uint32_t* out,
+                    void* stream);
+
+/* ---- stages of the spectral layer ------------------------------------------------------------------------------ */
+/* Pruned forward transform (replaces torch.fft.rfft2 + the two slices, models.py:89, 93-94):
+ *   xhat[mode][b][c] = sum_{h,w} x[b][c][h][w] exp(-2 pi i (kx h/H + ky w/W)).
+ * grad_scale != 0 multiplies by alive(kx2) * c_ky / (H W): the adjoint of the inverse transform (backward of irfft2). */
+int pno_dft_fwd(const pno_plan_t* plan, const float* x, int B, int C, int grad_scale, float* xhat_re, float* xhat_im,
+                void* stream);
+/* Pruned inverse transform + fused epilogue (replaces zeros + scatter + torch.fft.irfft2, models.py:92-97, and the
+ * add + activation of the block, models.py:306):
+ *   s = sum_mode coef * Re(yhat[mode][b][c] exp(+2 pi i (...)))          coef = alive c_ky/(HW) (adjoint != 0: coef = 1)
+ *   v = s + (addend ? addend[b][c][h][w] : 0);  if (pre_act) pre_act = v;  y = act(v)                               */
+int pno_dft_inv(const pno_plan_t* plan, const float* yhat_re, const float* yhat_im, int B, int C, int adjoint,
+                const float* addend, int act, float* y, float* pre_act, void* stream);
+/* Per-mode complex channel mix with in-kernel weight sampling (replaces sample_weights + compl_mul2d,
+ * models.py:63-78, 33-35):  yhat[mode][b][o] = sum_i xhat[mode][b][i] * (mu + exp(lv/2) * eps)[mode][i][o].
+ * lv1 == lv2 == NULL selects the mean weights (sample=False / eval gate, models.py:79-80, 86). */
+int pno_mix_fwd(const pno_plan_t* plan, int engine, const float* xhat_re, const float* xhat_im, int B, int Ci, int Co,
+                const float* mu1, const float* mu2, const float* lv1, const float* lv2, uint64_t seed,
+                uint32_t sample_idx, uint32_t site, float* yhat_re, float* yhat_im, void* stream);
+/* dxhat[mode][b][i] = sum_o ghat[mode][b][o] * conj(W[mode][i][o])  (W re-sampled from the same counters) */
+int pno_mix_bwd_dx(const pno_plan_t* plan, int engine, const float* ghat_re, const float* ghat_im, int B, int Ci, int Co,
+                   const float* mu1, const float* mu2, const float* lv1, const float* lv2, uint64_t seed,
+                   uint32_t sample_idx, uint32_t site, float* dxhat_re, float* dxhat_im, void* stream);
+/* dmu[mode][i][o] = sum_b conj(xhat[mode][b][i]) * ghat[mode][b][o];
+ * dlv = 0.5 exp(lv/2) (eps_re Re dmu + eps_im Im dmu)   (written, not accumulated; dlv* may be NULL) */
+int pno_mix_bwd_dw(const pno_plan_t* plan, int engine, const float* xhat_re, const float* xhat_im, const float* ghat_re,
+                   const float* ghat_im, int B, int Ci, int Co, const float* lv1, const float* lv2, uint64_t seed,
+                   uint32_t sample_idx, uint32_t site, float* dmu1, float* dmu2, float* dlv1, float* dlv2, void* stream);
+
+/* ---- whole layer / block --------------------------------------------------------------------------------------- */
+/* SpectralConv2d(_Probabilistic).forward (models.py:37-50, 82-98) with the PNO-block epilogue fused
+ * (models.py:306): y = act(spectral(x) + addend).  addend may be NULL and act PNO_ACT_NONE for the bare layer.
+ * keep_xhat != 0 leaves xhat in the first 2*M*B*Ci floats of `workspace` for pno_spectral_bwd. */
+int pno_spectral_fwd(const pno_plan_t* plan, int engine, const float* x, int B, int Ci, int Co, const float* mu1,
+                     const float* mu2, const float* lv1, const float* lv2, uint64_t seed, uint32_t sample_idx,
+                     uint32_t site, const float* addend, int act, float* y, float* pre_act, void* workspace,
+                     void* stream);
+/* Backward of the spectral branch for upstream gradient g = dL/d(spectral output) [B][Co][H][W].
+ * xhat_saved: the xhat planes kept by pno_spectral_fwd (NULL: recomputed from x).  Any of dx / dmu* / dlv* may be
+ * NULL to skip it. */
+int pno_spectral_bwd(const pno_plan_t* plan, int engine, const float* x, const float* xhat_saved, const float* g, int B,
+                     int Ci, int Co, const float* mu1, const float* mu2, const float* lv1, const float* lv2,
+                     uint64_t seed, uint32_t sample_idx, uint32_t site, float* dx, float* dmu1, float* dmu2, float* dlv1,
+                     float* dlv2, void* workspace, void* stream);
+
+/* Local branch: 1x1 conv mean (+ reparameterised activation-space noise), models.py:288-290, 298-303, 309-314, 264-275:
+ *   m = Wm x + bm;  if (Wl) { lv = clamp(Wl x + bl, -10, 10); s = max(exp(lv/2), 1e-6); out = m + eps s } else out = m
+ * x [B][Ci][HW], out [B][Co][HW]; eps element index uses the GLOBAL batch index batch_offset + b.
+ * dout_dlv (may be NULL) receives d out / d(Wl x + bl) = 0.5 eps s [|lv|<10][s>1e-6] for the backward pass. */
+int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
+                  const float* Wl, const float* bl, uint64_t seed, uint32_t sample_idx, uint32_t site,
+                  uint64_t batch_offset, float* out, float* dout_dlv, void* stream);
+
+/* gz = g * act'(pre_act)  (backward of models.py:306) */
+int pno_act_bwd(const float* pre_act, const float* g, uint64_t n, int act, float* gz, void* stream);
+
+/* ---- KL (models.py:100-104) ------------------------------------------------------------------------------------ */
+/* *kl_accum (double, device) += -0.5 sum(1 + lv - re^2 - im^2 - exp(lv)) over n elements of one block */
+int pno_kl_fwd(const float* mu, const float* lv, uint64_t n, double* kl_accum, void* stream);
+/* dmu (+)= gscale * mu ; dlv (+)= gscale * (-0.5 (1 - exp(lv))) ; gscale read from device memory */
+int pno_kl_bwd(const float* mu, const float* lv, uint64_t n, const float* gscale, int accumulate, float* dmu, float* dlv,
+               void* stream);
+
+/* ---- MC predictive moments (models.py:361-368) ----------------------------------------------------------------- */
+int pno_mc_accumulate(const float* y, uint64_t n, double* sum, double* sumsq, void* stream);
+/* mean = sum/S; std = sqrt((sumsq - S mean^2)/(S-1)) (unbiased; S == 1 -> NaN like torch.std) */
+int pno_mc_finalize(const double* sum, const double* sumsq, uint64_t n, uint32_t S, float* mean, float* std,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNO_B200_H */

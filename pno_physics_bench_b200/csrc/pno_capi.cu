@@ -1,0 +1,225 @@
+// extern "C" surface of libpno_b200.so (see include/pno_b200.h): plans, argument validation, engine dispatch and the
+// whole-layer compositions.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "pno_common.cuh"
+#include "pno_tc.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pno_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+unsigned long long g_pno_launches = 0;
+
+extern "C" int pno_version(void) { return PNO_VERSION; }
+extern "C" uint64_t pno_launch_count(void) { return g_pno_launches; }
+extern "C" const char* pno_last_error(void) { return g_err; }
+
+extern "C" int pno_check_device(void) {
+    int dev = 0;
+    PNO_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    PNO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) PNO_FAIL(PNO_E_ARCH, "libpno_b200 is built for sm_100a only; device %d is sm_%d*", dev, major);
+    return PNO_OK;
+}
+
+extern "C" int pno_plan_create(int H, int W, int m1, int m2, pno_plan_t** out) {
+    if (!out) PNO_FAIL(PNO_E_INVALID, "pno_plan_create: null output");
+    *out = nullptr;
+    if (H <= 0 || W <= 0 || m1 <= 0 || m2 <= 0) PNO_FAIL(PNO_E_INVALID, "pno_plan_create: non-positive size");
+    if (m1 > H || m2 > W / 2 + 1)
+        PNO_FAIL(PNO_E_MODES, "modes (%d, %d) exceed the spectrum of a %dx%d grid (%d, %d)", m1, m2, H, W, H, W / 2 + 1);
+    int rc = pno_check_device();
+    if (rc) return rc;
+    pno_plan* p = new pno_plan();
+    p->H = H; p->W = W; p->m1 = m1; p->m2 = m2; p->M = 2 * m1 * m2;
+    p->tc_tables = nullptr;
+    PNO_CUDA(cudaGetDevice(&p->device));
+    std::vector<float2> th(H), tw(W);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int n = 0; n < H; ++n) th[n] = make_float2((float)cos(two_pi * n / H), (float)sin(two_pi * n / H));
+    for (int n = 0; n < W; ++n) tw[n] = make_float2((float)cos(two_pi * n / W), (float)sin(two_pi * n / W));
+    std::vector<int> kx(2 * m1);
+    std::vector<float> coef((size_t)2 * m1 * m2);
+    for (int j = 0; j < m1; ++j) { kx[j] = j; kx[m1 + j] = H - m1 + j; }
+    for (int r = 0; r < 2 * m1; ++r) {
+        // reference models.py:93-94: the second slice assignment overwrites the first where they overlap
+        const bool alive = r >= m1 || kx[r] < H - m1;
+        for (int ky = 0; ky < m2; ++ky) {
+            const bool self_conj = ky == 0 || (W % 2 == 0 && ky == W / 2);
+            coef[(size_t)r * m2 + ky] = alive ? (float)((self_conj ? 1.0 : 2.0) / ((double)H * W)) : 0.f;
+        }
+    }
+    PNO_CUDA(cudaMalloc(&p->tabH, sizeof(float2) * H));
+    PNO_CUDA(cudaMalloc(&p->tabW, sizeof(float2) * W));
+    PNO_CUDA(cudaMalloc(&p->kx, sizeof(int) * 2 * m1));
+    PNO_CUDA(cudaMalloc(&p->coef, sizeof(float) * coef.size()));
+    PNO_CUDA(cudaMemcpy(p->tabH, th.data(), sizeof(float2) * H, cudaMemcpyHostToDevice));
+    PNO_CUDA(cudaMemcpy(p->tabW, tw.data(), sizeof(float2) * W, cudaMemcpyHostToDevice));
+    PNO_CUDA(cudaMemcpy(p->kx, kx.data(), sizeof(int) * 2 * m1, cudaMemcpyHostToDevice));
+    PNO_CUDA(cudaMemcpy(p->coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+    *out = p;
+    return PNO_OK;
+}
+
+extern "C" int pno_plan_destroy(pno_plan_t* p) {
+    if (!p) return PNO_OK;
+    tc_plan_release(p);
+    cudaFree(p->tabH);
+    cudaFree(p->tabW);
+    cudaFree(p->kx);
+    cudaFree(p->coef);
+    delete p;
+    return PNO_OK;
+}
+
+extern "C" size_t pno_spectral_workspace_bytes(const pno_plan_t* p, int B, int Ci, int Co) {
+    if (!p || B <= 0 || Ci <= 0 || Co <= 0) return 0;
+    const size_t mb = (size_t)p->M * B;
+    return sizeof(float) * (2 * mb * Ci + 2 * mb * Co + 2 * mb * Ci);
+}
+
+static int check_common(const pno_plan* p, int B, int Ci, int Co, const char* who) {
+    if (!p) PNO_FAIL(PNO_E_INVALID, "%s: null plan", who);
+    if (B <= 0 || Ci <= 0 || Co <= 0) PNO_FAIL(PNO_E_INVALID, "%s: non-positive B/Ci/Co (%d, %d, %d)", who, B, Ci, Co);
+    return PNO_OK;
+}
+
+extern "C" int pno_dft_fwd(const pno_plan_t* p, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
+                           void* stream) {
+    int rc = check_common(p, B, C, C, "pno_dft_fwd");
+    if (rc) return rc;
+    if (!x || !xr || !xi) PNO_FAIL(PNO_E_INVALID, "pno_dft_fwd: null pointer");
+    return simt_dft_fwd(p, x, B, C, grad_scale, xr, xi, as_stream(stream));
+}
+
+extern "C" int pno_dft_inv(const pno_plan_t* p, const float* yr, const float* yi, int B, int C, int adjoint,
+                           const float* addend, int act, float* y, float* pre_act, void* stream) {
+    int rc = check_common(p, B, C, C, "pno_dft_inv");
+    if (rc) return rc;
+    if (!yr || !yi || !y) PNO_FAIL(PNO_E_INVALID, "pno_dft_inv: null pointer");
+    return simt_dft_inv(p, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream));
+}
+
+static int check_lv(const float* lv1, const float* lv2, const char* who) {
+    if ((lv1 == nullptr) != (lv2 == nullptr)) PNO_FAIL(PNO_E_INVALID, "%s: lv1 and lv2 must both be set or both be NULL", who);
+    return PNO_OK;
+}
+
+extern "C" int pno_mix_fwd(const pno_plan_t* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co,
+                           const float* mu1, const float* mu2, const float* lv1, const float* lv2, uint64_t seed,
+                           uint32_t sample_idx, uint32_t site, float* yr, float* yi, void* stream) {
+    int rc = check_common(p, B, Ci, Co, "pno_mix_fwd");
+    if (rc) return rc;
+    if ((rc = check_lv(lv1, lv2, "pno_mix_fwd"))) return rc;
+    if (!xr || !xi || !mu1 || !mu2 || !yr || !yi) PNO_FAIL(PNO_E_INVALID, "pno_mix_fwd: null pointer");
+    const PhiloxKey key = make_key(seed, sample_idx, site);
+    if (engine != PNO_ENGINE_FP32)
+        return tc_mix_fwd(p, engine, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
+    return simt_mix_fwd(p, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
+}
+
+extern "C" int pno_mix_bwd_dx(const pno_plan_t* p, int engine, const float* gr, const float* gi, int B, int Ci, int Co,
+                              const float* mu1, const float* mu2, const float* lv1, const float* lv2, uint64_t seed,
+                              uint32_t sample_idx, uint32_t site, float* dxr, float* dxi, void* stream) {
+    int rc = check_common(p, B, Ci, Co, "pno_mix_bwd_dx");
+    if (rc) return rc;
+    if ((rc = check_lv(lv1, lv2, "pno_mix_bwd_dx"))) return rc;
+    if (!gr || !gi || !mu1 || !mu2 || !dxr || !dxi) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dx: null pointer");
+    (void)engine;   // backward kernels run on the fp32 engine in this version
+    return simt_mix_bwd_dx(p, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, make_key(seed, sample_idx, site), dxr, dxi,
+                           as_stream(stream));
+}
+
+extern "C" int pno_mix_bwd_dw(const pno_plan_t* p, int engine, const float* xr, const float* xi, const float* gr,
+                              const float* gi, int B, int Ci, int Co, const float* lv1, const float* lv2, uint64_t seed,
+                              uint32_t sample_idx, uint32_t site, float* dmu1, float* dmu2, float* dlv1, float* dlv2,
+                              void* stream) {
+    int rc = check_common(p, B, Ci, Co, "pno_mix_bwd_dw");
+    if (rc) return rc;
+    if ((rc = check_lv(lv1, lv2, "pno_mix_bwd_dw"))) return rc;
+    if (!xr || !xi || !gr || !gi) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dw: null pointer");
+    if ((dmu1 == nullptr) != (dmu2 == nullptr) || (dlv1 == nullptr) != (dlv2 == nullptr))
+        PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dw: gradient outputs must be given per pair");
+    (void)engine;
+    return simt_mix_bwd_dw(p, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, make_key(seed, sample_idx, site), dmu1, dmu2, dlv1,
+                           dlv2, as_stream(stream));
+}
+
+extern "C" int pno_spectral_fwd(const pno_plan_t* p, int engine, const float* x, int B, int Ci, int Co, const float* mu1,
+                                const float* mu2, const float* lv1, const float* lv2, uint64_t seed, uint32_t sample_idx,
+                                uint32_t site, const float* addend, int act, float* y, float* pre_act, void* workspace,
+                                void* stream) {
+    int rc = check_common(p, B, Ci, Co, "pno_spectral_fwd");
+    if (rc) return rc;
+    if (!x || !y || !workspace) PNO_FAIL(PNO_E_INVALID, "pno_spectral_fwd: null pointer");
+    const size_t mb = (size_t)p->M * B;
+    float* xr = static_cast<float*>(workspace);
+    float* xi = xr + mb * Ci;
+    float* yr = xi + mb * Ci;
+    float* yi = yr + mb * Co;
+    if ((rc = pno_dft_fwd(p, x, B, Ci, 0, xr, xi, stream))) return rc;
+    if ((rc = pno_mix_fwd(p, engine, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, seed, sample_idx, site, yr, yi, stream)))
+        return rc;
+    return pno_dft_inv(p, yr, yi, B, Co, 0, addend, act, y, pre_act, stream);
+}
+
+extern "C" int pno_spectral_bwd(const pno_plan_t* p, int engine, const float* x, const float* xhat_saved, const float* g,
+                                int B, int Ci, int Co, const float* mu1, const float* mu2, const float* lv1,
+                                const float* lv2, uint64_t seed, uint32_t sample_idx, uint32_t site, float* dx,
+                                float* dmu1, float* dmu2, float* dlv1, float* dlv2, void* workspace, void* stream) {
+    int rc = check_common(p, B, Ci, Co, "pno_spectral_bwd");
+    if (rc) return rc;
+    if (!g || !workspace) PNO_FAIL(PNO_E_INVALID, "pno_spectral_bwd: null pointer");
+    const size_t mb = (size_t)p->M * B;
+    float* xr = static_cast<float*>(workspace);
+    float* xi = xr + mb * Ci;
+    float* gr = xi + mb * Ci;
+    float* gi = gr + mb * Co;
+    float* dxr = gi + mb * Co;
+    float* dxi = dxr + mb * Ci;
+    if ((rc = pno_dft_fwd(p, g, B, Co, 1, gr, gi, stream))) return rc;
+    if (dmu1 || dlv1) {
+        const float *sxr = xr, *sxi = xi;
+        if (xhat_saved) {
+            sxr = xhat_saved;
+            sxi = xhat_saved + mb * Ci;
+        } else {
+            if (!x) PNO_FAIL(PNO_E_INVALID, "pno_spectral_bwd: need x or xhat_saved for the weight gradients");
+            if ((rc = pno_dft_fwd(p, x, B, Ci, 0, xr, xi, stream))) return rc;
+        }
+        if ((rc = pno_mix_bwd_dw(p, engine, sxr, sxi, gr, gi, B, Ci, Co, lv1, lv2, seed, sample_idx, site, dmu1, dmu2,
+                                 dlv1, dlv2, stream)))
+            return rc;
+    }
+    if (dx) {
+        if ((rc = pno_mix_bwd_dx(p, engine, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, seed, sample_idx, site, dxr, dxi,
+                                 stream)))
+            return rc;
+        if ((rc = pno_dft_inv(p, dxr, dxi, B, Ci, 1, nullptr, PNO_ACT_NONE, dx, nullptr, stream))) return rc;
+    }
+    return PNO_OK;
+}
+
+extern "C" int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
+                             const float* Wl, const float* bl, uint64_t seed, uint32_t sample_idx, uint32_t site,
+                             uint64_t batch_offset, float* out, float* dout_dlv, void* stream) {
+    if (B <= 0 || Ci <= 0 || Co <= 0 || HW <= 0) PNO_FAIL(PNO_E_INVALID, "pno_local_fwd: non-positive size");
+    if (!x || !Wm || !out) PNO_FAIL(PNO_E_INVALID, "pno_local_fwd: null pointer");
+    if (B > 65535) PNO_FAIL(PNO_E_INVALID, "pno_local_fwd: batch %d exceeds the grid limit", B);
+    const PhiloxKey key = make_key(seed, sample_idx, site);
+    if (engine != PNO_ENGINE_FP32) {
+        const int rc = tc_local_fwd(engine, x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv,
+                                    as_stream(stream));
+        if (rc != PNO_E_UNSUPPORTED) return rc;   // shapes the tensor-core kernel does not tile run on CUDA cores
+    }
+    return simt_local_fwd(x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv, as_stream(stream));
+}

@@ -1,0 +1,15 @@
+// Tensor-core engines (tcgen05 + TMEM).  Shapes a kernel does not tile return PNO_E_UNSUPPORTED with a message;
+// the C ABI reports that to the caller (there is no silent fallback for an explicitly requested engine).
+#include "pno_tc.cuh"
+
+void tc_plan_release(pno_plan* p) { (void)p; }
+
+int tc_mix_fwd(const pno_plan*, int, const float*, const float*, int, int, int, const float*, const float*, const float*,
+               const float*, PhiloxKey, float*, float*, cudaStream_t) {
+    PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core mix engine is not built into this version");
+}
+
+int tc_local_fwd(int, const float*, int, int, int, int, const float*, const float*, const float*, const float*, PhiloxKey,
+                 uint64_t, float*, float*, cudaStream_t) {
+    PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core local engine is not built into this version");
+}

@@ -1,0 +1,10 @@
+// Tensor-core (tcgen05 / TMEM / TMA) engines: entry points called from pno_capi.cu.
+#pragma once
+#include "pno_common.cuh"
+
+void tc_plan_release(pno_plan* p);
+int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
+               const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st);
+int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
+                 const float* Wl, const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv,
+                 cudaStream_t st);

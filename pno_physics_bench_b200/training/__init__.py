@@ -1,0 +1,2 @@
+from .losses import ELBOLoss, PNOLoss  # noqa: F401
+from .trainer import PNOTrainer  # noqa: F401

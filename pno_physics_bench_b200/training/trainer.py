@@ -1,0 +1,173 @@
+"""PNOTrainer mirror (reference training/trainer.py:34-575): same constructor signature, `fit` / `evaluate` /
+`save_checkpoint` / `load_checkpoint`, same checkpoint dict keys, same step order (zero_grad -> sampled forward ->
+loss -> backward -> clip_grad_norm_ -> optimizer.step).  Additions: `train_step` is public, the step's Philox seed is
+shared across data-parallel ranks, gradients are averaged with bucketed NCCL all-reduces, and per-step `.item()` host
+syncs are deferred to the end of the epoch."""
+import logging
+import time
+from pathlib import Path
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import functional as F_
+from ..distributed import allreduce_gradients, shared_seed, world
+from .losses import ELBOLoss
+
+logger = logging.getLogger(__name__)
+
+
+class PNOTrainer:
+    def __init__(self, model: nn.Module, loss_fn: Optional[nn.Module] = None, optimizer=None, scheduler=None,
+                 device: Optional[str] = None, gradient_clipping: Optional[float] = 1.0, mixed_precision: bool = False,
+                 num_samples: int = 5, kl_weight: float = 1e-4, log_interval: int = 10, use_wandb: bool = False,
+                 wandb_project: Optional[str] = None, callbacks: Optional[List] = None, seed: Optional[int] = None,
+                 group=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.model = model.to(self.device)
+        self.loss_fn = loss_fn if loss_fn is not None else ELBOLoss(kl_weight=kl_weight, num_samples=num_samples)
+        self.optimizer = optimizer if optimizer is not None else torch.optim.AdamW(
+            self.model.parameters(), lr=1e-3, weight_decay=1e-4)
+        self.scheduler = scheduler
+        self.gradient_clipping = gradient_clipping
+        self.mixed_precision = mixed_precision      # accepted for signature compatibility; the kernels choose their
+        self.num_samples = num_samples              # arithmetic through model.set_engine(), not autocast
+        self.log_interval = log_interval
+        self.use_wandb = False
+        self.callbacks = callbacks or []
+        self.group = group
+        self.current_epoch = 0
+        self.global_step = 0
+        self.best_val_loss = float("inf")
+        self.training_history = {"train_loss": [], "val_loss": [], "learning_rate": []}
+        self.seed = shared_seed(seed, self.device, group)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def train_step(self, inputs, targets, batch_offset: int = 0) -> Dict[str, torch.Tensor]:
+        """One optimisation step (trainer.py:242-295).  Returns the loss dict as device tensors (no host sync)."""
+        self.model.train()
+        inputs = inputs.to(self.device, non_blocking=True)
+        targets = targets.to(self.device, non_blocking=True)
+        self.optimizer.zero_grad()
+        with F_.noise_scope(self.seed, self.global_step, batch_offset):
+            outputs = self.model(inputs, sample=True, return_kl=True)
+            losses = self.loss_fn(outputs, targets, self.model)
+            losses["total"].backward()
+        allreduce_gradients(self.model.parameters(), self.group)
+        if self.gradient_clipping:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.gradient_clipping)
+        self.optimizer.step()
+        self.global_step += 1
+        return losses
+
+    def _train_epoch(self, loader) -> Dict[str, float]:
+        sums, count = {}, 0
+        rank, ws = world(self.group)
+        for batch_idx, (inputs, targets) in enumerate(loader):
+            for cb in self.callbacks:
+                cb.on_batch_begin(batch_idx, inputs, targets, self)
+            bs = inputs.shape[0]
+            losses = self.train_step(inputs, targets, batch_offset=rank * bs)
+            for k, v in losses.items():
+                sums[k] = sums.get(k, 0.0) + v.detach() * bs
+            count += bs
+            for cb in self.callbacks:
+                cb.on_batch_end(batch_idx, losses, self)
+        return {k: float(v) / max(count, 1) for k, v in sums.items()}
+
+    def _validate_epoch(self, loader) -> Dict[str, float]:
+        """trainer.py:321-397: predict_with_uncertainty(S=num_samples) -> (mean, 2 log std) -> loss."""
+        self.model.eval()
+        sums, count = {}, 0
+        with torch.no_grad():
+            for inputs, targets in loader:
+                inputs, targets = inputs.to(self.device), targets.to(self.device)
+                mean, std = self.model.predict_with_uncertainty(inputs, num_samples=self.num_samples)
+                losses = self.loss_fn((mean, 2 * torch.log(std.clamp(min=1e-6))), targets, self.model)
+                bs = inputs.shape[0]
+                for k, v in losses.items():
+                    sums[k] = sums.get(k, 0.0) + v.detach() * bs
+                count += bs
+        return {k: float(v) / max(count, 1) for k, v in sums.items()}
+
+    def fit(self, train_loader, val_loader=None, epochs: int = 100, save_dir: Optional[str] = None,
+            resume_from: Optional[str] = None) -> Dict[str, List[float]]:
+        if resume_from:
+            self.load_checkpoint(resume_from)
+        for cb in self.callbacks:
+            cb.on_train_begin(self)
+        t0 = time.time()
+        for epoch in range(self.current_epoch, epochs):
+            self.current_epoch = epoch
+            for cb in self.callbacks:
+                cb.on_epoch_begin(epoch, self)
+            train = self._train_epoch(train_loader)
+            val = self._validate_epoch(val_loader) if val_loader is not None else {}
+            if self.scheduler is not None:
+                self.scheduler.step()
+            self.training_history["train_loss"].append(train.get("total", float("nan")))
+            self.training_history["val_loss"].append(val.get("total", float("nan")))
+            self.training_history["learning_rate"].append(self.optimizer.param_groups[0]["lr"])
+            if val and val["total"] < self.best_val_loss:
+                self.best_val_loss = val["total"]
+                if save_dir:
+                    self.save_checkpoint(Path(save_dir) / "best_model.pt")
+            if (epoch + 1) % self.log_interval == 0:
+                logger.info("epoch %d train %.4e val %.4e", epoch + 1, train.get("total", float("nan")),
+                            val.get("total", float("nan")))
+            stop = False
+            for cb in self.callbacks:
+                if cb.on_epoch_end(epoch, {"train": train, "val": val}, self):
+                    stop = True
+            if stop:
+                break
+        self.current_epoch = epochs
+        logger.info("training finished in %.1f s", time.time() - t0)
+        for cb in self.callbacks:
+            cb.on_train_end(self)
+        return self.training_history
+
+    def evaluate(self, loader, num_samples: int = 100) -> Dict[str, float]:
+        """trainer.py:499-575 (loss part): MC predictive mean/std with S=100, MSE and NLL."""
+        self.model.eval()
+        se = nll = 0.0
+        count = 0
+        with torch.no_grad():
+            for inputs, targets in loader:
+                inputs, targets = inputs.to(self.device), targets.to(self.device)
+                mean, std = self.model.predict_with_uncertainty(inputs, num_samples=num_samples)
+                std = std.clamp(min=1e-6)
+                se = se + ((mean - targets) ** 2).sum()
+                nll = nll + (0.5 * (1.8378770664093453 + 2 * torch.log(std) + (targets - mean) ** 2 / std ** 2)).sum()
+                count += targets.numel()
+        return {"mse": float(se) / max(count, 1), "nll": float(nll) / max(count, 1)}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def save_checkpoint(self, path, metadata: Optional[dict] = None):
+        """Same dict layout as trainer.py:440-463; tensors are saved in the reference's logical shapes."""
+        path = Path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        ckpt = {
+            "epoch": self.current_epoch,
+            "model_state_dict": {k: v.contiguous() for k, v in self.model.state_dict().items()},
+            "best_val_loss": self.best_val_loss,
+            "training_history": self.training_history,
+            "optimizer_state_dict": self.optimizer.state_dict(),
+            "metadata": metadata or {},
+        }
+        if self.scheduler is not None:
+            ckpt["scheduler_state_dict"] = self.scheduler.state_dict()
+        torch.save(ckpt, path)
+
+    def load_checkpoint(self, path):
+        ckpt = torch.load(path, map_location=self.device, weights_only=False)
+        self.model.load_state_dict(ckpt["model_state_dict"])
+        if "optimizer_state_dict" in ckpt:
+            self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        if self.scheduler is not None and "scheduler_state_dict" in ckpt:
+            self.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+        self.current_epoch = ckpt.get("epoch", 0)
+        self.best_val_loss = ckpt.get("best_val_loss", float("inf"))
+        self.training_history = ckpt.get("training_history", self.training_history)
+        return ckpt
