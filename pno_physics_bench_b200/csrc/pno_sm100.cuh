@@ -1,0 +1,191 @@
+// sm_100a building blocks used by the tensor-core engines: mbarrier, TMA (cp.async.bulk.tensor), tcgen05.mma with
+// shared-memory matrix descriptors, TMEM allocation / loads.  Inline PTX only; no CUTLASS dependency.
+//
+// Every mbarrier wait is bounded: a wait that exceeds ~2 s of SM clock traps instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sm100 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug, not a slow kernel -> fail loudly, do not hang
+            printf("pno_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// ---- proxies / fences --------------------------------------------------------------------------------------------------
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- TMA ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// ---- TMEM --------------------------------------------------------------------------------------------------------------
+// one full warp; ncols a power of two in [32, 512]; the base address is written to *slot (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 8 consecutive 32-bit columns: thread t of the warp gets lane (lane_base + t), columns col .. col+7
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) {
+    return base + ((uint32_t)lane << 16) + (uint32_t)col;
+}
+
+// ---- tcgen05.mma -------------------------------------------------------------------------------------------------------
+enum : uint32_t { FMT_BF16 = 1, FMT_TF32 = 2 };
+enum : uint32_t { MAJOR_K = 0, MAJOR_MN = 1 };
+enum : uint32_t { SWIZZLE_NONE = 0, SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6 };
+
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): fp32 accumulate, dense
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, int M, int N, uint32_t a_major, uint32_t b_major,
+                                                  uint32_t a_neg = 0, uint32_t b_neg = 0) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_neg << 13) | (b_neg << 14) | (a_major << 15) | (b_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout_type & 7) << 61;
+    return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- canonical SWIZZLE_128B tile addressing for 4-byte elements (tile base 1024-byte aligned) ---------------------------
+// K-major [R rows][K]: K split into blocks of 32 elements (128 B); block kb is a dense [R x 128 B] region.
+__host__ __device__ __forceinline__ uint32_t kmajor_sw128_off(int r, int k, int R) {
+    const int kb = k >> 5, kk = k & 31;
+    return (uint32_t)(kb * R * 128 + r * 128 + ((((kk >> 2) ^ (r & 7)) << 4) | ((kk & 3) << 2)));
+}
+// MN-major [K rows][N]: N split into blocks of 32 elements; block nb is a dense [Kt x 128 B] region (one K row per line).
+__host__ __device__ __forceinline__ uint32_t mnmajor_sw128_off(int k, int n, int Kt) {
+    const int nb = n >> 5, nn = n & 31;
+    return (uint32_t)(nb * Kt * 128 + k * 128 + ((((nn >> 2) ^ (k & 7)) << 4) | ((nn & 3) << 2)));
+}
+
+}  // namespace sm100
+
+// ---- host: tensor maps --------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+int pno_encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle128);

@@ -1,0 +1,34 @@
+"""Tensor-core (tcgen05 / TMEM / TMA) engine tests on a B200: descriptor self-tests first, then the fused kernels
+against the fp32 CUDA-core engine and the oracle."""
+import itertools
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from pno_physics_bench_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("flags,n,k", [(f, n, k) for f in range(16) for n, k in ((64, 64), (128, 32))]
+                         + [(0b110000 | 0b1010, 96, 96), (0b010000, 32, 128), (0b100101, 256, 64)])
+def test_umma_selftest(flags, n, k):
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(flags * 1000 + n + k)
+    a = tf32_trunc(torch.randn(128, k, generator=gen)).to(DEV)
+    b = tf32_trunc(torch.randn(k, n, generator=gen)).to(DEV)
+    a_src = a.t().contiguous() if flags & 1 else a
+    b_src = b if flags & 2 else b.t().contiguous()
+    d = torch.full((128, n), float("nan"), device=DEV)
+    _lib.check(lib.pno_selftest_umma(flags, n, k, a.data_ptr(), b.data_ptr(), a_src.data_ptr(), b_src.data_ptr(),
+                                     d.data_ptr(), _lib.stream_ptr()), "selftest")
+    torch.cuda.synchronize()
+    sign = (-1.0 if flags & 16 else 1.0) * (-1.0 if flags & 32 else 1.0)
+    want = sign * (a.double() @ b.double())
+    assert rel_l2(d, want) < 1e-6, f"flags={flags:06b}"
