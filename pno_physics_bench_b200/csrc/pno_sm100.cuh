@@ -125,7 +125,7 @@ __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) 
 // ---- tcgen05.mma -------------------------------------------------------------------------------------------------------
 enum : uint32_t { FMT_BF16 = 1, FMT_TF32 = 2 };
 enum : uint32_t { MAJOR_K = 0, MAJOR_MN = 1 };
-enum : uint32_t { SWIZZLE_NONE = 0, SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6 };
+enum : uint32_t { SWIZZLE_NONE = 0, SWIZZLE_128B_BASE32B = 1, SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6 };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): fp32 accumulate, dense
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, int M, int N, uint32_t a_major, uint32_t b_major,
@@ -178,9 +178,12 @@ __host__ __device__ __forceinline__ uint32_t kmajor_sw128_off(int r, int k, int 
     return (uint32_t)(kb * R * 128 + r * 128 + ((((kk >> 2) ^ (r & 7)) << 4) | ((kk & 3) << 2)));
 }
 // MN-major [K rows][N]: N split into blocks of 32 elements; block nb is a dense [Kt x 128 B] region (one K row per line).
+// 32-bit MN-major operands only exist in the SWIZZLE_128B_BASE32B form (32-byte chunks XOR (row & 3); atom = 4 K rows):
+// descriptor LBO = Kt*128 (next block of 32 N), SBO = 512 (next 4 K rows), one K=8 instruction spans 1024 bytes.
+// TMA writes this layout with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and a {32 elements, Kt rows} box.
 __host__ __device__ __forceinline__ uint32_t mnmajor_sw128_off(int k, int n, int Kt) {
     const int nb = n >> 5, nn = n & 31;
-    return (uint32_t)(nb * Kt * 128 + k * 128 + ((((nn >> 2) ^ (k & 7)) << 4) | ((nn & 3) << 2)));
+    return (uint32_t)(nb * Kt * 128 + k * 128 + ((((nn >> 3) ^ (k & 3)) << 5) | ((nn & 7) << 2)));
 }
 
 }  // namespace sm100
@@ -188,4 +191,4 @@ __host__ __device__ __forceinline__ uint32_t mnmajor_sw128_off(int k, int n, int
 // ---- host: tensor maps --------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 int pno_encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle128);
+                    const uint32_t* box, int swizzle /* 0 none, 1 = 128B (16-byte atoms), 2 = 128B with 32-byte atoms */);

@@ -8,7 +8,7 @@
 using namespace sm100;
 
 int pno_encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle128) {
+                    const uint32_t* box, int swizzle) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -25,7 +25,9 @@ int pno_encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];     // strides of dims 1..rank-1
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) PNO_FAIL(PNO_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return PNO_OK;
@@ -104,9 +106,9 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const SelfTestArgs a, con
         for (int ks = 0; ks < K / 8; ++ks) {
             uint64_t ad, bd;
             if (!a.a_mn) ad = make_sdesc(a0 + (ks >> 2) * 128 * 128 + (ks & 3) * 32, 16, 1024, SWIZZLE_128B);
-            else         ad = make_sdesc(a0 + ks * 1024, (uint32_t)K * 128, 1024, SWIZZLE_128B);
+            else         ad = make_sdesc(a0 + ks * 1024, (uint32_t)K * 128, 512, SWIZZLE_128B_BASE32B);
             if (!a.b_mn) bd = make_sdesc(b0 + (ks >> 2) * N * 128 + (ks & 3) * 32, 16, 1024, SWIZZLE_128B);
-            else         bd = make_sdesc(b0 + ks * 1024, (uint32_t)K * 128, 1024, SWIZZLE_128B);
+            else         bd = make_sdesc(b0 + ks * 1024, (uint32_t)K * 128, 512, SWIZZLE_128B_BASE32B);
             mma_tf32_ss(tmem, ad, bd, idesc, ks > 0);
         }
         mma_commit(&bar_mma);
@@ -149,7 +151,7 @@ extern "C" int pno_selftest_umma(int flags, int N, int K, const float* A, const 
         uint32_t box[2];
         if (!a.a_mn) { dims[0] = K; dims[1] = 128; str[0] = (uint64_t)K * 4; box[0] = 32; box[1] = 128; }
         else         { dims[0] = 128; dims[1] = K; str[0] = 128 * 4; box[0] = 32; box[1] = K; }
-        if ((rc = pno_encode_tmap(&tmA, A_tma_src, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmA, A_tma_src, 2, dims, str, box, a.a_mn ? 2 : 1))) return rc;
     }
     if (a.b_tma) {
         // K-major: source Bt [N rows][K] -> box {32 k, N rows}; MN-major: source B [K rows][N] -> box {32 n, K rows}
@@ -157,7 +159,7 @@ extern "C" int pno_selftest_umma(int flags, int N, int K, const float* A, const 
         uint32_t box[2];
         if (!a.b_mn) { dims[0] = K; dims[1] = N; str[0] = (uint64_t)K * 4; box[0] = 32; box[1] = N; }
         else         { dims[0] = N; dims[1] = K; str[0] = (uint64_t)N * 4; box[0] = 32; box[1] = K; }
-        if ((rc = pno_encode_tmap(&tmB, B_tma_src, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmB, B_tma_src, 2, dims, str, box, a.b_mn ? 2 : 1))) return rc;
     }
     const size_t smem = 1024 + (size_t)128 * K * 4 + (size_t)K * N * 4;
     PNO_CUDA(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
