@@ -2,7 +2,7 @@
 """Headline benchmark: MC-sample fields/s of `predict_with_uncertainty` at 64x64, hidden 256, modes 20 (BASELINE.json
 config 3: batch 64, S MC samples), on N B200s of one node, plus the spectral-conv roofline and a CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--engine fp32|tf32x3|bf16] [--mc-samples S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--engine fp32|tf32x3|tf32] [--mc-samples S]
     python bench.py --impl reference ...        # the reference's algorithm (oracle port) on the host CPU cores
 
 A "step" is one `predict_with_uncertainty(x, num_samples=S*N)` over one batch of 64 synthetic fields: S samples per
@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("PNO_BENCH_ENGINE", "fp32"), choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--engine", default=os.environ.get("PNO_BENCH_ENGINE", "fp32"), choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--mc-samples", type=int, default=int(os.environ.get("PNO_BENCH_MC_SAMPLES", "20")),
                     help="MC samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -271,7 +271,7 @@ def main():
         # every MC sample streams all parameters once (2.5 GB) and the working set per layer (> 1 GB) exceeds the 126 MB L2
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-equivalent)", "bf16": "bf16"}[args.engine],
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-equivalent)", "tf32": "tf32"}[args.engine],
                 "data": "synthetic",
                 "config": {"workload": f"cfg3: predict_with_uncertainty 64x64 in3 hid256 L4 modes20, batch {B} x {S} MC "
                                        f"samples per GPU per step", "engine": args.engine,

@@ -50,7 +50,8 @@ enum { PNO_ACT_NONE = 0, PNO_ACT_GELU = 1, PNO_ACT_RELU = 2 };   /* models.py:22
 enum {
     PNO_ENGINE_FP32 = 0,      /* fp32 FMA on CUDA cores: any shape, reference-grade fp32 (rel-L2 <= 1e-5)      */
     PNO_ENGINE_TC_TF32X3 = 1, /* tcgen05 tensor cores, error-compensated 3xTF32 (rel-L2 <= 1e-5)                */
-    PNO_ENGINE_TC_BF16 = 2    /* tcgen05 tensor cores, bf16 operands / fp32 accumulate (rel-L2 <= 2e-2)         */
+    PNO_ENGINE_TC_TF32 = 2    /* tcgen05 tensor cores, single-pass TF32 operands / fp32 accumulate: the reduced-
+                                 precision mode (rel-L2 ~1e-3, inside the 2e-2 budget of the bf16-compute mode)   */
 };
 
 typedef struct pno_plan pno_plan_t;

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libpno_b200.so")
 
 PNO_OK, PNO_E_INVALID, PNO_E_MODES, PNO_E_CUDA, PNO_E_ARCH, PNO_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-ENGINE_FP32, ENGINE_TC_TF32X3, ENGINE_TC_BF16 = 0, 1, 2
-ENGINES = {"fp32": ENGINE_FP32, "tf32x3": ENGINE_TC_TF32X3, "bf16": ENGINE_TC_BF16}
+ENGINE_FP32, ENGINE_TC_TF32X3, ENGINE_TC_TF32 = 0, 1, 2
+ENGINES = {"fp32": ENGINE_FP32, "tf32x3": ENGINE_TC_TF32X3, "tf32": ENGINE_TC_TF32}
 
 _c_float_p = ctypes.c_void_p      # device pointers travel as integers
 _u64, _u32, _int, _vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p

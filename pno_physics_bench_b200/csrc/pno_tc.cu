@@ -9,7 +9,3 @@ int tc_mix_fwd(const pno_plan*, int, const float*, const float*, int, int, int, 
     PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core mix engine is not built into this version");
 }
 
-int tc_local_fwd(int, const float*, int, int, int, int, const float*, const float*, const float*, const float*, PhiloxKey,
-                 uint64_t, float*, float*, cudaStream_t) {
-    PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core local engine is not built into this version");
-}

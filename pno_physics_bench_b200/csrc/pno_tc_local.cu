@@ -1,0 +1,279 @@
+// Local branch of the PNO block on the tensor cores (engines PNO_ENGINE_TC_*):
+//   out[b][o][p] = (Wm x[b])[o][p] + bm[o] + eps * clamp(exp(0.5 clamp((Wl x[b])[o][p] + bl[o], -10, 10)), 1e-6)
+// (reference models.py:298-303 + 264-275) as ONE persistent, warp-specialised kernel:
+//   warp 0      TMA producer: x tile [32 i][128 p] (MN-major B operand, straight from the NCHW tensor) and the Wm / Wl tiles
+//               [128 o][32 i] (K-major A operands) into a multi-stage shared-memory ring
+//   warps 2-5   (3xTF32 only) split every staged tile into tf32 hi (in place) + lo (second buffer)
+//   warp 1      one thread issues tcgen05.mma kind::tf32 into two TMEM accumulators (mean, log-var), double buffered
+//   warps 6-9   epilogue: tcgen05.ld -> bias, clamp/exp, Philox noise, (d out / d lv for backward) -> global
+// A tile is (batch item b, 128 output channels, 128 pixels); tiles are statically strided over the persistent grid with the
+// output-channel tile fastest so that the CTAs sharing an x tile run at the same time (L2 reuse).
+#include "pno_sm100.cuh"
+#include "pno_tc.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int TM = 128;          // output channels per tile (UMMA M)
+constexpr int TN = 128;          // pixels per tile (UMMA N)
+constexpr int TK = 32;           // input channels per stage (one 128-byte swizzle row)
+constexpr int TILE_BYTES = TM * TK * 4;   // 16 KB, same for A [128][32] and B [32][128]
+
+struct LocalArgs {
+    int B, Ci, Co, HW;
+    int noisy, want_dlv;
+    const float *bm, *bl;
+    float *out, *dlv;
+    PhiloxKey key;
+    uint64_t batch_offset;
+    int n_tiles, p_tiles, o_tiles;
+};
+
+template <int NSPLIT>
+struct Cfg {
+    static constexpr int kStages = NSPLIT == 3 ? 2 : 4;
+    static constexpr int kOperandBytes = 3 * TILE_BYTES;                         // Am, Al, X
+    static constexpr int kStageBytes = kOperandBytes * (NSPLIT == 3 ? 2 : 1);    // + lo copies
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+__device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-nearest on the 13 dropped mantissa bits
+    float4 r;
+    r.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+    r.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+    r.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+    r.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+    return r;
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
+           const __grid_constant__ CUtensorMap tmWl) {
+    using C = Cfg<NSPLIT>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar_raw[C::kStages], bar_split[C::kStages], bar_empty[C::kStages];
+    __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = a.Ci / TK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(&bar_raw[s], 1);
+            mbar_init(&bar_split[s], 128);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_tfull[s], 1);
+            mbar_init(&bar_tempty[s], 128);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmWm);
+        tma_prefetch_desc(&tmWl);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    unsigned char* st = stage_ptr(stage);
+                    mbar_arrive_expect_tx(&bar_raw[stage], (a.noisy ? 3 : 2) * TILE_BYTES);
+                    tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
+                    if (a.noisy) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
+                    // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, 4} lands as [4 p-blocks][32 rows][128 B]
+                    tma_load_3d(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(FMT_TF32, TM, TN, MAJOR_K, MAJOR_MN);
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&bar_tempty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_m = tmem + acc * 256, d_l = d_m + 128;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t s0 = smem_u32(stage_ptr(stage));
+                    const uint32_t am = s0, al = s0 + TILE_BYTES, xb = s0 + 2 * TILE_BYTES;
+                    const uint32_t lo = C::kOperandBytes;      // byte distance from a hi tile to its lo copy
+#pragma unroll
+                    for (int ks = 0; ks < TK / 8; ++ks) {
+                        const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
+                        const uint64_t dx_hi = make_sdesc(xb + ks * 1024, TK * 128, 512, SWIZZLE_128B_BASE32B);
+                        const uint64_t dm_hi = make_sdesc(am + ks * 32, 16, 1024, SWIZZLE_128B);
+                        mma_tf32_ss(d_m, dm_hi, dx_hi, idesc, acc_flag);
+                        if (NSPLIT == 3) {
+                            const uint64_t dx_lo = make_sdesc(xb + lo + ks * 1024, TK * 128, 512, SWIZZLE_128B_BASE32B);
+                            const uint64_t dm_lo = make_sdesc(am + lo + ks * 32, 16, 1024, SWIZZLE_128B);
+                            mma_tf32_ss(d_m, dm_lo, dx_hi, idesc, 1u);
+                            mma_tf32_ss(d_m, dm_hi, dx_lo, idesc, 1u);
+                        }
+                        if (a.noisy) {
+                            const uint64_t dl_hi = make_sdesc(al + ks * 32, 16, 1024, SWIZZLE_128B);
+                            mma_tf32_ss(d_l, dl_hi, dx_hi, idesc, acc_flag);
+                            if (NSPLIT == 3) {
+                                const uint64_t dx_lo = make_sdesc(xb + lo + ks * 1024, TK * 128, 512, SWIZZLE_128B_BASE32B);
+                                const uint64_t dl_lo = make_sdesc(al + lo + ks * 32, 16, 1024, SWIZZLE_128B);
+                                mma_tf32_ss(d_l, dl_lo, dx_hi, idesc, 1u);
+                                mma_tf32_ss(d_l, dl_hi, dx_lo, idesc, 1u);
+                            }
+                        }
+                    }
+                    mma_commit(&bar_empty[stage]);       // frees the stage when these MMAs have read it
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&bar_tfull[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        // ================================ hi/lo splitter (3xTF32) ================================
+        if (NSPLIT == 3) {
+            const int t = threadIdx.x - 64;   // 0..127
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&bar_raw[stage], phase);
+                    float4* hi = reinterpret_cast<float4*>(stage_ptr(stage));
+                    float4* lo = reinterpret_cast<float4*>(stage_ptr(stage) + C::kOperandBytes);
+                    constexpr int kVec = TILE_BYTES / 16;
+#pragma unroll 4
+                    for (int i = t; i < 3 * kVec; i += 128) {
+                        if (!a.noisy && i >= kVec && i < 2 * kVec) continue;
+                        const float4 v = hi[i];
+                        const float4 h = tf32_hi(v);
+                        hi[i] = h;
+                        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bar_split[stage]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
+            const int acc = it & 1;
+            mbar_wait(&bar_tfull[acc], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const int o = ot * TM + q * 32 + lane;
+            const float bias_m = a.bm ? a.bm[o] : 0.f;
+            const float bias_l = (a.noisy && a.bl) ? a.bl[o] : 0.f;
+            const size_t row = ((size_t)b * a.Co + o) * a.HW + (size_t)pt * TN;
+            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN;
+            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * 256), t_l = t_m + 128;
+#pragma unroll 1
+            for (int c = 0; c < TN; c += 8) {
+                float m[8], l[8], v[8], d[8];
+                tmem_ld8(t_m + c, m);
+                if (a.noisy) tmem_ld8(t_l + c, l);
+                tmem_ld_wait();
+                if (a.noisy) {
+                    const float4 z0 = philox_quad_normals(a.key, (e_row + c) >> 2);
+                    const float4 z1 = philox_quad_normals(a.key, ((e_row + c) >> 2) + 1);
+                    const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float lv = l[j] + bias_l;
+                        const float s_raw = expf(0.5f * fminf(fmaxf(lv, -10.f), 10.f));
+                        const float s = fmaxf(s_raw, 1e-6f);
+                        v[j] = fmaf(z[j], s, m[j] + bias_m);
+                        d[j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = m[j] + bias_m;
+                }
+                float4* dst = reinterpret_cast<float4*>(a.out + row + c);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                if (a.noisy && a.want_dlv) {
+                    float4* dd = reinterpret_cast<float4*>(a.dlv + row + c);
+                    dd[0] = make_float4(d[0], d[1], d[2], d[3]);
+                    dd[1] = make_float4(d[4], d[5], d[6], d[7]);
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&bar_tempty[acc]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int NSPLIT>
+int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NSPLIT>::kSmemBytes));
+        attr = true;
+    }
+    int dev = 0, sms = 148;
+    PNO_CUDA(cudaGetDevice(&dev));
+    PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    k_tc_local<NSPLIT><<<grid, kThreads, Cfg<NSPLIT>::kSmemBytes, st>>>(a, tmX, tmWm, tmWl);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+}  // namespace
+
+int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
+                 const float* Wl, const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv,
+                 cudaStream_t st) {
+    if (Ci % TK || Co % TM || HW % TN)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_fwd tiles Ci%%32 == 0, Co%%128 == 0, HW%%128 == 0 (got %d, %d, %d)", Ci, Co, HW);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wm) | reinterpret_cast<uintptr_t>(Wl) |
+         reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout_dlv)) & 15)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_fwd needs 16-byte aligned tensors");
+    LocalArgs a;
+    a.B = B; a.Ci = Ci; a.Co = Co; a.HW = HW;
+    a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;
+    a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset;
+    a.o_tiles = Co / TM; a.p_tiles = HW / TN; a.n_tiles = B * a.o_tiles * a.p_tiles;
+    CUtensorMap tmX, tmWm, tmWl;
+    int rc;
+    {   // x as (p % 32, row = b*Ci + i, p / 32)
+        const uint64_t dims[3] = {32, (uint64_t)B * Ci, (uint64_t)HW / 32};
+        const uint64_t str[2] = {(uint64_t)HW * 4, 128};
+        const uint32_t box[3] = {32, TK, TN / 32};
+        if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
+        const uint64_t str[1] = {(uint64_t)Ci * 4};
+        const uint32_t box[2] = {TK, TM};
+        if ((rc = pno_encode_tmap(&tmWm, Wm, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWl, Wl ? Wl : Wm, 2, dims, str, box, 1))) return rc;
+    }
+    if (engine == PNO_ENGINE_TC_TF32X3) return launch<3>(a, tmX, tmWm, tmWl, st);
+    return launch<1>(a, tmX, tmWm, tmWl, st);
+}

@@ -223,7 +223,7 @@ class ProbabilisticNeuralOperator(nn.Module):
 
     # -- configuration ------------------------------------------------------------------------------------------------
     def set_engine(self, engine):
-        """'fp32' (CUDA cores, any shape), 'tf32x3' / 'bf16' (tcgen05 tensor cores)."""
+        """'fp32' (CUDA cores, any shape), 'tf32x3' (tcgen05, fp32-grade) or 'tf32' (tcgen05, reduced precision)."""
         self.engine = _engine_code(engine)
         for layer in self.fourier_layers:
             layer.engine = self.engine

@@ -32,3 +32,29 @@ def test_umma_selftest(flags, n, k):
     sign = (-1.0 if flags & 16 else 1.0) * (-1.0 if flags & 32 else 1.0)
     want = sign * (a.double() @ b.double())
     assert rel_l2(d, want) < 1e-6, f"flags={flags:06b}"
+
+
+def _local_case(b, ci, co, h, w, noisy, engine, gen):
+    from pno_physics_bench_b200 import functional as F_
+    x = torch.randn(b, ci, h, w, generator=gen).to(DEV).requires_grad_(True)
+    wm = (torch.randn(co, ci, 1, 1, generator=gen) / ci ** 0.5).to(DEV).requires_grad_(True)
+    bm = torch.randn(co, generator=gen).to(DEV).requires_grad_(True)
+    wl = (torch.randn(co, ci, 1, 1, generator=gen) * 0.3).to(DEV).requires_grad_(True) if noisy else None
+    bl = (torch.randn(co, generator=gen) * 2 - 4).to(DEV).requires_grad_(True) if noisy else None
+    out = F_.local_branch(x, wm, bm, wl, bl, seed=11, sample_idx=2, site=5, batch_offset=3, engine=_lib.ENGINES[engine])
+    up = torch.randn(out.shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    out.backward(up)
+    grads = [t.grad.clone() for t in (x, wm, bm) + ((wl, bl) if noisy else ())]
+    return out.detach(), grads
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("noisy", [False, True])
+@pytest.mark.parametrize("shape", [(2, 32, 128, 16, 16), (3, 256, 256, 64, 64), (1, 64, 384, 8, 48)])
+def test_local_branch_tensor_core_vs_cuda_core(engine, tol, noisy, shape):
+    b, ci, co, h, w = shape
+    ref_out, ref_g = _local_case(b, ci, co, h, w, noisy, "fp32", torch.Generator().manual_seed(sum(shape)))
+    out, g = _local_case(b, ci, co, h, w, noisy, engine, torch.Generator().manual_seed(sum(shape)))
+    assert rel_l2(out, ref_out) < tol
+    for a_, b_ in zip(g, ref_g):
+        assert rel_l2(a_, b_) < 10 * tol
