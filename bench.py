@@ -110,12 +110,12 @@ def layer_roofline(model, engine, device, iters=5):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         flush.zero_()
         ev[0].record()
-        _lib.check(lib.pno_dft_fwd(plan, x.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st))
+        _lib.check(lib.pno_dft_fwd(plan, eng, x.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st))
         ev[1].record()
         _lib.check(lib.pno_mix_fwd(plan, eng, xr.data_ptr(), xi.data_ptr(), B, C, C, n1.data_ptr(), n2.data_ptr(),
                                    l1.data_ptr(), l2.data_ptr(), 1234, it, 1, yr.data_ptr(), yi.data_ptr(), st))
         ev[2].record()
-        _lib.check(lib.pno_dft_inv(plan, yr.data_ptr(), yi.data_ptr(), B, C, 0, 0, _lib.ACT_NONE, y.data_ptr(), 0, st))
+        _lib.check(lib.pno_dft_inv(plan, eng, yr.data_ptr(), yi.data_ptr(), B, C, 0, 0, _lib.ACT_NONE, y.data_ptr(), 0, st))
         ev[3].record()
         torch.cuda.synchronize()
         if it >= 2:

@@ -46,7 +46,8 @@ enum {
 
 enum { PNO_ACT_NONE = 0, PNO_ACT_GELU = 1, PNO_ACT_RELU = 2 };   /* models.py:224-229 (exact-erf GELU) */
 
-/* arithmetic engines */
+/* arithmetic engines.  The tensor-core engines tile the shapes documented in each kernel file (the BASELINE configs);
+ * a stage whose shape they do not tile runs on the CUDA-core engine instead (same results to fp32 accuracy). */
 enum {
     PNO_ENGINE_FP32 = 0,      /* fp32 FMA on CUDA cores: any shape, reference-grade fp32 (rel-L2 <= 1e-5)      */
     PNO_ENGINE_TC_TF32X3 = 1, /* tcgen05 tensor cores, error-compensated 3xTF32 (rel-L2 <= 1e-5)                */
@@ -84,13 +85,13 @@ int pno_philox_bits(uint64_t seed, uint32_t sample_idx, uint32_t site, uint64_t 
 /* Pruned forward transform (replaces torch.fft.rfft2 + the two slices, models.py:89, 93-94):
  *   xhat[mode][b][c] = sum_{h,w} x[b][c][h][w] exp(-2 pi i (kx h/H + ky w/W)).
  * grad_scale != 0 multiplies by alive(kx2) * c_ky / (H W): the adjoint of the inverse transform (backward of irfft2). */
-int pno_dft_fwd(const pno_plan_t* plan, const float* x, int B, int C, int grad_scale, float* xhat_re, float* xhat_im,
-                void* stream);
+int pno_dft_fwd(const pno_plan_t* plan, int engine, const float* x, int B, int C, int grad_scale, float* xhat_re,
+                float* xhat_im, void* stream);
 /* Pruned inverse transform + fused epilogue (replaces zeros + scatter + torch.fft.irfft2, models.py:92-97, and the
  * add + activation of the block, models.py:306):
  *   s = sum_mode coef * Re(yhat[mode][b][c] exp(+2 pi i (...)))          coef = alive c_ky/(HW) (adjoint != 0: coef = 1)
  *   v = s + (addend ? addend[b][c][h][w] : 0);  if (pre_act) pre_act = v;  y = act(v)                               */
-int pno_dft_inv(const pno_plan_t* plan, const float* yhat_re, const float* yhat_im, int B, int C, int adjoint,
+int pno_dft_inv(const pno_plan_t* plan, int engine, const float* yhat_re, const float* yhat_im, int B, int C, int adjoint,
                 const float* addend, int act, float* y, float* pre_act, void* stream);
 /* Per-mode complex channel mix with in-kernel weight sampling (replaces sample_weights + compl_mul2d,
  * models.py:63-78, 33-35):  yhat[mode][b][o] = sum_i xhat[mode][b][i] * (mu + exp(lv/2) * eps)[mode][i][o].

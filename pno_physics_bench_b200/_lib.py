@@ -32,8 +32,8 @@ SIGNATURES = {
     "pno_philox_normal_activation": (_int, [_u64, _u32, _u32, _u64, _u64, _vp, _vp]),
     "pno_philox_normal_spectral": (_int, [_u64, _u32, _u32, _int, _int, _int, _int, _vp, _vp, _vp]),
     "pno_philox_bits": (_int, [_u64, _u32, _u32, _u64, _u64, _vp, _vp]),
-    "pno_dft_fwd": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
-    "pno_dft_inv": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _int, _vp, _vp, _vp]),
+    "pno_dft_fwd": (_int, [_vp, _int, _vp, _int, _int, _int, _vp, _vp, _vp]),
+    "pno_dft_inv": (_int, [_vp, _int, _vp, _vp, _int, _int, _int, _vp, _int, _vp, _vp, _vp]),
     "pno_mix_fwd": (_int, [_vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp]),
     "pno_mix_bwd_dx": (_int, [_vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _vp, _vp,
                               _vp]),

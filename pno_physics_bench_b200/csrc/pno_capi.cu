@@ -93,19 +93,27 @@ static int check_common(const pno_plan* p, int B, int Ci, int Co, const char* wh
     return PNO_OK;
 }
 
-extern "C" int pno_dft_fwd(const pno_plan_t* p, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
-                           void* stream) {
+extern "C" int pno_dft_fwd(const pno_plan_t* p, int engine, const float* x, int B, int C, int grad_scale, float* xr,
+                           float* xi, void* stream) {
     int rc = check_common(p, B, C, C, "pno_dft_fwd");
     if (rc) return rc;
     if (!x || !xr || !xi) PNO_FAIL(PNO_E_INVALID, "pno_dft_fwd: null pointer");
+    if (engine != PNO_ENGINE_FP32) {
+        rc = tc_dft_fwd(p, engine, x, B, C, grad_scale, xr, xi, as_stream(stream));
+        if (rc != PNO_E_UNSUPPORTED) return rc;
+    }
     return simt_dft_fwd(p, x, B, C, grad_scale, xr, xi, as_stream(stream));
 }
 
-extern "C" int pno_dft_inv(const pno_plan_t* p, const float* yr, const float* yi, int B, int C, int adjoint,
+extern "C" int pno_dft_inv(const pno_plan_t* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
                            const float* addend, int act, float* y, float* pre_act, void* stream) {
     int rc = check_common(p, B, C, C, "pno_dft_inv");
     if (rc) return rc;
     if (!yr || !yi || !y) PNO_FAIL(PNO_E_INVALID, "pno_dft_inv: null pointer");
+    if (engine != PNO_ENGINE_FP32) {
+        rc = tc_dft_inv(p, engine, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream));
+        if (rc != PNO_E_UNSUPPORTED) return rc;
+    }
     return simt_dft_inv(p, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream));
 }
 
@@ -122,8 +130,10 @@ extern "C" int pno_mix_fwd(const pno_plan_t* p, int engine, const float* xr, con
     if ((rc = check_lv(lv1, lv2, "pno_mix_fwd"))) return rc;
     if (!xr || !xi || !mu1 || !mu2 || !yr || !yi) PNO_FAIL(PNO_E_INVALID, "pno_mix_fwd: null pointer");
     const PhiloxKey key = make_key(seed, sample_idx, site);
-    if (engine != PNO_ENGINE_FP32)
-        return tc_mix_fwd(p, engine, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
+    if (engine != PNO_ENGINE_FP32) {
+        rc = tc_mix_fwd(p, engine, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
+        if (rc != PNO_E_UNSUPPORTED) return rc;
+    }
     return simt_mix_fwd(p, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
 }
 
@@ -166,10 +176,10 @@ extern "C" int pno_spectral_fwd(const pno_plan_t* p, int engine, const float* x,
     float* xi = xr + mb * Ci;
     float* yr = xi + mb * Ci;
     float* yi = yr + mb * Co;
-    if ((rc = pno_dft_fwd(p, x, B, Ci, 0, xr, xi, stream))) return rc;
+    if ((rc = pno_dft_fwd(p, engine, x, B, Ci, 0, xr, xi, stream))) return rc;
     if ((rc = pno_mix_fwd(p, engine, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, seed, sample_idx, site, yr, yi, stream)))
         return rc;
-    return pno_dft_inv(p, yr, yi, B, Co, 0, addend, act, y, pre_act, stream);
+    return pno_dft_inv(p, engine, yr, yi, B, Co, 0, addend, act, y, pre_act, stream);
 }
 
 extern "C" int pno_spectral_bwd(const pno_plan_t* p, int engine, const float* x, const float* xhat_saved, const float* g,
@@ -186,7 +196,7 @@ extern "C" int pno_spectral_bwd(const pno_plan_t* p, int engine, const float* x,
     float* gi = gr + mb * Co;
     float* dxr = gi + mb * Co;
     float* dxi = dxr + mb * Ci;
-    if ((rc = pno_dft_fwd(p, g, B, Co, 1, gr, gi, stream))) return rc;
+    if ((rc = pno_dft_fwd(p, engine, g, B, Co, 1, gr, gi, stream))) return rc;
     if (dmu1 || dlv1) {
         const float *sxr = xr, *sxi = xi;
         if (xhat_saved) {
@@ -194,7 +204,7 @@ extern "C" int pno_spectral_bwd(const pno_plan_t* p, int engine, const float* x,
             sxi = xhat_saved + mb * Ci;
         } else {
             if (!x) PNO_FAIL(PNO_E_INVALID, "pno_spectral_bwd: need x or xhat_saved for the weight gradients");
-            if ((rc = pno_dft_fwd(p, x, B, Ci, 0, xr, xi, stream))) return rc;
+            if ((rc = pno_dft_fwd(p, engine, x, B, Ci, 0, xr, xi, stream))) return rc;
         }
         if ((rc = pno_mix_bwd_dw(p, engine, sxr, sxi, gr, gi, B, Ci, Co, lv1, lv2, seed, sample_idx, site, dmu1, dmu2,
                                  dlv1, dlv2, stream)))
@@ -204,7 +214,7 @@ extern "C" int pno_spectral_bwd(const pno_plan_t* p, int engine, const float* x,
         if ((rc = pno_mix_bwd_dx(p, engine, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, seed, sample_idx, site, dxr, dxi,
                                  stream)))
             return rc;
-        if ((rc = pno_dft_inv(p, dxr, dxi, B, Ci, 1, nullptr, PNO_ACT_NONE, dx, nullptr, stream))) return rc;
+        if ((rc = pno_dft_inv(p, engine, dxr, dxi, B, Ci, 1, nullptr, PNO_ACT_NONE, dx, nullptr, stream))) return rc;
     }
     return PNO_OK;
 }

@@ -2,10 +2,14 @@
 // the C ABI reports that to the caller (there is no silent fallback for an explicitly requested engine).
 #include "pno_tc.cuh"
 
-void tc_plan_release(pno_plan* p) { (void)p; }
 
 int tc_mix_fwd(const pno_plan*, int, const float*, const float*, int, int, int, const float*, const float*, const float*,
                const float*, PhiloxKey, float*, float*, cudaStream_t) {
     PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core mix engine is not built into this version");
 }
 
+
+int tc_dft_inv(const pno_plan*, int, const float*, const float*, int, int, int, const float*, int, float*, float*,
+               cudaStream_t) {
+    PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core inverse transform is not built into this version");
+}

@@ -3,6 +3,11 @@
 #include "pno_common.cuh"
 
 void tc_plan_release(pno_plan* p);
+int tc_tables_get(const pno_plan* p, void** tables);
+int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
+               cudaStream_t st);
+int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
+               const float* addend, int act, float* y, float* pre_act, cudaStream_t st);
 int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
                const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st);
 int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,

@@ -48,7 +48,7 @@ def _local_case(b, ci, co, h, w, noisy, engine, gen):
     return out.detach(), grads
 
 
-@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
 @pytest.mark.parametrize("noisy", [False, True])
 @pytest.mark.parametrize("shape", [(2, 32, 128, 16, 16), (3, 256, 256, 64, 64), (1, 64, 384, 8, 48)])
 def test_local_branch_tensor_core_vs_cuda_core(engine, tol, noisy, shape):
@@ -58,3 +58,34 @@ def test_local_branch_tensor_core_vs_cuda_core(engine, tol, noisy, shape):
     assert rel_l2(out, ref_out) < tol
     for a_, b_ in zip(g, ref_g):
         assert rel_l2(a_, b_) < 10 * tol
+
+
+def _dft_fwd(x, m1, m2, engine, grad_scale=0):
+    lib = _lib.load()
+    b, c, h, w = x.shape
+    plan = _lib.plan(h, w, m1, m2, x.device)
+    m = 2 * m1 * m2
+    xr = torch.full((m, b, c), float("nan"), device=x.device)
+    xi = torch.full((m, b, c), float("nan"), device=x.device)
+    _lib.check(lib.pno_dft_fwd(plan, _lib.ENGINES[engine], x.data_ptr(), b, c, grad_scale, xr.data_ptr(), xi.data_ptr(),
+                               _lib.stream_ptr()), "pno_dft_fwd")
+    torch.cuda.synchronize()
+    return xr, xi
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("shape", [(2, 8, 64, 64, 20, 20), (1, 16, 64, 64, 12, 12), (3, 8, 128, 128, 32, 32),
+                                   (2, 16, 32, 96, 8, 12), (64, 256, 64, 64, 20, 20)])
+def test_dft_fwd_tensor_core_vs_cuda_core(engine, tol, shape):
+    b, c, h, w, m1, m2 = shape
+    x = torch.randn(b, c, h, w, generator=torch.Generator().manual_seed(sum(shape))).to(DEV)
+    for gs in (0, 1):
+        rr, ri = _dft_fwd(x, m1, m2, "fp32", gs)
+        tr, ti = _dft_fwd(x, m1, m2, engine, gs)
+        assert rel_l2(tr, rr) < tol and rel_l2(ti, ri) < tol, (gs, rel_l2(tr, rr), rel_l2(ti, ri))
+    # and against torch.fft directly (fp64)
+    xf = torch.fft.rfft2(x.double())
+    want = torch.cat([xf[:, :, :m1, :m2], xf[:, :, h - m1:, :m2]], dim=2)          # [b,c,2m1,m2]
+    want = want.permute(2, 3, 0, 1).reshape(2 * m1 * m2, b, c)
+    tr, ti = _dft_fwd(x, m1, m2, engine, 0)
+    assert rel_l2(torch.complex(tr.double(), ti.double()), want) < max(tol, 5e-7)
