@@ -151,7 +151,8 @@ int pno_mc_finalize(const double* sum, const double* sumsq, uint64_t n, uint32_t
 
 /* ---- hardware self-test of the tcgen05 / TMA building blocks ---------------------------------------------------- */
 /* One CTA computes D[128][N] = (+-A)[128][K] * (+-B)[K][N] on the tensor cores (kind::tf32).
- * flags: bit0 A MN-major, bit1 B MN-major, bit2 A staged by TMA, bit3 B staged by TMA, bit4 negate A, bit5 negate B.
+ * flags: bit0 A MN-major, bit1 B MN-major, bit2 A staged by TMA, bit3 B staged by TMA, bit4 negate A, bit5 negate B,
+ * bit6 both operands K-major in SWIZZLE_32B slab form (one 32-byte slab per K=8 step; K%8 == 0, N%16 == 0).
  * A [128][K], B [K][N] row-major; the TMA sources are the arrays whose contiguous axis is the operand's major axis
  * (K-major A: A itself; MN-major A: A^T [K][128]; K-major B: B^T [N][K]; MN-major B: B itself). */
 int pno_selftest_umma(int flags, int N, int K, const float* A, const float* B, const float* A_tma_src,

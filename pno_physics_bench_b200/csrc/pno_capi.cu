@@ -42,6 +42,7 @@ extern "C" int pno_plan_create(int H, int W, int m1, int m2, pno_plan_t** out) {
     pno_plan* p = new pno_plan();
     p->H = H; p->W = W; p->m1 = m1; p->m2 = m2; p->M = 2 * m1 * m2;
     p->tc_tables = nullptr;
+    p->tc_tables_inv = nullptr;
     PNO_CUDA(cudaGetDevice(&p->device));
     std::vector<float2> th(H), tw(W);
     const double two_pi = 6.283185307179586476925286766559;
@@ -73,6 +74,7 @@ extern "C" int pno_plan_create(int H, int W, int m1, int m2, pno_plan_t** out) {
 extern "C" int pno_plan_destroy(pno_plan_t* p) {
     if (!p) return PNO_OK;
     tc_plan_release(p);
+    tc_plan_release_inv(p);
     cudaFree(p->tabH);
     cudaFree(p->tabW);
     cudaFree(p->kx);

@@ -46,6 +46,7 @@ struct pno_plan {
     float* coef;      // [2*m1*m2] alive(kx2) * c_ky / (H*W)
     // dense twiddle matrices for the tensor-core engines (allocated lazily by the engines that use them)
     void* tc_tables;
+    void* tc_tables_inv;
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

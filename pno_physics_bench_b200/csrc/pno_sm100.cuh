@@ -187,6 +187,14 @@ __host__ __device__ __forceinline__ uint32_t mnmajor_sw128_off(int k, int n, int
     return (uint32_t)(nb * Kt * 128 + k * 128 + ((((nn >> 3) ^ (k & 3)) << 5) | ((nn & 7) << 2)));
 }
 
+// K-major "slab" form with SWIZZLE_32B: one slab per K=8 step (32 bytes per row), slab s = dense [R rows x 32 B] region
+// (R a multiple of 8).  No padding of K to 32: a K=40 operand is exactly 5 slabs.  Descriptor: start = slab base,
+// SBO = 256 (8 rows), layout SWIZZLE_32B.  16-byte chunk index is XORed with bit 2 of the row.
+__host__ __device__ __forceinline__ uint32_t kslab_sw32_off(int r, int k, int R) {
+    const int s = k >> 3, kk = k & 7;
+    return (uint32_t)(s * R * 32 + r * 32 + ((((kk >> 2) ^ ((r >> 2) & 1)) << 4) | ((kk & 3) << 2)));
+}
+
 }  // namespace sm100
 
 // ---- host: tensor maps --------------------------------------------------------------------------------------------------

@@ -8,8 +8,3 @@ int tc_mix_fwd(const pno_plan*, int, const float*, const float*, int, int, int, 
     PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core mix engine is not built into this version");
 }
 
-
-int tc_dft_inv(const pno_plan*, int, const float*, const float*, int, int, int, const float*, int, float*, float*,
-               cudaStream_t) {
-    PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core inverse transform is not built into this version");
-}

@@ -3,6 +3,7 @@
 #include "pno_common.cuh"
 
 void tc_plan_release(pno_plan* p);
+void tc_plan_release_inv(pno_plan* p);
 int tc_tables_get(const pno_plan* p, void** tables);
 int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
                cudaStream_t st);

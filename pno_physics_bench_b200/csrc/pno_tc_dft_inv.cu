@@ -1,0 +1,390 @@
+// Pruned inverse 2-D transform + block epilogue on the tensor cores (engines PNO_ENGINE_TC_*):
+//   y[b][c][h][w] = act( sum_{kx2,ky} coef * Re(yhat[kx2*m2+ky][b][c] e^{+2 pi i (kx h/H + ky w/W)}) + addend )
+// (reference models.py:92-97 + 306; adjoint != 0 gives the backward of the forward transform) as two chained GEMMs per
+// group of G consecutive channels, all operands in K-major SWIZZLE_32B "slab" form so that K = 2*m1 and K = 2*m2 need no
+// padding:
+//   loaders     yhat[mode][b][c0..c0+G) (32-byte runs) -> tf32 hi/lo -> B1 slabs  Yre/Yim[(img,ky)][kx2]
+//   stage 1     Zre[h][(img,ky)] = C Yre^T - S Yim^T ; Zim = S Yre^T + C Yim^T          (A = column twiddles, M = 128 lanes = h)
+//   transposer  TMEM Z -> registers -> * c_ky/(HW) -> tf32 hi/lo -> Zt slabs [(img,h)][(re|im, ky)]
+//   stage 2     y[(img,h)][w] = Zt * TwB^T            TwB[w][(re|im,ky)] = cos | -sin (2 pi ky w / W)
+//   epilogue    TMEM -> + addend -> pre_act -> activation -> global rows (each thread owns one image row)
+//   warp 1 MMA issuer, warps 2-5 loaders, warps 6-9 transposer + epilogue (warp 0 idle: no TMA in this kernel)
+#include <math.h>
+
+#include <vector>
+
+#include "pno_sm100.cuh"
+#include "pno_tc.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kThreads = 320;
+
+struct InvGeom {
+    int H, W, m1, m2, B, C;
+    int K1, K2;      // 2*m1, 2*m2
+    int S1, S2;      // slabs: K1/8, K2/8
+    int G, IPT, TPG; // images per group / per 128-row tile, tiles per group
+    int N1;          // G*m2
+    int n_groups;
+    int adjoint, act;
+    int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, zt_one, zt_buf, smem_bytes;
+};
+
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
+             const float* __restrict__ coef, const float* __restrict__ yr, const float* __restrict__ yi,
+             const float* __restrict__ addend, float* __restrict__ y, float* __restrict__ pre_act) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar_b1_full, bar_b1_empty, bar_d1_full, bar_d1_empty;
+    __shared__ __align__(8) uint64_t bar_zt_full[2], bar_zt_empty[2], bar_d2_full[2], bar_d2_empty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_scale[64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_b1_full, 128);
+        mbar_init(&bar_b1_empty, 1);
+        mbar_init(&bar_d1_full, 1);
+        mbar_init(&bar_d1_empty, 128);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_zt_full[s], 128);
+            mbar_init(&bar_zt_empty[s], 1);
+            mbar_init(&bar_d2_full[s], 1);
+            mbar_init(&bar_d2_empty[s], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    // twiddle tables -> slab form.  tabA_g: (C hi, C lo, S hi, S lo) each [H][K1]; tabB_g: (hi, lo) each [W][K2]
+    for (int e = threadIdx.x; e < 4 * g.H * g.K1; e += kThreads) {
+        const int t = e / (g.H * g.K1), r = (e / g.K1) % g.H, k = e % g.K1;
+        *reinterpret_cast<float*>(smem + g.off_tabA + t * g.tabA_one + kslab_sw32_off(r, k, g.H)) = tabA_g[e];
+    }
+    for (int e = threadIdx.x; e < 2 * g.W * g.K2; e += kThreads) {
+        const int t = e / (g.W * g.K2), r = (e / g.K2) % g.W, k = e % g.K2;
+        *reinterpret_cast<float*>(smem + g.off_tabB + t * g.tabB_one + kslab_sw32_off(r, k, g.W)) = tabB_g[e];
+    }
+    if (threadIdx.x < g.m2) s_scale[threadIdx.x] = g.adjoint ? 1.f : coef[g.m1 * g.m2 + threadIdx.x];   // an alive row
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int d2_col = 2 * g.N1;
+
+    if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t id1 = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K);
+            const uint32_t id1n = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K, 1, 0);
+            const uint32_t id2 = make_idesc(FMT_TF32, 128, g.W, MAJOR_K, MAJOR_K);
+            const uint32_t tA = smem_u32(smem + g.off_tabA), tB = smem_u32(smem + g.off_tabB);
+            const uint32_t b1 = smem_u32(smem + g.off_b1), zt = smem_u32(smem + g.off_zt);
+            const uint32_t slabA = g.H * 32, slabB1 = g.N1 * 32, slabZ = 128 * 32, slabTB = g.W * 32;
+            int ng = 0, nt = 0;
+            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
+                mbar_wait(&bar_b1_full, ng & 1);
+                mbar_wait(&bar_d1_empty, (ng & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_re = tmem, d_im = tmem + g.N1;
+                for (int s = 0; s < g.S1; ++s) {
+                    const uint32_t first = s ? 1u : 0u;
+                    const uint64_t c_hi = make_sdesc(tA + 0 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
+                    const uint64_t s_hi = make_sdesc(tA + 2 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
+                    const uint64_t re_hi = make_sdesc(b1 + 0 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
+                    const uint64_t im_hi = make_sdesc(b1 + 2 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
+                    mma_tf32_ss(d_re, c_hi, re_hi, id1, first);
+                    mma_tf32_ss(d_re, s_hi, im_hi, id1n, 1u);
+                    mma_tf32_ss(d_im, s_hi, re_hi, id1, first);
+                    mma_tf32_ss(d_im, c_hi, im_hi, id1, 1u);
+                    if (NSPLIT == 3) {
+                        const uint64_t c_lo = make_sdesc(tA + 1 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
+                        const uint64_t s_lo = make_sdesc(tA + 3 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
+                        const uint64_t re_lo = make_sdesc(b1 + 1 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
+                        const uint64_t im_lo = make_sdesc(b1 + 3 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
+                        mma_tf32_ss(d_re, c_lo, re_hi, id1, 1u);
+                        mma_tf32_ss(d_re, c_hi, re_lo, id1, 1u);
+                        mma_tf32_ss(d_re, s_lo, im_hi, id1n, 1u);
+                        mma_tf32_ss(d_re, s_hi, im_lo, id1n, 1u);
+                        mma_tf32_ss(d_im, s_lo, re_hi, id1, 1u);
+                        mma_tf32_ss(d_im, s_hi, re_lo, id1, 1u);
+                        mma_tf32_ss(d_im, c_lo, im_hi, id1, 1u);
+                        mma_tf32_ss(d_im, c_hi, im_lo, id1, 1u);
+                    }
+                }
+                mma_commit(&bar_b1_empty);
+                mma_commit(&bar_d1_full);
+                for (int j = 0; j < g.TPG; ++j, ++nt) {
+                    const int zb = nt & 1;
+                    mbar_wait(&bar_zt_full[zb], (nt >> 1) & 1);
+                    mbar_wait(&bar_d2_empty[zb], ((nt >> 1) & 1) ^ 1);
+                    tc_fence_after_sync();
+                    const uint32_t d2 = tmem + d2_col + zb * g.W;
+                    const uint32_t zbase = zt + zb * g.zt_buf;
+                    for (int s = 0; s < g.S2; ++s) {
+                        const uint64_t z_hi = make_sdesc(zbase + s * slabZ, 16, 256, SWIZZLE_32B);
+                        const uint64_t w_hi = make_sdesc(tB + s * slabTB, 16, 256, SWIZZLE_32B);
+                        mma_tf32_ss(d2, z_hi, w_hi, id2, s ? 1u : 0u);
+                        if (NSPLIT == 3) {
+                            const uint64_t z_lo = make_sdesc(zbase + g.zt_one + s * slabZ, 16, 256, SWIZZLE_32B);
+                            const uint64_t w_lo = make_sdesc(tB + g.tabB_one + s * slabTB, 16, 256, SWIZZLE_32B);
+                            mma_tf32_ss(d2, z_lo, w_hi, id2, 1u);
+                            mma_tf32_ss(d2, z_hi, w_lo, id2, 1u);
+                        }
+                    }
+                    mma_commit(&bar_zt_empty[zb]);
+                    mma_commit(&bar_d2_full[zb]);
+                }
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ================================ loaders: yhat -> B1 slabs ================================
+        const int t = threadIdx.x - 64;
+        unsigned char* b1 = smem + g.off_b1;
+        const int items = 2 * g.m2 * g.K1;
+        int ng = 0;
+        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
+            const int img0 = grp * g.G;
+            const int b = img0 / g.C, c0 = img0 % g.C;
+            mbar_wait(&bar_b1_empty, (ng & 1) ^ 1);
+            for (int e = t; e < items; e += 128) {
+                const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
+                const float* src = (part ? yi : yr) + ((size_t)(kx2 * g.m2 + ky) * g.B + b) * g.C + c0;
+                float v[8];
+                if (g.G == 8) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                } else if (g.G == 4) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(src);
+                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+                } else {
+                    for (int i = 0; i < g.G; ++i) v[i] = src[i];
+                }
+                unsigned char* dst0 = b1 + (part ? 2 : 0) * g.b1_one;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < g.G) {
+                        const uint32_t off = kslab_sw32_off(i * g.m2 + ky, kx2, g.N1);
+                        if (NSPLIT == 3) {
+                            const float h = tf32_rn(v[i]);
+                            *reinterpret_cast<float*>(dst0 + off) = h;
+                            *reinterpret_cast<float*>(dst0 + g.b1_one + off) = v[i] - h;
+                        } else {
+                            *reinterpret_cast<float*>(dst0 + off) = v[i];
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bar_b1_full);
+        }
+    } else if (warp >= 6) {
+        // ================================ transposer + epilogue ================================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool t_active_warp = q * 32 < g.H;          // warp holds valid stage-1 lanes (h < H)
+        int ng = 0, nT = 0, nE = 0;
+
+        auto transpose_tile = [&](int j) {
+            const int zb = nT & 1;
+            mbar_wait(&bar_zt_empty[zb], ((nT >> 1) & 1) ^ 1);
+            if (t_active_warp) {
+                unsigned char* zt = smem + g.off_zt + zb * g.zt_buf;
+                for (int il = 0; il < g.IPT; ++il) {
+                    const int img = j * g.IPT + il;                  // image within the group
+                    const int zrow = il * g.H + row;                 // row of the stage-2 A tile (row < H here)
+                    for (int part = 0; part < 2; ++part) {
+                        for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
+                            uint32_t r0, r1, r2, r3;
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                                         : "r"(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + ky0)));
+                            tmem_ld_wait();
+                            if (row < g.H) {
+                                float4 v = make_float4(__uint_as_float(r0) * s_scale[ky0], __uint_as_float(r1) * s_scale[ky0 + 1],
+                                                       __uint_as_float(r2) * s_scale[ky0 + 2], __uint_as_float(r3) * s_scale[ky0 + 3]);
+                                const uint32_t off = kslab_sw32_off(zrow, part * g.m2 + ky0, 128);
+                                if (NSPLIT == 3) {
+                                    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                                    *reinterpret_cast<float4*>(zt + off) = h;
+                                    *reinterpret_cast<float4*>(zt + g.zt_one + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                                } else {
+                                    *reinterpret_cast<float4*>(zt + off) = v;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            mbar_arrive(&bar_zt_full[zb]);
+            ++nT;
+        };
+
+        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
+            const int img0 = grp * g.G;
+            mbar_wait(&bar_d1_full, ng & 1);
+            tc_fence_after_sync();
+            transpose_tile(0);
+            for (int j = 0; j < g.TPG; ++j) {
+                if (j + 1 < g.TPG) transpose_tile(j + 1);
+                else mbar_arrive(&bar_d1_empty);          // every stage-1 accumulator of this group has been read
+                // ---- epilogue of tile j ----
+                const int db = nE & 1;
+                mbar_wait(&bar_d2_full[db], (nE >> 1) & 1);
+                tc_fence_after_sync();
+                const int img = img0 + j * g.IPT + row / g.H;         // global image index b*C + c
+                const size_t gofs = ((size_t)img * g.H + (row % g.H)) * g.W;
+                const uint32_t ta = tmem_addr(tmem, q * 32, d2_col + db * g.W);
+                for (int c = 0; c < g.W; c += 8) {
+                    float v[8];
+                    tmem_ld8(ta + c, v);
+                    tmem_ld_wait();
+                    if (addend) {
+                        const float4 a0 = *reinterpret_cast<const float4*>(addend + gofs + c);
+                        const float4 a1 = *reinterpret_cast<const float4*>(addend + gofs + c + 4);
+                        v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                        v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                    }
+                    if (pre_act) {
+                        reinterpret_cast<float4*>(pre_act + gofs + c)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        reinterpret_cast<float4*>(pre_act + gofs + c)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], g.act);
+                    reinterpret_cast<float4*>(y + gofs + c)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<float4*>(y + gofs + c)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                tc_fence_before_sync();
+                mbar_arrive(&bar_d2_empty[db]);
+                ++nE;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+inline float tf32_round_h(double v) {
+    float f = (float)v;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+int pad_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct InvTables {
+    float* tabA;   // (C hi, C lo, S hi, S lo) [H][K1], dead kx2 columns zeroed
+    float* tabB;   // (hi, lo) [W][K2]
+};
+
+}  // namespace
+
+// Tables are cached on the plan through a second opaque slot owned by this translation unit.
+static int inv_tables_get(const pno_plan* cp, InvTables** out) {
+    pno_plan* p = const_cast<pno_plan*>(cp);
+    if (p->tc_tables_inv) { *out = static_cast<InvTables*>(p->tc_tables_inv); return PNO_OK; }
+    const int H = p->H, W = p->W, m1 = p->m1, m2 = p->m2, K1 = 2 * m1, K2 = 2 * m2;
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<float> a((size_t)4 * H * K1, 0.f), bt((size_t)2 * W * K2, 0.f);
+    for (int h = 0; h < H; ++h)
+        for (int r = 0; r < K1; ++r) {
+            const int kx = r < m1 ? r : H - 2 * m1 + r;
+            const bool alive = r >= m1 || kx < H - m1;          // models.py:93-94 overwrite
+            const double ang = two_pi * (double)((long long)kx * h % H) / H;
+            const double c = alive ? cos(ang) : 0.0, s = alive ? sin(ang) : 0.0;
+            const float ch = tf32_round_h(c), sh = tf32_round_h(s);
+            const size_t e = (size_t)h * K1 + r, one = (size_t)H * K1;
+            a[0 * one + e] = ch; a[1 * one + e] = tf32_round_h(c - (double)ch);
+            a[2 * one + e] = sh; a[3 * one + e] = tf32_round_h(s - (double)sh);
+        }
+    for (int w = 0; w < W; ++w)
+        for (int k = 0; k < K2; ++k) {
+            const int ky = k % m2;
+            const double ang = two_pi * (double)((long long)ky * w % W) / W;
+            const double v = k < m2 ? cos(ang) : -sin(ang);
+            const float hi = tf32_round_h(v);
+            bt[(size_t)w * K2 + k] = hi;
+            bt[(size_t)W * K2 + (size_t)w * K2 + k] = tf32_round_h(v - (double)hi);
+        }
+    InvTables* t = new InvTables();
+    PNO_CUDA(cudaMalloc(&t->tabA, a.size() * 4));
+    PNO_CUDA(cudaMalloc(&t->tabB, bt.size() * 4));
+    PNO_CUDA(cudaMemcpy(t->tabA, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    PNO_CUDA(cudaMemcpy(t->tabB, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice));
+    p->tc_tables_inv = t;
+    *out = t;
+    return PNO_OK;
+}
+
+void tc_plan_release_inv(pno_plan* p) {
+    if (!p->tc_tables_inv) return;
+    InvTables* t = static_cast<InvTables*>(p->tc_tables_inv);
+    cudaFree(t->tabA);
+    cudaFree(t->tabB);
+    delete t;
+    p->tc_tables_inv = nullptr;
+}
+
+int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
+               const float* addend, int act, float* y, float* pre_act, cudaStream_t st) {
+    const int H = p->H, W = p->W, m1 = p->m1, m2 = p->m2;
+    if (!(H == 32 || H == 64 || H == 128) || W % 16 || W > 256 || W < 16 || m1 % 4 || m2 % 4 || m2 > 64)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv tiles H in {32,64,128}, W%%16 == 0, W <= 256, m1%%4 == 0, m2%%4 == 0");
+    const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
+    InvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.H = H; g.W = W; g.m1 = m1; g.m2 = m2; g.B = B; g.C = C; g.adjoint = adjoint; g.act = act;
+    g.K1 = 2 * m1; g.K2 = 2 * m2; g.S1 = g.K1 / 8; g.S2 = g.K2 / 8;
+    g.IPT = 128 / H;
+    const int nbuf = x3 ? 2 : 1;          // hi (+ lo)
+    bool ok = false;
+    for (int G = 8; G >= g.IPT && G >= 1; G >>= 1) {
+        if (C % G || (G * m2) % 16 || G * m2 > 256 || 2 * G * m2 + 2 * W > 512) continue;
+        g.G = G; g.N1 = G * m2; g.TPG = G / g.IPT;
+        g.tabA_one = g.S1 * H * 32;
+        g.tabB_one = g.S2 * W * 32;
+        g.b1_one = g.S1 * g.N1 * 32;
+        g.zt_one = g.S2 * 128 * 32;
+        g.zt_buf = nbuf * g.zt_one;
+        g.off_tabA = 0;
+        g.off_tabB = pad_up(4 * g.tabA_one + 128 * 32, 1024);                   // slack: M = 128 reads past H rows
+        g.off_b1 = g.off_tabB + pad_up(2 * g.tabB_one, 1024);
+        g.off_zt = g.off_b1 + pad_up(2 * nbuf * g.b1_one, 1024);
+        g.smem_bytes = g.off_zt + 2 * g.zt_buf + 1024;
+        if (g.smem_bytes <= 224 * 1024) { ok = true; break; }
+    }
+    if (!ok) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv: no channel grouping fits (C = %d, m2 = %d, W = %d)", C, m2, W);
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(pre_act) |
+         reinterpret_cast<uintptr_t>(yr) | reinterpret_cast<uintptr_t>(yi)) & 15)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv needs 16-byte aligned tensors");
+    g.n_groups = B * C / g.G;
+    InvTables* t = nullptr;
+    int rc = inv_tables_get(p, &t);
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    PNO_CUDA(cudaGetDevice(&dev));
+    PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = g.n_groups < sms ? g.n_groups : sms;
+    if (x3) {
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        k_tc_dft_inv<3><<<grid, kThreads, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y, pre_act);
+    } else {
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        k_tc_dft_inv<1><<<grid, kThreads, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y, pre_act);
+    }
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}

@@ -40,6 +40,7 @@ struct SelfTestArgs {
     int a_mn, b_mn;        // operand majorness (0 = K-major)
     int a_tma, b_tma;      // staged by TMA instead of by threads
     int a_neg, b_neg;
+    int slab;              // both operands K-major in SWIZZLE_32B slab form (staged by threads)
     const float *A, *B;    // logical A[128][K], B[K][N], row-major
     float* D;              // [128][N]
 };
@@ -84,13 +85,13 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const SelfTestArgs a, con
     if (!a.a_tma)
         for (int e = tid; e < 128 * K; e += 128) {
             const int m = e / K, k = e % K;
-            const uint32_t off = a.a_mn ? mnmajor_sw128_off(k, m, K) : kmajor_sw128_off(m, k, 128);
+            const uint32_t off = a.slab ? kslab_sw32_off(m, k, 128) : a.a_mn ? mnmajor_sw128_off(k, m, K) : kmajor_sw128_off(m, k, 128);
             *reinterpret_cast<float*>(sA + off) = a.A[e];
         }
     if (!a.b_tma)
         for (int e = tid; e < K * N; e += 128) {
             const int k = e / N, n = e % N;
-            const uint32_t off = a.b_mn ? mnmajor_sw128_off(k, n, K) : kmajor_sw128_off(n, k, N);
+            const uint32_t off = a.slab ? kslab_sw32_off(n, k, N) : a.b_mn ? mnmajor_sw128_off(k, n, K) : kmajor_sw128_off(n, k, N);
             *reinterpret_cast<float*>(sB + off) = a.B[e];
         }
     fence_proxy_async_smem();
@@ -105,6 +106,12 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const SelfTestArgs a, con
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
         for (int ks = 0; ks < K / 8; ++ks) {
             uint64_t ad, bd;
+            if (a.slab) {
+                ad = make_sdesc(a0 + ks * 128 * 32, 16, 256, SWIZZLE_32B);
+                bd = make_sdesc(b0 + ks * N * 32, 16, 256, SWIZZLE_32B);
+                mma_tf32_ss(tmem, ad, bd, idesc, ks > 0);
+                continue;
+            }
             if (!a.a_mn) ad = make_sdesc(a0 + (ks >> 2) * 128 * 128 + (ks & 3) * 32, 16, 1024, SWIZZLE_128B);
             else         ad = make_sdesc(a0 + ks * 1024, (uint32_t)K * 128, 512, SWIZZLE_128B_BASE32B);
             if (!a.b_mn) bd = make_sdesc(b0 + (ks >> 2) * N * 128 + (ks & 3) * 32, 16, 1024, SWIZZLE_128B);
@@ -134,13 +141,16 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const SelfTestArgs a, con
 // A: [128][K] row-major (K-major source) -- for TMA + MN-major the caller passes At [K][128] in A_src_tma.
 extern "C" int pno_selftest_umma(int flags, int N, int K, const float* A, const float* B, const float* A_tma_src,
                                  const float* B_tma_src, float* D, void* stream) {
-    if (N % 32 || N < 32 || N > 256 || K % 32 || K < 32 || K > 128) PNO_FAIL(PNO_E_INVALID, "selftest: N%%32, K%%32 required");
+    const bool slab = (flags >> 6) & 1;
+    if (slab ? (N % 16 || N < 16 || N > 256 || K % 8 || K < 8 || K > 128 || (flags & 15))
+             : (N % 32 || N < 32 || N > 256 || K % 32 || K < 32 || K > 128))
+        PNO_FAIL(PNO_E_INVALID, "selftest: unsupported N / K / flags combination");
     int rc = pno_check_device();
     if (rc) return rc;
     SelfTestArgs a;
     a.N = N; a.K = K;
     a.a_mn = flags & 1; a.b_mn = (flags >> 1) & 1; a.a_tma = (flags >> 2) & 1; a.b_tma = (flags >> 3) & 1;
-    a.a_neg = (flags >> 4) & 1; a.b_neg = (flags >> 5) & 1;
+    a.a_neg = (flags >> 4) & 1; a.b_neg = (flags >> 5) & 1; a.slab = (flags >> 6) & 1;
     a.A = A; a.B = B; a.D = D;
     CUtensorMap tmA, tmB;
     memset(&tmA, 0, sizeof(tmA));

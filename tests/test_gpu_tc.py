@@ -17,7 +17,8 @@ def tf32_trunc(t):
 
 
 @pytest.mark.parametrize("flags,n,k", [(f, n, k) for f in range(16) for n, k in ((64, 64), (128, 32))]
-                         + [(0b110000 | 0b1010, 96, 96), (0b010000, 32, 128), (0b100101, 256, 64)])
+                         + [(0b110000 | 0b1010, 96, 96), (0b010000, 32, 128), (0b100101, 256, 64),
+                            (0b1000000, 64, 40), (0b1010000, 160, 40), (0b1000000, 48, 24), (0b1100000, 16, 8)])
 def test_umma_selftest(flags, n, k):
     lib = _lib.load()
     gen = torch.Generator().manual_seed(flags * 1000 + n + k)
@@ -89,3 +90,31 @@ def test_dft_fwd_tensor_core_vs_cuda_core(engine, tol, shape):
     want = want.permute(2, 3, 0, 1).reshape(2 * m1 * m2, b, c)
     tr, ti = _dft_fwd(x, m1, m2, engine, 0)
     assert rel_l2(torch.complex(tr.double(), ti.double()), want) < max(tol, 5e-7)
+
+
+def _dft_inv(yr, yi, h, w, m1, m2, engine, adjoint=0, addend=None, act=0, want_pre=False):
+    lib = _lib.load()
+    m, b, c = yr.shape
+    plan = _lib.plan(h, w, m1, m2, yr.device)
+    y = torch.full((b, c, h, w), float("nan"), device=yr.device)
+    pre = torch.full((b, c, h, w), float("nan"), device=yr.device) if want_pre else None
+    _lib.check(lib.pno_dft_inv(plan, _lib.ENGINES[engine], yr.data_ptr(), yi.data_ptr(), b, c, adjoint, _lib.ptr(addend),
+                               act, y.data_ptr(), _lib.ptr(pre), _lib.stream_ptr()), "pno_dft_inv")
+    torch.cuda.synchronize()
+    return y, pre
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("shape", [(2, 8, 64, 64, 20, 20), (1, 16, 64, 64, 12, 12), (3, 8, 128, 128, 32, 32),
+                                   (2, 16, 32, 96, 8, 12), (1, 4, 64, 48, 36, 8), (64, 256, 64, 64, 20, 20)])
+def test_dft_inv_tensor_core_vs_cuda_core(engine, tol, shape):
+    b, c, h, w, m1, m2 = shape
+    gen = torch.Generator().manual_seed(sum(shape))
+    m = 2 * m1 * m2
+    yr = torch.randn(m, b, c, generator=gen).to(DEV)
+    yi = torch.randn(m, b, c, generator=gen).to(DEV)
+    add = torch.randn(b, c, h, w, generator=gen).to(DEV)
+    for adjoint, addend, act in ((0, None, 0), (1, None, 0), (0, add, 1), (0, add, 2)):
+        ref, ref_pre = _dft_inv(yr, yi, h, w, m1, m2, "fp32", adjoint, addend, act, True)
+        out, pre = _dft_inv(yr, yi, h, w, m1, m2, engine, adjoint, addend, act, True)
+        assert rel_l2(out, ref) < tol and rel_l2(pre, ref_pre) < tol, (adjoint, act, rel_l2(out, ref))
