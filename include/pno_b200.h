@@ -89,7 +89,7 @@ int pno_dft_fwd(const pno_plan_t* plan, int engine, const float* x, int B, int C
                 float* xhat_im, void* stream);
 /* Pruned inverse transform + fused epilogue (replaces zeros + scatter + torch.fft.irfft2, models.py:92-97, and the
  * add + activation of the block, models.py:306):
- *   s = sum_mode coef * Re(yhat[mode][b][c] exp(+2 pi i (...)))          coef = alive c_ky/(HW) (adjoint != 0: coef = 1)
+ *   s = sum_mode coef * Re(yhat[mode][b][c] exp(+2 pi i (...)))          coef = alive c_ky/(HW) (adjoint != 0: coef = alive)
  *   v = s + (addend ? addend[b][c][h][w] : 0);  if (pre_act) pre_act = v;  y = act(v)                               */
 int pno_dft_inv(const pno_plan_t* plan, int engine, const float* yhat_re, const float* yhat_im, int B, int C, int adjoint,
                 const float* addend, int act, float* y, float* pre_act, void* stream);

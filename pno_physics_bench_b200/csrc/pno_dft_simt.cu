@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) k_dft_inv(const pno_plan p, const Df
     for (int i = threadIdx.x; i < g.M * ng; i += kThreads) {
         const int m = i / ng, gi = i - m * ng;
         const size_t o = ((size_t)m * B + b) * C + c0 + gi;
-        const float cf = adjoint ? 1.f : p.coef[m];
+        const float cf = adjoint ? (p.coef[m] != 0.f ? 1.f : 0.f) : p.coef[m];
         s.spec[(size_t)gi * g.M + m] = make_float2(yr[o] * cf, yi[o] * cf);
     }
     __syncthreads();

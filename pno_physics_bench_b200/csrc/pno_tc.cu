@@ -3,8 +3,3 @@
 #include "pno_tc.cuh"
 
 
-int tc_mix_fwd(const pno_plan*, int, const float*, const float*, int, int, int, const float*, const float*, const float*,
-               const float*, PhiloxKey, float*, float*, cudaStream_t) {
-    PNO_FAIL(PNO_E_UNSUPPORTED, "tensor-core mix engine is not built into this version");
-}
-

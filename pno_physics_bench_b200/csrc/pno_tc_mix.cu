@@ -1,0 +1,283 @@
+// Fused weight sampling + per-mode complex channel mix on the tensor cores (engines PNO_ENGINE_TC_*):
+//   yhat[mode][b][o] = sum_i xhat[mode][b][i] * (mu + exp(lv/2) * eps)[mode][i][o]        (reference models.py:63-78, 33-35, 93-94)
+// The sampled weights exist only as swizzled shared-memory operand tiles: eps comes from the Philox stream in-kernel, mu and
+// log_var are streamed from HBM exactly once per call with coalesced 16-byte loads, nothing is written back.
+// Work item = (mode, tile of 128 output channels); per item the transposed product D[o][b] is accumulated in TMEM:
+//   Dre = Wre^T Xre^T - Wim^T Xim^T ,  Dim = Wim^T Xre^T + Wre^T Xim^T           (A = generated W tiles, negate-A bit; B = xhat via TMA)
+//   warp 0        TMA producer: xhat tiles [B rows][32 i] (re, im) of the item's mode
+//   warp 1        MMA issuer
+//   warps 2-9     generators: mu/lv -> Philox/Box-Muller -> W = mu + sigma*eps -> tf32 hi/lo -> K-major SW128 tiles [128 o][32 i];
+//                 they also split the xhat tiles into hi/lo (3xTF32)
+//   warps 10-13   epilogue: TMEM -> yhat[mode][b][o] (coalesced over o)
+#include "pno_sm100.cuh"
+#include "pno_tc.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kThreads = 448;
+constexpr int kGen = 256;        // generator threads
+constexpr int TM = 128;          // output channels per item
+constexpr int TK = 32;           // input channels per stage
+constexpr int W_TILE = TM * TK * 4;      // 16 KB
+
+struct MixGeom {
+    int B, Ci, Co, m1m2, Cop, n_modes, o_tiles, n_items, KB;
+    int sampled;
+    int x_tile;        // B * 128 bytes
+    int stage_bytes, stages, smem_bytes;
+    const float *mu1, *mu2, *lv1, *lv2;
+    float *yr, *yi;
+    PhiloxKey key;
+};
+
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+// stage layout: [Wre hi][Wim hi][Wre lo][Wim lo][Xre hi][Xim hi][Xre lo][Xim lo]   (lo parts only used by 3xTF32)
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __grid_constant__ CUtensorMap tmXi) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kMaxStages = 4;
+    __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_ready[kMaxStages], bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&bar_raw[s], 1);
+            mbar_init(&bar_ready[s], kGen);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_tfull[s], 1);
+            mbar_init(&bar_tempty[s], 128);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmXr);
+        tma_prefetch_desc(&tmXi);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int acc_cols = 2 * g.B;                   // Dre | Dim
+    const int x_off = 4 * W_TILE;                   // byte offset of the xhat tiles inside a stage
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int mode = item / g.o_tiles;
+                for (int kb = 0; kb < g.KB; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    unsigned char* st = smem + (size_t)stage * g.stage_bytes + x_off;
+                    mbar_arrive_expect_tx(&bar_raw[stage], 2 * g.x_tile);
+                    tma_load_2d(st, &tmXr, &bar_raw[stage], kb * TK, mode * g.B);
+                    tma_load_2d(st + g.x_tile, &tmXi, &bar_raw[stage], kb * TK, mode * g.B);
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K);
+            const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K, 1, 0);
+            int stage = 0, phase = 0, it = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&bar_tempty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_re = tmem + acc * acc_cols, d_im = d_re + g.B;
+                for (int kb = 0; kb < g.KB; ++kb) {
+                    mbar_wait(&bar_ready[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t s0 = smem_u32(smem + (size_t)stage * g.stage_bytes);
+                    const uint32_t wre = s0, wim = s0 + W_TILE, wre_lo = s0 + 2 * W_TILE, wim_lo = s0 + 3 * W_TILE;
+                    const uint32_t xre = s0 + x_off, xim = xre + g.x_tile, xre_lo = xim + g.x_tile, xim_lo = xre_lo + g.x_tile;
+#pragma unroll
+                    for (int ks = 0; ks < TK / 8; ++ks) {
+                        const uint32_t first = (kb | ks) ? 1u : 0u;
+                        const uint32_t o = ks * 32;
+                        const uint64_t a_re = make_sdesc(wre + o, 16, 1024, SWIZZLE_128B);
+                        const uint64_t a_im = make_sdesc(wim + o, 16, 1024, SWIZZLE_128B);
+                        const uint64_t b_re = make_sdesc(xre + o, 16, 1024, SWIZZLE_128B);
+                        const uint64_t b_im = make_sdesc(xim + o, 16, 1024, SWIZZLE_128B);
+                        mma_tf32_ss(d_re, a_re, b_re, idesc, first);
+                        mma_tf32_ss(d_re, a_im, b_im, idesc_n, 1u);
+                        mma_tf32_ss(d_im, a_im, b_re, idesc, first);
+                        mma_tf32_ss(d_im, a_re, b_im, idesc, 1u);
+                        if (NSPLIT == 3) {
+                            const uint64_t a_re_l = make_sdesc(wre_lo + o, 16, 1024, SWIZZLE_128B);
+                            const uint64_t a_im_l = make_sdesc(wim_lo + o, 16, 1024, SWIZZLE_128B);
+                            const uint64_t b_re_l = make_sdesc(xre_lo + o, 16, 1024, SWIZZLE_128B);
+                            const uint64_t b_im_l = make_sdesc(xim_lo + o, 16, 1024, SWIZZLE_128B);
+                            mma_tf32_ss(d_re, a_re_l, b_re, idesc, 1u);
+                            mma_tf32_ss(d_re, a_re, b_re_l, idesc, 1u);
+                            mma_tf32_ss(d_re, a_im_l, b_im, idesc_n, 1u);
+                            mma_tf32_ss(d_re, a_im, b_im_l, idesc_n, 1u);
+                            mma_tf32_ss(d_im, a_im_l, b_re, idesc, 1u);
+                            mma_tf32_ss(d_im, a_im, b_re_l, idesc, 1u);
+                            mma_tf32_ss(d_im, a_re_l, b_im, idesc, 1u);
+                            mma_tf32_ss(d_im, a_re, b_im_l, idesc, 1u);
+                        }
+                    }
+                    mma_commit(&bar_empty[stage]);
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&bar_tfull[acc]);
+            }
+        }
+    } else if (warp < 10) {
+        // ================================ generators ================================
+        const int t = threadIdx.x - 64;             // 0..255
+        int stage = 0, phase = 0;
+        for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+            const int mode = item / g.o_tiles, ot = item % g.o_tiles;
+            const int blk = mode >= g.m1m2;
+            const int mb = mode - blk * g.m1m2;
+            const float* mu = blk ? g.mu2 : g.mu1;
+            const float* lv = blk ? g.lv2 : g.lv1;
+            for (int kb = 0; kb < g.KB; ++kb) {
+                mbar_wait(&bar_raw[stage], phase);              // xhat landed => the stage is ours to fill
+                unsigned char* st = smem + (size_t)stage * g.stage_bytes;
+                // ---- weights: thread item = (o pair p, quad of 4 consecutive i) ----
+#pragma unroll 1
+                for (int it2 = t; it2 < 64 * 8; it2 += kGen) {
+                    const int p = it2 & 63, iq = it2 >> 6;
+                    const int o = ot * TM + 2 * p;              // global output channel (even)
+                    float wr[2][4], wi[2][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = kb * TK + iq * 4 + j;
+                        const size_t base = ((size_t)mb * g.Ci + i) * g.Co + o;
+                        const float4 m4 = *reinterpret_cast<const float4*>(mu + 2 * base);     // (re, im) of o, o+1
+                        wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
+                        if (g.sampled) {
+                            const float2 l2 = *reinterpret_cast<const float2*>(lv + base);
+                            const float4 z = philox_quad_normals(g.key, spectral_quad(blk, g.m1m2, mb, g.Ci, g.Cop, i, o >> 1));
+                            const float s0 = __expf(0.5f * l2.x), s1 = __expf(0.5f * l2.y);
+                            wr[0][j] = fmaf(s0, z.x, wr[0][j]); wi[0][j] = fmaf(s0, z.y, wi[0][j]);
+                            wr[1][j] = fmaf(s1, z.z, wr[1][j]); wi[1][j] = fmaf(s1, z.w, wi[1][j]);
+                        }
+                    }
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        const int row = 2 * p + r2;
+                        const uint32_t off = row * 128 + ((iq ^ (row & 7)) << 4);
+                        const float4 vr = make_float4(wr[r2][0], wr[r2][1], wr[r2][2], wr[r2][3]);
+                        const float4 vi = make_float4(wi[r2][0], wi[r2][1], wi[r2][2], wi[r2][3]);
+                        if (NSPLIT == 3) {
+                            const float4 hr = make_float4(tf32_rn(vr.x), tf32_rn(vr.y), tf32_rn(vr.z), tf32_rn(vr.w));
+                            const float4 hi = make_float4(tf32_rn(vi.x), tf32_rn(vi.y), tf32_rn(vi.z), tf32_rn(vi.w));
+                            *reinterpret_cast<float4*>(st + off) = hr;
+                            *reinterpret_cast<float4*>(st + W_TILE + off) = hi;
+                            *reinterpret_cast<float4*>(st + 2 * W_TILE + off) = make_float4(vr.x - hr.x, vr.y - hr.y, vr.z - hr.z, vr.w - hr.w);
+                            *reinterpret_cast<float4*>(st + 3 * W_TILE + off) = make_float4(vi.x - hi.x, vi.y - hi.y, vi.z - hi.z, vi.w - hi.w);
+                        } else {
+                            *reinterpret_cast<float4*>(st + off) = vr;
+                            *reinterpret_cast<float4*>(st + W_TILE + off) = vi;
+                        }
+                    }
+                }
+                // ---- xhat tiles: hi in place, lo behind (layout-agnostic elementwise pass) ----
+                if (NSPLIT == 3) {
+                    float4* xh = reinterpret_cast<float4*>(st + x_off);
+                    float4* xl = reinterpret_cast<float4*>(st + x_off + 2 * g.x_tile);
+                    for (int i = t; i < 2 * g.x_tile / 16; i += kGen) {
+                        const float4 v = xh[i];
+                        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                        xh[i] = h;
+                        xl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar_ready[stage]);
+                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp & 3;
+        int it = 0;
+        for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+            const int mode = item / g.o_tiles, ot = item % g.o_tiles;
+            const int acc = it & 1;
+            mbar_wait(&bar_tfull[acc], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const int o = ot * TM + q * 32 + lane;
+            float* dr = g.yr + (size_t)mode * g.B * g.Co + o;
+            float* di = g.yi + (size_t)mode * g.B * g.Co + o;
+            const uint32_t ta = tmem_addr(tmem, q * 32, acc * acc_cols);
+            for (int b0 = 0; b0 < g.B; b0 += 8) {
+                float vr[8], vi[8];
+                tmem_ld8(ta + b0, vr);
+                tmem_ld8(ta + g.B + b0, vi);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    dr[(size_t)(b0 + j) * g.Co] = vr[j];
+                    di[(size_t)(b0 + j) * g.Co] = vi[j];
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&bar_tempty[acc]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
+               const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st) {
+    if (B % 16 || B < 16 || B > 128 || Ci % TK || Co % TM)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd tiles B%%16 == 0, 16 <= B <= 128, Ci%%32 == 0, Co%%128 == 0 (got %d, %d, %d)", B, Ci, Co);
+    if ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(xi) | reinterpret_cast<uintptr_t>(mu1) |
+         reinterpret_cast<uintptr_t>(mu2) | reinterpret_cast<uintptr_t>(lv1) | reinterpret_cast<uintptr_t>(lv2)) & 15)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd needs 16-byte aligned tensors");
+    const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
+    MixGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
+    g.o_tiles = Co / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = Ci / TK;
+    g.sampled = lv1 != nullptr;
+    g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = yr; g.yi = yi; g.key = key;
+    g.x_tile = B * 128;
+    g.stage_bytes = 4 * W_TILE + 4 * g.x_tile;
+    g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
+    g.stages = 4;
+    while (g.stages > 2 && g.stages * g.stage_bytes + 1024 > 220 * 1024) --g.stages;
+    g.smem_bytes = g.stages * g.stage_bytes + 1024;
+    if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd: %d bytes of shared memory needed", g.smem_bytes);
+    CUtensorMap tmXr, tmXi;
+    int rc;
+    {
+        const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)p->M * B};
+        const uint64_t str[1] = {(uint64_t)Ci * 4};
+        const uint32_t box[2] = {TK, (uint32_t)B};
+        if ((rc = pno_encode_tmap(&tmXr, xr, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmXi, xi, 2, dims, str, box, 1))) return rc;
+    }
+    int dev = 0, sms = 148;
+    PNO_CUDA(cudaGetDevice(&dev));
+    PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = g.n_items < sms ? g.n_items : sms;
+    if (x3) {
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        k_tc_mix_fwd<3><<<grid, kThreads, g.smem_bytes, st>>>(g, tmXr, tmXi);
+    } else {
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        k_tc_mix_fwd<1><<<grid, kThreads, g.smem_bytes, st>>>(g, tmXr, tmXi);
+    }
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}

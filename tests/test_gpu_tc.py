@@ -118,3 +118,81 @@ def test_dft_inv_tensor_core_vs_cuda_core(engine, tol, shape):
         ref, ref_pre = _dft_inv(yr, yi, h, w, m1, m2, "fp32", adjoint, addend, act, True)
         out, pre = _dft_inv(yr, yi, h, w, m1, m2, engine, adjoint, addend, act, True)
         assert rel_l2(out, ref) < tol and rel_l2(pre, ref_pre) < tol, (adjoint, act, rel_l2(out, ref))
+
+
+def _mix(xr, xi, layer, sampled, engine):
+    lib = _lib.load()
+    m, b, ci = xr.shape
+    co = layer.out_channels
+    plan = _lib.plan(64, 64, layer.modes1, layer.modes2, xr.device)
+    n = [t.detach().permute(2, 3, 0, 1) for t in (layer.weights1, layer.weights2, layer.weights1_log_var, layer.weights2_log_var)]
+    assert all(t.is_contiguous() for t in n)
+    yr = torch.full((m, b, co), float("nan"), device=xr.device)
+    yi = torch.full((m, b, co), float("nan"), device=xr.device)
+    _lib.check(lib.pno_mix_fwd(plan, _lib.ENGINES[engine], xr.data_ptr(), xi.data_ptr(), b, ci, co, n[0].data_ptr(),
+                               n[1].data_ptr(), n[2].data_ptr() if sampled else 0, n[3].data_ptr() if sampled else 0,
+                               777, 3, 9, yr.data_ptr(), yi.data_ptr(), _lib.stream_ptr()), "pno_mix_fwd")
+    torch.cuda.synchronize()
+    return yr, yi
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("sampled", [False, True])
+@pytest.mark.parametrize("shape", [(16, 128, 128, 4, 4), (64, 256, 256, 20, 20), (32, 64, 256, 5, 3), (128, 128, 128, 2, 2)])
+def test_mix_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
+    import pno_physics_bench_b200 as pno
+    b, ci, co, m1, m2 = shape
+    gen = torch.Generator().manual_seed(sum(shape))
+    layer = pno.SpectralConv2d_Probabilistic(ci, co, m1, m2)
+    with torch.no_grad():
+        for w_, lv in ((layer.weights1, layer.weights1_log_var), (layer.weights2, layer.weights2_log_var)):
+            w_.copy_(torch.complex(torch.randn(w_.shape, generator=gen), torch.randn(w_.shape, generator=gen)) / ci ** 0.5)
+            lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 6)
+    layer = layer.to(DEV)
+    m = 2 * m1 * m2
+    xr = torch.randn(m, b, ci, generator=gen).to(DEV)
+    xi = torch.randn(m, b, ci, generator=gen).to(DEV)
+    rr, ri = _mix(xr, xi, layer, sampled, "fp32")
+    tr, ti = _mix(xr, xi, layer, sampled, engine)
+    assert rel_l2(tr, rr) < tol and rel_l2(ti, ri) < tol, (rel_l2(tr, rr), rel_l2(ti, ri))
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 2e-2)])
+def test_model_tensor_core_engines_against_oracle(engine, tol):
+    """A model whose every stage is tiled by the tensor-core kernels (hid 128, 32x32, modes 8, batch 16): forward + backward."""
+    import pno_physics_bench_b200 as pno
+    from pno_physics_bench_b200 import functional as F_
+    from oracle import pno_oracle as orc
+    gen = torch.Generator().manual_seed(17)
+    torch.manual_seed(17)
+    hid, nl, modes, b, hw = 128, 2, 8, 16, 32
+    model = pno.ProbabilisticNeuralOperator(3, hid, nl, modes, engine=engine)
+    with torch.no_grad():
+        for layer in model.fourier_layers:
+            for w_, lv in ((layer.weights1, layer.weights1_log_var), (layer.weights2, layer.weights2_log_var)):
+                w_.copy_(torch.complex(torch.randn(w_.shape, generator=gen), torch.randn(w_.shape, generator=gen)) / hid ** 0.5)
+                lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 6)
+        for conv in [model.lift_log_var, model.project_log_var, *model.linear_log_var]:
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * 0.05)
+            conv.bias.copy_(torch.randn(conv.bias.shape, generator=gen) - 3.0)
+    model = model.to(DEV).train()
+    x = torch.randn(b, 3, hw, hw, generator=gen)
+    tgt = torch.randn(b, 1, hw, hw, generator=gen)
+    seed, sidx = 99, 4
+    with pno.noise_scope(seed, sidx):
+        y = model(x.to(DEV), sample=True)
+    loss = torch.mean((y - tgt.to(DEV)) ** 2) + 1e-4 * model.kl_divergence()
+    loss.backward()
+    table = {0: F_.materialize_activation_noise(seed, sidx, 0, (b, hid, hw, hw)).cpu(),
+             1 + 3 * nl: F_.materialize_activation_noise(seed, sidx, 1 + 3 * nl, (b, 1, hw, hw)).cpu()}
+    for l in range(nl):
+        re, im = F_.materialize_spectral_noise(seed, sidx, 1 + 3 * l, hid, hid, modes, modes)
+        table[1 + 3 * l] = (re.cpu(), im.cpu())
+        table[2 + 3 * l] = F_.materialize_activation_noise(seed, sidx, 2 + 3 * l, (b, hid, hw, hw)).cpu()
+    p = {k: v.detach().cpu().contiguous().requires_grad_(True) for k, v in model.state_dict().items()}
+    yo = orc.pno_forward(p, x, orc.InjectedNoise(table), True, True, "gelu")
+    lo = torch.mean((yo - tgt) ** 2) + 1e-4 * orc.pno_kl(p)
+    lo.backward()
+    assert rel_l2(y, yo) < tol and rel_l2(loss, lo) < tol
+    for k, v in model.named_parameters():
+        assert rel_l2(v.grad, p[k].grad) < 5 * tol, k
