@@ -30,7 +30,7 @@ struct InvGeom {
     int N1;          // G*m2
     int n_groups;
     int adjoint, act;
-    int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, zt_one, zt_buf, smem_bytes;
+    int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, b1_im, zt_one, zt_buf, smem_bytes;
 };
 
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
@@ -99,7 +99,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     const uint64_t c_hi = make_sdesc(tA + 0 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
                     const uint64_t s_hi = make_sdesc(tA + 2 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
                     const uint64_t re_hi = make_sdesc(b1 + 0 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
-                    const uint64_t im_hi = make_sdesc(b1 + 2 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
+                    const uint64_t im_hi = make_sdesc(b1 + g.b1_im + s * slabB1, 16, 256, SWIZZLE_32B);
                     mma_tf32_ss(d_re, c_hi, re_hi, id1, first);
                     mma_tf32_ss(d_re, s_hi, im_hi, id1n, 1u);
                     mma_tf32_ss(d_im, s_hi, re_hi, id1, first);
@@ -108,7 +108,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                         const uint64_t c_lo = make_sdesc(tA + 1 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
                         const uint64_t s_lo = make_sdesc(tA + 3 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
                         const uint64_t re_lo = make_sdesc(b1 + 1 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
-                        const uint64_t im_lo = make_sdesc(b1 + 3 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
+                        const uint64_t im_lo = make_sdesc(b1 + g.b1_im + g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
                         mma_tf32_ss(d_re, c_lo, re_hi, id1, 1u);
                         mma_tf32_ss(d_re, c_hi, re_lo, id1, 1u);
                         mma_tf32_ss(d_re, s_lo, im_hi, id1n, 1u);
@@ -167,7 +167,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 } else {
                     for (int i = 0; i < g.G; ++i) v[i] = src[i];
                 }
-                unsigned char* dst0 = b1 + (part ? 2 : 0) * g.b1_one;
+                unsigned char* dst0 = b1 + (part ? g.b1_im : 0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (i < g.G) {
@@ -357,6 +357,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
         g.tabA_one = g.S1 * H * 32;
         g.tabB_one = g.S2 * W * 32;
         g.b1_one = g.S1 * g.N1 * 32;
+        g.b1_im = nbuf * g.b1_one;              // B1 layout: [Yre hi][Yre lo]? [Yim hi][Yim lo]?
         g.zt_one = g.S2 * 128 * 32;
         g.zt_buf = nbuf * g.zt_one;
         g.off_tabA = 0;

@@ -136,7 +136,7 @@ def _mix(xr, xi, layer, sampled, engine):
     return yr, yi
 
 
-@pytest.mark.parametrize("engine,tol", [("tf32x3", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 5e-6), ("tf32", 2e-3)])   # fp32 CUDA-core sums of 512 terms are ~2e-6 themselves
 @pytest.mark.parametrize("sampled", [False, True])
 @pytest.mark.parametrize("shape", [(16, 128, 128, 4, 4), (64, 256, 256, 20, 20), (32, 64, 256, 5, 3), (128, 128, 128, 2, 2)])
 def test_mix_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
