@@ -114,10 +114,160 @@ __global__ void __launch_bounds__(kThreads) k_local_fwd(const float* __restrict_
     }
 }
 
+// ---- reparameterisation epilogue shared by the thin kernels below ------------------------------------------------------
+__device__ __forceinline__ void reparam4(const float m[4], const float l[4], const PhiloxKey& key, uint64_t e0, float v[4],
+                                         float d[4]) {
+    float z[4];
+    if ((e0 & 3) == 0) {
+        const float4 zz = philox_quad_normals(key, e0 >> 2);
+        z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) z[p] = philox_normal_at(key, e0 + p);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float lvc = fminf(fmaxf(l[p], -10.f), 10.f);
+        const float s_raw = expf(0.5f * lvc);
+        const float s = fmaxf(s_raw, 1e-6f);
+        v[p] = fmaf(z[p], s, m[p]);
+        d[p] = ((l[p] >= -10.f) && (l[p] <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[p] * s : 0.f;
+    }
+}
+
+// Lift (models.py:288-290): Ci <= 8 input channels.  One thread = 4 consecutive pixels x a chunk of output channels; the
+// kernel is a pure streaming write of out (and d out / d lv).   grid (ceil(HW/4/256), ceil(Co/kLiftChunk), B), HW % 4 == 0
+constexpr int kLiftChunk = 32;
+template <bool kNoise>
+__global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restrict__ x, int Ci, int Co, int HW,
+                                                            const float* __restrict__ Wm, const float* __restrict__ bm,
+                                                            const float* __restrict__ Wl, const float* __restrict__ bl,
+                                                            PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
+                                                            float* __restrict__ dout_dlv) {
+    __shared__ float swm[kLiftChunk][8], swl[kLiftChunk][8], sbm[kLiftChunk], sbl[kLiftChunk];
+    const int o_base = blockIdx.y * kLiftChunk, b = blockIdx.z;
+    for (int e = threadIdx.x; e < kLiftChunk * 8; e += kThreads) {
+        const int ol = e >> 3, i = e & 7, o = o_base + ol;
+        const bool ok = o < Co && i < Ci;
+        swm[ol][i] = ok ? Wm[(size_t)o * Ci + i] : 0.f;
+        swl[ol][i] = (ok && kNoise) ? Wl[(size_t)o * Ci + i] : 0.f;
+        if (i == 0) {
+            sbm[ol] = (o < Co && bm) ? bm[o] : 0.f;
+            sbl[ol] = (o < Co && kNoise && bl) ? bl[o] : 0.f;
+        }
+    }
+    __syncthreads();
+    const int p0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (p0 >= HW) return;
+    float xv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < Ci) {
+            const float4 t = *reinterpret_cast<const float4*>(x + ((size_t)b * Ci + i) * HW + p0);
+            xv[i][0] = t.x; xv[i][1] = t.y; xv[i][2] = t.z; xv[i][3] = t.w;
+        } else {
+            xv[i][0] = xv[i][1] = xv[i][2] = xv[i][3] = 0.f;
+        }
+    }
+    for (int ol = 0; ol < kLiftChunk && o_base + ol < Co; ++ol) {
+        const int o = o_base + ol;
+        float m[4] = {sbm[ol], sbm[ol], sbm[ol], sbm[ol]}, l[4] = {sbl[ol], sbl[ol], sbl[ol], sbl[ol]};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float wm = swm[ol][i], wl = swl[ol][i];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                m[p] = fmaf(wm, xv[i][p], m[p]);
+                if (kNoise) l[p] = fmaf(wl, xv[i][p], l[p]);
+            }
+        }
+        const size_t off = ((size_t)b * Co + o) * HW + p0;
+        if (kNoise) {
+            float v[4], d[4];
+            reparam4(m, l, key, ((batch_offset + b) * (uint64_t)Co + o) * (uint64_t)HW + p0, v, d);
+            *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+            if (dout_dlv) *reinterpret_cast<float4*>(dout_dlv + off) = make_float4(d[0], d[1], d[2], d[3]);
+        } else {
+            *reinterpret_cast<float4*>(out + off) = make_float4(m[0], m[1], m[2], m[3]);
+        }
+    }
+}
+
+// Projection (models.py:309-314): Co <= 4 output channels.  One thread = 4 consecutive pixels, streaming read of x.
+// grid (ceil(HW/4/256), B), HW % 4 == 0
+template <bool kNoise>
+__global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __restrict__ x, int Ci, int Co, int HW,
+                                                             const float* __restrict__ Wm, const float* __restrict__ bm,
+                                                             const float* __restrict__ Wl, const float* __restrict__ bl,
+                                                             PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
+                                                             float* __restrict__ dout_dlv) {
+    extern __shared__ float sw[];          // [2][Co][Ci]
+    const int b = blockIdx.y;
+    for (int e = threadIdx.x; e < Co * Ci; e += kThreads) {
+        sw[e] = Wm[e];
+        sw[Co * Ci + e] = kNoise ? Wl[e] : 0.f;
+    }
+    __syncthreads();
+    const int p0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (p0 >= HW) return;
+    float m[4][4] = {}, l[4][4] = {};
+    const float* xb = x + (size_t)b * Ci * HW + p0;
+#pragma unroll 8
+    for (int i = 0; i < Ci; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(xb + (size_t)i * HW);
+        const float xv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (o < Co) {
+                const float wm = sw[o * Ci + i], wl = sw[(Co + o) * Ci + i];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    m[o][p] = fmaf(wm, xv[p], m[o][p]);
+                    if (kNoise) l[o][p] = fmaf(wl, xv[p], l[o][p]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        if (o >= Co) break;
+        const float bias_m = bm ? bm[o] : 0.f, bias_l = (kNoise && bl) ? bl[o] : 0.f;
+        const size_t off = ((size_t)b * Co + o) * HW + p0;
+        float mm[4], ll[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { mm[p] = m[o][p] + bias_m; ll[p] = l[o][p] + bias_l; }
+        if (kNoise) {
+            float v[4], d[4];
+            reparam4(mm, ll, key, ((batch_offset + b) * (uint64_t)Co + o) * (uint64_t)HW + p0, v, d);
+            *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+            if (dout_dlv) *reinterpret_cast<float4*>(dout_dlv + off) = make_float4(d[0], d[1], d[2], d[3]);
+        } else {
+            *reinterpret_cast<float4*>(out + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        }
+    }
+}
+
 }  // namespace
 
 int simt_local_fwd(const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm, const float* Wl,
                    const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv, cudaStream_t st) {
+    const bool aligned = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                             reinterpret_cast<uintptr_t>(dout_dlv)) & 15) == 0;
+    if (aligned && Ci <= 8) {            // lift-shaped: streaming write
+        dim3 g((HW / 4 + kThreads - 1) / kThreads, (Co + kLiftChunk - 1) / kLiftChunk, B);
+        if (Wl) k_local_thin_in<true><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        else k_local_thin_in<false><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        PNO_LAUNCH_CHECK();
+        return PNO_OK;
+    }
+    if (aligned && Co <= 4 && (size_t)2 * Co * Ci * 4 <= 48 * 1024) {   // projection-shaped: streaming read
+        dim3 g((HW / 4 + kThreads - 1) / kThreads, B);
+        const size_t smem = (size_t)2 * Co * Ci * 4;
+        if (Wl) k_local_thin_out<true><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        else k_local_thin_out<false><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        PNO_LAUNCH_CHECK();
+        return PNO_OK;
+    }
     dim3 grid((HW + TP - 1) / TP, (Co + TO - 1) / TO, B);
     if (Wl)
         k_local_fwd<true><<<grid, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);

@@ -35,7 +35,22 @@ struct InvGeom {
 
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
-template <int NSPLIT>
+// Coalesced row store through a per-warp shared-memory transpose: on entry lane r holds 32 consecutive floats of row
+// (row0 + r); on exit every store instruction has written 4 rows x 128 contiguous bytes.  sc = 32 x 8 float4 per warp.
+__device__ __forceinline__ void warp_store_rows32(float4* sc, int lane, const float v[32], float* base, size_t row_stride) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sc[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), ch = lane & 7;
+        const float4 t = sc[rr * 8 + (ch ^ (rr & 7))];
+        *reinterpret_cast<float4*>(base + (size_t)rr * row_stride + 4 * ch) = t;
+    }
+    __syncwarp();
+}
+
+template <int NSPLIT, int G>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
              const float* __restrict__ coef, const float* __restrict__ yr, const float* __restrict__ yi,
@@ -46,6 +61,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     __shared__ __align__(8) uint64_t bar_zt_full[2], bar_zt_empty[2], bar_d2_full[2], bar_d2_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_scale[64];
+    __shared__ float4 s_scratch[4][256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -154,30 +170,36 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             const int img0 = grp * g.G;
             const int b = img0 / g.C, c0 = img0 % g.C;
             mbar_wait(&bar_b1_empty, (ng & 1) ^ 1);
-            for (int e = t; e < items; e += 128) {
-                const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
-                const float* src = (part ? yi : yr) + ((size_t)(kx2 * g.m2 + ky) * g.B + b) * g.C + c0;
-                float v[8];
-                if (g.G == 8) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
-                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-                } else if (g.G == 4) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(src);
-                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
-                } else {
-                    for (int i = 0; i < g.G; ++i) v[i] = src[i];
-                }
-                unsigned char* dst0 = b1 + (part ? g.b1_im : 0);
+            constexpr int U = 7;                       // items in flight per thread: all loads first, then the scatter
+            for (int e0 = t; e0 < items; e0 += 128 * U) {
+                float4 va[U], vb[U];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i < g.G) {
-                        const uint32_t off = kslab_sw32_off(i * g.m2 + ky, kx2, g.N1);
-                        if (NSPLIT == 3) {
-                            const float h = tf32_rn(v[i]);
-                            *reinterpret_cast<float*>(dst0 + off) = h;
-                            *reinterpret_cast<float*>(dst0 + g.b1_one + off) = v[i] - h;
-                        } else {
-                            *reinterpret_cast<float*>(dst0 + off) = v[i];
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * 128;
+                    if (e < items) {
+                        const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
+                        const float* src = (part ? yi : yr) + ((size_t)(kx2 * g.m2 + ky) * g.B + b) * g.C + c0;
+                        va[u] = *reinterpret_cast<const float4*>(src);
+                        if (G == 8) vb[u] = *reinterpret_cast<const float4*>(src + 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * 128;
+                    if (e < items) {
+                        const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
+                        const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                        unsigned char* dst0 = b1 + (part ? g.b1_im : 0);
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            const uint32_t off = kslab_sw32_off(i * g.m2 + ky, kx2, g.N1);
+                            if (NSPLIT == 3) {
+                                const float h = tf32_rn(v[i]);
+                                *reinterpret_cast<float*>(dst0 + off) = h;
+                                *reinterpret_cast<float*>(dst0 + g.b1_one + off) = v[i] - h;
+                            } else {
+                                *reinterpret_cast<float*>(dst0 + off) = v[i];
+                            }
                         }
                     }
                 }
@@ -201,22 +223,34 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     const int img = j * g.IPT + il;                  // image within the group
                     const int zrow = il * g.H + row;                 // row of the stage-2 A tile (row < H here)
                     for (int part = 0; part < 2; ++part) {
-                        for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
-                            uint32_t r0, r1, r2, r3;
-                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                                         : "r"(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + ky0)));
+                        for (int kyb = 0; kyb < g.m2; kyb += 32) {          // up to 8 x4 loads in flight, one wait
+                            uint32_t r[8][4];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (kyb + 4 * c < g.m2)
+                                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(r[c][0]), "=r"(r[c][1]), "=r"(r[c][2]), "=r"(r[c][3])
+                                                 : "r"(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + kyb + 4 * c)));
                             tmem_ld_wait();
                             if (row < g.H) {
-                                float4 v = make_float4(__uint_as_float(r0) * s_scale[ky0], __uint_as_float(r1) * s_scale[ky0 + 1],
-                                                       __uint_as_float(r2) * s_scale[ky0 + 2], __uint_as_float(r3) * s_scale[ky0 + 3]);
-                                const uint32_t off = kslab_sw32_off(zrow, part * g.m2 + ky0, 128);
-                                if (NSPLIT == 3) {
-                                    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                                    *reinterpret_cast<float4*>(zt + off) = h;
-                                    *reinterpret_cast<float4*>(zt + g.zt_one + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                                } else {
-                                    *reinterpret_cast<float4*>(zt + off) = v;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const int ky0 = kyb + 4 * c;
+                                    if (ky0 < g.m2) {
+                                        const float4 v = make_float4(__uint_as_float(r[c][0]) * s_scale[ky0],
+                                                                     __uint_as_float(r[c][1]) * s_scale[ky0 + 1],
+                                                                     __uint_as_float(r[c][2]) * s_scale[ky0 + 2],
+                                                                     __uint_as_float(r[c][3]) * s_scale[ky0 + 3]);
+                                        const uint32_t off = kslab_sw32_off(zrow, part * g.m2 + ky0, 128);
+                                        if (NSPLIT == 3) {
+                                            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                                            *reinterpret_cast<float4*>(zt + off) = h;
+                                            *reinterpret_cast<float4*>(zt + g.zt_one + off) =
+                                                make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                                        } else {
+                                            *reinterpret_cast<float4*>(zt + off) = v;
+                                        }
+                                    }
                                 }
                             }
                         }
@@ -230,7 +264,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         };
 
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
-            const int img0 = grp * g.G;
+            const int img0 = grp * G;
             mbar_wait(&bar_d1_full, ng & 1);
             tc_fence_after_sync();
             transpose_tile(0);
@@ -241,27 +275,47 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 const int db = nE & 1;
                 mbar_wait(&bar_d2_full[db], (nE >> 1) & 1);
                 tc_fence_after_sync();
-                const int img = img0 + j * g.IPT + row / g.H;         // global image index b*C + c
-                const size_t gofs = ((size_t)img * g.H + (row % g.H)) * g.W;
+                const size_t tile_row0 = (size_t)(img0 + j * g.IPT) * g.H;     // rows of the [B*C*H][W] view are consecutive
+                const size_t gofs = (tile_row0 + row) * g.W;
+                const size_t wofs = (tile_row0 + q * 32) * g.W;              // first row of this warp
                 const uint32_t ta = tmem_addr(tmem, q * 32, d2_col + db * g.W);
-                for (int c = 0; c < g.W; c += 8) {
-                    float v[8];
-                    tmem_ld8(ta + c, v);
-                    tmem_ld_wait();
-                    if (addend) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(addend + gofs + c);
-                        const float4 a1 = *reinterpret_cast<const float4*>(addend + gofs + c + 4);
-                        v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                        v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-                    }
-                    if (pre_act) {
-                        reinterpret_cast<float4*>(pre_act + gofs + c)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        reinterpret_cast<float4*>(pre_act + gofs + c)[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    }
+                float4* sc = s_scratch[q];
+                for (int c = 0; c < g.W; c += 32) {
+                    const int nv = (g.W - c) >= 32 ? 8 : (g.W - c) / 4;      // float4 chunks in this column block (W % 16 == 0)
+                    float v[32];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], g.act);
-                    reinterpret_cast<float4*>(y + gofs + c)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    reinterpret_cast<float4*>(y + gofs + c)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < nv && addend) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(addend + gofs + c + 4 * k);
+                            v[4 * k] = a4.x; v[4 * k + 1] = a4.y; v[4 * k + 2] = a4.z; v[4 * k + 3] = a4.w;
+                        } else {
+                            v[4 * k] = v[4 * k + 1] = v[4 * k + 2] = v[4 * k + 3] = 0.f;
+                        }
+                    }
+                    float d[32];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (2 * k < nv) tmem_ld8(ta + c + 8 * k, d + 8 * k);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] += (k < 4 * nv) ? d[k] : 0.f;
+                    if (nv == 8) {
+                        if (pre_act) warp_store_rows32(sc, lane, v, pre_act + wofs + c, g.W);
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) v[k] = act_apply(v[k], g.act);
+                        warp_store_rows32(sc, lane, v, y + wofs + c, g.W);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < nv) {
+                                if (pre_act)
+                                    *reinterpret_cast<float4*>(pre_act + gofs + c + 4 * k) =
+                                        make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                                *reinterpret_cast<float4*>(y + gofs + c + 4 * k) =
+                                    make_float4(act_apply(v[4 * k], g.act), act_apply(v[4 * k + 1], g.act),
+                                                act_apply(v[4 * k + 2], g.act), act_apply(v[4 * k + 3], g.act));
+                            }
+                    }
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bar_d2_empty[db]);
@@ -351,7 +405,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     g.IPT = 128 / H;
     const int nbuf = x3 ? 2 : 1;          // hi (+ lo)
     bool ok = false;
-    for (int G = 8; G >= g.IPT && G >= 1; G >>= 1) {
+    for (int G = 8; G >= g.IPT && G >= 4; G >>= 1) {
         if (C % G || (G * m2) % 16 || G * m2 > 256 || 2 * G * m2 + 2 * W > 512) continue;
         g.G = G; g.N1 = G * m2; g.TPG = G / g.IPT;
         g.tabA_one = g.S1 * H * 32;
@@ -365,7 +419,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
         g.off_b1 = g.off_tabB + pad_up(2 * g.tabB_one, 1024);
         g.off_zt = g.off_b1 + pad_up(2 * nbuf * g.b1_one, 1024);
         g.smem_bytes = g.off_zt + 2 * g.zt_buf + 1024;
-        if (g.smem_bytes <= 224 * 1024) { ok = true; break; }
+        if (g.smem_bytes <= 208 * 1024) { ok = true; break; }     // 227 KB minus the static scratch and barriers
     }
     if (!ok) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv: no channel grouping fits (C = %d, m2 = %d, W = %d)", C, m2, W);
     if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(pre_act) |
@@ -379,13 +433,17 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = g.n_groups < sms ? g.n_groups : sms;
-    if (x3) {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        k_tc_dft_inv<3><<<grid, kThreads, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y, pre_act);
-    } else {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        k_tc_dft_inv<1><<<grid, kThreads, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y, pre_act);
-    }
+#define PNO_LAUNCH_INV(NS, GG)                                                                                          \
+    do {                                                                                                               \
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<NS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes)); \
+        k_tc_dft_inv<NS, GG><<<grid, kThreads, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y,   \
+                                                                    pre_act);                                          \
+    } while (0)
+    if (x3 && g.G == 8) PNO_LAUNCH_INV(3, 8);
+    else if (x3) PNO_LAUNCH_INV(3, 4);
+    else if (g.G == 8) PNO_LAUNCH_INV(1, 8);
+    else PNO_LAUNCH_INV(1, 4);
+#undef PNO_LAUNCH_INV
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
