@@ -149,6 +149,10 @@ int pno_mc_accumulate(const float* y, uint64_t n, double* sum, double* sumsq, vo
 int pno_mc_finalize(const double* sum, const double* sumsq, uint64_t n, uint32_t S, float* mean, float* std,
                     void* stream);
 
+/* Diagnostics: device buffer (>= 148*16 int64) into which the tensor-core kernels dump per-CTA barrier-wait cycle counters
+ * (NULL switches it off, the default).  Used by tools/phase_times.py to find the stage a pipeline is waiting on. */
+int pno_debug_set_buffer(void* device_ptr);
+
 /* ---- hardware self-test of the tcgen05 / TMA building blocks ---------------------------------------------------- */
 /* One CTA computes D[128][N] = (+-A)[128][K] * (+-B)[K][N] on the tensor cores (kind::tf32).
  * flags: bit0 A MN-major, bit1 B MN-major, bit2 A staged by TMA, bit3 B staged by TMA, bit4 negate A, bit5 negate B,

@@ -17,6 +17,12 @@ void pno_set_error(const char* fmt, ...) {
 }
 
 unsigned long long g_pno_launches = 0;
+long long* g_pno_debug_buffer = nullptr;
+
+extern "C" int pno_debug_set_buffer(void* device_ptr) {
+    g_pno_debug_buffer = static_cast<long long*>(device_ptr);
+    return PNO_OK;
+}
 
 extern "C" int pno_version(void) { return PNO_VERSION; }
 extern "C" uint64_t pno_launch_count(void) { return g_pno_launches; }

@@ -143,6 +143,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             const uint32_t idesc1 = make_idesc(FMT_TF32, 128, g.N1p, MAJOR_K, MAJOR_K);
             const uint32_t idesc2 = make_idesc(FMT_TF32, 128, g.N2p, MAJOR_K, MAJOR_K);
             const uint32_t idesc2n = make_idesc(FMT_TF32, 128, g.N2p, MAJOR_K, MAJOR_K, 1, 0);
+            const uint32_t khi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;     // all operands: K-major SW128
             int stage = 0, phase = 0;
             int n1 = 0;      // stage-1 tiles issued
             int n2 = 0;      // stage-2 tiles issued
@@ -157,19 +158,16 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 for (int kb = 0; kb < g.KB1; ++kb) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
                     tc_fence_after_sync();
-                    const uint32_t s0 = smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes);
-                    const uint32_t x_hi = s0, x_lo = s0 + g.x_bytes, tw_hi = s0 + 2 * g.x_bytes, tw_lo = tw_hi + g.tw_bytes;
+                    const uint32_t x_hi = sdesc_base(smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), 16, 1024, SWIZZLE_128B).lo;
+                    const uint32_t x_lo = x_hi + (g.x_bytes >> 4), tw_hi = x_hi + 2 * (g.x_bytes >> 4), tw_lo = tw_hi + (g.tw_bytes >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t accf = (kb | ks) ? 1u : 0u;
-                        const uint64_t a_hi = make_sdesc(x_hi + ks * 32, 16, 1024, SWIZZLE_128B);
-                        const uint64_t b_hi = make_sdesc(tw_hi + ks * 32, 16, 1024, SWIZZLE_128B);
-                        mma_tf32_ss(d1, a_hi, b_hi, idesc1, accf);
+                        const uint32_t o = ks * 2;
+                        mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf);
                         if (NSPLIT == 3) {
-                            const uint64_t a_lo = make_sdesc(x_lo + ks * 32, 16, 1024, SWIZZLE_128B);
-                            const uint64_t b_lo = make_sdesc(tw_lo + ks * 32, 16, 1024, SWIZZLE_128B);
-                            mma_tf32_ss(d1, a_lo, b_hi, idesc1, 1u);
-                            mma_tf32_ss(d1, a_hi, b_lo, idesc1, 1u);
+                            mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u);
+                            mma_tf32(d1, x_hi + o, khi, tw_lo + o, khi, idesc1, 1u);
                         }
                     }
                     mma_commit(&bar_empty[stage]);
@@ -191,36 +189,30 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 const int tiles_per_slot = g.H > 128 ? g.H / 128 : 1;
                 const int slot = t / tiles_per_slot, part = t % tiles_per_slot;
                 const uint32_t d_re = tmem + d2_base + slot * 2 * g.N2p, d_im = d_re + g.N2p;
-                const uint32_t tb = smem_u32(tab), bb = smem_u32(b2);
+                const uint32_t tb = sdesc_base(smem_u32(tab), 16, 1024, SWIZZLE_128B).lo;
+                const uint32_t bb = sdesc_base(smem_u32(b2), 16, 1024, SWIZZLE_128B).lo;
+                const uint32_t t1 = tab_one >> 4, bo1 = b2_one >> 4;       // (C hi, C lo, S hi, S lo) / (Rre hi, Rre lo, Rim hi, Rim lo)
                 const int nkb = KT / 32;
                 for (int kb = 0; kb < nkb; ++kb) {
                     const int tkb = part * 4 + kb;              // k-block inside the full-H tables
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t first = (part | kb | ks) ? 1u : 0u;
-                        const uint32_t toff = tkb * tab_kb + ks * 32, boff = kb * b2_kb + ks * 32;
-                        const uint64_t c_hi = make_sdesc(tb + 0 * tab_one + toff, 16, 1024, SWIZZLE_128B);
-                        const uint64_t s_hi = make_sdesc(tb + 2 * tab_one + toff, 16, 1024, SWIZZLE_128B);
-                        const uint64_t re_hi = make_sdesc(bb + 0 * b2_one + boff, 16, 1024, SWIZZLE_128B);
-                        const uint64_t im_hi = make_sdesc(bb + 2 * b2_one + boff, 16, 1024, SWIZZLE_128B);
+                        const uint32_t c = tb + ((tkb * tab_kb) >> 4) + ks * 2, r = bb + ((kb * b2_kb) >> 4) + ks * 2;
                         // Xre += C Rre + S Rim ; Xim += C Rim - S Rre
-                        mma_tf32_ss(d_re, c_hi, re_hi, idesc2, first);
-                        mma_tf32_ss(d_re, s_hi, im_hi, idesc2, 1u);
-                        mma_tf32_ss(d_im, c_hi, im_hi, idesc2, first);
-                        mma_tf32_ss(d_im, s_hi, re_hi, idesc2n, 1u);
+                        mma_tf32(d_re, c, khi, r, khi, idesc2, first);
+                        mma_tf32(d_re, c + 2 * t1, khi, r + 2 * bo1, khi, idesc2, 1u);
+                        mma_tf32(d_im, c, khi, r + 2 * bo1, khi, idesc2, first);
+                        mma_tf32(d_im, c + 2 * t1, khi, r, khi, idesc2n, 1u);
                         if (NSPLIT == 3) {
-                            const uint64_t c_lo = make_sdesc(tb + 1 * tab_one + toff, 16, 1024, SWIZZLE_128B);
-                            const uint64_t s_lo = make_sdesc(tb + 3 * tab_one + toff, 16, 1024, SWIZZLE_128B);
-                            const uint64_t re_lo = make_sdesc(bb + 1 * b2_one + boff, 16, 1024, SWIZZLE_128B);
-                            const uint64_t im_lo = make_sdesc(bb + 3 * b2_one + boff, 16, 1024, SWIZZLE_128B);
-                            mma_tf32_ss(d_re, c_lo, re_hi, idesc2, 1u);
-                            mma_tf32_ss(d_re, c_hi, re_lo, idesc2, 1u);
-                            mma_tf32_ss(d_re, s_lo, im_hi, idesc2, 1u);
-                            mma_tf32_ss(d_re, s_hi, im_lo, idesc2, 1u);
-                            mma_tf32_ss(d_im, c_lo, im_hi, idesc2, 1u);
-                            mma_tf32_ss(d_im, c_hi, im_lo, idesc2, 1u);
-                            mma_tf32_ss(d_im, s_lo, re_hi, idesc2n, 1u);
-                            mma_tf32_ss(d_im, s_hi, re_lo, idesc2n, 1u);
+                            mma_tf32(d_re, c + t1, khi, r, khi, idesc2, 1u);
+                            mma_tf32(d_re, c, khi, r + bo1, khi, idesc2, 1u);
+                            mma_tf32(d_re, c + 3 * t1, khi, r + 2 * bo1, khi, idesc2, 1u);
+                            mma_tf32(d_re, c + 2 * t1, khi, r + 3 * bo1, khi, idesc2, 1u);
+                            mma_tf32(d_im, c + t1, khi, r + 2 * bo1, khi, idesc2, 1u);
+                            mma_tf32(d_im, c, khi, r + 3 * bo1, khi, idesc2, 1u);
+                            mma_tf32(d_im, c + 3 * t1, khi, r, khi, idesc2n, 1u);
+                            mma_tf32(d_im, c + 2 * t1, khi, r + bo1, khi, idesc2n, 1u);
                         }
                     }
                 }

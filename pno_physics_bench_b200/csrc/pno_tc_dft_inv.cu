@@ -8,8 +8,9 @@
 //   transposer  TMEM Z -> registers -> * c_ky/(HW) -> tf32 hi/lo -> Zt slabs [(img,h)][(re|im, ky)]
 //   stage 2     y[(img,h)][w] = Zt * TwB^T            TwB[w][(re|im,ky)] = cos | -sin (2 pi ky w / W)
 //   epilogue    TMEM -> + addend -> pre_act -> activation -> global rows (each thread owns one image row)
-//   warp 1 MMA issuer, warps 2-5 loaders, warps 6-9 transposer + epilogue (warp 0 idle: no TMA in this kernel)
+//   warp 1 MMA issuer, warps 2-5 loaders, warps 6-9 transposer, warps 10-17 epilogue (warp 0 idle: no TMA in this kernel)
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -20,7 +21,7 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 576;
 
 struct InvGeom {
     int H, W, m1, m2, B, C;
@@ -31,7 +32,15 @@ struct InvGeom {
     int n_groups;
     int adjoint, act;
     int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, b1_im, zt_one, zt_buf, smem_bytes;
+    long long* dbg;   // optional per-CTA wait-cycle counters (pno_debug_set_buffer)
+    int dbg_mma;      // diagnostics: the issuer also waits for its own batches (serialises the pipeline)
 };
+
+__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
@@ -50,6 +59,20 @@ __device__ __forceinline__ void warp_store_rows32(float4* sc, int lane, const fl
     __syncwarp();
 }
 
+// 16-column variant: lane r holds 16 consecutive floats of row (row0 + r); each store instruction writes 8 rows x 64 bytes.
+__device__ __forceinline__ void warp_store_rows16(float4* sc, int lane, const float v[16], float* base, size_t row_stride) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sc[lane * 4 + (c ^ (lane & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + (lane >> 2), ch = lane & 3;
+        const float4 t = sc[rr * 4 + (ch ^ (rr & 3))];
+        *reinterpret_cast<float4*>(base + (size_t)rr * row_stride + 4 * ch) = t;
+    }
+    __syncwarp();
+}
+
 template <int NSPLIT, int G>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
@@ -61,9 +84,11 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     __shared__ __align__(8) uint64_t bar_zt_full[2], bar_zt_empty[2], bar_d2_full[2], bar_d2_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_scale[64];
-    __shared__ float4 s_scratch[4][256];
+    __shared__ float4 s_scratch[8][128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+    const long long t_start = clock64();
     if (threadIdx.x == 0) {
         mbar_init(&bar_b1_full, 128);
         mbar_init(&bar_b1_empty, 1);
@@ -73,7 +98,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             mbar_init(&bar_zt_full[s], 128);
             mbar_init(&bar_zt_empty[s], 1);
             mbar_init(&bar_d2_full[s], 1);
-            mbar_init(&bar_d2_empty[s], 128);
+            mbar_init(&bar_d2_empty[s], 256);
         }
         fence_mbar_init();
     }
@@ -101,62 +126,67 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             const uint32_t id1 = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K);
             const uint32_t id1n = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K, 1, 0);
             const uint32_t id2 = make_idesc(FMT_TF32, 128, g.W, MAJOR_K, MAJOR_K);
-            const uint32_t tA = smem_u32(smem + g.off_tabA), tB = smem_u32(smem + g.off_tabB);
-            const uint32_t b1 = smem_u32(smem + g.off_b1), zt = smem_u32(smem + g.off_zt);
-            const uint32_t slabA = g.H * 32, slabB1 = g.N1 * 32, slabZ = 128 * 32, slabTB = g.W * 32;
+            // descriptor words: every operand is K-major SW32 slabs (LBO 16, SBO 256); only the low word changes per MMA
+            const uint32_t dhi = sdesc_base(0, 16, 256, SWIZZLE_32B).hi;
+            const uint32_t tA = sdesc_base(smem_u32(smem + g.off_tabA), 16, 256, SWIZZLE_32B).lo;
+            const uint32_t tB = sdesc_base(smem_u32(smem + g.off_tabB), 16, 256, SWIZZLE_32B).lo;
+            const uint32_t b1 = sdesc_base(smem_u32(smem + g.off_b1), 16, 256, SWIZZLE_32B).lo;
+            const uint32_t zt = sdesc_base(smem_u32(smem + g.off_zt), 16, 256, SWIZZLE_32B).lo;
+            const uint32_t slabA = g.H * 2, slabB1 = g.N1 * 2, slabZ = 128 * 2, slabTB = g.W * 2;     // slab strides in 16-byte units
+            const uint32_t tA1 = g.tabA_one >> 4, b1o = g.b1_one >> 4, b1i = g.b1_im >> 4;
             int ng = 0, nt = 0;
             for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
-                mbar_wait(&bar_b1_full, ng & 1);
-                mbar_wait(&bar_d1_empty, (ng & 1) ^ 1);
+                wait_t(&bar_b1_full, ng & 1, w0);
+                wait_t(&bar_d1_empty, (ng & 1) ^ 1, w1);
                 tc_fence_after_sync();
                 const uint32_t d_re = tmem, d_im = tmem + g.N1;
-                for (int s = 0; s < g.S1; ++s) {
+                uint32_t a = tA, b = b1;
+                for (int s = 0; s < g.S1; ++s, a += slabA, b += slabB1) {
                     const uint32_t first = s ? 1u : 0u;
-                    const uint64_t c_hi = make_sdesc(tA + 0 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
-                    const uint64_t s_hi = make_sdesc(tA + 2 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
-                    const uint64_t re_hi = make_sdesc(b1 + 0 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
-                    const uint64_t im_hi = make_sdesc(b1 + g.b1_im + s * slabB1, 16, 256, SWIZZLE_32B);
-                    mma_tf32_ss(d_re, c_hi, re_hi, id1, first);
-                    mma_tf32_ss(d_re, s_hi, im_hi, id1n, 1u);
-                    mma_tf32_ss(d_im, s_hi, re_hi, id1, first);
-                    mma_tf32_ss(d_im, c_hi, im_hi, id1, 1u);
+                    // (C hi, C lo, S hi, S lo) at a + {0,1,2,3}*tA1;  (Yre hi, Yre lo) at b + {0, b1o}, (Yim hi, Yim lo) at b + b1i + {0, b1o}
+                    mma_tf32(d_re, a, dhi, b, dhi, id1, first);
+                    mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i, dhi, id1n, 1u);
+                    mma_tf32(d_im, a + 2 * tA1, dhi, b, dhi, id1, first);
+                    mma_tf32(d_im, a, dhi, b + b1i, dhi, id1, 1u);
                     if (NSPLIT == 3) {
-                        const uint64_t c_lo = make_sdesc(tA + 1 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
-                        const uint64_t s_lo = make_sdesc(tA + 3 * g.tabA_one + s * slabA, 16, 256, SWIZZLE_32B);
-                        const uint64_t re_lo = make_sdesc(b1 + 1 * g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
-                        const uint64_t im_lo = make_sdesc(b1 + g.b1_im + g.b1_one + s * slabB1, 16, 256, SWIZZLE_32B);
-                        mma_tf32_ss(d_re, c_lo, re_hi, id1, 1u);
-                        mma_tf32_ss(d_re, c_hi, re_lo, id1, 1u);
-                        mma_tf32_ss(d_re, s_lo, im_hi, id1n, 1u);
-                        mma_tf32_ss(d_re, s_hi, im_lo, id1n, 1u);
-                        mma_tf32_ss(d_im, s_lo, re_hi, id1, 1u);
-                        mma_tf32_ss(d_im, s_hi, re_lo, id1, 1u);
-                        mma_tf32_ss(d_im, c_lo, im_hi, id1, 1u);
-                        mma_tf32_ss(d_im, c_hi, im_lo, id1, 1u);
+                        mma_tf32(d_re, a + tA1, dhi, b, dhi, id1, 1u);
+                        mma_tf32(d_re, a, dhi, b + b1o, dhi, id1, 1u);
+                        mma_tf32(d_re, a + 3 * tA1, dhi, b + b1i, dhi, id1n, 1u);
+                        mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i + b1o, dhi, id1n, 1u);
+                        mma_tf32(d_im, a + 3 * tA1, dhi, b, dhi, id1, 1u);
+                        mma_tf32(d_im, a + 2 * tA1, dhi, b + b1o, dhi, id1, 1u);
+                        mma_tf32(d_im, a + tA1, dhi, b + b1i, dhi, id1, 1u);
+                        mma_tf32(d_im, a, dhi, b + b1i + b1o, dhi, id1, 1u);
                     }
                 }
                 mma_commit(&bar_b1_empty);
                 mma_commit(&bar_d1_full);
+                if (g.dbg_mma) {                         // diagnostics: issue -> completion latency of the stage-1 batch
+                    const long long tq = clock64();
+                    mbar_wait(&bar_d1_full, ng & 1);
+                    w4 += clock64() - tq;
+                }
                 for (int j = 0; j < g.TPG; ++j, ++nt) {
                     const int zb = nt & 1;
-                    mbar_wait(&bar_zt_full[zb], (nt >> 1) & 1);
-                    mbar_wait(&bar_d2_empty[zb], ((nt >> 1) & 1) ^ 1);
+                    wait_t(&bar_zt_full[zb], (nt >> 1) & 1, w2);
+                    wait_t(&bar_d2_empty[zb], ((nt >> 1) & 1) ^ 1, w3);
                     tc_fence_after_sync();
                     const uint32_t d2 = tmem + d2_col + zb * g.W;
-                    const uint32_t zbase = zt + zb * g.zt_buf;
-                    for (int s = 0; s < g.S2; ++s) {
-                        const uint64_t z_hi = make_sdesc(zbase + s * slabZ, 16, 256, SWIZZLE_32B);
-                        const uint64_t w_hi = make_sdesc(tB + s * slabTB, 16, 256, SWIZZLE_32B);
-                        mma_tf32_ss(d2, z_hi, w_hi, id2, s ? 1u : 0u);
+                    uint32_t z = zt + zb * (g.zt_buf >> 4), w = tB;
+                    for (int s = 0; s < g.S2; ++s, z += slabZ, w += slabTB) {
+                        mma_tf32(d2, z, dhi, w, dhi, id2, s ? 1u : 0u);
                         if (NSPLIT == 3) {
-                            const uint64_t z_lo = make_sdesc(zbase + g.zt_one + s * slabZ, 16, 256, SWIZZLE_32B);
-                            const uint64_t w_lo = make_sdesc(tB + g.tabB_one + s * slabTB, 16, 256, SWIZZLE_32B);
-                            mma_tf32_ss(d2, z_lo, w_hi, id2, 1u);
-                            mma_tf32_ss(d2, z_hi, w_lo, id2, 1u);
+                            mma_tf32(d2, z + (g.zt_one >> 4), dhi, w, dhi, id2, 1u);
+                            mma_tf32(d2, z, dhi, w + (g.tabB_one >> 4), dhi, id2, 1u);
                         }
                     }
                     mma_commit(&bar_zt_empty[zb]);
                     mma_commit(&bar_d2_full[zb]);
+                    if (g.dbg_mma) {
+                        const long long tq = clock64();
+                        mbar_wait(&bar_d2_full[zb], (nt >> 1) & 1);
+                        w5 += clock64() - tq;
+                    }
                 }
             }
         }
@@ -169,7 +199,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
             const int img0 = grp * g.G;
             const int b = img0 / g.C, c0 = img0 % g.C;
-            mbar_wait(&bar_b1_empty, (ng & 1) ^ 1);
+            wait_t(&bar_b1_empty, (ng & 1) ^ 1, w0);
             constexpr int U = 7;                       // items in flight per thread: all loads first, then the scatter
             for (int e0 = t; e0 < items; e0 += 128 * U) {
                 float4 va[U], vb[U];
@@ -207,16 +237,16 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             fence_proxy_async_smem();
             mbar_arrive(&bar_b1_full);
         }
-    } else if (warp >= 6) {
-        // ================================ transposer + epilogue ================================
+    } else if (warp >= 6 && warp < 10) {
+        // ================================ transposer ================================
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const bool t_active_warp = q * 32 < g.H;          // warp holds valid stage-1 lanes (h < H)
-        int ng = 0, nT = 0, nE = 0;
+        int ng = 0, nT = 0;
 
         auto transpose_tile = [&](int j) {
             const int zb = nT & 1;
-            mbar_wait(&bar_zt_empty[zb], ((nT >> 1) & 1) ^ 1);
+            wait_t(&bar_zt_empty[zb], ((nT >> 1) & 1) ^ 1, w0);
             if (t_active_warp) {
                 unsigned char* zt = smem + g.off_zt + zb * g.zt_buf;
                 for (int il = 0; il < g.IPT; ++il) {
@@ -264,64 +294,66 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         };
 
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
-            const int img0 = grp * G;
-            mbar_wait(&bar_d1_full, ng & 1);
+            wait_t(&bar_d1_full, ng & 1, w1);
             tc_fence_after_sync();
-            transpose_tile(0);
-            for (int j = 0; j < g.TPG; ++j) {
-                if (j + 1 < g.TPG) transpose_tile(j + 1);
-                else mbar_arrive(&bar_d1_empty);          // every stage-1 accumulator of this group has been read
-                // ---- epilogue of tile j ----
+            for (int j = 0; j < g.TPG; ++j) transpose_tile(j);
+            mbar_arrive(&bar_d1_empty);                   // every stage-1 accumulator of this group has been read
+        }
+    } else if (warp >= 10) {
+        // ================================ epilogue ================================
+        // 8 warps: two per TMEM lane quarter, each taking half of the W columns in 16-column passes
+        const int q = warp & 3, half = (warp - 10) >> 2;
+        const int row = q * 32 + lane;
+        float4* sc = s_scratch[warp - 10];
+        const int c_lo = half * (g.W / 2), c_hi = c_lo + g.W / 2;      // W % 32 == 0 on this path
+        int nE = 0;
+        for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+            const int img0 = grp * G;
+            for (int j = 0; j < g.TPG; ++j, ++nE) {
                 const int db = nE & 1;
-                mbar_wait(&bar_d2_full[db], (nE >> 1) & 1);
-                tc_fence_after_sync();
                 const size_t tile_row0 = (size_t)(img0 + j * g.IPT) * g.H;     // rows of the [B*C*H][W] view are consecutive
                 const size_t gofs = (tile_row0 + row) * g.W;
                 const size_t wofs = (tile_row0 + q * 32) * g.W;              // first row of this warp
                 const uint32_t ta = tmem_addr(tmem, q * 32, d2_col + db * g.W);
-                float4* sc = s_scratch[q];
-                for (int c = 0; c < g.W; c += 32) {
-                    const int nv = (g.W - c) >= 32 ? 8 : (g.W - c) / 4;      // float4 chunks in this column block (W % 16 == 0)
-                    float v[32];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (k < nv && addend) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(addend + gofs + c + 4 * k);
-                            v[4 * k] = a4.x; v[4 * k + 1] = a4.y; v[4 * k + 2] = a4.z; v[4 * k + 3] = a4.w;
-                        } else {
-                            v[4 * k] = v[4 * k + 1] = v[4 * k + 2] = v[4 * k + 3] = 0.f;
-                        }
-                    }
-                    float d[32];
+                // the addend chunk is fetched before the accumulator is ready, so DRAM latency hides behind the wait
+                float4 a_nxt[4];
+                auto fetch = [&](int c) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (2 * k < nv) tmem_ld8(ta + c + 8 * k, d + 8 * k);
+                        a_nxt[k] = addend ? *reinterpret_cast<const float4*>(addend + gofs + c + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                fetch(c_lo);
+                wait_t(&bar_d2_full[db], (nE >> 1) & 1, w2);
+                tc_fence_after_sync();
+                for (int c = c_lo; c < c_hi; c += 16) {
+                    float v[16];
+                    long long tq = clock64();
+                    tmem_ld16(ta + c, v);
+                    float4 a_cur[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a_cur[k] = a_nxt[k];
+                    if (c + 16 < c_hi) fetch(c + 16);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] += (k < 4 * nv) ? d[k] : 0.f;
-                    if (nv == 8) {
-                        if (pre_act) warp_store_rows32(sc, lane, v, pre_act + wofs + c, g.W);
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) v[k] = act_apply(v[k], g.act);
-                        warp_store_rows32(sc, lane, v, y + wofs + c, g.W);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (k < nv) {
-                                if (pre_act)
-                                    *reinterpret_cast<float4*>(pre_act + gofs + c + 4 * k) =
-                                        make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                                *reinterpret_cast<float4*>(y + gofs + c + 4 * k) =
-                                    make_float4(act_apply(v[4 * k], g.act), act_apply(v[4 * k + 1], g.act),
-                                                act_apply(v[4 * k + 2], g.act), act_apply(v[4 * k + 3], g.act));
-                            }
+                    for (int k = 0; k < 4; ++k) {
+                        v[4 * k] += a_cur[k].x; v[4 * k + 1] += a_cur[k].y; v[4 * k + 2] += a_cur[k].z; v[4 * k + 3] += a_cur[k].w;
                     }
+                    { const long long t2 = clock64(); w0 += t2 - tq; tq = t2; }
+                    if (pre_act) warp_store_rows16(sc, lane, v, pre_act + wofs + c, g.W);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = act_apply_fast(v[k], g.act);
+                    { const long long t2 = clock64(); w1 += t2 - tq; tq = t2; }
+                    warp_store_rows16(sc, lane, v, y + wofs + c, g.W);
+                    { const long long t2 = clock64(); w3 += t2 - tq; tq = t2; }
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bar_d2_empty[db]);
-                ++nE;
             }
         }
+    }
+    if (g.dbg && lane == 0 && (warp == 1 || warp == 6 || warp == 10)) {
+        long long* d = g.dbg + ((size_t)blockIdx.x * 3 + (warp == 1 ? 0 : warp == 6 ? 1 : 2)) * 7;
+        d[0] = w0; d[1] = w1; d[2] = w2; d[3] = w3; d[4] = clock64() - t_start; d[5] = w4; d[6] = w5;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -395,8 +427,8 @@ void tc_plan_release_inv(pno_plan* p) {
 int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
                const float* addend, int act, float* y, float* pre_act, cudaStream_t st) {
     const int H = p->H, W = p->W, m1 = p->m1, m2 = p->m2;
-    if (!(H == 32 || H == 64 || H == 128) || W % 16 || W > 256 || W < 16 || m1 % 4 || m2 % 4 || m2 > 64)
-        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv tiles H in {32,64,128}, W%%16 == 0, W <= 256, m1%%4 == 0, m2%%4 == 0");
+    if (!(H == 32 || H == 64 || H == 128) || W % 32 || W > 256 || W < 32 || m1 % 4 || m2 % 4 || m2 > 64)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv tiles H in {32,64,128}, W%%32 == 0, W <= 256, m1%%4 == 0, m2%%4 == 0");
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
     InvGeom g;
     memset(&g, 0, sizeof(g));
@@ -426,6 +458,8 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
          reinterpret_cast<uintptr_t>(yr) | reinterpret_cast<uintptr_t>(yi)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv needs 16-byte aligned tensors");
     g.n_groups = B * C / g.G;
+    g.dbg = g_pno_debug_buffer;
+    g.dbg_mma = g_pno_debug_buffer != nullptr && getenv("PNO_DEBUG_MMA") != nullptr;
     InvTables* t = nullptr;
     int rc = inv_tables_get(p, &t);
     if (rc) return rc;

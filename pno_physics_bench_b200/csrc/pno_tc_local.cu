@@ -107,6 +107,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(FMT_TF32, TM, TN, MAJOR_K, MAJOR_MN);
+            const uint32_t ahi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
+            const uint32_t bhi = sdesc_base(0, TK * 128, 512, SWIZZLE_128B_BASE32B).hi;
             int stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
@@ -117,28 +119,24 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(stage_ptr(stage));
-                    const uint32_t am = s0, al = s0 + TILE_BYTES, xb = s0 + 2 * TILE_BYTES;
-                    const uint32_t lo = C::kOperandBytes;      // byte distance from a hi tile to its lo copy
+                    const uint32_t am = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;                       // A tiles: K-major SW128
+                    const uint32_t al = am + (TILE_BYTES >> 4);
+                    const uint32_t xb = sdesc_base(s0 + 2 * TILE_BYTES, TK * 128, 512, SWIZZLE_128B_BASE32B).lo;   // B: MN-major
+                    const uint32_t lo = C::kOperandBytes >> 4;       // distance from a hi tile to its lo copy
 #pragma unroll
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
-                        const uint64_t dx_hi = make_sdesc(xb + ks * 1024, TK * 128, 512, SWIZZLE_128B_BASE32B);
-                        const uint64_t dm_hi = make_sdesc(am + ks * 32, 16, 1024, SWIZZLE_128B);
-                        mma_tf32_ss(d_m, dm_hi, dx_hi, idesc, acc_flag);
+                        const uint32_t ao = ks * 2, bo = ks * 64;    // 32 B / 1024 B per K step
+                        mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag);
                         if (NSPLIT == 3) {
-                            const uint64_t dx_lo = make_sdesc(xb + lo + ks * 1024, TK * 128, 512, SWIZZLE_128B_BASE32B);
-                            const uint64_t dm_lo = make_sdesc(am + lo + ks * 32, 16, 1024, SWIZZLE_128B);
-                            mma_tf32_ss(d_m, dm_lo, dx_hi, idesc, 1u);
-                            mma_tf32_ss(d_m, dm_hi, dx_lo, idesc, 1u);
+                            mma_tf32(d_m, am + lo + ao, ahi, xb + bo, bhi, idesc, 1u);
+                            mma_tf32(d_m, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u);
                         }
                         if (a.noisy) {
-                            const uint64_t dl_hi = make_sdesc(al + ks * 32, 16, 1024, SWIZZLE_128B);
-                            mma_tf32_ss(d_l, dl_hi, dx_hi, idesc, acc_flag);
+                            mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag);
                             if (NSPLIT == 3) {
-                                const uint64_t dx_lo = make_sdesc(xb + lo + ks * 1024, TK * 128, 512, SWIZZLE_128B_BASE32B);
-                                const uint64_t dl_lo = make_sdesc(al + lo + ks * 32, 16, 1024, SWIZZLE_128B);
-                                mma_tf32_ss(d_l, dl_lo, dx_hi, idesc, 1u);
-                                mma_tf32_ss(d_l, dl_hi, dx_lo, idesc, 1u);
+                                mma_tf32(d_l, al + lo + ao, ahi, xb + bo, bhi, idesc, 1u);
+                                mma_tf32(d_l, al + ao, ahi, xb + lo + bo, bhi, idesc, 1u);
                             }
                         }
                     }

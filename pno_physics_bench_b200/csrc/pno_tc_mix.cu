@@ -89,6 +89,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         if (lane == 0) {
             const uint32_t idesc = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K);
             const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K, 1, 0);
+            const uint32_t dhi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
             int stage = 0, phase = 0, it = 0;
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
                 const int acc = it & 1;
@@ -99,33 +100,28 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     mbar_wait(&bar_ready[stage], phase);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(smem + (size_t)stage * g.stage_bytes);
-                    const uint32_t wre = s0, wim = s0 + W_TILE, wre_lo = s0 + 2 * W_TILE, wim_lo = s0 + 3 * W_TILE;
-                    const uint32_t xre = s0 + x_off, xim = xre + g.x_tile, xre_lo = xim + g.x_tile, xim_lo = xre_lo + g.x_tile;
+                    // low descriptor words of the 8 operand tiles of this stage (all K-major SW128: LBO 16, SBO 1024)
+                    const uint32_t wre = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;
+                    const uint32_t wim = wre + (W_TILE >> 4), wre_l = wre + 2 * (W_TILE >> 4), wim_l = wre + 3 * (W_TILE >> 4);
+                    const uint32_t xre = wre + (x_off >> 4), xim = xre + (g.x_tile >> 4), xre_l = xim + (g.x_tile >> 4),
+                                   xim_l = xre_l + (g.x_tile >> 4);
 #pragma unroll
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t first = (kb | ks) ? 1u : 0u;
-                        const uint32_t o = ks * 32;
-                        const uint64_t a_re = make_sdesc(wre + o, 16, 1024, SWIZZLE_128B);
-                        const uint64_t a_im = make_sdesc(wim + o, 16, 1024, SWIZZLE_128B);
-                        const uint64_t b_re = make_sdesc(xre + o, 16, 1024, SWIZZLE_128B);
-                        const uint64_t b_im = make_sdesc(xim + o, 16, 1024, SWIZZLE_128B);
-                        mma_tf32_ss(d_re, a_re, b_re, idesc, first);
-                        mma_tf32_ss(d_re, a_im, b_im, idesc_n, 1u);
-                        mma_tf32_ss(d_im, a_im, b_re, idesc, first);
-                        mma_tf32_ss(d_im, a_re, b_im, idesc, 1u);
+                        const uint32_t o = ks * 2;              // 32 bytes per K step
+                        mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first);
+                        mma_tf32(d_re, wim + o, dhi, xim + o, dhi, idesc_n, 1u);
+                        mma_tf32(d_im, wim + o, dhi, xre + o, dhi, idesc, first);
+                        mma_tf32(d_im, wre + o, dhi, xim + o, dhi, idesc, 1u);
                         if (NSPLIT == 3) {
-                            const uint64_t a_re_l = make_sdesc(wre_lo + o, 16, 1024, SWIZZLE_128B);
-                            const uint64_t a_im_l = make_sdesc(wim_lo + o, 16, 1024, SWIZZLE_128B);
-                            const uint64_t b_re_l = make_sdesc(xre_lo + o, 16, 1024, SWIZZLE_128B);
-                            const uint64_t b_im_l = make_sdesc(xim_lo + o, 16, 1024, SWIZZLE_128B);
-                            mma_tf32_ss(d_re, a_re_l, b_re, idesc, 1u);
-                            mma_tf32_ss(d_re, a_re, b_re_l, idesc, 1u);
-                            mma_tf32_ss(d_re, a_im_l, b_im, idesc_n, 1u);
-                            mma_tf32_ss(d_re, a_im, b_im_l, idesc_n, 1u);
-                            mma_tf32_ss(d_im, a_im_l, b_re, idesc, 1u);
-                            mma_tf32_ss(d_im, a_im, b_re_l, idesc, 1u);
-                            mma_tf32_ss(d_im, a_re_l, b_im, idesc, 1u);
-                            mma_tf32_ss(d_im, a_re, b_im_l, idesc, 1u);
+                            mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u);
+                            mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u);
+                            mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, idesc_n, 1u);
+                            mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, idesc_n, 1u);
+                            mma_tf32(d_im, wim_l + o, dhi, xre + o, dhi, idesc, 1u);
+                            mma_tf32(d_im, wim + o, dhi, xre_l + o, dhi, idesc, 1u);
+                            mma_tf32(d_im, wre_l + o, dhi, xim + o, dhi, idesc, 1u);
+                            mma_tf32(d_im, wre + o, dhi, xim_l + o, dhi, idesc, 1u);
                         }
                     }
                     mma_commit(&bar_empty[stage]);
