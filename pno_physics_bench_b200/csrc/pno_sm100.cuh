@@ -220,6 +220,24 @@ __host__ __device__ __forceinline__ uint32_t kslab_sw32_off(int r, int k, int R)
     return (uint32_t)(s * R * 32 + r * 32 + ((((kk >> 2) ^ ((r >> 2) & 1)) << 4) | ((kk & 3) << 2)));
 }
 
+
+// ---- coalesced row stores through a per-warp shared-memory transpose ------------------------------------------------------
+// The 32x32b TMEM load gives lane r a run of consecutive columns of row (row0 + r).  Storing those runs directly makes every
+// store instruction touch 32 different lines; passing them through a conflict-free [32 rows][16 floats] scratch turns each
+// store instruction into 8 rows x 64 contiguous bytes (4x fewer L1 wavefronts).  sc = 32 x 4 float4 per warp.
+__device__ __forceinline__ void warp_store_rows16(float4* sc, int lane, const float v[16], float* base, size_t row_stride) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sc[lane * 4 + (c ^ (lane & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + (lane >> 2), ch = lane & 3;
+        const float4 t = sc[rr * 4 + (ch ^ (rr & 3))];
+        *reinterpret_cast<float4*>(base + (size_t)rr * row_stride + 4 * ch) = t;
+    }
+    __syncwarp();
+}
+
 }  // namespace sm100
 
 // ---- host: tensor maps --------------------------------------------------------------------------------------------------

@@ -8,7 +8,8 @@
 //   transposer  TMEM Z -> registers -> * c_ky/(HW) -> tf32 hi/lo -> Zt slabs [(img,h)][(re|im, ky)]
 //   stage 2     y[(img,h)][w] = Zt * TwB^T            TwB[w][(re|im,ky)] = cos | -sin (2 pi ky w / W)
 //   epilogue    TMEM -> + addend -> pre_act -> activation -> global rows (each thread owns one image row)
-//   warp 1 MMA issuer, warps 2-5 loaders, warps 6-9 transposer, warps 10-17 epilogue (warp 0 idle: no TMA in this kernel)
+//   warp 1 MMA issuer, warps 2-5 loaders, warps 6-9 transposer, warps 10.. epilogue (8 or 16 warps: addend + exact GELU + stores
+//   make it the issue-bound role; warp 0 idle: no TMA in this kernel)
 #include <math.h>
 #include <stdlib.h>
 
@@ -21,7 +22,7 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 576;
+constexpr int kMaxThreads = 320 + 16 * 32;
 
 struct InvGeom {
     int H, W, m1, m2, B, C;
@@ -31,6 +32,7 @@ struct InvGeom {
     int N1;          // G*m2
     int n_groups;
     int adjoint, act;
+    int epi_warps, off_scratch;   // epilogue warps (8 or 16) and their transpose scratch (2 KB per warp)
     int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, b1_im, zt_one, zt_buf, smem_bytes;
     long long* dbg;   // optional per-CTA wait-cycle counters (pno_debug_set_buffer)
     int dbg_mma;      // diagnostics: the issuer also waits for its own batches (serialises the pipeline)
@@ -59,22 +61,8 @@ __device__ __forceinline__ void warp_store_rows32(float4* sc, int lane, const fl
     __syncwarp();
 }
 
-// 16-column variant: lane r holds 16 consecutive floats of row (row0 + r); each store instruction writes 8 rows x 64 bytes.
-__device__ __forceinline__ void warp_store_rows16(float4* sc, int lane, const float v[16], float* base, size_t row_stride) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sc[lane * 4 + (c ^ (lane & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int rr = 8 * i + (lane >> 2), ch = lane & 3;
-        const float4 t = sc[rr * 4 + (ch ^ (rr & 3))];
-        *reinterpret_cast<float4*>(base + (size_t)rr * row_stride + 4 * ch) = t;
-    }
-    __syncwarp();
-}
-
 template <int NSPLIT, int G>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
              const float* __restrict__ coef, const float* __restrict__ yr, const float* __restrict__ yi,
              const float* __restrict__ addend, float* __restrict__ y, float* __restrict__ pre_act) {
@@ -84,7 +72,6 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     __shared__ __align__(8) uint64_t bar_zt_full[2], bar_zt_empty[2], bar_d2_full[2], bar_d2_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_scale[64];
-    __shared__ float4 s_scratch[8][128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
@@ -98,17 +85,17 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             mbar_init(&bar_zt_full[s], 128);
             mbar_init(&bar_zt_empty[s], 1);
             mbar_init(&bar_d2_full[s], 1);
-            mbar_init(&bar_d2_empty[s], 256);
+            mbar_init(&bar_d2_empty[s], g.epi_warps * 32);
         }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
     // twiddle tables -> slab form.  tabA_g: (C hi, C lo, S hi, S lo) each [H][K1]; tabB_g: (hi, lo) each [W][K2]
-    for (int e = threadIdx.x; e < 4 * g.H * g.K1; e += kThreads) {
+    for (int e = threadIdx.x; e < 4 * g.H * g.K1; e += blockDim.x) {
         const int t = e / (g.H * g.K1), r = (e / g.K1) % g.H, k = e % g.K1;
         *reinterpret_cast<float*>(smem + g.off_tabA + t * g.tabA_one + kslab_sw32_off(r, k, g.H)) = tabA_g[e];
     }
-    for (int e = threadIdx.x; e < 2 * g.W * g.K2; e += kThreads) {
+    for (int e = threadIdx.x; e < 2 * g.W * g.K2; e += blockDim.x) {
         const int t = e / (g.W * g.K2), r = (e / g.K2) % g.W, k = e % g.K2;
         *reinterpret_cast<float*>(smem + g.off_tabB + t * g.tabB_one + kslab_sw32_off(r, k, g.W)) = tabB_g[e];
     }
@@ -200,7 +187,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             const int img0 = grp * g.G;
             const int b = img0 / g.C, c0 = img0 % g.C;
             wait_t(&bar_b1_empty, (ng & 1) ^ 1, w0);
-            constexpr int U = 7;                       // items in flight per thread: all loads first, then the scatter
+            constexpr int U = G == 8 ? 4 : 7;          // items in flight per thread (register budget: 72 with 832 threads): loads first, then the scatter
             for (int e0 = t; e0 < items; e0 += 128 * U) {
                 float4 va[U], vb[U];
 #pragma unroll
@@ -301,11 +288,11 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         }
     } else if (warp >= 10) {
         // ================================ epilogue ================================
-        // 8 warps: two per TMEM lane quarter, each taking half of the W columns in 16-column passes
-        const int q = warp & 3, half = (warp - 10) >> 2;
+        // epi_warps / 4 warps per TMEM lane quarter, each taking an equal share of the W columns in 16-column passes
+        const int q = warp & 3, chunk = (warp - 10) >> 2, n_chunks = g.epi_warps >> 2;
         const int row = q * 32 + lane;
-        float4* sc = s_scratch[warp - 10];
-        const int c_lo = half * (g.W / 2), c_hi = c_lo + g.W / 2;      // W % 32 == 0 on this path
+        float4* sc = reinterpret_cast<float4*>(smem + g.off_scratch) + (warp - 10) * 128;
+        const int c_lo = chunk * (g.W / n_chunks), c_hi = c_lo + g.W / n_chunks;
         int nE = 0;
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
             const int img0 = grp * G;
@@ -450,8 +437,12 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
         g.off_tabB = pad_up(4 * g.tabA_one + 128 * 32, 1024);                   // slack: M = 128 reads past H rows
         g.off_b1 = g.off_tabB + pad_up(2 * g.tabB_one, 1024);
         g.off_zt = g.off_b1 + pad_up(2 * nbuf * g.b1_one, 1024);
-        g.smem_bytes = g.off_zt + 2 * g.zt_buf + 1024;
-        if (g.smem_bytes <= 208 * 1024) { ok = true; break; }     // 227 KB minus the static scratch and barriers
+        g.off_scratch = g.off_zt + 2 * g.zt_buf;
+        for (g.epi_warps = (W % 64 == 0) ? 16 : 8; g.epi_warps >= 8; g.epi_warps -= 8) {
+            g.smem_bytes = g.off_scratch + g.epi_warps * 2048 + 1024;
+            if (g.smem_bytes <= 226 * 1024) { ok = true; break; }     // 227 KB minus the static barriers / scale table
+        }
+        if (ok) break;
     }
     if (!ok) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv: no channel grouping fits (C = %d, m2 = %d, W = %d)", C, m2, W);
     if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(pre_act) |
@@ -470,7 +461,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
 #define PNO_LAUNCH_INV(NS, GG)                                                                                          \
     do {                                                                                                               \
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<NS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes)); \
-        k_tc_dft_inv<NS, GG><<<grid, kThreads, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y,   \
+        k_tc_dft_inv<NS, GG><<<grid, 320 + g.epi_warps * 32, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y,   \
                                                                     pre_act);                                          \
     } while (0)
     if (x3 && g.G == 8) PNO_LAUNCH_INV(3, 8);

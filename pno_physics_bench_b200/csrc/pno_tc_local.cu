@@ -5,7 +5,8 @@
 //               [128 o][32 i] (K-major A operands) into a multi-stage shared-memory ring
 //   warps 2-5   (3xTF32 only) split every staged tile into tf32 hi (in place) + lo (second buffer)
 //   warp 1      one thread issues tcgen05.mma kind::tf32 into two TMEM accumulators (mean, log-var), double buffered
-//   warps 6-9   epilogue: tcgen05.ld -> bias, clamp/exp, Philox noise, (d out / d lv for backward) -> global
+//   warps 6-21  epilogue (16 warps = 4 per scheduler; the noise generation makes this the issue-bound role): tcgen05.ld ->
+//               bias, clamp/exp, Philox noise, (d out / d lv for backward) -> shared-memory transpose -> coalesced global rows
 // A tile is (batch item b, 128 output channels, 128 pixels); tiles are statically strided over the persistent grid with the
 // output-channel tile fastest so that the CTAs sharing an x tile run at the same time (L2 reuse).
 #include "pno_sm100.cuh"
@@ -15,7 +16,8 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 64 + 128 + kEpiWarps * 32;
 constexpr int TM = 128;          // output channels per tile (UMMA M)
 constexpr int TN = 128;          // pixels per tile (UMMA N)
 constexpr int TK = 32;           // input channels per stage (one 128-byte swizzle row)
@@ -48,7 +50,7 @@ __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-neares
     return r;
 }
 
-template <int NSPLIT>
+template <int NSPLIT, bool NOISY, bool DLV>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
            const __grid_constant__ CUtensorMap tmWl) {
@@ -58,6 +60,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     __shared__ __align__(8) uint64_t bar_raw[C::kStages], bar_split[C::kStages], bar_empty[C::kStages];
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float4 s_scratch[kEpiWarps][128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = a.Ci / TK;
@@ -70,7 +73,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], 128);
+            mbar_init(&bar_tempty[s], kEpiWarps * 32);
         }
         fence_mbar_init();
         tma_prefetch_desc(&tmX);
@@ -94,9 +97,9 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     unsigned char* st = stage_ptr(stage);
-                    mbar_arrive_expect_tx(&bar_raw[stage], (a.noisy ? 3 : 2) * TILE_BYTES);
+                    mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 3 : 2) * TILE_BYTES);
                     tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
-                    if (a.noisy) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
+                    if (NOISY) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
                     // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, 4} lands as [4 p-blocks][32 rows][128 B]
                     tma_load_3d(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -132,7 +135,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                             mma_tf32(d_m, am + lo + ao, ahi, xb + bo, bhi, idesc, 1u);
                             mma_tf32(d_m, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u);
                         }
-                        if (a.noisy) {
+                        if (NOISY) {
                             mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag);
                             if (NSPLIT == 3) {
                                 mma_tf32(d_l, al + lo + ao, ahi, xb + bo, bhi, idesc, 1u);
@@ -159,7 +162,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     constexpr int kVec = TILE_BYTES / 16;
 #pragma unroll 4
                     for (int i = t; i < 3 * kVec; i += 128) {
-                        if (!a.noisy && i >= kVec && i < 2 * kVec) continue;
+                        if (!NOISY && i >= kVec && i < 2 * kVec) continue;
                         const float4 v = hi[i];
                         const float4 h = tf32_hi(v);
                         hi[i] = h;
@@ -174,48 +177,47 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     } else {
         // ================================ epilogue ================================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int cc = (warp - 6) >> 2;         // 32-column chunk of the 128-pixel tile
+        float4* sc = s_scratch[warp - 6];
         int it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
             const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
             const int acc = it & 1;
-            mbar_wait(&bar_tfull[acc], (it >> 1) & 1);
-            tc_fence_after_sync();
             const int o = ot * TM + q * 32 + lane;
             const float bias_m = a.bm ? a.bm[o] : 0.f;
-            const float bias_l = (a.noisy && a.bl) ? a.bl[o] : 0.f;
-            const size_t row = ((size_t)b * a.Co + o) * a.HW + (size_t)pt * TN;
-            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN;
-            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * 256), t_l = t_m + 128;
+            const float bias_l = (NOISY && a.bl) ? a.bl[o] : 0.f;
+            // first row of this warp / Philox element of this thread's row
+            const size_t wrow = ((size_t)b * a.Co + ot * TM + q * 32) * a.HW + (size_t)pt * TN + cc * 32;
+            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN + cc * 32;
+            mbar_wait(&bar_tfull[acc], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * 256 + cc * 32), t_l = t_m + 128;
 #pragma unroll 1
-            for (int c = 0; c < TN; c += 8) {
-                float m[8], l[8], v[8], d[8];
-                tmem_ld8(t_m + c, m);
-                if (a.noisy) tmem_ld8(t_l + c, l);
+            for (int c = 0; c < 32; c += 16) {
+                float v[16], l[16];
+                tmem_ld16(t_m + c, v);
+                if (NOISY) tmem_ld16(t_l + c, l);
                 tmem_ld_wait();
-                if (a.noisy) {
-                    const float4 z0 = philox_quad_normals(a.key, (e_row + c) >> 2);
-                    const float4 z1 = philox_quad_normals(a.key, ((e_row + c) >> 2) + 1);
-                    const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                if (NOISY) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float lv = l[j] + bias_l;
-                        const float s_raw = expf(0.5f * fminf(fmaxf(lv, -10.f), 10.f));
-                        const float s = fmaxf(s_raw, 1e-6f);
-                        v[j] = fmaf(z[j], s, m[j] + bias_m);
-                        d[j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 z4 = philox_quad_normals(a.key, ((e_row + c) >> 2) + k);
+                        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float lv = l[4 * k + j] + bias_l;
+                            const float s_raw = __expf(0.5f * fminf(fmaxf(lv, -10.f), 10.f));
+                            const float s = fmaxf(s_raw, 1e-6f);
+                            v[4 * k + j] = fmaf(z[j], s, v[4 * k + j] + bias_m);
+                            if (DLV) l[4 * k + j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;
+                        }
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = m[j] + bias_m;
+                    for (int j = 0; j < 16; ++j) v[j] += bias_m;
                 }
-                float4* dst = reinterpret_cast<float4*>(a.out + row + c);
-                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                if (a.noisy && a.want_dlv) {
-                    float4* dd = reinterpret_cast<float4*>(a.dlv + row + c);
-                    dd[0] = make_float4(d[0], d[1], d[2], d[3]);
-                    dd[1] = make_float4(d[4], d[5], d[6], d[7]);
-                }
+                warp_store_rows16(sc, lane, v, a.out + wrow + c, a.HW);
+                if (NOISY && DLV) warp_store_rows16(sc, lane, l, a.dlv + wrow + c, a.HW);
             }
             tc_fence_before_sync();
             mbar_arrive(&bar_tempty[acc]);
@@ -226,20 +228,23 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-template <int NSPLIT>
+template <int NSPLIT, bool NOISY, bool DLV>
 int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NSPLIT>::kSmemBytes));
-        attr = true;
-    }
+    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NSPLIT>::kSmemBytes));
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    k_tc_local<NSPLIT><<<grid, kThreads, Cfg<NSPLIT>::kSmemBytes, st>>>(a, tmX, tmWm, tmWl);
+    k_tc_local<NSPLIT, NOISY, DLV><<<grid, kThreads, Cfg<NSPLIT>::kSmemBytes, st>>>(a, tmX, tmWm, tmWl);
     PNO_LAUNCH_CHECK();
     return PNO_OK;
+}
+
+template <int NSPLIT>
+int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
+    if (!a.noisy) return launch<NSPLIT, false, false>(a, tmX, tmWm, tmWl, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true>(a, tmX, tmWm, tmWl, st);
+    return launch<NSPLIT, true, false>(a, tmX, tmWm, tmWl, st);
 }
 
 }  // namespace
@@ -272,6 +277,6 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         if ((rc = pno_encode_tmap(&tmWm, Wm, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmWl, Wl ? Wl : Wm, 2, dims, str, box, 1))) return rc;
     }
-    if (engine == PNO_ENGINE_TC_TF32X3) return launch<3>(a, tmX, tmWm, tmWl, st);
-    return launch<1>(a, tmX, tmWm, tmWl, st);
+    if (engine == PNO_ENGINE_TC_TF32X3) return launch_ns<3>(a, tmX, tmWm, tmWl, st);
+    return launch_ns<1>(a, tmX, tmWm, tmWl, st);
 }

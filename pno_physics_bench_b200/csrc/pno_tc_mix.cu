@@ -6,9 +6,11 @@
 //   Dre = Wre^T Xre^T - Wim^T Xim^T ,  Dim = Wim^T Xre^T + Wre^T Xim^T           (A = generated W tiles, negate-A bit; B = xhat via TMA)
 //   warp 0        TMA producer: xhat tiles [B rows][32 i] (re, im) of the item's mode
 //   warp 1        MMA issuer
-//   warps 2-9     generators: mu/lv -> Philox/Box-Muller -> W = mu + sigma*eps -> tf32 hi/lo -> K-major SW128 tiles [128 o][32 i];
-//                 they also split the xhat tiles into hi/lo (3xTF32)
-//   warps 10-13   epilogue: TMEM -> yhat[mode][b][o] (coalesced over o)
+//   warps 2-17    generators (16 warps = 4 per scheduler: the kernel is bound by Philox / Box-Muller issue slots and by the
+//                 latency of the mu / log_var stream, so the loads of k-block n+1 are in flight in registers while k-block n
+//                 is computed): mu/lv -> Philox/Box-Muller -> W = mu + sigma*eps -> (tf32 hi/lo) -> K-major SW128 tiles
+//                 [128 o][32 i]; they also split the xhat tiles into hi/lo (3xTF32)
+//   warps 18-21   epilogue: TMEM -> yhat[mode][b][o] (coalesced over o)
 #include "pno_sm100.cuh"
 #include "pno_tc.cuh"
 
@@ -16,15 +18,14 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 448;
-constexpr int kGen = 256;        // generator threads
+constexpr int kGen = 512;        // generator threads
+constexpr int kThreads = 64 + kGen + 128;
 constexpr int TM = 128;          // output channels per item
 constexpr int TK = 32;           // input channels per stage
 constexpr int W_TILE = TM * TK * 4;      // 16 KB
 
 struct MixGeom {
     int B, Ci, Co, m1m2, Cop, n_modes, o_tiles, n_items, KB;
-    int sampled;
     int x_tile;        // B * 128 bytes
     int stage_bytes, stages, smem_bytes;
     const float *mu1, *mu2, *lv1, *lv2;
@@ -33,14 +34,17 @@ struct MixGeom {
 };
 
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_rn4(const float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+__device__ __forceinline__ float4 sub4(const float4 a, const float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
-// stage layout: [Wre hi][Wim hi][Wre lo][Wim lo][Xre hi][Xim hi][Xre lo][Xim lo]   (lo parts only used by 3xTF32)
-template <int NSPLIT>
+// stage layout, NSPLIT == 1: [Wre][Wim][Xre][Xim];  NSPLIT == 3: [Wre hi][Wim hi][Wre lo][Wim lo][Xre hi][Xim hi][Xre lo][Xim lo]
+template <int NSPLIT, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __grid_constant__ CUtensorMap tmXi) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kMaxStages = 4;
+    constexpr int NW = NSPLIT == 3 ? 4 : 2;         // W tiles per stage
     __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_ready[kMaxStages], bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
@@ -66,7 +70,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const int acc_cols = 2 * g.B;                   // Dre | Dim
-    const int x_off = 4 * W_TILE;                   // byte offset of the xhat tiles inside a stage
+    const int x_off = NW * W_TILE;                  // byte offset of the xhat tiles inside a stage
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -100,7 +104,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     mbar_wait(&bar_ready[stage], phase);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(smem + (size_t)stage * g.stage_bytes);
-                    // low descriptor words of the 8 operand tiles of this stage (all K-major SW128: LBO 16, SBO 1024)
+                    // low descriptor words of the operand tiles of this stage (all K-major SW128: LBO 16, SBO 1024)
                     const uint32_t wre = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;
                     const uint32_t wim = wre + (W_TILE >> 4), wre_l = wre + 2 * (W_TILE >> 4), wim_l = wre + 3 * (W_TILE >> 4);
                     const uint32_t xre = wre + (x_off >> 4), xim = xre + (g.x_tile >> 4), xre_l = xim + (g.x_tile >> 4),
@@ -130,56 +134,74 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 mma_commit(&bar_tfull[acc]);
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 2 + kGen / 32) {
         // ================================ generators ================================
-        const int t = threadIdx.x - 64;             // 0..255
-        int stage = 0, phase = 0;
-        for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-            const int mode = item / g.o_tiles, ot = item % g.o_tiles;
+        // thread = (o pair p, quad iq of 4 consecutive i): one Philox call per (i, o pair) feeds (re, im) of o and o+1
+        const int t = threadIdx.x - 64;             // 0..511
+        const int p = t & 63, iq = t >> 6;
+        float4 bm[4];                               // mu of (o, o+1) at the 4 i of this thread, next k-block in flight
+        float2 bl[4];                               // log_var of (o, o+1)
+        const float* mu_n = nullptr;                // addresses of the k-block the buffers hold / will hold
+        const float* lv_n = nullptr;
+        uint64_t quad_n = 0;
+        auto locate = [&](int item, int kb) {
+            const int mode = item / g.o_tiles, ot = item - mode * g.o_tiles;
             const int blk = mode >= g.m1m2;
             const int mb = mode - blk * g.m1m2;
-            const float* mu = blk ? g.mu2 : g.mu1;
-            const float* lv = blk ? g.lv2 : g.lv1;
+            const int i0 = kb * TK + iq * 4;
+            const size_t base = ((size_t)mb * g.Ci + i0) * g.Co + ot * TM + 2 * p;
+            mu_n = (blk ? g.mu2 : g.mu1) + 2 * base;
+            lv_n = SAMPLED ? (blk ? g.lv2 : g.lv1) + base : nullptr;
+            quad_n = ((uint64_t)mode * g.Ci + i0) * g.Cop + ((ot * TM) >> 1) + p;
+        };
+        auto fetch = [&](int j) {
+            bm[j] = __ldg(reinterpret_cast<const float4*>(mu_n + (size_t)2 * j * g.Co));
+            if (SAMPLED) bl[j] = __ldg(reinterpret_cast<const float2*>(lv_n + (size_t)j * g.Co));
+        };
+        int item_n = blockIdx.x, kb_n = 0;
+        if (item_n < g.n_items) {
+            locate(item_n, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fetch(j);
+        }
+        int stage = 0, phase = 0;
+        for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             for (int kb = 0; kb < g.KB; ++kb) {
+                const uint64_t quad = quad_n;       // Philox counters of the k-block held in the buffers
+                if (++kb_n == g.KB) { kb_n = 0; item_n += gridDim.x; }
+                const bool more = item_n < g.n_items;
+                if (more) locate(item_n, kb_n);
                 mbar_wait(&bar_raw[stage], phase);              // xhat landed => the stage is ours to fill
                 unsigned char* st = smem + (size_t)stage * g.stage_bytes;
-                // ---- weights: thread item = (o pair p, quad of 4 consecutive i) ----
-#pragma unroll 1
-                for (int it2 = t; it2 < 64 * 8; it2 += kGen) {
-                    const int p = it2 & 63, iq = it2 >> 6;
-                    const int o = ot * TM + 2 * p;              // global output channel (even)
-                    float wr[2][4], wi[2][4];
+                float wr[2][4], wi[2][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = kb * TK + iq * 4 + j;
-                        const size_t base = ((size_t)mb * g.Ci + i) * g.Co + o;
-                        const float4 m4 = *reinterpret_cast<const float4*>(mu + 2 * base);     // (re, im) of o, o+1
-                        wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
-                        if (g.sampled) {
-                            const float2 l2 = *reinterpret_cast<const float2*>(lv + base);
-                            const float4 z = philox_quad_normals(g.key, spectral_quad(blk, g.m1m2, mb, g.Ci, g.Cop, i, o >> 1));
-                            const float s0 = __expf(0.5f * l2.x), s1 = __expf(0.5f * l2.y);
-                            wr[0][j] = fmaf(s0, z.x, wr[0][j]); wi[0][j] = fmaf(s0, z.y, wi[0][j]);
-                            wr[1][j] = fmaf(s1, z.z, wr[1][j]); wi[1][j] = fmaf(s1, z.w, wi[1][j]);
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    const float4 m4 = bm[j];
+                    const float2 l2 = bl[j];
+                    if (more) fetch(j);                          // refill the slot just consumed: next k-block's loads in flight
+                    wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
+                    if (SAMPLED) {
+                        const float4 z = philox_quad_normals(g.key, quad + (uint64_t)j * g.Cop);
+                        const float s0 = __expf(0.5f * l2.x), s1 = __expf(0.5f * l2.y);
+                        wr[0][j] = fmaf(s0, z.x, wr[0][j]); wi[0][j] = fmaf(s0, z.y, wi[0][j]);
+                        wr[1][j] = fmaf(s1, z.z, wr[1][j]); wi[1][j] = fmaf(s1, z.w, wi[1][j]);
                     }
+                }
 #pragma unroll
-                    for (int r2 = 0; r2 < 2; ++r2) {
-                        const int row = 2 * p + r2;
-                        const uint32_t off = row * 128 + ((iq ^ (row & 7)) << 4);
-                        const float4 vr = make_float4(wr[r2][0], wr[r2][1], wr[r2][2], wr[r2][3]);
-                        const float4 vi = make_float4(wi[r2][0], wi[r2][1], wi[r2][2], wi[r2][3]);
-                        if (NSPLIT == 3) {
-                            const float4 hr = make_float4(tf32_rn(vr.x), tf32_rn(vr.y), tf32_rn(vr.z), tf32_rn(vr.w));
-                            const float4 hi = make_float4(tf32_rn(vi.x), tf32_rn(vi.y), tf32_rn(vi.z), tf32_rn(vi.w));
-                            *reinterpret_cast<float4*>(st + off) = hr;
-                            *reinterpret_cast<float4*>(st + W_TILE + off) = hi;
-                            *reinterpret_cast<float4*>(st + 2 * W_TILE + off) = make_float4(vr.x - hr.x, vr.y - hr.y, vr.z - hr.z, vr.w - hr.w);
-                            *reinterpret_cast<float4*>(st + 3 * W_TILE + off) = make_float4(vi.x - hi.x, vi.y - hi.y, vi.z - hi.z, vi.w - hi.w);
-                        } else {
-                            *reinterpret_cast<float4*>(st + off) = vr;
-                            *reinterpret_cast<float4*>(st + W_TILE + off) = vi;
-                        }
+                for (int r2 = 0; r2 < 2; ++r2) {
+                    const int row = 2 * p + r2;
+                    const uint32_t off = row * 128 + ((iq ^ (row & 7)) << 4);
+                    const float4 vr = make_float4(wr[r2][0], wr[r2][1], wr[r2][2], wr[r2][3]);
+                    const float4 vi = make_float4(wi[r2][0], wi[r2][1], wi[r2][2], wi[r2][3]);
+                    if (NSPLIT == 3) {
+                        const float4 hr = tf32_rn4(vr), hi = tf32_rn4(vi);
+                        *reinterpret_cast<float4*>(st + off) = hr;
+                        *reinterpret_cast<float4*>(st + W_TILE + off) = hi;
+                        *reinterpret_cast<float4*>(st + 2 * W_TILE + off) = sub4(vr, hr);
+                        *reinterpret_cast<float4*>(st + 3 * W_TILE + off) = sub4(vi, hi);
+                    } else {
+                        *reinterpret_cast<float4*>(st + off) = vr;
+                        *reinterpret_cast<float4*>(st + W_TILE + off) = vi;
                     }
                 }
                 // ---- xhat tiles: hi in place, lo behind (layout-agnostic elementwise pass) ----
@@ -188,9 +210,9 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     float4* xl = reinterpret_cast<float4*>(st + x_off + 2 * g.x_tile);
                     for (int i = t; i < 2 * g.x_tile / 16; i += kGen) {
                         const float4 v = xh[i];
-                        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                        const float4 h = tf32_rn4(v);
                         xh[i] = h;
-                        xl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        xl[i] = sub4(v, h);
                     }
                 }
                 fence_proxy_async_smem();
@@ -211,13 +233,13 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
             float* dr = g.yr + (size_t)mode * g.B * g.Co + o;
             float* di = g.yi + (size_t)mode * g.B * g.Co + o;
             const uint32_t ta = tmem_addr(tmem, q * 32, acc * acc_cols);
-            for (int b0 = 0; b0 < g.B; b0 += 8) {
-                float vr[8], vi[8];
-                tmem_ld8(ta + b0, vr);
-                tmem_ld8(ta + g.B + b0, vi);
+            for (int b0 = 0; b0 < g.B; b0 += 16) {
+                float vr[16], vi[16];
+                tmem_ld16(ta + b0, vr);
+                tmem_ld16(ta + g.B + b0, vi);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     dr[(size_t)(b0 + j) * g.Co] = vr[j];
                     di[(size_t)(b0 + j) * g.Co] = vi[j];
                 }
@@ -245,10 +267,9 @@ int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, 
     memset(&g, 0, sizeof(g));
     g.B = B; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
     g.o_tiles = Co / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = Ci / TK;
-    g.sampled = lv1 != nullptr;
     g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = yr; g.yi = yi; g.key = key;
     g.x_tile = B * 128;
-    g.stage_bytes = 4 * W_TILE + 4 * g.x_tile;
+    g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
     g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
     g.stages = 4;
     while (g.stages > 2 && g.stages * g.stage_bytes + 1024 > 220 * 1024) --g.stages;
@@ -267,13 +288,17 @@ int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, 
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = g.n_items < sms ? g.n_items : sms;
-    if (x3) {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        k_tc_mix_fwd<3><<<grid, kThreads, g.smem_bytes, st>>>(g, tmXr, tmXi);
-    } else {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        k_tc_mix_fwd<1><<<grid, kThreads, g.smem_bytes, st>>>(g, tmXr, tmXi);
-    }
+    const bool sampled = lv1 != nullptr;
+#define PNO_LAUNCH_MIX(NS, SM)                                                                                          \
+    do {                                                                                                               \
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<NS, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
+        k_tc_mix_fwd<NS, SM><<<grid, kThreads, g.smem_bytes, st>>>(g, tmXr, tmXi);                                     \
+    } while (0)
+    if (x3 && sampled) PNO_LAUNCH_MIX(3, true);
+    else if (x3) PNO_LAUNCH_MIX(3, false);
+    else if (sampled) PNO_LAUNCH_MIX(1, true);
+    else PNO_LAUNCH_MIX(1, false);
+#undef PNO_LAUNCH_MIX
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
