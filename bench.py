@@ -88,52 +88,89 @@ def build_model(engine, device):
     return model.to(device)
 
 
-def layer_roofline(model, engine, device, iters=5):
-    """Time the three kernels of one spectral layer (cfg-3 shape) with CUDA events; roofline of the dominant one (mix)."""
+def block_kernel_times(engine, device, iters=5):
+    """CUDA-event time (on torch's current stream, the stream the kernels are launched on) of each of the four kernels of
+    one PNO block at the cfg-3 shape, L2 flushed before every launch, with each kernel's ALGORITHMIC HBM bytes:
+      local   : x read + local written (+ the two 1x1 weight matrices)
+      dft_fwd : x read + truncated spectrum written
+      mix     : spectrum read + spectrum written + mu (8 B) + log_var (4 B) per weight     <- SURVEY.md 8(d) parameter term
+      dft_inv : spectrum read + local read + y written
+    """
     from pno_physics_bench_b200 import _lib
     lib = _lib.load()
     B, C, H, W, m = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["modes"]
     M = 2 * m * m
-    layer = model.fourier_layers[0]
     plan = _lib.plan(H, W, m, m, device)
-    x = torch.randn(B, C, H, W, device=device)
-    y = torch.empty_like(x)
-    xr, xi, yr, yi = (torch.empty(M, B, C, device=device) for _ in range(4))
-    n1, n2 = layer.weights1.detach().permute(2, 3, 0, 1), layer.weights2.detach().permute(2, 3, 0, 1)
-    l1, l2 = layer.weights1_log_var.detach().permute(2, 3, 0, 1), layer.weights2_log_var.detach().permute(2, 3, 0, 1)
-    assert n1.is_contiguous() and l1.is_contiguous()
+    g = torch.Generator(device=device).manual_seed(0)
+    x = torch.randn(B, C, H, W, device=device, generator=g)
+    loc, y = torch.empty_like(x), torch.empty_like(x)
+    xr, xi, yr, yi = (torch.randn(M, B, C, device=device, generator=g) for _ in range(4))
+    mu1, mu2 = (torch.randn(m, m, C, C, 2, device=device, generator=g) / C for _ in range(2))
+    lv1, lv2 = (torch.full((m, m, C, C), -4.6, device=device) for _ in range(2))
+    wm, wl = torch.randn(C, C, device=device, generator=g) / 16, torch.randn(C, C, device=device, generator=g) / 64
+    bm, bl = torch.zeros(C, device=device), torch.full((C,), -3.0, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
-    st = _lib.stream_ptr()
-    eng = _lib.ENGINES[engine]
-    t = {"dft_fwd": [], "mix": [], "dft_inv": []}
-    for it in range(iters + 2):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        flush.zero_()
-        ev[0].record()
-        _lib.check(lib.pno_dft_fwd(plan, eng, x.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st))
-        ev[1].record()
-        _lib.check(lib.pno_mix_fwd(plan, eng, xr.data_ptr(), xi.data_ptr(), B, C, C, n1.data_ptr(), n2.data_ptr(),
-                                   l1.data_ptr(), l2.data_ptr(), 1234, it, 1, yr.data_ptr(), yi.data_ptr(), st))
-        ev[2].record()
-        _lib.check(lib.pno_dft_inv(plan, eng, yr.data_ptr(), yi.data_ptr(), B, C, 0, 0, _lib.ACT_NONE, y.data_ptr(), 0, st))
-        ev[3].record()
-        torch.cuda.synchronize()
-        if it >= 2:
-            for k, name in enumerate(("dft_fwd", "mix", "dft_inv")):
-                t[name].append(ev[k].elapsed_time(ev[k + 1]))
-    ms = {k: sum(v) / len(v) for k, v in t.items()}
+    st, eng = _lib.stream_ptr(), _lib.ENGINES[engine]
+    calls = {
+        "local": lambda it: lib.pno_local_fwd(eng, x.data_ptr(), B, C, C, H * W, wm.data_ptr(), bm.data_ptr(), wl.data_ptr(),
+                                              bl.data_ptr(), 1234, it, 2, 0, loc.data_ptr(), 0, st),
+        "dft_fwd": lambda it: lib.pno_dft_fwd(plan, eng, x.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st),
+        "mix": lambda it: lib.pno_mix_fwd(plan, eng, xr.data_ptr(), xi.data_ptr(), B, C, C, mu1.data_ptr(), mu2.data_ptr(),
+                                          lv1.data_ptr(), lv2.data_ptr(), 1234, it, 1, yr.data_ptr(), yi.data_ptr(), st),
+        "dft_inv": lambda it: lib.pno_dft_inv(plan, eng, yr.data_ptr(), yi.data_ptr(), B, C, 0, loc.data_ptr(), _lib.ACT_GELU,
+                                              y.data_ptr(), 0, st),
+    }
+    act = 4.0 * B * C * H * W            # one fp32 activation tensor
+    spec = 4.0 * M * B * C * 2           # one truncated spectrum (re + im planes)
+    nbytes = {"local": 2 * act + 8.0 * C * C, "dft_fwd": act + spec, "mix": 2 * spec + 12.0 * C * C * M,
+              "dft_inv": spec + 2 * act}
+    out = {}
+    for name, fn in calls.items():
+        ts = []
+        for it in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(fn(it), name)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+        us = sum(ts) / len(ts)
+        out[name] = {"us": round(us, 1), "bytes": nbytes[name], "gbs": round(nbytes[name] / us / 1e3, 1)}
+    return out
+
+
+def ncu_traffic(kernel):
+    """dram bytes (read + write) per launch of `kernel` from the committed `ncu --set full` summary, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+def layer_roofline(engine, device):
+    """Roofline of the dominant kernel of the block (the slowest of the four) + the whole spectral layer / block."""
+    k = block_kernel_times(engine, device)
     hbm, tc, src = measured_peaks()
-    # algorithmic bytes of the mix kernel per launch: mu (8 B) + log_var (4 B) per weight, xhat read + yhat written once
-    mix_bytes = 12.0 * C * C * M + 8.0 * M * B * C + 8.0 * M * B * C
-    layer_bytes = 4.0 * B * C * H * W * 2 + 12.0 * C * C * M            # SURVEY.md 8(d): x in + y out + mu + log_var
-    achieved = mix_bytes / (ms["mix"] * 1e-3) / 1e9
-    layer_total = sum(ms.values())
-    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
-            "traffic": None, "peak_source": src, "kernel": "mix_fwd (sample weights + per-mode complex channel mix)",
-            "kernel_ms": round(ms["mix"], 4), "algorithmic_bytes": mix_bytes,
-            "layer": {"ms": {k: round(v, 4) for k, v in ms.items()}, "total_ms": round(layer_total, 4),
-                      "algorithmic_bytes": layer_bytes,
-                      "frac_of_hbm_roofline": round(layer_bytes / (layer_total * 1e-3) / 1e9 / hbm, 4)}}
+    top = max(k, key=lambda n: k[n]["us"])
+    B, C, H, W, m = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["modes"]
+    layer_bytes = 4.0 * B * C * H * W * 2 + 12.0 * C * C * 2 * m * m        # SURVEY.md 8(d): x in + y out + mu + log_var
+    layer_us = k["dft_fwd"]["us"] + k["mix"]["us"] + k["dft_inv"]["us"]
+    block_us = layer_us + k["local"]["us"]
+    names = {"local": "k_tc_local (1x1 mean + log-var convs + reparameterised noise)",
+             "dft_fwd": "k_tc_dft_fwd (pruned forward transform)",
+             "mix": "k_tc_mix_fwd (weight sampling + per-mode complex channel mix)",
+             "dft_inv": "k_tc_dft_inv (pruned inverse transform + local add + GELU)"}
+    return {"bound": "hbm", "achieved": k[top]["gbs"], "peak": hbm, "unit": "GB/s", "frac": round(k[top]["gbs"] / hbm, 4),
+            "traffic": ncu_traffic(top), "peak_source": src, "kernel": names[top], "kernel_us": k[top]["us"],
+            "algorithmic_bytes": k[top]["bytes"],
+            "kernels": {n: {"us": v["us"], "gbs": v["gbs"], "frac": round(v["gbs"] / hbm, 4), "traffic": ncu_traffic(n)}
+                        for n, v in k.items()},
+            "layer": {"us": round(layer_us, 1), "algorithmic_bytes": layer_bytes,
+                      "frac_of_hbm_roofline": round(layer_bytes / layer_us / 1e3 / hbm, 4)},
+            "block_us": round(block_us, 1)}
 
 
 def cpu_baseline(sample_b=64, threads=None, reps=1):
@@ -195,7 +232,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("PNO_BENCH_ENGINE", "fp32"), choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--engine", default=os.environ.get("PNO_BENCH_ENGINE", "tf32"), choices=["fp32", "tf32x3", "tf32"],
+                    help="tf32 = the reduced-precision (bf16-compute class, rel-L2 <= 2e-2) mode of BASELINE.json; tf32x3 = the fp32-parity mode")
+    ap.add_argument("--no-strict", action="store_true", help="skip the secondary fp32-parity (tf32x3) measurement")
     ap.add_argument("--mc-samples", type=int, default=int(os.environ.get("PNO_BENCH_MC_SAMPLES", "20")),
                     help="MC samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -260,9 +299,21 @@ def main():
     fields = B * total_samples
     value = fields / (ms_step * 1e-3)
     e2e_value = fields / (ms_e2e / args.steps * 1e-3)
+    # secondary measurement in the fp32-parity mode (error-compensated 3xTF32): one warm-up + one timed step
+    strict = None
+    if not args.no_strict and args.engine != "tf32x3":
+        model.set_engine("tf32x3")
+        step_resident(0)
+        ms_strict = timed(step_resident, 1)
+        model.set_engine(args.engine)
+        strict = {"engine": "tf32x3", "value": round(fields / (ms_strict * 1e-3), 2), "unit": UNIT,
+                  "ms_per_step": round(ms_strict, 3), "parity": "rel-L2 <= 1e-5 vs the fp32 reference (tests/test_gpu_tc.py)"}
     roof = base = None
     if rank == 0:
-        roof = layer_roofline(model, args.engine, device)
+        roof = layer_roofline(args.engine, device)
+        if strict is not None:
+            ks = block_kernel_times("tf32x3", device, iters=3)
+            strict["block_kernels_us"] = {n: v["us"] for n, v in ks.items()}
         if not args.no_cpu_baseline and world == 1:
             base = cpu_baseline()
     if world > 1:
@@ -276,11 +327,15 @@ def main():
                 "config": {"workload": f"cfg3: predict_with_uncertainty 64x64 in3 hid256 L4 modes20, batch {B} x {S} MC "
                                        f"samples per GPU per step", "engine": args.engine,
                            "l2": "inputs larger than L2 (2.5 GB of parameters + >1 GB of activations streamed per sample)",
+                           "precision_mode": {"tf32": "north_star's reduced-precision (bf16-compute class) mode: tf32 operands, fp32 "
+                                                      "accumulate, rel-L2 <= 2e-2 tested; fp32-parity numbers under `strict`",
+                                              "tf32x3": "fp32-parity mode (3xTF32, rel-L2 <= 1e-5)",
+                                              "fp32": "fp32 CUDA-core engine"}[args.engine],
                            "parallelism": f"mc-sample sharding x{world}, 1 all-reduce of 2x[B,1,H,W] fp64 per step"},
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": mean_host.numel() * 8},
-                "roofline": roof, "cpu_baseline": base}
+                "roofline": roof, "cpu_baseline": base, "strict": strict}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -44,6 +44,13 @@ __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long
     acc += clock64() - t0;
 }
 
+// event trace of CTA 0 (diagnostics): role r writes (clock << 8 | event) into dbg[4096 + r * 512 + n]
+#define TRACE(role, ev)                                                                                     \
+    do {                                                                                                    \
+        if (g.dbg && blockIdx.x == 0 && lane == 0 && trace_n < 512)                                         \
+            g.dbg[4096 + (role) * 512 + trace_n++] = ((clock64() - t_start) << 8) | (long long)(ev);       \
+    } while (0)
+
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 // Coalesced row store through a per-warp shared-memory transpose: on entry lane r holds 32 consecutive floats of row
@@ -75,6 +82,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+    int trace_n = 0;
     const long long t_start = clock64();
     if (threadIdx.x == 0) {
         mbar_init(&bar_b1_full, 128);
@@ -124,7 +132,9 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             int ng = 0, nt = 0;
             for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
                 wait_t(&bar_b1_full, ng & 1, w0);
+                TRACE(0, 1);
                 wait_t(&bar_d1_empty, (ng & 1) ^ 1, w1);
+                TRACE(0, 2);
                 tc_fence_after_sync();
                 const uint32_t d_re = tmem, d_im = tmem + g.N1;
                 uint32_t a = tA, b = b1;
@@ -148,6 +158,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 }
                 mma_commit(&bar_b1_empty);
                 mma_commit(&bar_d1_full);
+                TRACE(0, 3);
                 if (g.dbg_mma) {                         // diagnostics: issue -> completion latency of the stage-1 batch
                     const long long tq = clock64();
                     mbar_wait(&bar_d1_full, ng & 1);
@@ -156,7 +167,9 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 for (int j = 0; j < g.TPG; ++j, ++nt) {
                     const int zb = nt & 1;
                     wait_t(&bar_zt_full[zb], (nt >> 1) & 1, w2);
+                    TRACE(0, 4);
                     wait_t(&bar_d2_empty[zb], ((nt >> 1) & 1) ^ 1, w3);
+                    TRACE(0, 5);
                     tc_fence_after_sync();
                     const uint32_t d2 = tmem + d2_col + zb * g.W;
                     uint32_t z = zt + zb * (g.zt_buf >> 4), w = tB;
@@ -169,6 +182,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     }
                     mma_commit(&bar_zt_empty[zb]);
                     mma_commit(&bar_d2_full[zb]);
+                    TRACE(0, 6);
                     if (g.dbg_mma) {
                         const long long tq = clock64();
                         mbar_wait(&bar_d2_full[zb], (nt >> 1) & 1);
@@ -187,6 +201,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             const int img0 = grp * g.G;
             const int b = img0 / g.C, c0 = img0 % g.C;
             wait_t(&bar_b1_empty, (ng & 1) ^ 1, w0);
+            if (warp == 2) TRACE(3, 1);
             constexpr int U = G == 8 ? 4 : 7;          // items in flight per thread (register budget: 72 with 832 threads): loads first, then the scatter
             for (int e0 = t; e0 < items; e0 += 128 * U) {
                 float4 va[U], vb[U];
@@ -221,8 +236,10 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     }
                 }
             }
+            if (warp == 2) TRACE(3, 2);
             fence_proxy_async_smem();
             mbar_arrive(&bar_b1_full);
+            if (warp == 2) TRACE(3, 3);
         }
     } else if (warp >= 6 && warp < 10) {
         // ================================ transposer ================================
@@ -234,6 +251,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         auto transpose_tile = [&](int j) {
             const int zb = nT & 1;
             wait_t(&bar_zt_empty[zb], ((nT >> 1) & 1) ^ 1, w0);
+            if (warp == 8) TRACE(1, 2);
             if (t_active_warp) {
                 unsigned char* zt = smem + g.off_zt + zb * g.zt_buf;
                 for (int il = 0; il < g.IPT; ++il) {
@@ -249,6 +267,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                                                  : "=r"(r[c][0]), "=r"(r[c][1]), "=r"(r[c][2]), "=r"(r[c][3])
                                                  : "r"(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + kyb + 4 * c)));
                             tmem_ld_wait();
+                            if (warp == 8) TRACE(1, 5);
                             if (row < g.H) {
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
@@ -274,14 +293,17 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     }
                 }
             }
+            if (warp == 8) TRACE(1, 3);
             tc_fence_before_sync();
             fence_proxy_async_smem();
             mbar_arrive(&bar_zt_full[zb]);
+            if (warp == 8) TRACE(1, 4);
             ++nT;
         };
 
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
             wait_t(&bar_d1_full, ng & 1, w1);
+            if (warp == 8) TRACE(1, 1);
             tc_fence_after_sync();
             for (int j = 0; j < g.TPG; ++j) transpose_tile(j);
             mbar_arrive(&bar_d1_empty);                   // every stage-1 accumulator of this group has been read
@@ -311,6 +333,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 };
                 fetch(c_lo);
                 wait_t(&bar_d2_full[db], (nE >> 1) & 1, w2);
+                if (warp == 10) TRACE(2, 1);
+                if (warp == 10 + g.epi_warps - 1) TRACE(4, 1);
                 tc_fence_after_sync();
                 for (int c = c_lo; c < c_hi; c += 16) {
                     float v[16];
@@ -335,6 +359,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bar_d2_empty[db]);
+                if (warp == 10) TRACE(2, 2);
+                if (warp == 10 + g.epi_warps - 1) TRACE(4, 2);
             }
         }
     }
