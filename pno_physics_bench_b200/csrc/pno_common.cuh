@@ -53,6 +53,17 @@ struct pno_plan {
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// single-instruction approximations (flush-to-zero forms: no denormal fix-up code around the MUFU)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_exp(float x) { return fast_ex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller.  Normative definition: oracle/philox.py.
 // ---------------------------------------------------------------------------------------------------------------------
 struct PhiloxKey {
@@ -91,12 +102,9 @@ __device__ __forceinline__ uint4 philox_quad_bits(const PhiloxKey& key, uint64_t
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     const float u1 = fmaf((float)(a >> 9), 1.1920928955078125e-7f, 5.9604644775390625e-8f);
     const float u2m = fmaf((float)(b >> 9), 1.1920928955078125e-7f, 5.9604644775390625e-8f - 0.5f);
-    float lg, r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(lg * -1.3862943611198906f));      // sqrt(-2 ln u1)
-    float s, c;
-    __sincosf(6.283185307179586f * u2m, &s, &c);
-    return make_float2(r * c, r * s);
+    const float r = fast_sqrt(fast_lg2(u1) * -1.3862943611198906f);      // sqrt(-2 ln u1)
+    const float t = 6.283185307179586f * u2m;
+    return make_float2(r * fast_cos(t), r * fast_sin(t));
 }
 
 __device__ __forceinline__ float4 philox_quad_normals(const PhiloxKey& key, uint64_t q) {
@@ -130,13 +138,13 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // complementary form on the negative side so that the small tail keeps its relative accuracy.  ~14 instructions vs ~40.
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
     float p = fmaf(t, 1.061405429f, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float ec = p * t * __expf(-z * z);          // erfc(|x|/sqrt2)
-    return 0.5f * x * (x >= 0.f ? 2.0f - ec : ec);
+    const float ec = p * t * fast_ex2(z * z * -1.4426950408889634f);          // erfc(|x|/sqrt2)
+    return fmaf(z * -0.70710678118654752f, ec, fmaxf(x, 0.f));             // max(x,0) - |x|/2 * erfc(|x|/sqrt2)
 }
 __device__ __forceinline__ float act_apply_fast(float v, int act) {
     if (act == PNO_ACT_GELU) return gelu_fast(v);

@@ -160,15 +160,19 @@ __device__ __forceinline__ SDesc sdesc_base(uint32_t smem_addr, uint32_t lbo_byt
     d.hi = ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout_type & 7) << 29);
     return d;
 }
+// The whole issuer warp runs the issue loop and `elected` (1 on exactly one lane) predicates the instruction itself: with
+// warp-uniform control flow ptxas keeps the descriptor arithmetic in uniform registers instead of computing it in vector
+// registers and paying an R2UR round trip per operand, which is what bounds the issue rate of small (N <= 64) MMAs.
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                         uint32_t idesc, uint32_t accumulate) {
+                                         uint32_t idesc, uint32_t accumulate, uint32_t elected = 1u) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
         "mov.b64 da, {%1, %2};\n\t"
         "mov.b64 db, {%3, %4};\n\t"
         "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
         : "memory");
 }
 
@@ -192,9 +196,13 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uin
         : "memory");
 }
 // all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void mma_commit(uint64_t* bar, uint32_t elected = 1u) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(elected)
+        : "memory");
 }
 
 // ---- canonical SWIZZLE_128B tile addressing for 4-byte elements (tile base 1024-byte aligned) ---------------------------
@@ -226,19 +234,44 @@ __host__ __device__ __forceinline__ uint32_t kslab_sw32_off(int r, int k, int R)
 // store instruction touch 32 different lines; passing them through a conflict-free [32 rows][16 floats] scratch turns each
 // store instruction into 8 rows x 64 contiguous bytes (4x fewer L1 wavefronts).  sc = 32 x 4 float4 per warp.
 __device__ __forceinline__ void warp_store_rows16(float4* sc, int lane, const float v[16], float* base, size_t row_stride) {
+    const uint32_t s0 = smem_u32(sc);          // explicit shared-space accesses (a generic pointer costs a window check per access)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) sc[lane * 4 + (c ^ (lane & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + 16u * (lane * 4 + (c ^ (lane & 3)))), "f"(v[4 * c]),
+                     "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                     : "memory");
     __syncwarp();
+    float* dst = base + (size_t)(lane >> 2) * row_stride + 4 * (lane & 3);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int rr = 8 * i + (lane >> 2), ch = lane & 3;
-        const float4 t = sc[rr * 4 + (ch ^ (rr & 3))];
-        *reinterpret_cast<float4*>(base + (size_t)rr * row_stride + 4 * ch) = t;
+        float4 t;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                     : "r"(s0 + 16u * (rr * 4 + (ch ^ (rr & 3)))));
+        *reinterpret_cast<float4*>(dst) = t;
+        dst += 8 * row_stride;
     }
     __syncwarp();
 }
 
 }  // namespace sm100
+
+// ---- diagnostics (compiled in only with -DPNO_TRACE: `make EXTRA=-DPNO_TRACE`) -------------------------------------------
+// Event trace of CTA 0: role r appends (cycles since kernel start << 8 | event) to dbg[4096 + r * 512 + n]
+// (pno_debug_set_buffer supplies dbg; tools/trace_*.py print the merged timeline).  Production builds compile these away.
+#ifdef PNO_TRACE
+#define PNO_TRACE_DECL() const long long trace_t0 = clock64(); int trace_n = 0
+#define PNO_TRACE_EV(dbg, role, ev)                                                                    \
+    do {                                                                                               \
+        if ((dbg) && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n < 512)                      \
+            (dbg)[4096 + (role) * 512 + trace_n++] = ((clock64() - trace_t0) << 8) | (long long)(ev);  \
+    } while (0)
+#else
+#define PNO_TRACE_DECL() do {} while (0)
+#define PNO_TRACE_EV(dbg, role, ev) do {} while (0)
+#endif
+
 
 // ---- host: tensor maps --------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).

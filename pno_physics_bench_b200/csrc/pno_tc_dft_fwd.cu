@@ -5,11 +5,14 @@
 //   transposer:        TMEM R -> registers -> (tf32 hi/lo) -> K-major swizzled smem operands Rre[(img,ky)][h], Rim[..][h]
 //   stage 2 (columns): Xre[kx2][(img,ky)] = C Rre^T + S Rim^T ;  Xim = C Rim^T - S Rre^T        (A = twiddles, negate-A bit)
 // Stage-2 accumulators of a "super tile" (up to 8 consecutive channels) stay in TMEM so that the epilogue writes
-// [mode][b][c] with 32-byte contiguous channel runs.
-//   warp 0      TMA producer (x row tiles + the matching TwT k-block; C/S tables once)
-//   warp 1      MMA issuer (both stages, software pipelined)
-//   warps 2-5   tf32 hi/lo splitter of the x tiles (3xTF32 only)
-//   warps 6-9   transposer + epilogue
+// [mode][b][c] with 32-byte contiguous channel runs.  All twiddle tables are shared-memory resident; the ring only carries x.
+//   warp 0        TMA producer (tables once, then x row tiles)
+//   warp 1        MMA issuer (both stages, software pipelined).  A tcgen05.mma costs >= ~53 cycles whatever its N
+//                 (tools/micro/mma_rate.cu), so stage 2 runs once per batch of TPB tiles with N = TPB*IPT*m2 (160 at the
+//                 headline shape) instead of once per tile with N = 48
+//   warps 2-5     tf32 hi/lo splitter of the x tiles (3xTF32 only)
+//   warps 6-13    transposer: two warps per TMEM lane quarter (cos columns / sin columns), all loads of a tile in flight
+//   warps 14-21   epilogue: two warps per lane quarter (re / im plane); only quarters holding kx2 < 2*m1 have work
 #include <math.h>
 
 #include <vector>
@@ -21,24 +24,28 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 64 + 128 + 256 + 256;
 
 struct FwdGeom {
     int H, W, m1, m2, M;
     int B, C;
     int IPT;        // images per 128-row tile (H <= 128)
     int N1p;        // stage-1 N: 2*m2 padded to 16
-    int N2p;        // stage-2 N: IPT*m2 padded to 16
+    int N2p;        // stage-2 N: TPB*IPT*m2 padded to 16
     int R2;         // rows of the C / S tables: 2*m1 padded to 8
     int KB1;        // W / 32
     int KB2;        // H / 32
     int TPS;        // tiles per super tile
+    int TPB;        // tiles per stage-2 batch (TPS % TPB == 0)
     int n_super;    // super tiles in the launch
     int grad_scale;
     int stages;
     // shared-memory byte offsets (from the 1024-aligned base)
-    int off_tab, off_ring, off_b2, stage_bytes, x_bytes, tw_bytes, tab_bytes, b2_bytes, smem_bytes;
+    int off_tab, off_tw, off_ring, off_b2, stage_bytes, x_bytes, tw_one, tab_one, b2_one, b2_bytes, smem_bytes;
+    long long* dbg;   // optional event trace (PNO_TRACE builds)
 };
+
+#define TRACE(role, ev) PNO_TRACE_EV(g.dbg, role, ev)
 
 struct TcTables {
     float *twT_hi, *twT_lo;   // [N1p][W]
@@ -57,6 +64,16 @@ inline float tf32_round_host(double v) {
     return f;
 }
 
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict__ xr, float* __restrict__ xi,
@@ -66,13 +83,14 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
              const __grid_constant__ CUtensorMap tmSLo) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kMaxStages = 4;
+    constexpr int kMaxStages = 8;
     __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_split[kMaxStages], bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_tab, bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty, bar_d2_full,
         bar_d2_empty;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    PNO_TRACE_DECL();
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&bar_raw[s], 1);
@@ -82,12 +100,12 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         mbar_init(&bar_tab, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_d1_full[s], 1);
-            mbar_init(&bar_d1_empty[s], 128);
+            mbar_init(&bar_d1_empty[s], 256);
         }
-        mbar_init(&bar_b2_full, 128);
+        mbar_init(&bar_b2_full, 256 * g.TPB);
         mbar_init(&bar_b2_empty, 1);
         mbar_init(&bar_d2_full, 1);
-        mbar_init(&bar_d2_empty, 128);
+        mbar_init(&bar_d2_empty, 256);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -96,42 +114,43 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
 
-    // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then TPS slots of 2*N2p (re | im)
+    constexpr int NT = NSPLIT == 3 ? 2 : 1;            // hi (+ lo) copies of every operand
+    // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then TPS/TPB slots of 2*N2p (re | im)
     const int d2_base = 2 * g.N1p;
-    // tables: (C hi, C lo, S hi, S lo), each KB2 k-blocks of [R2 x 128 B]
+    // tables: (C hi, [C lo], S hi, [S lo]), each KB2 k-blocks of [R2 x 128 B]; TwT (hi, [lo]) each KB1 k-blocks of [N1p x 128 B]
     unsigned char* tab = smem + g.off_tab;
+    unsigned char* twt = smem + g.off_tw;
     const int tab_kb = g.R2 * 128;
-    const int tab_one = g.KB2 * tab_kb;
-    // B2 operands: (Rre hi, Rre lo, Rim hi, Rim lo), each KB2x (<=4) k-blocks of [N2p x 128 B]
-    unsigned char* b2 = smem + g.off_b2;
-    const int KT = g.H < 128 ? g.H : 128;            // h rows covered by one tile
+    const int tw_kb = g.N1p * 128;
+    // B2 operands: (Rre hi, [Rre lo], Rim hi, [Rim lo]), each KB2 k-blocks of [N2p x 128 B]; rows = (tile in batch, image, ky)
     const int b2_kb = g.N2p * 128;
-    const int b2_one = (KT / 32) * b2_kb;
-
-    const int my_super0 = blockIdx.x;
-    const int total_tiles_per_cta_step = g.TPS;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bar_tab, 4 * tab_one);
+            mbar_arrive_expect_tx(&bar_tab, 2 * NT * g.tab_one + NT * g.tw_one);
             for (int kb = 0; kb < g.KB2; ++kb) {
-                tma_load_2d(tab + 0 * tab_one + kb * tab_kb, &tmCHi, &bar_tab, kb * 32, 0);
-                tma_load_2d(tab + 1 * tab_one + kb * tab_kb, &tmCLo, &bar_tab, kb * 32, 0);
-                tma_load_2d(tab + 2 * tab_one + kb * tab_kb, &tmSHi, &bar_tab, kb * 32, 0);
-                tma_load_2d(tab + 3 * tab_one + kb * tab_kb, &tmSLo, &bar_tab, kb * 32, 0);
+                tma_load_2d(tab + 0 * g.tab_one + kb * tab_kb, &tmCHi, &bar_tab, kb * 32, 0);
+                tma_load_2d(tab + NT * g.tab_one + kb * tab_kb, &tmSHi, &bar_tab, kb * 32, 0);
+                if (NSPLIT == 3) {
+                    tma_load_2d(tab + 1 * g.tab_one + kb * tab_kb, &tmCLo, &bar_tab, kb * 32, 0);
+                    tma_load_2d(tab + 3 * g.tab_one + kb * tab_kb, &tmSLo, &bar_tab, kb * 32, 0);
+                }
+            }
+            for (int kb = 0; kb < g.KB1; ++kb) {
+                tma_load_2d(twt + kb * tw_kb, &tmTwHi, &bar_tab, kb * 32, 0);
+                if (NSPLIT == 3) tma_load_2d(twt + g.tw_one + kb * tw_kb, &tmTwLo, &bar_tab, kb * 32, 0);
             }
             int stage = 0, phase = 0;
-            for (int sup = my_super0; sup < g.n_super; sup += gridDim.x) {
-                for (int t = 0; t < total_tiles_per_cta_step; ++t) {
+            for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
+                for (int t = 0; t < g.TPS; ++t) {
                     const int row0 = (sup * g.TPS + t) * 128;          // row of the [B*C*H][W] view
                     for (int kb = 0; kb < g.KB1; ++kb) {
                         mbar_wait(&bar_empty[stage], phase ^ 1);
+                        TRACE(3, 1);
                         unsigned char* st = smem + g.off_ring + (size_t)stage * g.stage_bytes;
-                        mbar_arrive_expect_tx(&bar_raw[stage], g.x_bytes + 2 * g.tw_bytes);
+                        mbar_arrive_expect_tx(&bar_raw[stage], g.x_bytes);
                         tma_load_2d(st, &tmX, &bar_raw[stage], kb * 32, row0);
-                        tma_load_2d(st + 2 * g.x_bytes, &tmTwHi, &bar_raw[stage], kb * 32, 0);
-                        tma_load_2d(st + 2 * g.x_bytes + g.tw_bytes, &tmTwLo, &bar_raw[stage], kb * 32, 0);
                         if (++stage == g.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -139,11 +158,15 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+            const uint32_t el = lane == 0;
             const uint32_t idesc1 = make_idesc(FMT_TF32, 128, g.N1p, MAJOR_K, MAJOR_K);
             const uint32_t idesc2 = make_idesc(FMT_TF32, 128, g.N2p, MAJOR_K, MAJOR_K);
             const uint32_t idesc2n = make_idesc(FMT_TF32, 128, g.N2p, MAJOR_K, MAJOR_K, 1, 0);
             const uint32_t khi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;     // all operands: K-major SW128
+            const uint32_t tb = sdesc_base(smem_u32(tab), 16, 1024, SWIZZLE_128B).lo;
+            const uint32_t twb = sdesc_base(smem_u32(twt), 16, 1024, SWIZZLE_128B).lo;
+            const uint32_t t1 = g.tab_one >> 4, bo1 = g.b2_one >> 4;
             int stage = 0, phase = 0;
             int n1 = 0;      // stage-1 tiles issued
             int n2 = 0;      // stage-2 tiles issued
@@ -157,76 +180,77 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 const uint32_t d1 = tmem + buf * g.N1p;
                 for (int kb = 0; kb < g.KB1; ++kb) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
+                    TRACE(0, 5);
                     tc_fence_after_sync();
                     const uint32_t x_hi = sdesc_base(smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), 16, 1024, SWIZZLE_128B).lo;
-                    const uint32_t x_lo = x_hi + (g.x_bytes >> 4), tw_hi = x_hi + 2 * (g.x_bytes >> 4), tw_lo = tw_hi + (g.tw_bytes >> 4);
+                    const uint32_t x_lo = x_hi + (g.x_bytes >> 4);
+                    const uint32_t tw_hi = twb + ((kb * tw_kb) >> 4), tw_lo = tw_hi + (g.tw_one >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t accf = (kb | ks) ? 1u : 0u;
                         const uint32_t o = ks * 2;
-                        mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf);
+                        mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf, el);
                         if (NSPLIT == 3) {
-                            mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u);
-                            mma_tf32(d1, x_hi + o, khi, tw_lo + o, khi, idesc1, 1u);
+                            mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u, el);
+                            mma_tf32(d1, x_hi + o, khi, tw_lo + o, khi, idesc1, 1u, el);
                         }
                     }
-                    mma_commit(&bar_empty[stage]);
+                    mma_commit(&bar_empty[stage], el);
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&bar_d1_full[buf]);
+                mma_commit(&bar_d1_full[buf], el);
+                TRACE(0, 1);
                 ++n1;
             };
 
-            auto issue_stage2 = [&]() {
-                const int t = n2 % g.TPS;                       // tile within its super tile
-                if (t == 0) {                                   // first write into the D2 slots of a new super tile
+            auto issue_stage2 = [&]() {                         // one batch of TPB tiles
+                const int slot = n2 % (g.TPS / g.TPB);          // batch within its super tile = accumulator slot
+                if (slot == 0) {                                // first write into the D2 slots of a new super tile
                     mbar_wait(&bar_d2_empty, (nsup & 1) ^ 1);
+                    TRACE(0, 4);
                     ++nsup;
                 }
                 mbar_wait(&bar_b2_full, n2 & 1);
+                TRACE(0, 2);
                 tc_fence_after_sync();
-                // slot: one per image group (tile if H <= 128, image if H > 128); k-range of this tile inside C/S
-                const int tiles_per_slot = g.H > 128 ? g.H / 128 : 1;
-                const int slot = t / tiles_per_slot, part = t % tiles_per_slot;
                 const uint32_t d_re = tmem + d2_base + slot * 2 * g.N2p, d_im = d_re + g.N2p;
-                const uint32_t tb = sdesc_base(smem_u32(tab), 16, 1024, SWIZZLE_128B).lo;
-                const uint32_t bb = sdesc_base(smem_u32(b2), 16, 1024, SWIZZLE_128B).lo;
-                const uint32_t t1 = tab_one >> 4, bo1 = b2_one >> 4;       // (C hi, C lo, S hi, S lo) / (Rre hi, Rre lo, Rim hi, Rim lo)
-                const int nkb = KT / 32;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const int tkb = part * 4 + kb;              // k-block inside the full-H tables
+                const uint32_t bbase = sdesc_base(smem_u32(smem + g.off_b2), 16, 1024, SWIZZLE_128B).lo;
+                // tables (C hi, [C lo], S hi, [S lo]) at tb + {0, t1, NT*t1, (NT+1)*t1}; B2 (Rre hi, [Rre lo], Rim hi, [Rim lo]) likewise
+                for (int kb = 0; kb < g.KB2; ++kb) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t first = (part | kb | ks) ? 1u : 0u;
-                        const uint32_t c = tb + ((tkb * tab_kb) >> 4) + ks * 2, r = bb + ((kb * b2_kb) >> 4) + ks * 2;
+                        const uint32_t first = (kb | ks) ? 1u : 0u;
+                        const uint32_t c = tb + ((kb * tab_kb) >> 4) + ks * 2, r = bbase + ((kb * b2_kb) >> 4) + ks * 2;
+                        const uint32_t sn = c + NT * t1, ri = r + NT * bo1;
                         // Xre += C Rre + S Rim ; Xim += C Rim - S Rre
-                        mma_tf32(d_re, c, khi, r, khi, idesc2, first);
-                        mma_tf32(d_re, c + 2 * t1, khi, r + 2 * bo1, khi, idesc2, 1u);
-                        mma_tf32(d_im, c, khi, r + 2 * bo1, khi, idesc2, first);
-                        mma_tf32(d_im, c + 2 * t1, khi, r, khi, idesc2n, 1u);
+                        mma_tf32(d_re, c, khi, r, khi, idesc2, first, el);
+                        mma_tf32(d_re, sn, khi, ri, khi, idesc2, 1u, el);
+                        mma_tf32(d_im, c, khi, ri, khi, idesc2, first, el);
+                        mma_tf32(d_im, sn, khi, r, khi, idesc2n, 1u, el);
                         if (NSPLIT == 3) {
-                            mma_tf32(d_re, c + t1, khi, r, khi, idesc2, 1u);
-                            mma_tf32(d_re, c, khi, r + bo1, khi, idesc2, 1u);
-                            mma_tf32(d_re, c + 3 * t1, khi, r + 2 * bo1, khi, idesc2, 1u);
-                            mma_tf32(d_re, c + 2 * t1, khi, r + 3 * bo1, khi, idesc2, 1u);
-                            mma_tf32(d_im, c + t1, khi, r + 2 * bo1, khi, idesc2, 1u);
-                            mma_tf32(d_im, c, khi, r + 3 * bo1, khi, idesc2, 1u);
-                            mma_tf32(d_im, c + 3 * t1, khi, r, khi, idesc2n, 1u);
-                            mma_tf32(d_im, c + 2 * t1, khi, r + bo1, khi, idesc2n, 1u);
+                            mma_tf32(d_re, c + t1, khi, r, khi, idesc2, 1u, el);
+                            mma_tf32(d_re, c, khi, r + bo1, khi, idesc2, 1u, el);
+                            mma_tf32(d_re, sn + t1, khi, ri, khi, idesc2, 1u, el);
+                            mma_tf32(d_re, sn, khi, ri + bo1, khi, idesc2, 1u, el);
+                            mma_tf32(d_im, c + t1, khi, ri, khi, idesc2, 1u, el);
+                            mma_tf32(d_im, c, khi, ri + bo1, khi, idesc2, 1u, el);
+                            mma_tf32(d_im, sn + t1, khi, r, khi, idesc2n, 1u, el);
+                            mma_tf32(d_im, sn, khi, r + bo1, khi, idesc2n, 1u, el);
                         }
                     }
                 }
-                mma_commit(&bar_b2_empty);
-                if (t == g.TPS - 1) mma_commit(&bar_d2_full);
+                mma_commit(&bar_b2_empty, el);
+                if (slot == g.TPS / g.TPB - 1) mma_commit(&bar_d2_full, el);
+                TRACE(0, 3);
                 ++n2;
             };
 
             int my_tiles = 0;
-            for (int sup = my_super0; sup < g.n_super; sup += gridDim.x) my_tiles += g.TPS;
+            for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) my_tiles += g.TPS;
             if (my_tiles > 0) issue_stage1();
             for (int t = 0; t < my_tiles; ++t) {
                 if (t + 1 < my_tiles) issue_stage1();
-                issue_stage2();
+                if ((t + 1) % g.TPB == 0) issue_stage2();
             }
         }
     } else if (warp < 6) {
@@ -234,7 +258,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         if (NSPLIT == 3) {
             const int t = threadIdx.x - 64;
             int stage = 0, phase = 0;
-            for (int sup = my_super0; sup < g.n_super; sup += gridDim.x) {
+            for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
                 for (int tt = 0; tt < g.TPS * g.KB1; ++tt) {
                     mbar_wait(&bar_raw[stage], phase);
                     float4* hi = reinterpret_cast<float4*>(smem + g.off_ring + (size_t)stage * g.stage_bytes);
@@ -242,11 +266,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
 #pragma unroll 4
                     for (int i = t; i < g.x_bytes / 16; i += 128) {
                         const float4 v = hi[i];
-                        float4 h;
-                        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-                        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-                        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-                        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
                         hi[i] = h;
                         lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                     }
@@ -256,41 +276,50 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 }
             }
         }
-    } else {
-        // ================================ transposer + epilogue ================================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;                       // TMEM lane = row of the 128-row tile
-        const int img_l = g.H < 128 ? row / g.H : 0;         // image within the tile
-        const int hk = g.H < 128 ? row % g.H : row;          // k index inside this tile's h range
-        int n = 0, nsup = 0;
-        for (int sup = my_super0; sup < g.n_super; sup += gridDim.x, ++nsup) {
+    } else if (warp < 14) {
+        // ================================ transposer ================================
+        // thread = row (img_l, h) of the tile (TMEM lane) x one half of the stage-1 columns (cos -> Rre, -sin -> Rim)
+        const int q = warp & 3, im = (warp - 6) >> 2;
+        const int row = q * 32 + lane;
+        const int img_l = row / g.H, hk = row % g.H;
+        // element (n2 = img_l*m2 + ky, k = hk) of a K-major SW128 [N2p x 32] k-block: only the row term depends on ky
+        const uint32_t col_off = (uint32_t)((hk >> 5) * b2_kb + ((hk & 3) << 2));
+        const int chunk = (hk & 31) >> 2;
+        int n = 0;
+        for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
             for (int t = 0; t < g.TPS; ++t, ++n) {
                 const int buf = n & 1;
+                const int tb_ = n % g.TPB, batch = n / g.TPB;       // tile within its stage-2 batch
                 mbar_wait(&bar_d1_full[buf], (n >> 1) & 1);
+                if (warp == 8) TRACE(1, 1);
                 tc_fence_after_sync();
-                mbar_wait(&bar_b2_empty, (n & 1) ^ 1);       // stage-2 MMAs of the previous tile have read B2
-                const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p);
-                // zero-free transposition: element (n2 = img_l*m2 + ky, k = hk) of Rre / Rim
-                for (int c0 = 0; c0 < 2 * g.m2; c0 += 4) {
-                    uint32_t r0, r1, r2, r3;
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                                 : "r"(t1 + c0));
-                    tmem_ld_wait();
-                    const float v[4] = {__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)};
+                if (tb_ == 0) mbar_wait(&bar_b2_empty, (batch & 1) ^ 1);   // stage 2 of the previous batch has read B2
+                if (warp == 8) TRACE(1, 2);
+                const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p + im * g.m2);
+                unsigned char* dst0 = smem + g.off_b2 + im * NT * g.b2_one + col_off;
+                const int r0 = (tb_ * g.IPT + img_l) * g.m2;
+                for (int c0 = 0; c0 < g.m2; c0 += 32) {          // up to 8 x4 loads in flight, one wait
+                    float v[8][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c2 = c0 + j;
-                        const int im = c2 >= g.m2;
-                        const int ky = c2 - im * g.m2;
-                        const uint32_t off = kmajor_sw128_off(img_l * g.m2 + ky, hk, g.N2p);
-                        unsigned char* dst = b2 + (im ? 2 : 0) * b2_one + off;
-                        if (NSPLIT == 3) {
-                            const float h = __uint_as_float((__float_as_uint(v[j]) + 0x1000u) & 0xFFFFE000u);
-                            *reinterpret_cast<float*>(dst) = h;
-                            *reinterpret_cast<float*>(dst + b2_one) = v[j] - h;
-                        } else {
-                            *reinterpret_cast<float*>(dst) = v[j];
+                    for (int u = 0; u < 8; ++u)
+                        if (c0 + 4 * u < g.m2) tmem_ld4(t1 + c0 + 4 * u, v[u]);
+                    tmem_ld_wait();
+                    if (warp == 8) TRACE(1, 3);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (c0 + 4 * u < g.m2) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r = r0 + c0 + 4 * u + j;
+                                unsigned char* dst = dst0 + r * 128 + ((chunk ^ (r & 7)) << 4);
+                                if (NSPLIT == 3) {
+                                    const float h = tf32_rn(v[u][j]);
+                                    *reinterpret_cast<float*>(dst) = h;
+                                    *reinterpret_cast<float*>(dst + g.b2_one) = v[u][j] - h;
+                                } else {
+                                    *reinterpret_cast<float*>(dst) = v[u][j];
+                                }
+                            }
                         }
                     }
                 }
@@ -298,51 +327,52 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 mbar_arrive(&bar_d1_empty[buf]);
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_b2_full);
+                if (warp == 8) TRACE(1, 4);
             }
-            // ---- epilogue of the super tile: lanes kx2 < 2*m1 hold Xre / Xim of GS images ----
+        }
+    } else {
+        // ================================ epilogue ================================
+        // lanes kx2 < 2*m1 of the D2 slots hold Xre / Xim of GS = TPS*IPT images; warp = (lane quarter, re / im plane)
+        const int q = warp & 3, part = (warp - 14) >> 2;
+        const int row = q * 32 + lane;
+        const int GS = g.TPS * g.IPT;                    // images (consecutive channels) per super tile
+        const bool warp_active = q * 32 < 2 * g.m1;      // warp-uniform: tcgen05.ld is warp-collective
+        const bool active = row < 2 * g.m1;
+        float* dst_plane = part ? xi : xr;
+        int nsup = 0;
+        for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x, ++nsup) {
             mbar_wait(&bar_d2_full, nsup & 1);
+            if (warp == 16) TRACE(2, 1);
             tc_fence_after_sync();
-            const int n_slots = g.H > 128 ? g.TPS / (g.H / 128) : g.TPS;
-            const int GS = n_slots * g.IPT;                  // images (consecutive channels) in this super tile
-            const int img0 = sup * GS;                       // first image = b*C + c0
-            const int b = img0 / g.C, c0 = img0 % g.C;
-            if (q * 32 < 2 * g.m1) {      // warp-uniform: tcgen05.ld is warp-collective, only the stores are predicated
-                const bool active = row < 2 * g.m1;
-                for (int part = 0; part < 2; ++part) {
-                    float* dst_plane = part ? xi : xr;
-                    for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
-                        float vals[4][8];
+            if (warp_active) {
+                const int img0 = sup * GS;                   // first image = b*C + c0
+                const int b = img0 / g.C, c0 = img0 % g.C;
+                for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
+                    float vals[8][4];
 #pragma unroll
-                        for (int gi = 0; gi < 8; ++gi) {
-                            if (gi < GS) {
-                                const int slot = gi / g.IPT, il = gi % g.IPT;
-                                const uint32_t ta = tmem_addr(tmem, q * 32,
-                                                              d2_base + slot * 2 * g.N2p + part * g.N2p + il * g.m2 + ky0);
-                                uint32_t r0, r1, r2, r3;
-                                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                                             : "r"(ta));
-                                tmem_ld_wait();
-                                vals[0][gi] = __uint_as_float(r0); vals[1][gi] = __uint_as_float(r1);
-                                vals[2][gi] = __uint_as_float(r2); vals[3][gi] = __uint_as_float(r3);
-                            } else {
-                                vals[0][gi] = vals[1][gi] = vals[2][gi] = vals[3][gi] = 0.f;
-                            }
+                    for (int gi = 0; gi < 8; ++gi) {
+                        if (gi < GS) {
+                            const int ipb = g.TPB * g.IPT;           // images per stage-2 batch (= accumulator slot)
+                            const int slot = gi / ipb, il = gi % ipb;
+                            tmem_ld4(tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + part * g.N2p + il * g.m2 + ky0), vals[gi]);
+                        } else {
+                            vals[gi][0] = vals[gi][1] = vals[gi][2] = vals[gi][3] = 0.f;
                         }
-                        if (active) {
+                    }
+                    tmem_ld_wait();
+                    if (active) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int mode = row * g.m2 + ky0 + j;
-                                const float cf = g.grad_scale ? coef[mode] : 1.f;
-                                float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0;
-                                if (GS == 8) {
-                                    reinterpret_cast<float4*>(dst)[0] = make_float4(vals[j][0] * cf, vals[j][1] * cf, vals[j][2] * cf, vals[j][3] * cf);
-                                    reinterpret_cast<float4*>(dst)[1] = make_float4(vals[j][4] * cf, vals[j][5] * cf, vals[j][6] * cf, vals[j][7] * cf);
-                                } else {
+                        for (int j = 0; j < 4; ++j) {
+                            const int mode = row * g.m2 + ky0 + j;
+                            const float cf = g.grad_scale ? coef[mode] : 1.f;
+                            float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0;
+                            if (GS == 8) {
+                                reinterpret_cast<float4*>(dst)[0] = make_float4(vals[0][j] * cf, vals[1][j] * cf, vals[2][j] * cf, vals[3][j] * cf);
+                                reinterpret_cast<float4*>(dst)[1] = make_float4(vals[4][j] * cf, vals[5][j] * cf, vals[6][j] * cf, vals[7][j] * cf);
+                            } else {
 #pragma unroll
-                                    for (int gi = 0; gi < 8; ++gi)
-                                        if (gi < GS) dst[gi] = vals[j][gi] * cf;
-                                }
+                                for (int gi = 0; gi < 8; ++gi)
+                                    if (gi < GS) dst[gi] = vals[gi][j] * cf;
                             }
                         }
                     }
@@ -350,6 +380,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             }
             tc_fence_before_sync();
             mbar_arrive(&bar_d2_empty);
+            if (warp == 16) TRACE(2, 2);
         }
     }
     tc_fence_before_sync();
@@ -425,36 +456,46 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     FwdGeom g;
     memset(&g, 0, sizeof(g));
     g.H = H; g.W = W; g.m1 = m1; g.m2 = m2; g.M = p->M; g.B = B; g.C = C; g.grad_scale = grad_scale;
+    const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
+    const int NT = x3 ? 2 : 1;
     g.IPT = 128 / H;
     g.N1p = pad_to(2 * m2, 16);
-    g.N2p = pad_to(g.IPT * m2, 16);
     g.R2 = pad_to(2 * m1, 8);
     g.KB1 = W / 32;
     g.KB2 = H / 32;
-    if (g.N1p > 256 || g.N2p > 256) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: too many modes for one MMA");
-    int slots = (512 - 2 * g.N1p) / (2 * g.N2p);
+    if (H > 128) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: H > 128");
+    g.x_bytes = 128 * 128;                        // [128 rows][32 floats]
+    g.stage_bytes = NT * g.x_bytes;
+    g.tab_one = g.KB2 * g.R2 * 128;
+    g.tw_one = g.KB1 * g.N1p * 128;
+    g.off_tab = 0;
+    g.off_tw = pad_to(2 * NT * g.tab_one, 1024);
+    g.off_b2 = g.off_tw + pad_to(NT * g.tw_one, 1024);
+    // M = 128 operand reads run past the R2 rows of the last table k-block: the regions that follow (TwT, B2, ring) are at
+    // least 16 KB, so those reads stay inside the allocation (the rows they produce are never read back).
+    // super tile = up to 8 consecutive channels (32-byte runs in the [mode][b][c] output); stage-2 batch = as many of its
+    // tiles as TMEM (512 columns), the MMA (N <= 256) and shared memory (>= 3 ring stages) allow
+    const int budget = 226 * 1024 - 1024;
+    bool fits = false;
     int want = 8 / g.IPT;
     if (want < 1) want = 1;
-    int ns = 1;
-    while (ns * 2 <= slots && ns * 2 <= want) ns *= 2;
-    const int GS = ns * g.IPT;
-    if (C % GS) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: channel count %d is not a multiple of %d", C, GS);
-    g.TPS = ns;                                   // H <= 128: one tile per slot
-    g.n_super = B * C / GS;
-    const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
-    g.x_bytes = 128 * 128;                        // [128 rows][32 floats]
-    g.tw_bytes = g.N1p * 128;
-    g.stage_bytes = pad_to(2 * g.x_bytes + 2 * g.tw_bytes, 1024);
-    g.tab_bytes = pad_to(4 * g.KB2 * g.R2 * 128 + 128 * 128, 1024);     // + slack: M=128 reads run past R2 rows
-    const int KT = H < 128 ? H : 128;
-    g.b2_bytes = pad_to(4 * (KT / 32) * g.N2p * 128, 1024);
-    g.off_tab = 0;
-    g.off_b2 = g.tab_bytes;
-    g.off_ring = g.off_b2 + g.b2_bytes;
-    g.stages = 4;
-    while (g.stages > 2 && g.off_ring + g.stages * g.stage_bytes + 1024 > 220 * 1024) --g.stages;
+    for (int ns = want; ns >= 1 && !fits; ns >>= 1) {
+        if (C % (ns * g.IPT)) continue;
+        g.TPS = ns;
+        for (g.TPB = g.TPS; g.TPB >= 1; g.TPB >>= 1) {
+            g.N2p = pad_to(g.TPB * g.IPT * m2, 16);
+            g.b2_one = g.KB2 * g.N2p * 128;
+            g.b2_bytes = pad_to(2 * NT * g.b2_one, 1024);
+            g.off_ring = g.off_b2 + g.b2_bytes;
+            g.stages = (budget - g.off_ring) / g.stage_bytes;
+            if (g.stages > 8) g.stages = 8;
+            if (g.N2p <= 256 && g.N1p <= 256 && 2 * g.N1p + (g.TPS / g.TPB) * 2 * g.N2p <= 512 && g.stages >= 3) { fits = true; break; }
+        }
+    }
+    if (!fits) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: tables and operands do not fit in shared / tensor memory");
+    g.n_super = B * C / (g.TPS * g.IPT);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
-    if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: %d bytes of shared memory needed", g.smem_bytes);
+    g.dbg = g_pno_debug_buffer;
     if ((reinterpret_cast<uintptr_t>(x) & 15)) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd needs a 16-byte aligned input");
 
     void* tv = nullptr;
@@ -489,10 +530,10 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = g.n_super < sms ? g.n_super : sms;
     if (x3) {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         k_tc_dft_fwd<3><<<grid, kThreads, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
     } else {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         k_tc_dft_fwd<1><<<grid, kThreads, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
     }
     PNO_LAUNCH_CHECK();

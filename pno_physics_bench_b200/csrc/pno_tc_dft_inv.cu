@@ -5,11 +5,13 @@
 // padding:
 //   loaders     yhat[mode][b][c0..c0+G) (32-byte runs) -> tf32 hi/lo -> B1 slabs  Yre/Yim[(img,ky)][kx2]
 //   stage 1     Zre[h][(img,ky)] = C Yre^T - S Yim^T ; Zim = S Yre^T + C Yim^T          (A = column twiddles, M = 128 lanes = h)
-//   transposer  TMEM Z -> registers -> * c_ky/(HW) -> tf32 hi/lo -> Zt slabs [(img,h)][(re|im, ky)]
-//   stage 2     y[(img,h)][w] = Zt * TwB^T            TwB[w][(re|im,ky)] = cos | -sin (2 pi ky w / W)
+//   transposer  TMEM Z -> registers -> tf32 hi/lo -> Zt slabs [(img,h)][(re|im, ky)]
+//   stage 2     y[(img,h)][w] = Zt * TwB^T            TwB[w][(re|im,ky)] = c_ky/(HW) * (cos | -sin)(2 pi ky w / W)
 //   epilogue    TMEM -> + addend -> pre_act -> activation -> global rows (each thread owns one image row)
-//   warp 1 MMA issuer, warps 2-5 loaders, warps 6-9 transposer, warps 10.. epilogue (8 or 16 warps: addend + exact GELU + stores
-//   make it the issue-bound role; warp 0 idle: no TMA in this kernel)
+//   warp 1 MMA issuer; warps 2-9 loaders + transposers; warps 10.. epilogue (8 or 16 warps: addend + exact GELU + stores make it
+//   the issue-bound role; warp 0 idle: no TMA in this kernel).  A warp can only read the TMEM lane quarter (warp % 4): for H <= 64
+//   the stage-1 accumulators live in quarters 0-1, so the four front warps of those quarters transpose (one accumulator half
+//   each) and the other four load; for H = 128 warps 2-5 load and warps 6-9 transpose both halves.
 #include <math.h>
 #include <stdlib.h>
 
@@ -22,7 +24,8 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kMaxThreads = 320 + 16 * 32;
+constexpr int kFront = 64 + 256;   // idle + issuer, loaders + transposers
+constexpr int kMaxThreads = kFront + 16 * 32;
 
 struct InvGeom {
     int H, W, m1, m2, B, C;
@@ -39,17 +42,16 @@ struct InvGeom {
 };
 
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+#ifdef PNO_TRACE
     const long long t0 = clock64();
     mbar_wait(bar, parity);
     acc += clock64() - t0;
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 
-// event trace of CTA 0 (diagnostics): role r writes (clock << 8 | event) into dbg[4096 + r * 512 + n]
-#define TRACE(role, ev)                                                                                     \
-    do {                                                                                                    \
-        if (g.dbg && blockIdx.x == 0 && lane == 0 && trace_n < 512)                                         \
-            g.dbg[4096 + (role) * 512 + trace_n++] = ((clock64() - t_start) << 8) | (long long)(ev);       \
-    } while (0)
+#define TRACE(role, ev) PNO_TRACE_EV(g.dbg, role, ev)
 
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
@@ -68,7 +70,7 @@ __device__ __forceinline__ void warp_store_rows32(float4* sc, int lane, const fl
     __syncwarp();
 }
 
-template <int NSPLIT, int G>
+template <int NSPLIT, int G, int ACT>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
              const float* __restrict__ coef, const float* __restrict__ yr, const float* __restrict__ yi,
@@ -78,12 +80,10 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     __shared__ __align__(8) uint64_t bar_b1_full, bar_b1_empty, bar_d1_full, bar_d1_empty;
     __shared__ __align__(8) uint64_t bar_zt_full[2], bar_zt_empty[2], bar_d2_full[2], bar_d2_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_scale[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
-    int trace_n = 0;
-    const long long t_start = clock64();
+    PNO_TRACE_DECL();
     if (threadIdx.x == 0) {
         mbar_init(&bar_b1_full, 128);
         mbar_init(&bar_b1_empty, 1);
@@ -98,26 +98,33 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
-    // twiddle tables -> slab form.  tabA_g: (C hi, C lo, S hi, S lo) each [H][K1]; tabB_g: (hi, lo) each [W][K2]
-    for (int e = threadIdx.x; e < 4 * g.H * g.K1; e += blockDim.x) {
-        const int t = e / (g.H * g.K1), r = (e / g.K1) % g.H, k = e % g.K1;
-        *reinterpret_cast<float*>(smem + g.off_tabA + t * g.tabA_one + kslab_sw32_off(r, k, g.H)) = tabA_g[e];
+    // twiddle tables: the plan holds them as the exact shared-memory image (slab-swizzled), so this is a straight copy
+    {
+        const float4* srcA = reinterpret_cast<const float4*>(tabA_g);
+        float4* dstA = reinterpret_cast<float4*>(smem + g.off_tabA);
+        for (int e = threadIdx.x; e < g.tabA_one / 4; e += blockDim.x) dstA[e] = srcA[e];        // 4 tables x tabA_one bytes
+        const float4* srcB = reinterpret_cast<const float4*>(tabB_g);
+        float4* dstB = reinterpret_cast<float4*>(smem + g.off_tabB);
+        for (int e = threadIdx.x; e < g.tabB_one / 8; e += blockDim.x) dstB[e] = srcB[e];        // 2 tables x tabB_one bytes
     }
-    for (int e = threadIdx.x; e < 2 * g.W * g.K2; e += blockDim.x) {
-        const int t = e / (g.W * g.K2), r = (e / g.K2) % g.W, k = e % g.K2;
-        *reinterpret_cast<float*>(smem + g.off_tabB + t * g.tabB_one + kslab_sw32_off(r, k, g.W)) = tabB_g[e];
-    }
-    if (threadIdx.x < g.m2) s_scale[threadIdx.x] = g.adjoint ? 1.f : coef[g.m1 * g.m2 + threadIdx.x];   // an alive row
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const int d2_col = 2 * g.N1;
+    // role of the front warps 2..9
+    const bool small_h = g.H <= 64;
+    const bool front = warp >= 2 && warp < 10;
+    const bool is_trans = front && (small_h ? (warp & 3) < 2 : warp >= 6);
+    const bool is_loader = front && !is_trans;
+    const int lw = small_h ? (((warp - 2) >> 2) * 2 + ((warp & 3) - 2)) : warp - 2;     // loader warp index 0..3
+    const int part_lo = small_h ? (warp - 4) >> 2 : 0, part_hi = small_h ? part_lo + 1 : 2;   // accumulator halves of a transposer warp
 
     if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+            const uint32_t el = lane == 0;
             const uint32_t id1 = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K);
             const uint32_t id1n = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K, 1, 0);
             const uint32_t id2 = make_idesc(FMT_TF32, 128, g.W, MAJOR_K, MAJOR_K);
@@ -141,29 +148,31 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 for (int s = 0; s < g.S1; ++s, a += slabA, b += slabB1) {
                     const uint32_t first = s ? 1u : 0u;
                     // (C hi, C lo, S hi, S lo) at a + {0,1,2,3}*tA1;  (Yre hi, Yre lo) at b + {0, b1o}, (Yim hi, Yim lo) at b + b1i + {0, b1o}
-                    mma_tf32(d_re, a, dhi, b, dhi, id1, first);
-                    mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i, dhi, id1n, 1u);
-                    mma_tf32(d_im, a + 2 * tA1, dhi, b, dhi, id1, first);
-                    mma_tf32(d_im, a, dhi, b + b1i, dhi, id1, 1u);
+                    mma_tf32(d_re, a, dhi, b, dhi, id1, first, el);
+                    mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i, dhi, id1n, 1u, el);
+                    mma_tf32(d_im, a + 2 * tA1, dhi, b, dhi, id1, first, el);
+                    mma_tf32(d_im, a, dhi, b + b1i, dhi, id1, 1u, el);
                     if (NSPLIT == 3) {
-                        mma_tf32(d_re, a + tA1, dhi, b, dhi, id1, 1u);
-                        mma_tf32(d_re, a, dhi, b + b1o, dhi, id1, 1u);
-                        mma_tf32(d_re, a + 3 * tA1, dhi, b + b1i, dhi, id1n, 1u);
-                        mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i + b1o, dhi, id1n, 1u);
-                        mma_tf32(d_im, a + 3 * tA1, dhi, b, dhi, id1, 1u);
-                        mma_tf32(d_im, a + 2 * tA1, dhi, b + b1o, dhi, id1, 1u);
-                        mma_tf32(d_im, a + tA1, dhi, b + b1i, dhi, id1, 1u);
-                        mma_tf32(d_im, a, dhi, b + b1i + b1o, dhi, id1, 1u);
+                        mma_tf32(d_re, a + tA1, dhi, b, dhi, id1, 1u, el);
+                        mma_tf32(d_re, a, dhi, b + b1o, dhi, id1, 1u, el);
+                        mma_tf32(d_re, a + 3 * tA1, dhi, b + b1i, dhi, id1n, 1u, el);
+                        mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i + b1o, dhi, id1n, 1u, el);
+                        mma_tf32(d_im, a + 3 * tA1, dhi, b, dhi, id1, 1u, el);
+                        mma_tf32(d_im, a + 2 * tA1, dhi, b + b1o, dhi, id1, 1u, el);
+                        mma_tf32(d_im, a + tA1, dhi, b + b1i, dhi, id1, 1u, el);
+                        mma_tf32(d_im, a, dhi, b + b1i + b1o, dhi, id1, 1u, el);
                     }
                 }
-                mma_commit(&bar_b1_empty);
-                mma_commit(&bar_d1_full);
+                mma_commit(&bar_b1_empty, el);
+                mma_commit(&bar_d1_full, el);
                 TRACE(0, 3);
+#ifdef PNO_TRACE
                 if (g.dbg_mma) {                         // diagnostics: issue -> completion latency of the stage-1 batch
                     const long long tq = clock64();
                     mbar_wait(&bar_d1_full, ng & 1);
                     w4 += clock64() - tq;
                 }
+#endif
                 for (int j = 0; j < g.TPG; ++j, ++nt) {
                     const int zb = nt & 1;
                     wait_t(&bar_zt_full[zb], (nt >> 1) & 1, w2);
@@ -174,26 +183,28 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     const uint32_t d2 = tmem + d2_col + zb * g.W;
                     uint32_t z = zt + zb * (g.zt_buf >> 4), w = tB;
                     for (int s = 0; s < g.S2; ++s, z += slabZ, w += slabTB) {
-                        mma_tf32(d2, z, dhi, w, dhi, id2, s ? 1u : 0u);
+                        mma_tf32(d2, z, dhi, w, dhi, id2, s ? 1u : 0u, el);
                         if (NSPLIT == 3) {
-                            mma_tf32(d2, z + (g.zt_one >> 4), dhi, w, dhi, id2, 1u);
-                            mma_tf32(d2, z, dhi, w + (g.tabB_one >> 4), dhi, id2, 1u);
+                            mma_tf32(d2, z + (g.zt_one >> 4), dhi, w, dhi, id2, 1u, el);
+                            mma_tf32(d2, z, dhi, w + (g.tabB_one >> 4), dhi, id2, 1u, el);
                         }
                     }
-                    mma_commit(&bar_zt_empty[zb]);
-                    mma_commit(&bar_d2_full[zb]);
+                    mma_commit(&bar_zt_empty[zb], el);
+                    mma_commit(&bar_d2_full[zb], el);
                     TRACE(0, 6);
+#ifdef PNO_TRACE
                     if (g.dbg_mma) {
                         const long long tq = clock64();
                         mbar_wait(&bar_d2_full[zb], (nt >> 1) & 1);
                         w5 += clock64() - tq;
                     }
+#endif
                 }
             }
         }
-    } else if (warp >= 2 && warp < 6) {
+    } else if (is_loader) {
         // ================================ loaders: yhat -> B1 slabs ================================
-        const int t = threadIdx.x - 64;
+        const int t = lw * 32 + lane;
         unsigned char* b1 = smem + g.off_b1;
         const int items = 2 * g.m2 * g.K1;
         int ng = 0;
@@ -241,8 +252,9 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             mbar_arrive(&bar_b1_full);
             if (warp == 2) TRACE(3, 3);
         }
-    } else if (warp >= 6 && warp < 10) {
+    } else if (is_trans) {
         // ================================ transposer ================================
+        // thread = stage-1 lane (row h) x accumulator halves [part_lo, part_hi) (re / im)
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const bool t_active_warp = q * 32 < g.H;          // warp holds valid stage-1 lanes (h < H)
@@ -257,35 +269,34 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 for (int il = 0; il < g.IPT; ++il) {
                     const int img = j * g.IPT + il;                  // image within the group
                     const int zrow = il * g.H + row;                 // row of the stage-2 A tile (row < H here)
-                    for (int part = 0; part < 2; ++part) {
-                        for (int kyb = 0; kyb < g.m2; kyb += 32) {          // up to 8 x4 loads in flight, one wait
-                            uint32_t r[8][4];
+                    const uint32_t rbase = zrow * 32, rsw = (zrow >> 2) & 1;
+                    for (int part = part_lo; part < part_hi; ++part)
+                    for (int kyb = 0; kyb < g.m2; kyb += 32) {          // up to 8 x4 loads in flight, one wait
+                        uint32_t r[8][4];
 #pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                if (kyb + 4 * c < g.m2)
-                                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                                 : "=r"(r[c][0]), "=r"(r[c][1]), "=r"(r[c][2]), "=r"(r[c][3])
-                                                 : "r"(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + kyb + 4 * c)));
-                            tmem_ld_wait();
-                            if (warp == 8) TRACE(1, 5);
-                            if (row < g.H) {
+                        for (int c = 0; c < 8; ++c)
+                            if (kyb + 4 * c < g.m2)
+                                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(r[c][0]), "=r"(r[c][1]), "=r"(r[c][2]), "=r"(r[c][3])
+                                             : "r"(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + kyb + 4 * c)));
+                        tmem_ld_wait();
+                        if (warp == 8) TRACE(1, 5);
+                        if (row < g.H) {
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) {
-                                    const int ky0 = kyb + 4 * c;
-                                    if (ky0 < g.m2) {
-                                        const float4 v = make_float4(__uint_as_float(r[c][0]) * s_scale[ky0],
-                                                                     __uint_as_float(r[c][1]) * s_scale[ky0 + 1],
-                                                                     __uint_as_float(r[c][2]) * s_scale[ky0 + 2],
-                                                                     __uint_as_float(r[c][3]) * s_scale[ky0 + 3]);
-                                        const uint32_t off = kslab_sw32_off(zrow, part * g.m2 + ky0, 128);
-                                        if (NSPLIT == 3) {
-                                            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                                            *reinterpret_cast<float4*>(zt + off) = h;
-                                            *reinterpret_cast<float4*>(zt + g.zt_one + off) =
-                                                make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                                        } else {
-                                            *reinterpret_cast<float4*>(zt + off) = v;
-                                        }
+                            for (int c = 0; c < 8; ++c) {
+                                const int ky0 = kyb + 4 * c;
+                                if (ky0 < g.m2) {
+                                    const float4 v = make_float4(__uint_as_float(r[c][0]), __uint_as_float(r[c][1]),
+                                                                 __uint_as_float(r[c][2]), __uint_as_float(r[c][3]));
+                                    const int k = part * g.m2 + ky0;          // multiple of 4: one 16-byte chunk of a slab row
+                                    const uint32_t off = (uint32_t)(k >> 3) * (128 * 32) + rbase + ((((k >> 2) & 1) ^ rsw) << 4);
+                                    if (NSPLIT == 3) {
+                                        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                                        *reinterpret_cast<float4*>(zt + off) = h;
+                                        *reinterpret_cast<float4*>(zt + g.zt_one + off) =
+                                            make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                                    } else {
+                                        *reinterpret_cast<float4*>(zt + off) = v;
                                     }
                                 }
                             }
@@ -311,9 +322,10 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     } else if (warp >= 10) {
         // ================================ epilogue ================================
         // epi_warps / 4 warps per TMEM lane quarter, each taking an equal share of the W columns in 16-column passes
-        const int q = warp & 3, chunk = (warp - 10) >> 2, n_chunks = g.epi_warps >> 2;
+        const int ew = warp - 10;
+        const int q = warp & 3, chunk = ew >> 2, n_chunks = g.epi_warps >> 2;
         const int row = q * 32 + lane;
-        float4* sc = reinterpret_cast<float4*>(smem + g.off_scratch) + (warp - 10) * 128;
+        float4* sc = reinterpret_cast<float4*>(smem + g.off_scratch) + ew * 128;
         const int c_lo = chunk * (g.W / n_chunks), c_hi = c_lo + g.W / n_chunks;
         int nE = 0;
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
@@ -324,50 +336,57 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 const size_t gofs = (tile_row0 + row) * g.W;
                 const size_t wofs = (tile_row0 + q * 32) * g.W;              // first row of this warp
                 const uint32_t ta = tmem_addr(tmem, q * 32, d2_col + db * g.W);
-                // the addend chunk is fetched before the accumulator is ready, so DRAM latency hides behind the wait
-                float4 a_nxt[4];
+                // the first addend chunk is fetched before the accumulator is ready, so DRAM latency hides behind the wait
+                float4 a4[4];
                 auto fetch = [&](int c) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        a_nxt[k] = addend ? *reinterpret_cast<const float4*>(addend + gofs + c + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a4[k] = addend ? __ldg(reinterpret_cast<const float4*>(addend + gofs + c + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 };
                 fetch(c_lo);
                 wait_t(&bar_d2_full[db], (nE >> 1) & 1, w2);
-                if (warp == 10) TRACE(2, 1);
-                if (warp == 10 + g.epi_warps - 1) TRACE(4, 1);
+                if (ew == 0) TRACE(2, 1);
+                if (ew == g.epi_warps - 1) TRACE(4, 1);
                 tc_fence_after_sync();
                 for (int c = c_lo; c < c_hi; c += 16) {
                     float v[16];
+#ifdef PNO_TRACE
                     long long tq = clock64();
+#endif
                     tmem_ld16(ta + c, v);
-                    float4 a_cur[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) a_cur[k] = a_nxt[k];
-                    if (c + 16 < c_hi) fetch(c + 16);
+                    if (c != c_lo) fetch(c);
                     tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        v[4 * k] += a_cur[k].x; v[4 * k + 1] += a_cur[k].y; v[4 * k + 2] += a_cur[k].z; v[4 * k + 3] += a_cur[k].w;
+                        v[4 * k] += a4[k].x; v[4 * k + 1] += a4[k].y; v[4 * k + 2] += a4[k].z; v[4 * k + 3] += a4[k].w;
                     }
+#ifdef PNO_TRACE
                     { const long long t2 = clock64(); w0 += t2 - tq; tq = t2; }
+#endif
                     if (pre_act) warp_store_rows16(sc, lane, v, pre_act + wofs + c, g.W);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = act_apply_fast(v[k], g.act);
+                    for (int k = 0; k < 16; ++k) v[k] = act_apply_fast(v[k], ACT);
+#ifdef PNO_TRACE
                     { const long long t2 = clock64(); w1 += t2 - tq; tq = t2; }
+#endif
                     warp_store_rows16(sc, lane, v, y + wofs + c, g.W);
+#ifdef PNO_TRACE
                     { const long long t2 = clock64(); w3 += t2 - tq; tq = t2; }
+#endif
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bar_d2_empty[db]);
-                if (warp == 10) TRACE(2, 2);
-                if (warp == 10 + g.epi_warps - 1) TRACE(4, 2);
+                if (ew == 0) TRACE(2, 2);
+                if (ew == g.epi_warps - 1) TRACE(4, 2);
             }
         }
     }
-    if (g.dbg && lane == 0 && (warp == 1 || warp == 6 || warp == 10)) {
-        long long* d = g.dbg + ((size_t)blockIdx.x * 3 + (warp == 1 ? 0 : warp == 6 ? 1 : 2)) * 7;
-        d[0] = w0; d[1] = w1; d[2] = w2; d[3] = w3; d[4] = clock64() - t_start; d[5] = w4; d[6] = w5;
+#ifdef PNO_TRACE
+    if (g.dbg && lane == 0 && (warp == 1 || warp == 8 || warp == 10)) {
+        long long* d = g.dbg + ((size_t)blockIdx.x * 3 + (warp == 1 ? 0 : warp == 8 ? 1 : 2)) * 7;
+        d[0] = w0; d[1] = w1; d[2] = w2; d[3] = w3; d[4] = clock64() - trace_t0; d[5] = w4; d[6] = w5;
     }
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
@@ -385,8 +404,9 @@ inline float tf32_round_h(double v) {
 int pad_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct InvTables {
-    float* tabA;   // (C hi, C lo, S hi, S lo) [H][K1], dead kx2 columns zeroed
-    float* tabB;   // (hi, lo) [W][K2]
+    float* tabA;      // shared-memory image: (C hi, C lo, S hi, S lo), each S1 slabs of [H rows x 32 B], dead kx2 columns zeroed
+    float* tabB;      // shared-memory image: (hi, lo), each S2 slabs of [W rows x 32 B]; entries carry c_ky / (H W)
+    float* tabB_adj;  // same without the scale (adjoint != 0)
 };
 
 }  // namespace
@@ -397,7 +417,8 @@ static int inv_tables_get(const pno_plan* cp, InvTables** out) {
     if (p->tc_tables_inv) { *out = static_cast<InvTables*>(p->tc_tables_inv); return PNO_OK; }
     const int H = p->H, W = p->W, m1 = p->m1, m2 = p->m2, K1 = 2 * m1, K2 = 2 * m2;
     const double two_pi = 6.283185307179586476925286766559;
-    std::vector<float> a((size_t)4 * H * K1, 0.f), bt((size_t)2 * W * K2, 0.f);
+    const size_t oneA = (size_t)(K1 / 8) * H * 8, oneB = (size_t)(K2 / 8) * W * 8;       // floats per table image
+    std::vector<float> a(4 * oneA, 0.f), bt(2 * oneB, 0.f), bta(2 * oneB, 0.f);
     for (int h = 0; h < H; ++h)
         for (int r = 0; r < K1; ++r) {
             const int kx = r < m1 ? r : H - 2 * m1 + r;
@@ -405,24 +426,29 @@ static int inv_tables_get(const pno_plan* cp, InvTables** out) {
             const double ang = two_pi * (double)((long long)kx * h % H) / H;
             const double c = alive ? cos(ang) : 0.0, s = alive ? sin(ang) : 0.0;
             const float ch = tf32_round_h(c), sh = tf32_round_h(s);
-            const size_t e = (size_t)h * K1 + r, one = (size_t)H * K1;
-            a[0 * one + e] = ch; a[1 * one + e] = tf32_round_h(c - (double)ch);
-            a[2 * one + e] = sh; a[3 * one + e] = tf32_round_h(s - (double)sh);
+            const size_t e = sm100::kslab_sw32_off(h, r, H) / 4;
+            a[0 * oneA + e] = ch; a[1 * oneA + e] = tf32_round_h(c - (double)ch);
+            a[2 * oneA + e] = sh; a[3 * oneA + e] = tf32_round_h(s - (double)sh);
         }
     for (int w = 0; w < W; ++w)
         for (int k = 0; k < K2; ++k) {
             const int ky = k % m2;
+            const bool self_conj = ky == 0 || (W % 2 == 0 && ky == W / 2);
+            const double scale = (self_conj ? 1.0 : 2.0) / ((double)H * W);      // c_ky / (H W): the irfft2 weights
             const double ang = two_pi * (double)((long long)ky * w % W) / W;
             const double v = k < m2 ? cos(ang) : -sin(ang);
-            const float hi = tf32_round_h(v);
-            bt[(size_t)w * K2 + k] = hi;
-            bt[(size_t)W * K2 + (size_t)w * K2 + k] = tf32_round_h(v - (double)hi);
+            const size_t e = sm100::kslab_sw32_off(w, k, W) / 4;
+            const float hi = tf32_round_h(v * scale), hia = tf32_round_h(v);
+            bt[e] = hi; bt[oneB + e] = tf32_round_h(v * scale - (double)hi);
+            bta[e] = hia; bta[oneB + e] = tf32_round_h(v - (double)hia);
         }
     InvTables* t = new InvTables();
     PNO_CUDA(cudaMalloc(&t->tabA, a.size() * 4));
     PNO_CUDA(cudaMalloc(&t->tabB, bt.size() * 4));
+    PNO_CUDA(cudaMalloc(&t->tabB_adj, bta.size() * 4));
     PNO_CUDA(cudaMemcpy(t->tabA, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
     PNO_CUDA(cudaMemcpy(t->tabB, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice));
+    PNO_CUDA(cudaMemcpy(t->tabB_adj, bta.data(), bta.size() * 4, cudaMemcpyHostToDevice));
     p->tc_tables_inv = t;
     *out = t;
     return PNO_OK;
@@ -433,6 +459,7 @@ void tc_plan_release_inv(pno_plan* p) {
     InvTables* t = static_cast<InvTables*>(p->tc_tables_inv);
     cudaFree(t->tabA);
     cudaFree(t->tabB);
+    cudaFree(t->tabB_adj);
     delete t;
     p->tc_tables_inv = nullptr;
 }
@@ -466,7 +493,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
         g.off_scratch = g.off_zt + 2 * g.zt_buf;
         for (g.epi_warps = (W % 64 == 0) ? 16 : 8; g.epi_warps >= 8; g.epi_warps -= 8) {
             g.smem_bytes = g.off_scratch + g.epi_warps * 2048 + 1024;
-            if (g.smem_bytes <= 226 * 1024) { ok = true; break; }     // 227 KB minus the static barriers / scale table
+            if (g.smem_bytes <= 226 * 1024) { ok = true; break; }     // 227 KB minus the static barriers
         }
         if (ok) break;
     }
@@ -480,20 +507,28 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     InvTables* t = nullptr;
     int rc = inv_tables_get(p, &t);
     if (rc) return rc;
+    const float* tabB = adjoint ? t->tabB_adj : t->tabB;
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = g.n_groups < sms ? g.n_groups : sms;
-#define PNO_LAUNCH_INV(NS, GG)                                                                                          \
-    do {                                                                                                               \
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<NS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes)); \
-        k_tc_dft_inv<NS, GG><<<grid, 320 + g.epi_warps * 32, g.smem_bytes, st>>>(g, t->tabA, t->tabB, p->coef, yr, yi, addend, y,   \
-                                                                    pre_act);                                          \
+#define PNO_LAUNCH_INV(NS, GG, AC)                                                                                         \
+    do {                                                                                                                   \
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<NS, GG, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes)); \
+        k_tc_dft_inv<NS, GG, AC><<<grid, kFront + g.epi_warps * 32, g.smem_bytes, st>>>(g, t->tabA, tabB, p->coef, yr, yi, \
+                                                                                        addend, y, pre_act);               \
     } while (0)
-    if (x3 && g.G == 8) PNO_LAUNCH_INV(3, 8);
-    else if (x3) PNO_LAUNCH_INV(3, 4);
-    else if (g.G == 8) PNO_LAUNCH_INV(1, 8);
-    else PNO_LAUNCH_INV(1, 4);
+#define PNO_LAUNCH_INV_ACT(NS, GG)                           \
+    do {                                                     \
+        if (act == PNO_ACT_GELU) PNO_LAUNCH_INV(NS, GG, PNO_ACT_GELU);      \
+        else if (act == PNO_ACT_RELU) PNO_LAUNCH_INV(NS, GG, PNO_ACT_RELU); \
+        else PNO_LAUNCH_INV(NS, GG, PNO_ACT_NONE);           \
+    } while (0)
+    if (x3 && g.G == 8) PNO_LAUNCH_INV_ACT(3, 8);
+    else if (x3) PNO_LAUNCH_INV_ACT(3, 4);
+    else if (g.G == 8) PNO_LAUNCH_INV_ACT(1, 8);
+    else PNO_LAUNCH_INV_ACT(1, 4);
+#undef PNO_LAUNCH_INV_ACT
 #undef PNO_LAUNCH_INV
     PNO_LAUNCH_CHECK();
     return PNO_OK;

@@ -108,7 +108,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+            const uint32_t el = lane == 0;
             const uint32_t idesc = make_idesc(FMT_TF32, TM, TN, MAJOR_K, MAJOR_MN);
             const uint32_t ahi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
             const uint32_t bhi = sdesc_base(0, TK * 128, 512, SWIZZLE_128B_BASE32B).hi;
@@ -130,23 +131,23 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
                         const uint32_t ao = ks * 2, bo = ks * 64;    // 32 B / 1024 B per K step
-                        mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag);
+                        mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
                         if (NSPLIT == 3) {
-                            mma_tf32(d_m, am + lo + ao, ahi, xb + bo, bhi, idesc, 1u);
-                            mma_tf32(d_m, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u);
+                            mma_tf32(d_m, am + lo + ao, ahi, xb + bo, bhi, idesc, 1u, el);
+                            mma_tf32(d_m, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u, el);
                         }
                         if (NOISY) {
-                            mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag);
+                            mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
                             if (NSPLIT == 3) {
-                                mma_tf32(d_l, al + lo + ao, ahi, xb + bo, bhi, idesc, 1u);
-                                mma_tf32(d_l, al + ao, ahi, xb + lo + bo, bhi, idesc, 1u);
+                                mma_tf32(d_l, al + lo + ao, ahi, xb + bo, bhi, idesc, 1u, el);
+                                mma_tf32(d_l, al + ao, ahi, xb + lo + bo, bhi, idesc, 1u, el);
                             }
                         }
                     }
-                    mma_commit(&bar_empty[stage]);       // frees the stage when these MMAs have read it
+                    mma_commit(&bar_empty[stage], el);       // frees the stage when these MMAs have read it
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&bar_tfull[acc]);
+                mma_commit(&bar_tfull[acc], el);
             }
         }
     } else if (warp < 6) {
@@ -206,7 +207,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float lv = l[4 * k + j] + bias_l;
-                            const float s_raw = __expf(0.5f * fminf(fmaxf(lv, -10.f), 10.f));
+                            const float s_raw = fast_ex2(0.72134752044448170f * fminf(fmaxf(lv, -10.f), 10.f));
                             const float s = fmaxf(s_raw, 1e-6f);
                             v[4 * k + j] = fmaf(z[j], s, v[4 * k + j] + bias_m);
                             if (DLV) l[4 * k + j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;

@@ -90,7 +90,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+            const uint32_t el = lane == 0;
             const uint32_t idesc = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K);
             const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K, 1, 0);
             const uint32_t dhi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
@@ -113,25 +114,25 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t first = (kb | ks) ? 1u : 0u;
                         const uint32_t o = ks * 2;              // 32 bytes per K step
-                        mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first);
-                        mma_tf32(d_re, wim + o, dhi, xim + o, dhi, idesc_n, 1u);
-                        mma_tf32(d_im, wim + o, dhi, xre + o, dhi, idesc, first);
-                        mma_tf32(d_im, wre + o, dhi, xim + o, dhi, idesc, 1u);
+                        mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first, el);
+                        mma_tf32(d_re, wim + o, dhi, xim + o, dhi, idesc_n, 1u, el);
+                        mma_tf32(d_im, wim + o, dhi, xre + o, dhi, idesc, first, el);
+                        mma_tf32(d_im, wre + o, dhi, xim + o, dhi, idesc, 1u, el);
                         if (NSPLIT == 3) {
-                            mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u);
-                            mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u);
-                            mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, idesc_n, 1u);
-                            mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, idesc_n, 1u);
-                            mma_tf32(d_im, wim_l + o, dhi, xre + o, dhi, idesc, 1u);
-                            mma_tf32(d_im, wim + o, dhi, xre_l + o, dhi, idesc, 1u);
-                            mma_tf32(d_im, wre_l + o, dhi, xim + o, dhi, idesc, 1u);
-                            mma_tf32(d_im, wre + o, dhi, xim_l + o, dhi, idesc, 1u);
+                            mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u, el);
+                            mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
+                            mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, idesc_n, 1u, el);
+                            mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, idesc_n, 1u, el);
+                            mma_tf32(d_im, wim_l + o, dhi, xre + o, dhi, idesc, 1u, el);
+                            mma_tf32(d_im, wim + o, dhi, xre_l + o, dhi, idesc, 1u, el);
+                            mma_tf32(d_im, wre_l + o, dhi, xim + o, dhi, idesc, 1u, el);
+                            mma_tf32(d_im, wre + o, dhi, xim_l + o, dhi, idesc, 1u, el);
                         }
                     }
-                    mma_commit(&bar_empty[stage]);
+                    mma_commit(&bar_empty[stage], el);
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&bar_tfull[acc]);
+                mma_commit(&bar_tfull[acc], el);
             }
         }
     } else if (warp < 2 + kGen / 32) {
@@ -182,7 +183,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
                     if (SAMPLED) {
                         const float4 z = philox_quad_normals(g.key, quad + (uint64_t)j * g.Cop);
-                        const float s0 = __expf(0.5f * l2.x), s1 = __expf(0.5f * l2.y);
+                        const float s0 = fast_ex2(0.72134752044448170f * l2.x), s1 = fast_ex2(0.72134752044448170f * l2.y);   // exp(lv/2)
                         wr[0][j] = fmaf(s0, z.x, wr[0][j]); wi[0][j] = fmaf(s0, z.y, wi[0][j]);
                         wr[1][j] = fmaf(s1, z.z, wr[1][j]); wi[1][j] = fmaf(s1, z.w, wi[1][j]);
                     }

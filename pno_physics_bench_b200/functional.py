@@ -83,7 +83,7 @@ def _check_x(x, ci):
 # ----------------------------------------------------------------------------------------------------------------------
 class _SpectralConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w1, w2, lv1, lv2, addend, seed, sample_idx, site, act, engine):
+    def forward(ctx, x, w1, w2, lv1, lv2, addend, seed, sample_idx, site, act, engine, grad_mode):
         lib = _lib.load()
         ci, co, m1, m2 = w1.shape
         _check_x(x, ci)
@@ -96,7 +96,7 @@ class _SpectralConvFn(torch.autograd.Function):
         l1 = native_spectral(lv1.detach())[0] if sampled else None
         l2 = native_spectral(lv2.detach())[0] if sampled else None
         add = addend.contiguous() if addend is not None else None
-        needs_grad = any(ctx.needs_input_grad)
+        needs_grad = grad_mode and any(ctx.needs_input_grad)   # under no_grad nothing is produced or kept for backward
         y = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
         pre = torch.empty_like(y) if (needs_grad and act != _lib.ACT_NONE) else None
         ws = torch.empty(lib.pno_spectral_workspace_bytes(plan, b, ci, co) // 4, dtype=torch.float32, device=x.device)
@@ -141,13 +141,14 @@ class _SpectralConvFn(torch.autograd.Function):
 
         return (dx, logical(dmu1) if ctx.needs_input_grad[1] else None, logical(dmu2) if ctx.needs_input_grad[2] else None,
                 logical(dlv1) if ctx.needs_input_grad[3] else None, logical(dlv2) if ctx.needs_input_grad[4] else None,
-                gz if (has_add and ctx.needs_input_grad[5]) else None, None, None, None, None, None)
+                gz if (has_add and ctx.needs_input_grad[5]) else None, None, None, None, None, None, None)
 
 
 def spectral_conv(x, w1, w2, lv1=None, lv2=None, *, addend=None, act=_lib.ACT_NONE, seed=0, sample_idx=0, site=0,
                   engine=_lib.ENGINE_FP32):
     """act(spectral(x; W) + addend) with W = mu (lv None) or mu + exp(lv/2)*eps(seed, sample_idx, site)."""
-    return _SpectralConvFn.apply(x, w1, w2, lv1, lv2, addend, int(seed), int(sample_idx), int(site), int(act), int(engine))
+    return _SpectralConvFn.apply(x, w1, w2, lv1, lv2, addend, int(seed), int(sample_idx), int(site), int(act), int(engine),
+                                  torch.is_grad_enabled())
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -155,7 +156,7 @@ def spectral_conv(x, w1, w2, lv1=None, lv2=None, *, addend=None, act=_lib.ACT_NO
 # ----------------------------------------------------------------------------------------------------------------------
 class _LocalFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wm, bm, wl, bl, seed, sample_idx, site, batch_offset, engine):
+    def forward(ctx, x, wm, bm, wl, bl, seed, sample_idx, site, batch_offset, engine, grad_mode):
         lib = _lib.load()
         _lib.require_cuda(x, "input")
         x = x.contiguous()
@@ -164,7 +165,7 @@ class _LocalFn(torch.autograd.Function):
         co = wm.shape[0]
         noisy = wl is not None
         out = torch.empty((b, co) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
-        needs_grad = any(ctx.needs_input_grad)
+        needs_grad = grad_mode and any(ctx.needs_input_grad)   # under no_grad nothing is produced or kept for backward
         dlv = torch.empty_like(out) if (noisy and needs_grad) else None
         wm_c = wm.detach().reshape(co, ci).contiguous()
         wl_c = wl.detach().reshape(co, ci).contiguous() if noisy else None
@@ -199,12 +200,13 @@ class _LocalFn(torch.autograd.Function):
             dwl = torch.einsum("bop,bip->oi", glv, x2).reshape(wshape)
         if noisy and ni[4] and has_bl:
             dbl = glv.sum(dim=(0, 2))
-        return dx, dwm, dbm, dwl, dbl, None, None, None, None, None
+        return dx, dwm, dbm, dwl, dbl, None, None, None, None, None, None
 
 
 def local_branch(x, wm, bm, wl=None, bl=None, *, seed=0, sample_idx=0, site=0, batch_offset=0, engine=_lib.ENGINE_FP32):
     """conv1x1(x; wm, bm) [+ eps * clamp(exp(0.5*clamp(conv1x1(x; wl, bl), -10, 10)), 1e-6)]  (models.py:264-275)."""
-    return _LocalFn.apply(x, wm, bm, wl, bl, int(seed), int(sample_idx), int(site), int(batch_offset), int(engine))
+    return _LocalFn.apply(x, wm, bm, wl, bl, int(seed), int(sample_idx), int(site), int(batch_offset), int(engine),
+                          torch.is_grad_enabled())
 
 
 # ----------------------------------------------------------------------------------------------------------------------
