@@ -128,7 +128,7 @@ __device__ __forceinline__ void reparam4(const float m[4], const float l[4], con
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const float lvc = fminf(fmaxf(l[p], -10.f), 10.f);
-        const float s_raw = expf(0.5f * lvc);
+        const float s_raw = fast_ex2(0.72134752044448170f * lvc);      // exp(lv/2), one MUFU
         const float s = fmaxf(s_raw, 1e-6f);
         v[p] = fmaf(z[p], s, m[p]);
         d[p] = ((l[p] >= -10.f) && (l[p] <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[p] * s : 0.f;
@@ -138,16 +138,16 @@ __device__ __forceinline__ void reparam4(const float m[4], const float l[4], con
 // Lift (models.py:288-290): Ci <= 8 input channels.  One thread = 4 consecutive pixels x a chunk of output channels; the
 // kernel is a pure streaming write of out (and d out / d lv).   grid (ceil(HW/4/256), ceil(Co/kLiftChunk), B), HW % 4 == 0
 constexpr int kLiftChunk = 32;
-template <bool kNoise>
+template <bool kNoise, int CIM>          // CIM: compile-time bound on Ci (4 or 8) so that the FMA loop has no dead iterations
 __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restrict__ x, int Ci, int Co, int HW,
                                                             const float* __restrict__ Wm, const float* __restrict__ bm,
                                                             const float* __restrict__ Wl, const float* __restrict__ bl,
                                                             PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
                                                             float* __restrict__ dout_dlv) {
-    __shared__ float swm[kLiftChunk][8], swl[kLiftChunk][8], sbm[kLiftChunk], sbl[kLiftChunk];
+    __shared__ float swm[kLiftChunk][CIM], swl[kLiftChunk][CIM], sbm[kLiftChunk], sbl[kLiftChunk];
     const int o_base = blockIdx.y * kLiftChunk, b = blockIdx.z;
-    for (int e = threadIdx.x; e < kLiftChunk * 8; e += kThreads) {
-        const int ol = e >> 3, i = e & 7, o = o_base + ol;
+    for (int e = threadIdx.x; e < kLiftChunk * CIM; e += kThreads) {
+        const int ol = e / CIM, i = e % CIM, o = o_base + ol;
         const bool ok = o < Co && i < Ci;
         swm[ol][i] = ok ? Wm[(size_t)o * Ci + i] : 0.f;
         swl[ol][i] = (ok && kNoise) ? Wl[(size_t)o * Ci + i] : 0.f;
@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restr
     __syncthreads();
     const int p0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
     if (p0 >= HW) return;
-    float xv[8][4];
+    float xv[CIM][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CIM; ++i) {
         if (i < Ci) {
             const float4 t = *reinterpret_cast<const float4*>(x + ((size_t)b * Ci + i) * HW + p0);
             xv[i][0] = t.x; xv[i][1] = t.y; xv[i][2] = t.z; xv[i][3] = t.w;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restr
         const int o = o_base + ol;
         float m[4] = {sbm[ol], sbm[ol], sbm[ol], sbm[ol]}, l[4] = {sbl[ol], sbl[ol], sbl[ol], sbl[ol]};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < CIM; ++i) {
             const float wm = swm[ol][i], wl = swl[ol][i];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
@@ -193,40 +193,71 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restr
     }
 }
 
-// Projection (models.py:309-314): Co <= 4 output channels.  One thread = 4 consecutive pixels, streaming read of x.
-// grid (ceil(HW/4/256), B), HW % 4 == 0
+// Projection (models.py:309-314): Co <= 4 output channels: a streaming read of x.  Block = 64 pixel quads x 4 channel
+// groups (each thread reduces a quarter of the input channels with 8 independent 16-byte loads in flight), partial sums
+// are combined through shared memory and the channel-group-0 threads run the reparameterisation epilogue.
+// grid (ceil(HW/4/64), B), HW % 4 == 0
+constexpr int kProjQuads = 64, kProjGroups = 4;
 template <bool kNoise>
 __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __restrict__ x, int Ci, int Co, int HW,
                                                              const float* __restrict__ Wm, const float* __restrict__ bm,
                                                              const float* __restrict__ Wl, const float* __restrict__ bl,
                                                              PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
                                                              float* __restrict__ dout_dlv) {
-    extern __shared__ float sw[];          // [2][Co][Ci]
+    extern __shared__ float sw[];          // [2][Co][Ci] weights, then [groups-1][quads][2*4*4] partial sums
+    float* red = sw + 2 * Co * Ci;
     const int b = blockIdx.y;
     for (int e = threadIdx.x; e < Co * Ci; e += kThreads) {
         sw[e] = Wm[e];
         sw[Co * Ci + e] = kNoise ? Wl[e] : 0.f;
     }
     __syncthreads();
-    const int p0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
-    if (p0 >= HW) return;
+    const int quad = threadIdx.x % kProjQuads, grp = threadIdx.x / kProjQuads;
+    const int p0 = (blockIdx.x * kProjQuads + quad) * 4;
+    const bool live = p0 < HW;
     float m[4][4] = {}, l[4][4] = {};
-    const float* xb = x + (size_t)b * Ci * HW + p0;
+    if (live) {
+        const int per = (Ci + kProjGroups - 1) / kProjGroups;
+        const int i0 = grp * per, i1 = min(Ci, i0 + per);
+        const float* xb = x + (size_t)b * Ci * HW + p0;
 #pragma unroll 8
-    for (int i = 0; i < Ci; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(xb + (size_t)i * HW);
-        const float xv[4] = {t.x, t.y, t.z, t.w};
+        for (int i = i0; i < i1; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(xb + (size_t)i * HW));
+            const float xv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            if (o < Co) {
-                const float wm = sw[o * Ci + i], wl = sw[(Co + o) * Ci + i];
+            for (int o = 0; o < 4; ++o) {
+                if (o < Co) {
+                    const float wm = sw[o * Ci + i], wl = sw[(Co + o) * Ci + i];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    m[o][p] = fmaf(wm, xv[p], m[o][p]);
-                    if (kNoise) l[o][p] = fmaf(wl, xv[p], l[o][p]);
+                    for (int p = 0; p < 4; ++p) {
+                        m[o][p] = fmaf(wm, xv[p], m[o][p]);
+                        if (kNoise) l[o][p] = fmaf(wl, xv[p], l[o][p]);
+                    }
                 }
             }
         }
+    }
+    if (grp > 0) {
+        float* r = red + ((size_t)(grp - 1) * kProjQuads + quad) * 32;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                r[o * 4 + p] = m[o][p];
+                r[16 + o * 4 + p] = l[o][p];
+            }
+    }
+    __syncthreads();
+    if (grp > 0 || !live) return;
+    for (int gg = 0; gg < kProjGroups - 1; ++gg) {
+        const float* r = red + ((size_t)gg * kProjQuads + quad) * 32;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                m[o][p] += r[o * 4 + p];
+                l[o][p] += r[16 + o * 4 + p];
+            }
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -255,14 +286,20 @@ int simt_local_fwd(const float* x, int B, int Ci, int Co, int HW, const float* W
                                              reinterpret_cast<uintptr_t>(dout_dlv)) & 15) == 0;
     if (aligned && Ci <= 8) {            // lift-shaped: streaming write
         dim3 g((HW / 4 + kThreads - 1) / kThreads, (Co + kLiftChunk - 1) / kLiftChunk, B);
-        if (Wl) k_local_thin_in<true><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
-        else k_local_thin_in<false><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        if (Ci <= 4) {
+            if (Wl) k_local_thin_in<true, 4><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+            else k_local_thin_in<false, 4><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        } else {
+            if (Wl) k_local_thin_in<true, 8><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+            else k_local_thin_in<false, 8><<<g, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+        }
         PNO_LAUNCH_CHECK();
         return PNO_OK;
     }
-    if (aligned && Co <= 4 && (size_t)2 * Co * Ci * 4 <= 48 * 1024) {   // projection-shaped: streaming read
-        dim3 g((HW / 4 + kThreads - 1) / kThreads, B);
-        const size_t smem = (size_t)2 * Co * Ci * 4;
+    const size_t proj_smem = ((size_t)2 * Co * Ci + (size_t)(kProjGroups - 1) * kProjQuads * 32) * 4;
+    if (aligned && Co <= 4 && proj_smem <= 48 * 1024) {   // projection-shaped: streaming read
+        dim3 g((HW / 4 + kProjQuads - 1) / kProjQuads, B);
+        const size_t smem = proj_smem;
         if (Wl) k_local_thin_out<true><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
         else k_local_thin_out<false><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
         PNO_LAUNCH_CHECK();

@@ -318,3 +318,41 @@ def test_trainer_step_matches_oracle():
         assert rel_l2(losses["kl"], ref["kl"]) < 1e-6
     for k, v in model.state_dict().items():
         assert rel_l2(v, p[k]) < 2e-5, k
+
+
+def test_mc_sample_sharding_is_invariant():
+    """SURVEY.md 8(e) / P9 on one GPU: the moments of the sample ranges two ranks would draw (GLOBAL sample indices), merged
+    the way the all-reduce merges them, give the unsharded predict_with_uncertainty result."""
+    from pno_physics_bench_b200 import distributed as D
+    torch.manual_seed(3)
+    model = pno.ProbabilisticNeuralOperator(input_dim=3, hidden_dim=16, num_layers=2, modes=4).to(DEV)
+    x = torch.randn(3, 3, 16, 16, device=DEV)
+    S, seed = 7, 4242
+    mean, std = model.predict_with_uncertainty(x, num_samples=S, seed=seed)
+    model.train()
+    s1 = torch.zeros(3, 1, 16, 16, dtype=torch.float64, device=DEV)
+    s2 = torch.zeros_like(s1)
+    with torch.no_grad():
+        for rank in range(2):
+            r1, r2 = torch.zeros_like(s1), torch.zeros_like(s1)
+            first, count = D.shard_range(S, rank, 2)
+            for s in range(first, first + count):
+                with pno.noise_scope(seed, s, 0):
+                    F_.mc_accumulate(model(x, sample=True), r1, r2)
+            s1 += r1
+            s2 += r2
+    mean2, std2 = F_.mc_finalize(s1, s2, S)
+    assert rel_l2(mean2, mean) < 1e-6 and rel_l2(std2, std) < 1e-6
+
+
+def test_batch_sharding_draws_the_same_activation_noise():
+    """Data-parallel invariance (P11): a batch shard run with its GLOBAL batch offset reproduces the rows of the full batch."""
+    torch.manual_seed(5)
+    model = pno.ProbabilisticNeuralOperator(input_dim=3, hidden_dim=16, num_layers=2, modes=4).to(DEV).train()
+    x = torch.randn(4, 3, 16, 16, device=DEV)
+    with torch.no_grad():
+        with pno.noise_scope(11, 2, 0):
+            full = model(x, sample=True)
+        with pno.noise_scope(11, 2, 2):
+            tail = model(x[2:].contiguous(), sample=True)
+    assert rel_l2(tail, full[2:]) < 1e-6
