@@ -229,6 +229,20 @@ __host__ __device__ __forceinline__ uint32_t kslab_sw32_off(int r, int k, int R)
 }
 
 
+// ---- explicit shared-space accesses ----------------------------------------------------------------------------------------
+// Pointers derived from the dynamic shared-memory base are generic to the compiler (LD.E / ST.E with a window check per
+// access); the hot staging loops address shared memory by its 32-bit window offset instead (LDS / STS).
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- coalesced row stores through a per-warp shared-memory transpose ------------------------------------------------------
 // The 32x32b TMEM load gives lane r a run of consecutive columns of row (row0 + r).  Storing those runs directly makes every
 // store instruction touch 32 different lines; passing them through a conflict-free [32 rows][16 floats] scratch turns each

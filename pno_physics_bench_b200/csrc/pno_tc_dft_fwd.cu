@@ -261,14 +261,13 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
                 for (int tt = 0; tt < g.TPS * g.KB1; ++tt) {
                     mbar_wait(&bar_raw[stage], phase);
-                    float4* hi = reinterpret_cast<float4*>(smem + g.off_ring + (size_t)stage * g.stage_bytes);
-                    float4* lo = reinterpret_cast<float4*>(smem + g.off_ring + (size_t)stage * g.stage_bytes + g.x_bytes);
+                    const uint32_t hi = smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), lo = hi + g.x_bytes;
 #pragma unroll 4
                     for (int i = t; i < g.x_bytes / 16; i += 128) {
-                        const float4 v = hi[i];
+                        const float4 v = lds128(hi + 16 * i);
                         const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                        hi[i] = h;
-                        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        sts128(hi + 16 * i, h);
+                        sts128(lo + 16 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar_split[stage]);
@@ -296,7 +295,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (tb_ == 0) mbar_wait(&bar_b2_empty, (batch & 1) ^ 1);   // stage 2 of the previous batch has read B2
                 if (warp == 8) TRACE(1, 2);
                 const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p + im * g.m2);
-                unsigned char* dst0 = smem + g.off_b2 + im * NT * g.b2_one + col_off;
+                const uint32_t dst0 = smem_u32(smem + g.off_b2) + im * NT * g.b2_one + col_off;
                 const int r0 = (tb_ * g.IPT + img_l) * g.m2;
                 for (int c0 = 0; c0 < g.m2; c0 += 32) {          // up to 8 x4 loads in flight, one wait
                     float v[8][4];
@@ -311,13 +310,13 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int r = r0 + c0 + 4 * u + j;
-                                unsigned char* dst = dst0 + r * 128 + ((chunk ^ (r & 7)) << 4);
+                                const uint32_t dst = dst0 + r * 128 + ((chunk ^ (r & 7)) << 4);
                                 if (NSPLIT == 3) {
                                     const float h = tf32_rn(v[u][j]);
-                                    *reinterpret_cast<float*>(dst) = h;
-                                    *reinterpret_cast<float*>(dst + g.b2_one) = v[u][j] - h;
+                                    sts32(dst, h);
+                                    sts32(dst + g.b2_one, v[u][j] - h);
                                 } else {
-                                    *reinterpret_cast<float*>(dst) = v[u][j];
+                                    sts32(dst, v[u][j]);
                                 }
                             }
                         }

@@ -232,16 +232,16 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     if (e < items) {
                         const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
                         const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-                        unsigned char* dst0 = b1 + (part ? g.b1_im : 0);
+                        const uint32_t dst0 = smem_u32(b1) + (part ? g.b1_im : 0);
 #pragma unroll
                         for (int i = 0; i < G; ++i) {
                             const uint32_t off = kslab_sw32_off(i * g.m2 + ky, kx2, g.N1);
                             if (NSPLIT == 3) {
                                 const float h = tf32_rn(v[i]);
-                                *reinterpret_cast<float*>(dst0 + off) = h;
-                                *reinterpret_cast<float*>(dst0 + g.b1_one + off) = v[i] - h;
+                                sts32(dst0 + off, h);
+                                sts32(dst0 + g.b1_one + off, v[i] - h);
                             } else {
-                                *reinterpret_cast<float*>(dst0 + off) = v[i];
+                                sts32(dst0 + off, v[i]);
                             }
                         }
                     }
@@ -265,7 +265,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             wait_t(&bar_zt_empty[zb], ((nT >> 1) & 1) ^ 1, w0);
             if (warp == 8) TRACE(1, 2);
             if (t_active_warp) {
-                unsigned char* zt = smem + g.off_zt + zb * g.zt_buf;
+                const uint32_t zt = smem_u32(smem + g.off_zt) + zb * g.zt_buf;
                 for (int il = 0; il < g.IPT; ++il) {
                     const int img = j * g.IPT + il;                  // image within the group
                     const int zrow = il * g.H + row;                 // row of the stage-2 A tile (row < H here)
@@ -292,11 +292,10 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                                     const uint32_t off = (uint32_t)(k >> 3) * (128 * 32) + rbase + ((((k >> 2) & 1) ^ rsw) << 4);
                                     if (NSPLIT == 3) {
                                         const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                                        *reinterpret_cast<float4*>(zt + off) = h;
-                                        *reinterpret_cast<float4*>(zt + g.zt_one + off) =
-                                            make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                                        sts128(zt + off, h);
+                                        sts128(zt + g.zt_one + off, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
                                     } else {
-                                        *reinterpret_cast<float4*>(zt + off) = v;
+                                        sts128(zt + off, v);
                                     }
                                 }
                             }
@@ -344,6 +343,12 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                         a4[k] = addend ? __ldg(reinterpret_cast<const float4*>(addend + gofs + c + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 };
                 fetch(c_lo);
+                // ... and the chunk of the tile after this one is pulled into L2 now, so that its fetch is an L2 hit
+                if (addend) {
+                    const size_t nxt_row0 = j + 1 < g.TPG ? tile_row0 + (size_t)g.IPT * g.H
+                                                           : (size_t)(grp + gridDim.x) * G * g.H;
+                    if (nxt_row0 + 128 <= (size_t)g.B * g.C * g.H) prefetch_l2(addend + (nxt_row0 + row) * g.W + c_lo);
+                }
                 wait_t(&bar_d2_full[db], (nE >> 1) & 1, w2);
                 if (ew == 0) TRACE(2, 1);
                 if (ew == g.epi_warps - 1) TRACE(4, 1);

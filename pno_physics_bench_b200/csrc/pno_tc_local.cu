@@ -158,16 +158,15 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_raw[stage], phase);
-                    float4* hi = reinterpret_cast<float4*>(stage_ptr(stage));
-                    float4* lo = reinterpret_cast<float4*>(stage_ptr(stage) + C::kOperandBytes);
+                    const uint32_t hi = smem_u32(stage_ptr(stage)), lo = hi + C::kOperandBytes;
                     constexpr int kVec = TILE_BYTES / 16;
 #pragma unroll 4
                     for (int i = t; i < 3 * kVec; i += 128) {
                         if (!NOISY && i >= kVec && i < 2 * kVec) continue;
-                        const float4 v = hi[i];
+                        const float4 v = lds128(hi + 16 * i);
                         const float4 h = tf32_hi(v);
-                        hi[i] = h;
-                        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        sts128(hi + 16 * i, h);
+                        sts128(lo + 16 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar_split[stage]);

@@ -173,7 +173,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 const bool more = item_n < g.n_items;
                 if (more) locate(item_n, kb_n);
                 mbar_wait(&bar_raw[stage], phase);              // xhat landed => the stage is ours to fill
-                unsigned char* st = smem + (size_t)stage * g.stage_bytes;
+                const uint32_t st = smem_u32(smem + (size_t)stage * g.stage_bytes);
                 float wr[2][4], wi[2][4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -196,24 +196,23 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     const float4 vi = make_float4(wi[r2][0], wi[r2][1], wi[r2][2], wi[r2][3]);
                     if (NSPLIT == 3) {
                         const float4 hr = tf32_rn4(vr), hi = tf32_rn4(vi);
-                        *reinterpret_cast<float4*>(st + off) = hr;
-                        *reinterpret_cast<float4*>(st + W_TILE + off) = hi;
-                        *reinterpret_cast<float4*>(st + 2 * W_TILE + off) = sub4(vr, hr);
-                        *reinterpret_cast<float4*>(st + 3 * W_TILE + off) = sub4(vi, hi);
+                        sts128(st + off, hr);
+                        sts128(st + W_TILE + off, hi);
+                        sts128(st + 2 * W_TILE + off, sub4(vr, hr));
+                        sts128(st + 3 * W_TILE + off, sub4(vi, hi));
                     } else {
-                        *reinterpret_cast<float4*>(st + off) = vr;
-                        *reinterpret_cast<float4*>(st + W_TILE + off) = vi;
+                        sts128(st + off, vr);
+                        sts128(st + W_TILE + off, vi);
                     }
                 }
                 // ---- xhat tiles: hi in place, lo behind (layout-agnostic elementwise pass) ----
                 if (NSPLIT == 3) {
-                    float4* xh = reinterpret_cast<float4*>(st + x_off);
-                    float4* xl = reinterpret_cast<float4*>(st + x_off + 2 * g.x_tile);
+                    const uint32_t xh = st + x_off, xl = st + x_off + 2 * g.x_tile;
                     for (int i = t; i < 2 * g.x_tile / 16; i += kGen) {
-                        const float4 v = xh[i];
+                        const float4 v = lds128(xh + 16 * i);
                         const float4 h = tf32_rn4(v);
-                        xh[i] = h;
-                        xl[i] = sub4(v, h);
+                        sts128(xh + 16 * i, h);
+                        sts128(xl + 16 * i, sub4(v, h));
                     }
                 }
                 fence_proxy_async_smem();
