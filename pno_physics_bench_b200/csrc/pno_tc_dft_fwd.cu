@@ -8,8 +8,9 @@
 // [mode][b][c] with 32-byte contiguous channel runs.  All twiddle tables are shared-memory resident; the ring only carries x.
 //   warp 0        TMA producer (tables once, then x row tiles)
 //   warp 1        MMA issuer (both stages, software pipelined).  A tcgen05.mma costs >= ~53 cycles whatever its N
-//                 (tools/micro/mma_rate.cu), so stage 2 runs once per batch of TPB tiles with N = TPB*IPT*m2 (160 at the
-//                 headline shape) instead of once per tile with N = 48
+//                 (tools/micro/mma_rate.cu), so stage 2 runs once per batch of TPB tiles with N = TPB*IPT*m2 (80 at the
+//                 headline shape) instead of once per tile with N = 48; B2 operands and stage-2 accumulators are double
+//                 buffered per batch so that transposer, stage 2 and epilogue of consecutive batches overlap
 //   warps 2-5     tf32 hi/lo splitter of the x tiles (3xTF32 only)
 //   warps 6-13    transposer: two warps per TMEM lane quarter (cos columns / sin columns), all loads of a tile in flight
 //   warps 14-21   epilogue: two warps per lane quarter (re / im plane); only quarters holding kx2 < 2*m1 have work
@@ -39,7 +40,7 @@ struct FwdGeom {
     int TPB;        // tiles per stage-2 batch (TPS % TPB == 0)
     int n_super;    // super tiles in the launch
     int grad_scale;
-    int stages;
+    int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
     // shared-memory byte offsets (from the 1024-aligned base)
     int off_tab, off_tw, off_ring, off_b2, stage_bytes, x_bytes, tw_one, tab_one, b2_one, b2_bytes, smem_bytes;
     long long* dbg;   // optional event trace (PNO_TRACE builds)
@@ -85,8 +86,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kMaxStages = 8;
     __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_split[kMaxStages], bar_empty[kMaxStages];
-    __shared__ __align__(8) uint64_t bar_tab, bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty, bar_d2_full,
-        bar_d2_empty;
+    __shared__ __align__(8) uint64_t bar_tab, bar_d1_full[2], bar_d1_empty[2], bar_b2_full[2], bar_b2_empty[2], bar_d2_full[2],
+        bar_d2_empty[2];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,11 +102,11 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_d1_full[s], 1);
             mbar_init(&bar_d1_empty[s], 256);
+            mbar_init(&bar_b2_full[s], 256 * g.TPB);
+            mbar_init(&bar_b2_empty[s], 1);
+            mbar_init(&bar_d2_full[s], 1);
+            mbar_init(&bar_d2_empty[s], 256);
         }
-        mbar_init(&bar_b2_full, 256 * g.TPB);
-        mbar_init(&bar_b2_empty, 1);
-        mbar_init(&bar_d2_full, 1);
-        mbar_init(&bar_d2_empty, 256);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -115,7 +116,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     const uint32_t tmem = tmem_slot;
 
     constexpr int NT = NSPLIT == 3 ? 2 : 1;            // hi (+ lo) copies of every operand
-    // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then TPS/TPB slots of 2*N2p (re | im)
+    // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then nslot buffers of 2*N2p (re | im), one batch each
     const int d2_base = 2 * g.N1p;
     // tables: (C hi, [C lo], S hi, [S lo]), each KB2 k-blocks of [R2 x 128 B]; TwT (hi, [lo]) each KB1 k-blocks of [N1p x 128 B]
     unsigned char* tab = smem + g.off_tab;
@@ -170,7 +171,6 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             int stage = 0, phase = 0;
             int n1 = 0;      // stage-1 tiles issued
             int n2 = 0;      // stage-2 tiles issued
-            int nsup = 0;    // super tiles started (stage 2)
             mbar_wait(&bar_tab, 0);
 
             auto issue_stage1 = [&]() {
@@ -204,17 +204,14 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             };
 
             auto issue_stage2 = [&]() {                         // one batch of TPB tiles
-                const int slot = n2 % (g.TPS / g.TPB);          // batch within its super tile = accumulator slot
-                if (slot == 0) {                                // first write into the D2 slots of a new super tile
-                    mbar_wait(&bar_d2_empty, (nsup & 1) ^ 1);
-                    TRACE(0, 4);
-                    ++nsup;
-                }
-                mbar_wait(&bar_b2_full, n2 & 1);
+                const int slot = n2 % g.nslot, bb = n2 % g.nb2;
+                mbar_wait(&bar_d2_empty[slot], ((n2 / g.nslot) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+                TRACE(0, 4);
+                mbar_wait(&bar_b2_full[bb], (n2 / g.nb2) & 1);
                 TRACE(0, 2);
                 tc_fence_after_sync();
                 const uint32_t d_re = tmem + d2_base + slot * 2 * g.N2p, d_im = d_re + g.N2p;
-                const uint32_t bbase = sdesc_base(smem_u32(smem + g.off_b2), 16, 1024, SWIZZLE_128B).lo;
+                const uint32_t bbase = sdesc_base(smem_u32(smem + g.off_b2 + bb * g.b2_bytes), 16, 1024, SWIZZLE_128B).lo;
                 // tables (C hi, [C lo], S hi, [S lo]) at tb + {0, t1, NT*t1, (NT+1)*t1}; B2 (Rre hi, [Rre lo], Rim hi, [Rim lo]) likewise
                 for (int kb = 0; kb < g.KB2; ++kb) {
 #pragma unroll
@@ -239,8 +236,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         }
                     }
                 }
-                mma_commit(&bar_b2_empty, el);
-                if (slot == g.TPS / g.TPB - 1) mma_commit(&bar_d2_full, el);
+                mma_commit(&bar_b2_empty[bb], el);
+                mma_commit(&bar_d2_full[slot], el);
                 TRACE(0, 3);
                 ++n2;
             };
@@ -292,10 +289,11 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 mbar_wait(&bar_d1_full[buf], (n >> 1) & 1);
                 if (warp == 8) TRACE(1, 1);
                 tc_fence_after_sync();
-                if (tb_ == 0) mbar_wait(&bar_b2_empty, (batch & 1) ^ 1);   // stage 2 of the previous batch has read B2
+                const int bb = batch % g.nb2;
+                if (tb_ == 0) mbar_wait(&bar_b2_empty[bb], ((batch / g.nb2) & 1) ^ 1);   // stage 2 of the batch that used this buffer is done
                 if (warp == 8) TRACE(1, 2);
                 const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p + im * g.m2);
-                const uint32_t dst0 = smem_u32(smem + g.off_b2) + im * NT * g.b2_one + col_off;
+                const uint32_t dst0 = smem_u32(smem + g.off_b2) + bb * g.b2_bytes + im * NT * g.b2_one + col_off;
                 const int r0 = (tb_ * g.IPT + img_l) * g.m2;
                 for (int c0 = 0; c0 < g.m2; c0 += 32) {          // up to 8 x4 loads in flight, one wait
                     float v[8][4];
@@ -325,61 +323,64 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 tc_fence_before_sync();
                 mbar_arrive(&bar_d1_empty[buf]);
                 fence_proxy_async_smem();
-                mbar_arrive(&bar_b2_full);
+                mbar_arrive(&bar_b2_full[bb]);
                 if (warp == 8) TRACE(1, 4);
             }
         }
     } else {
         // ================================ epilogue ================================
-        // lanes kx2 < 2*m1 of the D2 slots hold Xre / Xim of GS = TPS*IPT images; warp = (lane quarter, re / im plane)
+        // lanes kx2 < 2*m1 of a D2 buffer hold Xre / Xim of one batch = GB = TPB*IPT images (consecutive channels);
+        // warp = (lane quarter, re / im plane).  The batches of a super tile are adjacent pieces of the same 32-byte runs.
         const int q = warp & 3, part = (warp - 14) >> 2;
         const int row = q * 32 + lane;
-        const int GS = g.TPS * g.IPT;                    // images (consecutive channels) per super tile
+        const int GB = g.TPB * g.IPT;
         const bool warp_active = q * 32 < 2 * g.m1;      // warp-uniform: tcgen05.ld is warp-collective
         const bool active = row < 2 * g.m1;
         float* dst_plane = part ? xi : xr;
-        int nsup = 0;
-        for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x, ++nsup) {
-            mbar_wait(&bar_d2_full, nsup & 1);
-            if (warp == 16) TRACE(2, 1);
-            tc_fence_after_sync();
-            if (warp_active) {
-                const int img0 = sup * GS;                   // first image = b*C + c0
-                const int b = img0 / g.C, c0 = img0 % g.C;
-                for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
-                    float vals[8][4];
+        const int bps = g.TPS / g.TPB;                   // batches per super tile
+        int nb = 0;
+        for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
+            for (int k = 0; k < bps; ++k, ++nb) {
+                const int slot = nb % g.nslot;
+                mbar_wait(&bar_d2_full[slot], (nb / g.nslot) & 1);
+                if (warp == 16) TRACE(2, 1);
+                tc_fence_after_sync();
+                if (warp_active) {
+                    const int img0 = (sup * bps + k) * GB;       // first image = b*C + c0
+                    const int b = img0 / g.C, c0 = img0 % g.C;
+                    const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + part * g.N2p);
+                    for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
+                        float vals[8][4];
 #pragma unroll
-                    for (int gi = 0; gi < 8; ++gi) {
-                        if (gi < GS) {
-                            const int ipb = g.TPB * g.IPT;           // images per stage-2 batch (= accumulator slot)
-                            const int slot = gi / ipb, il = gi % ipb;
-                            tmem_ld4(tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + part * g.N2p + il * g.m2 + ky0), vals[gi]);
-                        } else {
-                            vals[gi][0] = vals[gi][1] = vals[gi][2] = vals[gi][3] = 0.f;
+                        for (int gi = 0; gi < 8; ++gi) {
+                            if (gi < GB) tmem_ld4(tb0 + gi * g.m2 + ky0, vals[gi]);
+                            else vals[gi][0] = vals[gi][1] = vals[gi][2] = vals[gi][3] = 0.f;
                         }
-                    }
-                    tmem_ld_wait();
-                    if (active) {
+                        tmem_ld_wait();
+                        if (active) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int mode = row * g.m2 + ky0 + j;
-                            const float cf = g.grad_scale ? coef[mode] : 1.f;
-                            float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0;
-                            if (GS == 8) {
-                                reinterpret_cast<float4*>(dst)[0] = make_float4(vals[0][j] * cf, vals[1][j] * cf, vals[2][j] * cf, vals[3][j] * cf);
-                                reinterpret_cast<float4*>(dst)[1] = make_float4(vals[4][j] * cf, vals[5][j] * cf, vals[6][j] * cf, vals[7][j] * cf);
-                            } else {
+                            for (int j = 0; j < 4; ++j) {
+                                const int mode = row * g.m2 + ky0 + j;
+                                const float cf = g.grad_scale ? coef[mode] : 1.f;
+                                float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0;
+                                if (GB == 8) {
+                                    reinterpret_cast<float4*>(dst)[0] = make_float4(vals[0][j] * cf, vals[1][j] * cf, vals[2][j] * cf, vals[3][j] * cf);
+                                    reinterpret_cast<float4*>(dst)[1] = make_float4(vals[4][j] * cf, vals[5][j] * cf, vals[6][j] * cf, vals[7][j] * cf);
+                                } else if (GB == 4) {
+                                    reinterpret_cast<float4*>(dst)[0] = make_float4(vals[0][j] * cf, vals[1][j] * cf, vals[2][j] * cf, vals[3][j] * cf);
+                                } else {
 #pragma unroll
-                                for (int gi = 0; gi < 8; ++gi)
-                                    if (gi < GS) dst[gi] = vals[gi][j] * cf;
+                                    for (int gi = 0; gi < 8; ++gi)
+                                        if (gi < GB) dst[gi] = vals[gi][j] * cf;
+                                }
                             }
                         }
                     }
                 }
+                tc_fence_before_sync();
+                mbar_arrive(&bar_d2_empty[slot]);
+                if (warp == 16) TRACE(2, 2);
             }
-            tc_fence_before_sync();
-            mbar_arrive(&bar_d2_empty);
-            if (warp == 16) TRACE(2, 2);
         }
     }
     tc_fence_before_sync();
@@ -478,19 +479,30 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     bool fits = false;
     int want = 8 / g.IPT;
     if (want < 1) want = 1;
-    for (int ns = want; ns >= 1 && !fits; ns >>= 1) {
+    int best = -1;
+    FwdGeom bg = g;
+    for (int ns = want; ns >= 1; ns >>= 1) {
         if (C % (ns * g.IPT)) continue;
-        g.TPS = ns;
-        for (g.TPB = g.TPS; g.TPB >= 1; g.TPB >>= 1) {
-            g.N2p = pad_to(g.TPB * g.IPT * m2, 16);
-            g.b2_one = g.KB2 * g.N2p * 128;
-            g.b2_bytes = pad_to(2 * NT * g.b2_one, 1024);
-            g.off_ring = g.off_b2 + g.b2_bytes;
-            g.stages = (budget - g.off_ring) / g.stage_bytes;
-            if (g.stages > 8) g.stages = 8;
-            if (g.N2p <= 256 && g.N1p <= 256 && 2 * g.N1p + (g.TPS / g.TPB) * 2 * g.N2p <= 512 && g.stages >= 3) { fits = true; break; }
+        for (int tpb = ns; tpb >= 1; tpb >>= 1) {
+            for (int nb2 = 2; nb2 >= 1; --nb2) {
+                FwdGeom c = g;
+                c.TPS = ns; c.TPB = tpb; c.nb2 = nb2;
+                c.N2p = pad_to(tpb * g.IPT * m2, 16);
+                c.nslot = 2 * g.N1p + 4 * c.N2p <= 512 ? 2 : 1;
+                c.b2_one = g.KB2 * c.N2p * 128;
+                c.b2_bytes = pad_to(2 * NT * c.b2_one, 1024);
+                c.off_ring = g.off_b2 + nb2 * c.b2_bytes;
+                c.stages = (budget - c.off_ring) / g.stage_bytes;
+                if (c.stages > 8) c.stages = 8;
+                if (c.N2p > 256 || g.N1p > 256 || 2 * g.N1p + c.nslot * 2 * c.N2p > 512 || c.stages < 2) continue;
+                // prefer >= 16-byte output runs, then overlap (two accumulator / operand buffers), then ring depth
+                const int gb = tpb * g.IPT;
+                const int score = (gb >= 4 ? 1000 : 0) + (ns * g.IPT >= 8 ? 500 : 0) + c.nslot * 100 + nb2 * 10 + (c.stages < 4 ? c.stages : 4);
+                if (score > best) { best = score; bg = c; fits = true; }
+            }
         }
     }
+    g = bg;
     if (!fits) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: tables and operands do not fit in shared / tensor memory");
     g.n_super = B * C / (g.TPS * g.IPT);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;

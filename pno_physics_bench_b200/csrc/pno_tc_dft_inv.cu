@@ -211,6 +211,16 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
             const int img0 = grp * g.G;
             const int b = img0 / g.C, c0 = img0 % g.C;
+            // the spectrum rows of the group AFTER this one are pulled into L2 while this loader would otherwise idle, so
+            // that its 32-byte gathers are L2 hits instead of DRAM round trips
+            if (grp + (int)gridDim.x < g.n_groups) {
+                const int imgn = (grp + gridDim.x) * g.G;
+                const int bn = imgn / g.C, cn = imgn % g.C;
+                for (int e = t; e < items; e += 128) {
+                    const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
+                    prefetch_l2((part ? yi : yr) + ((size_t)(kx2 * g.m2 + ky) * g.B + bn) * g.C + cn);
+                }
+            }
             wait_t(&bar_b1_empty, (ng & 1) ^ 1, w0);
             if (warp == 2) TRACE(3, 1);
             constexpr int U = G == 8 ? 4 : 7;          // items in flight per thread (register budget: 72 with 832 threads): loads first, then the scatter
