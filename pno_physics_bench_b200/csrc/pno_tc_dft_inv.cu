@@ -36,6 +36,8 @@ struct InvGeom {
     int n_groups;
     int adjoint, act;
     int epi_warps, off_scratch;   // epilogue warps (8 or 16) and their transpose scratch (2 KB per warp)
+    int nb1, nzt, nd2;            // buffer counts: B1 operand sets, Zt operand sets, stage-2 accumulators
+    int b1_buf;                   // bytes of one B1 operand set
     int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, b1_im, zt_one, zt_buf, smem_bytes;
     long long* dbg;   // optional per-CTA wait-cycle counters (pno_debug_set_buffer)
     int dbg_mma;      // diagnostics: the issuer also waits for its own batches (serialises the pipeline)
@@ -77,19 +79,21 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
              const float* __restrict__ addend, float* __restrict__ y, float* __restrict__ pre_act) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t bar_b1_full, bar_b1_empty, bar_d1_full, bar_d1_empty;
-    __shared__ __align__(8) uint64_t bar_zt_full[2], bar_zt_empty[2], bar_d2_full[2], bar_d2_empty[2];
+    __shared__ __align__(8) uint64_t bar_b1_full[2], bar_b1_empty[2], bar_d1_full, bar_d1_empty;
+    __shared__ __align__(8) uint64_t bar_zt_full[3], bar_zt_empty[3], bar_d2_full[3], bar_d2_empty[3];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
     PNO_TRACE_DECL();
     if (threadIdx.x == 0) {
-        mbar_init(&bar_b1_full, 128);
-        mbar_init(&bar_b1_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_b1_full[s], 128);
+            mbar_init(&bar_b1_empty[s], 1);
+        }
         mbar_init(&bar_d1_full, 1);
         mbar_init(&bar_d1_empty, 128);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 3; ++s) {
             mbar_init(&bar_zt_full[s], 128);
             mbar_init(&bar_zt_empty[s], 1);
             mbar_init(&bar_d2_full[s], 1);
@@ -100,12 +104,19 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
     // twiddle tables: the plan holds them as the exact shared-memory image (slab-swizzled), so this is a straight copy
     {
+        // global images: tabA = (C hi, C lo, S hi, S lo), tabB = (hi, lo); shared: (C hi, [C lo], S hi, [S lo]) and (hi, [lo])
+        constexpr int NTc = NSPLIT == 3 ? 2 : 1;
+        const int nA = g.tabA_one / 16, nB = g.tabB_one / 16;               // float4 per table
         const float4* srcA = reinterpret_cast<const float4*>(tabA_g);
         float4* dstA = reinterpret_cast<float4*>(smem + g.off_tabA);
-        for (int e = threadIdx.x; e < g.tabA_one / 4; e += blockDim.x) dstA[e] = srcA[e];        // 4 tables x tabA_one bytes
+        for (int e = threadIdx.x; e < 2 * NTc * nA; e += blockDim.x) {
+            const int tbl = e / nA, i = e - tbl * nA;                        // destination table index
+            const int src_tbl = NTc == 2 ? tbl : 2 * tbl;                    // 1x: C hi, S hi = global tables 0 and 2
+            dstA[e] = srcA[(size_t)src_tbl * nA + i];
+        }
         const float4* srcB = reinterpret_cast<const float4*>(tabB_g);
         float4* dstB = reinterpret_cast<float4*>(smem + g.off_tabB);
-        for (int e = threadIdx.x; e < g.tabB_one / 8; e += blockDim.x) dstB[e] = srcB[e];        // 2 tables x tabB_one bytes
+        for (int e = threadIdx.x; e < NTc * nB; e += blockDim.x) dstB[e] = srcB[e];
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -136,34 +147,37 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             const uint32_t zt = sdesc_base(smem_u32(smem + g.off_zt), 16, 256, SWIZZLE_32B).lo;
             const uint32_t slabA = g.H * 2, slabB1 = g.N1 * 2, slabZ = 128 * 2, slabTB = g.W * 2;     // slab strides in 16-byte units
             const uint32_t tA1 = g.tabA_one >> 4, b1o = g.b1_one >> 4, b1i = g.b1_im >> 4;
+            constexpr uint32_t NTc = NSPLIT == 3 ? 2 : 1;      // table copies: S hi sits NTc tables after C hi
             int ng = 0, nt = 0;
             for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
-                wait_t(&bar_b1_full, ng & 1, w0);
+                const int bb = ng % g.nb1;
+                wait_t(&bar_b1_full[bb], (ng / g.nb1) & 1, w0);
                 TRACE(0, 1);
                 wait_t(&bar_d1_empty, (ng & 1) ^ 1, w1);
                 TRACE(0, 2);
                 tc_fence_after_sync();
                 const uint32_t d_re = tmem, d_im = tmem + g.N1;
-                uint32_t a = tA, b = b1;
+                uint32_t a = tA, b = b1 + bb * (g.b1_buf >> 4);
                 for (int s = 0; s < g.S1; ++s, a += slabA, b += slabB1) {
                     const uint32_t first = s ? 1u : 0u;
-                    // (C hi, C lo, S hi, S lo) at a + {0,1,2,3}*tA1;  (Yre hi, Yre lo) at b + {0, b1o}, (Yim hi, Yim lo) at b + b1i + {0, b1o}
+                    // (C hi, [C lo], S hi, [S lo]) at a + {0, tA1, NTc*tA1, (NTc+1)*tA1};  (Yre hi, [Yre lo]) at b + {0, b1o}, (Yim ..) at b + b1i + ..
+                    const uint32_t sa = a + NTc * tA1;
                     mma_tf32(d_re, a, dhi, b, dhi, id1, first, el);
-                    mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i, dhi, id1n, 1u, el);
-                    mma_tf32(d_im, a + 2 * tA1, dhi, b, dhi, id1, first, el);
+                    mma_tf32(d_re, sa, dhi, b + b1i, dhi, id1n, 1u, el);
+                    mma_tf32(d_im, sa, dhi, b, dhi, id1, first, el);
                     mma_tf32(d_im, a, dhi, b + b1i, dhi, id1, 1u, el);
                     if (NSPLIT == 3) {
                         mma_tf32(d_re, a + tA1, dhi, b, dhi, id1, 1u, el);
                         mma_tf32(d_re, a, dhi, b + b1o, dhi, id1, 1u, el);
-                        mma_tf32(d_re, a + 3 * tA1, dhi, b + b1i, dhi, id1n, 1u, el);
-                        mma_tf32(d_re, a + 2 * tA1, dhi, b + b1i + b1o, dhi, id1n, 1u, el);
-                        mma_tf32(d_im, a + 3 * tA1, dhi, b, dhi, id1, 1u, el);
-                        mma_tf32(d_im, a + 2 * tA1, dhi, b + b1o, dhi, id1, 1u, el);
+                        mma_tf32(d_re, sa + tA1, dhi, b + b1i, dhi, id1n, 1u, el);
+                        mma_tf32(d_re, sa, dhi, b + b1i + b1o, dhi, id1n, 1u, el);
+                        mma_tf32(d_im, sa + tA1, dhi, b, dhi, id1, 1u, el);
+                        mma_tf32(d_im, sa, dhi, b + b1o, dhi, id1, 1u, el);
                         mma_tf32(d_im, a + tA1, dhi, b + b1i, dhi, id1, 1u, el);
                         mma_tf32(d_im, a, dhi, b + b1i + b1o, dhi, id1, 1u, el);
                     }
                 }
-                mma_commit(&bar_b1_empty, el);
+                mma_commit(&bar_b1_empty[bb], el);
                 mma_commit(&bar_d1_full, el);
                 TRACE(0, 3);
 #ifdef PNO_TRACE
@@ -174,13 +188,13 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 }
 #endif
                 for (int j = 0; j < g.TPG; ++j, ++nt) {
-                    const int zb = nt & 1;
-                    wait_t(&bar_zt_full[zb], (nt >> 1) & 1, w2);
+                    const int zb = nt % g.nzt, db = nt % g.nd2;
+                    wait_t(&bar_zt_full[zb], (nt / g.nzt) & 1, w2);
                     TRACE(0, 4);
-                    wait_t(&bar_d2_empty[zb], ((nt >> 1) & 1) ^ 1, w3);
+                    wait_t(&bar_d2_empty[db], ((nt / g.nd2) & 1) ^ 1, w3);
                     TRACE(0, 5);
                     tc_fence_after_sync();
-                    const uint32_t d2 = tmem + d2_col + zb * g.W;
+                    const uint32_t d2 = tmem + d2_col + db * g.W;
                     uint32_t z = zt + zb * (g.zt_buf >> 4), w = tB;
                     for (int s = 0; s < g.S2; ++s, z += slabZ, w += slabTB) {
                         mma_tf32(d2, z, dhi, w, dhi, id2, s ? 1u : 0u, el);
@@ -190,12 +204,12 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                         }
                     }
                     mma_commit(&bar_zt_empty[zb], el);
-                    mma_commit(&bar_d2_full[zb], el);
+                    mma_commit(&bar_d2_full[db], el);
                     TRACE(0, 6);
 #ifdef PNO_TRACE
                     if (g.dbg_mma) {
                         const long long tq = clock64();
-                        mbar_wait(&bar_d2_full[zb], (nt >> 1) & 1);
+                        mbar_wait(&bar_d2_full[db], (nt / g.nd2) & 1);
                         w5 += clock64() - tq;
                     }
 #endif
@@ -204,10 +218,22 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         }
     } else if (is_loader) {
         // ================================ loaders: yhat -> B1 slabs ================================
-        const int t = lw * 32 + lane;
+        // Warp item = (re/im plane, block of 8 kx2, block of 4 ky); lane = (ky & 3, kx2 & 7).  A lane gathers the G channels
+        // of its mode (one 16/32-byte run) and the warp writes, per channel, 4 slab rows x 32 B = 128 contiguous bytes of B1:
+        // conflict-free, and the index arithmetic is warp-uniform except for two lane terms.
+        const int kyb_n = g.m2 >> 2, kxb_n = g.K1 >> 3;
+        const int witems = 2 * kxb_n * kyb_n;
+        const int lkx = lane & 7, lky = lane >> 3;
+        const int q4 = g.m2 >> 2;                              // rows i*m2 + ky: ((row >> 2) & 1) = (i*q4 + (ky >> 2)) & 1
         unsigned char* b1 = smem + g.off_b1;
-        const int items = 2 * g.m2 * g.K1;
         int ng = 0;
+        auto decode = [&](int w, int& part, int& kx2, int& ky) {
+            part = w / (kxb_n * kyb_n);
+            const int r = w - part * kxb_n * kyb_n;
+            const int kxb = r / kyb_n, kyb = r - kxb * kyb_n;
+            kx2 = kxb * 8 + lkx;
+            ky = kyb * 4 + lky;
+        };
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
             const int img0 = grp * g.G;
             const int b = img0 / g.C, c0 = img0 % g.C;
@@ -215,43 +241,51 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             // that its 32-byte gathers are L2 hits instead of DRAM round trips
             if (grp + (int)gridDim.x < g.n_groups) {
                 const int imgn = (grp + gridDim.x) * g.G;
-                const int bn = imgn / g.C, cn = imgn % g.C;
-                for (int e = t; e < items; e += 128) {
-                    const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
-                    prefetch_l2((part ? yi : yr) + ((size_t)(kx2 * g.m2 + ky) * g.B + bn) * g.C + cn);
+                const size_t on = (size_t)(imgn / g.C) * g.C + imgn % g.C;
+                for (int w = lw; w < witems; w += 4) {
+                    int part, kx2, ky;
+                    decode(w, part, kx2, ky);
+                    prefetch_l2((part ? yi : yr) + (size_t)(kx2 * g.m2 + ky) * g.B * g.C + on);
                 }
             }
-            wait_t(&bar_b1_empty, (ng & 1) ^ 1, w0);
+            const int bb = ng % g.nb1;
+            wait_t(&bar_b1_empty[bb], ((ng / g.nb1) & 1) ^ 1, w0);
             if (warp == 2) TRACE(3, 1);
-            constexpr int U = G == 8 ? 4 : 7;          // items in flight per thread (register budget: 72 with 832 threads): loads first, then the scatter
-            for (int e0 = t; e0 < items; e0 += 128 * U) {
+            const size_t o_grp = (size_t)b * g.C + c0;
+            const uint32_t dbase = smem_u32(b1) + bb * g.b1_buf;
+            constexpr int U = G == 8 ? 4 : 7;          // warp items in flight (register budget): loads first, then the scatter
+            for (int w0i = lw; w0i < witems; w0i += 4 * U) {
                 float4 va[U], vb[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int e = e0 + u * 128;
-                    if (e < items) {
-                        const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
-                        const float* src = (part ? yi : yr) + ((size_t)(kx2 * g.m2 + ky) * g.B + b) * g.C + c0;
-                        va[u] = *reinterpret_cast<const float4*>(src);
-                        if (G == 8) vb[u] = *reinterpret_cast<const float4*>(src + 4);
+                    const int w = w0i + 4 * u;
+                    if (w < witems) {
+                        int part, kx2, ky;
+                        decode(w, part, kx2, ky);
+                        const float* src = (part ? yi : yr) + (size_t)(kx2 * g.m2 + ky) * g.B * g.C + o_grp;
+                        va[u] = __ldg(reinterpret_cast<const float4*>(src));
+                        if (G == 8) vb[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int e = e0 + u * 128;
-                    if (e < items) {
-                        const int kx2 = e % g.K1, ky = (e / g.K1) % g.m2, part = e / (g.K1 * g.m2);
+                    const int w = w0i + 4 * u;
+                    if (w < witems) {
+                        int part, kx2, ky;
+                        decode(w, part, kx2, ky);
                         const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-                        const uint32_t dst0 = smem_u32(b1) + (part ? g.b1_im : 0);
+                        // kslab_sw32_off(i*m2 + ky, kx2, N1) with the i-dependent terms separated
+                        const uint32_t base = dbase + (part ? g.b1_im : 0) + (uint32_t)(kx2 >> 3) * g.N1 * 32 + ky * 32 + ((kx2 & 3) << 2);
+                        const uint32_t sw0 = ((kx2 >> 2) ^ (ky >> 2)) & 1;
 #pragma unroll
                         for (int i = 0; i < G; ++i) {
-                            const uint32_t off = kslab_sw32_off(i * g.m2 + ky, kx2, g.N1);
+                            const uint32_t off = base + i * g.m2 * 32 + (((sw0 ^ (i * q4)) & 1) << 4);
                             if (NSPLIT == 3) {
                                 const float h = tf32_rn(v[i]);
-                                sts32(dst0 + off, h);
-                                sts32(dst0 + g.b1_one + off, v[i] - h);
+                                sts32(off, h);
+                                sts32(off + g.b1_one, v[i] - h);
                             } else {
-                                sts32(dst0 + off, v[i]);
+                                sts32(off, v[i]);
                             }
                         }
                     }
@@ -259,7 +293,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             }
             if (warp == 2) TRACE(3, 2);
             fence_proxy_async_smem();
-            mbar_arrive(&bar_b1_full);
+            mbar_arrive(&bar_b1_full[bb]);
             if (warp == 2) TRACE(3, 3);
         }
     } else if (is_trans) {
@@ -271,8 +305,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         int ng = 0, nT = 0;
 
         auto transpose_tile = [&](int j) {
-            const int zb = nT & 1;
-            wait_t(&bar_zt_empty[zb], ((nT >> 1) & 1) ^ 1, w0);
+            const int zb = nT % g.nzt;
+            wait_t(&bar_zt_empty[zb], ((nT / g.nzt) & 1) ^ 1, w0);
             if (warp == 8) TRACE(1, 2);
             if (t_active_warp) {
                 const uint32_t zt = smem_u32(smem + g.off_zt) + zb * g.zt_buf;
@@ -340,7 +374,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
             const int img0 = grp * G;
             for (int j = 0; j < g.TPG; ++j, ++nE) {
-                const int db = nE & 1;
+                const int db = nE % g.nd2;
                 const size_t tile_row0 = (size_t)(img0 + j * g.IPT) * g.H;     // rows of the [B*C*H][W] view are consecutive
                 const size_t gofs = (tile_row0 + row) * g.W;
                 const size_t wofs = (tile_row0 + q * 32) * g.W;              // first row of this warp
@@ -359,7 +393,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                                                            : (size_t)(grp + gridDim.x) * G * g.H;
                     if (nxt_row0 + 128 <= (size_t)g.B * g.C * g.H) prefetch_l2(addend + (nxt_row0 + row) * g.W + c_lo);
                 }
-                wait_t(&bar_d2_full[db], (nE >> 1) & 1, w2);
+                wait_t(&bar_d2_full[db], (nE / g.nd2) & 1, w2);
                 if (ew == 0) TRACE(2, 1);
                 if (ew == g.epi_warps - 1) TRACE(4, 1);
                 tc_fence_after_sync();
@@ -492,31 +526,53 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     g.IPT = 128 / H;
     const int nbuf = x3 ? 2 : 1;          // hi (+ lo)
     bool ok = false;
-    for (int G = 8; G >= g.IPT && G >= 4; G >>= 1) {
+    for (int G = 8; G >= g.IPT && G >= 4 && !ok; G >>= 1) {
         if (C % G || (G * m2) % 16 || G * m2 > 256 || 2 * G * m2 + 2 * W > 512) continue;
         g.G = G; g.N1 = G * m2; g.TPG = G / g.IPT;
         g.tabA_one = g.S1 * H * 32;
         g.tabB_one = g.S2 * W * 32;
         g.b1_one = g.S1 * g.N1 * 32;
         g.b1_im = nbuf * g.b1_one;              // B1 layout: [Yre hi][Yre lo]? [Yim hi][Yim lo]?
+        g.b1_buf = pad_up(2 * nbuf * g.b1_one, 1024);
         g.zt_one = g.S2 * 128 * 32;
         g.zt_buf = nbuf * g.zt_one;
         g.off_tabA = 0;
-        g.off_tabB = pad_up(4 * g.tabA_one + 128 * 32, 1024);                   // slack: M = 128 reads past H rows
-        g.off_b1 = g.off_tabB + pad_up(2 * g.tabB_one, 1024);
-        g.off_zt = g.off_b1 + pad_up(2 * nbuf * g.b1_one, 1024);
-        g.off_scratch = g.off_zt + 2 * g.zt_buf;
-        for (g.epi_warps = (W % 64 == 0) ? 16 : 8; g.epi_warps >= 8; g.epi_warps -= 8) {
-            g.smem_bytes = g.off_scratch + g.epi_warps * 2048 + 1024;
-            if (g.smem_bytes <= 226 * 1024) { ok = true; break; }     // 227 KB minus the static barriers
-        }
-        if (ok) break;
+        g.off_tabB = pad_up(2 * nbuf * g.tabA_one + 128 * 32, 1024);            // slack: M = 128 reads past H rows
+        g.off_b1 = g.off_tabB + pad_up(nbuf * g.tabB_one, 1024);
+        g.nd2 = (512 - 2 * g.N1) / W;           // stage-2 accumulators that fit in tensor memory
+        if (g.nd2 > 3) g.nd2 = 3;
+        // tuning overrides (diagnostics): PNO_INV_ND2 / PNO_INV_NB1 / PNO_INV_NZT cap the buffer counts
+        const char* e_nd2 = getenv("PNO_INV_ND2");
+        const char* e_nb1 = getenv("PNO_INV_NB1");
+        const char* e_nzt = getenv("PNO_INV_NZT");
+        if (e_nd2 && atoi(e_nd2) >= 1 && atoi(e_nd2) < g.nd2) g.nd2 = atoi(e_nd2);
+        // Measured on B200 (tools/inv_sweep.py): a second B1 set or a third Zt set pushes shared memory past ~200 KB, the L1
+        // carve-out that is left can no longer track the in-flight addend / spectrum loads, and the kernel gets ~10% SLOWER
+        // (224 -> 246 us at the headline shape).  Default: one B1 set, two Zt sets.
+        const int nb1_max = e_nb1 && atoi(e_nb1) == 2 ? 2 : 1, nzt_max = e_nzt && atoi(e_nzt) == 3 ? 3 : 2;
+        // deepest buffering that fits: prefer 16 epilogue warps, then a second B1 set, then a third Zt set
+        const int epi_max = (W % 64 == 0) ? 16 : 8;
+        int best = -1;
+        for (int epi = epi_max; epi >= 8; epi -= 8)
+            for (int nb1 = nb1_max; nb1 >= 1; --nb1)
+                for (int nzt = nzt_max; nzt >= 2; --nzt) {
+                    const int off_zt = g.off_b1 + nb1 * g.b1_buf;
+                    const int off_scratch = off_zt + nzt * g.zt_buf;
+                    const int bytes = off_scratch + epi * 2048 + 1024;
+                    if (bytes > 226 * 1024) continue;            // 227 KB minus the static barriers
+                    const int score = epi * 100 + nb1 * 10 + nzt;
+                    if (score > best) {
+                        best = score; ok = true;
+                        g.epi_warps = epi; g.nb1 = nb1; g.nzt = nzt; g.off_zt = off_zt; g.off_scratch = off_scratch; g.smem_bytes = bytes;
+                    }
+                }
     }
     if (!ok) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv: no channel grouping fits (C = %d, m2 = %d, W = %d)", C, m2, W);
     if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(pre_act) |
          reinterpret_cast<uintptr_t>(yr) | reinterpret_cast<uintptr_t>(yi)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv needs 16-byte aligned tensors");
     g.n_groups = B * C / g.G;
+    if (getenv("PNO_INV_PAD")) g.smem_bytes += atoi(getenv("PNO_INV_PAD")) * 1024;   // diagnostics: shrink the L1 carve-out
     g.dbg = g_pno_debug_buffer;
     g.dbg_mma = g_pno_debug_buffer != nullptr && getenv("PNO_DEBUG_MMA") != nullptr;
     InvTables* t = nullptr;
