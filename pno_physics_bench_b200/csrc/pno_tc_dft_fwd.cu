@@ -7,7 +7,7 @@
 // Stage-2 accumulators of a "super tile" (up to 8 consecutive channels) stay in TMEM so that the epilogue writes
 // [mode][b][c] with 32-byte contiguous channel runs.  All twiddle tables are shared-memory resident; the ring only carries x.
 //   warp 0        TMA producer (tables once, then x row tiles)
-//   warp 1        MMA issuer (both stages, software pipelined).  A tcgen05.mma costs >= ~53 cycles whatever its N
+//   warps 1, 22   MMA issuers (warp 22 only in 3xTF32 mode, where stage 2 gets its own issuer).  A tcgen05.mma costs >= ~53 cycles whatever its N
 //                 (tools/micro/mma_rate.cu), so stage 2 runs once per batch of TPB tiles with N = TPB*IPT*m2 (80 at the
 //                 headline shape) instead of once per tile with N = 48; B2 operands and stage-2 accumulators are double
 //                 buffered per batch so that transposer, stage 2 and epilogue of consecutive batches overlap
@@ -15,6 +15,7 @@
 //   warps 6-13    transposer: two warps per TMEM lane quarter (cos columns / sin columns), all loads of a tile in flight
 //   warps 14-21   epilogue: two warps per lane quarter (re / im plane); only quarters holding kx2 < 2*m1 have work
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -25,7 +26,7 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 64 + 128 + 256 + 256;
+constexpr int kThreads = 64 + 128 + 256 + 256 + 32;   // + the stage-2 issuer warp
 
 struct FwdGeom {
     int H, W, m1, m2, M;
@@ -40,6 +41,7 @@ struct FwdGeom {
     int TPB;        // tiles per stage-2 batch (TPS % TPB == 0)
     int n_super;    // super tiles in the launch
     int grad_scale;
+    int KPS;        // x k-blocks per ring stage (a whole tile when W <= 64: one barrier round trip per tile instead of per k-block)
     int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
     // shared-memory byte offsets (from the 1024-aligned base)
     int off_tab, off_tw, off_ring, off_b2, stage_bytes, x_bytes, tw_one, tab_one, b2_one, b2_bytes, smem_bytes;
@@ -146,19 +148,19 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
                 for (int t = 0; t < g.TPS; ++t) {
                     const int row0 = (sup * g.TPS + t) * 128;          // row of the [B*C*H][W] view
-                    for (int kb = 0; kb < g.KB1; ++kb) {
+                    for (int kb = 0; kb < g.KB1; kb += g.KPS) {
                         mbar_wait(&bar_empty[stage], phase ^ 1);
                         TRACE(3, 1);
                         unsigned char* st = smem + g.off_ring + (size_t)stage * g.stage_bytes;
-                        mbar_arrive_expect_tx(&bar_raw[stage], g.x_bytes);
-                        tma_load_2d(st, &tmX, &bar_raw[stage], kb * 32, row0);
+                        mbar_arrive_expect_tx(&bar_raw[stage], g.KPS * g.x_bytes);
+                        for (int j = 0; j < g.KPS; ++j) tma_load_2d(st + j * g.x_bytes, &tmX, &bar_raw[stage], (kb + j) * 32, row0);
                         if (++stage == g.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
+    } else if (warp == 1 || warp == 22) {
+        // ================================ MMA issuers: warp 1 = stage 1, warp 22 = stage 2 ================================
         {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
             const uint32_t idesc1 = make_idesc(FMT_TF32, 128, g.N1p, MAJOR_K, MAJOR_K);
@@ -178,21 +180,25 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 mbar_wait(&bar_d1_empty[buf], ((n1 >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d1 = tmem + buf * g.N1p;
-                for (int kb = 0; kb < g.KB1; ++kb) {
+                for (int kb0 = 0; kb0 < g.KB1; kb0 += g.KPS) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
                     TRACE(0, 5);
                     tc_fence_after_sync();
-                    const uint32_t x_hi = sdesc_base(smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), 16, 1024, SWIZZLE_128B).lo;
-                    const uint32_t x_lo = x_hi + (g.x_bytes >> 4);
-                    const uint32_t tw_hi = twb + ((kb * tw_kb) >> 4), tw_lo = tw_hi + (g.tw_one >> 4);
+                    const uint32_t st_lo = sdesc_base(smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), 16, 1024, SWIZZLE_128B).lo;
+                    for (int j = 0; j < g.KPS; ++j) {
+                        const int kb = kb0 + j;
+                        const uint32_t x_hi = st_lo + ((j * g.x_bytes) >> 4);
+                        const uint32_t x_lo = x_hi + ((g.KPS * g.x_bytes) >> 4);
+                        const uint32_t tw_hi = twb + ((kb * tw_kb) >> 4), tw_lo = tw_hi + (g.tw_one >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t accf = (kb | ks) ? 1u : 0u;
-                        const uint32_t o = ks * 2;
-                        mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf, el);
-                        if (NSPLIT == 3) {
-                            mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u, el);
-                            mma_tf32(d1, x_hi + o, khi, tw_lo + o, khi, idesc1, 1u, el);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t accf = (kb | ks) ? 1u : 0u;
+                            const uint32_t o = ks * 2;
+                            mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf, el);
+                            if (NSPLIT == 3) {
+                                mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u, el);
+                                mma_tf32(d1, x_hi + o, khi, tw_lo + o, khi, idesc1, 1u, el);
+                            }
                         }
                     }
                     mma_commit(&bar_empty[stage], el);
@@ -244,10 +250,21 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
 
             int my_tiles = 0;
             for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) my_tiles += g.TPS;
-            if (my_tiles > 0) issue_stage1();
-            for (int t = 0; t < my_tiles; ++t) {
-                if (t + 1 < my_tiles) issue_stage1();
-                if ((t + 1) % g.TPB == 0) issue_stage2();
+            if (NSPLIT == 3) {
+                // 3xTF32 triples the MMA count and the issue + commit cost of one thread becomes the bound: the two stages are
+                // issued by different warps (measured 230 -> 197 us at the headline shape)
+                if (warp == 1) {
+                    for (int t = 0; t < my_tiles; ++t) issue_stage1();
+                } else {
+                    for (int t = 0; t < my_tiles; t += g.TPB) issue_stage2();
+                }
+            } else if (warp == 1) {
+                // single pass: one issuer, software pipelined (two issuers contend and measure slower: 123 vs 132 us)
+                if (my_tiles > 0) issue_stage1();
+                for (int t = 0; t < my_tiles; ++t) {
+                    if (t + 1 < my_tiles) issue_stage1();
+                    if ((t + 1) % g.TPB == 0) issue_stage2();
+                }
             }
         }
     } else if (warp < 6) {
@@ -256,11 +273,11 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             const int t = threadIdx.x - 64;
             int stage = 0, phase = 0;
             for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
-                for (int tt = 0; tt < g.TPS * g.KB1; ++tt) {
+                for (int tt = 0; tt < g.TPS * (g.KB1 / g.KPS); ++tt) {
                     mbar_wait(&bar_raw[stage], phase);
-                    const uint32_t hi = smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), lo = hi + g.x_bytes;
+                    const uint32_t hi = smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), lo = hi + g.KPS * g.x_bytes;
 #pragma unroll 4
-                    for (int i = t; i < g.x_bytes / 16; i += 128) {
+                    for (int i = t; i < g.KPS * g.x_bytes / 16; i += 128) {
                         const float4 v = lds128(hi + 16 * i);
                         const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
                         sts128(hi + 16 * i, h);
@@ -327,7 +344,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (warp == 8) TRACE(1, 4);
             }
         }
-    } else {
+    } else if (warp < 22) {
         // ================================ epilogue ================================
         // lanes kx2 < 2*m1 of a D2 buffer hold Xre / Xim of one batch = GB = TPB*IPT images (consecutive channels);
         // warp = (lane quarter, re / im plane).  The batches of a super tile are adjacent pieces of the same 32-byte runs.
@@ -465,6 +482,7 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     g.KB2 = H / 32;
     if (H > 128) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: H > 128");
     g.x_bytes = 128 * 128;                        // [128 rows][32 floats]
+    g.KPS = 1;
     g.stage_bytes = NT * g.x_bytes;
     g.tab_one = g.KB2 * g.R2 * 128;
     g.tw_one = g.KB1 * g.N1p * 128;
@@ -484,20 +502,24 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     for (int ns = want; ns >= 1; ns >>= 1) {
         if (C % (ns * g.IPT)) continue;
         for (int tpb = ns; tpb >= 1; tpb >>= 1) {
-            for (int nb2 = 2; nb2 >= 1; --nb2) {
+            for (int nb2 = 2; nb2 >= 1; --nb2)
+            for (int kps = (g.KB1 <= 2 ? g.KB1 : 1); kps >= 1; kps -= (kps > 1 ? kps - 1 : 1)) {
                 FwdGeom c = g;
-                c.TPS = ns; c.TPB = tpb; c.nb2 = nb2;
+                c.TPS = ns; c.TPB = tpb; c.nb2 = nb2; c.KPS = kps;
+                c.stage_bytes = NT * kps * g.x_bytes;
                 c.N2p = pad_to(tpb * g.IPT * m2, 16);
                 c.nslot = 2 * g.N1p + 4 * c.N2p <= 512 ? 2 : 1;
                 c.b2_one = g.KB2 * c.N2p * 128;
                 c.b2_bytes = pad_to(2 * NT * c.b2_one, 1024);
                 c.off_ring = g.off_b2 + nb2 * c.b2_bytes;
-                c.stages = (budget - c.off_ring) / g.stage_bytes;
+                c.stages = (budget - c.off_ring) / c.stage_bytes;
                 if (c.stages > 8) c.stages = 8;
+                if (getenv("PNO_FWD_STAGES") && atoi(getenv("PNO_FWD_STAGES")) < c.stages) c.stages = atoi(getenv("PNO_FWD_STAGES"));   // diagnostics
+                if (getenv("PNO_FWD_KPS") && atoi(getenv("PNO_FWD_KPS")) != kps) continue;
                 if (c.N2p > 256 || g.N1p > 256 || 2 * g.N1p + c.nslot * 2 * c.N2p > 512 || c.stages < 2) continue;
                 // prefer >= 16-byte output runs, then overlap (two accumulator / operand buffers), then ring depth
                 const int gb = tpb * g.IPT;
-                const int score = (gb >= 4 ? 1000 : 0) + (ns * g.IPT >= 8 ? 500 : 0) + c.nslot * 100 + nb2 * 10 + (c.stages < 4 ? c.stages : 4);
+                const int score = (gb >= 4 ? 1000 : 0) + (ns * g.IPT >= 8 ? 500 : 0) + c.nslot * 100 + nb2 * 10 + (kps > 1 ? 5 : 0) + (c.stages < 4 ? c.stages : 4);   // measured: whole-tile stages 130 us vs 142 us
                 if (score > best) { best = score; bg = c; fits = true; }
             }
         }
@@ -545,7 +567,7 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
         k_tc_dft_fwd<3><<<grid, kThreads, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
     } else {
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        k_tc_dft_fwd<1><<<grid, kThreads, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
+        k_tc_dft_fwd<1><<<grid, kThreads - 32, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
     }
     PNO_LAUNCH_CHECK();
     return PNO_OK;

@@ -134,6 +134,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
 
     if (warp == 1) {
         // ================================ MMA issuer ================================
+        // (a second issuer warp for stage 2 was measured: no gain in single-pass mode, slower in 3xTF32 mode)
         {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
             const uint32_t id1 = make_idesc(FMT_TF32, 128, g.N1, MAJOR_K, MAJOR_K);
@@ -150,6 +151,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             constexpr uint32_t NTc = NSPLIT == 3 ? 2 : 1;      // table copies: S hi sits NTc tables after C hi
             int ng = 0, nt = 0;
             for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
+                {
                 const int bb = ng % g.nb1;
                 wait_t(&bar_b1_full[bb], (ng / g.nb1) & 1, w0);
                 TRACE(0, 1);
@@ -187,6 +189,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     w4 += clock64() - tq;
                 }
 #endif
+                }
                 for (int j = 0; j < g.TPG; ++j, ++nt) {
                     const int zb = nt % g.nzt, db = nt % g.nd2;
                     wait_t(&bar_zt_full[zb], (nt / g.nzt) & 1, w2);

@@ -11,6 +11,8 @@
 //                 is computed): mu/lv -> Philox/Box-Muller -> W = mu + sigma*eps -> (tf32 hi/lo) -> K-major SW128 tiles
 //                 [128 o][32 i]; they also split the xhat tiles into hi/lo (3xTF32)
 //   warps 18-21   epilogue: TMEM -> yhat[mode][b][o] (coalesced over o)
+#include <stdlib.h>
+
 #include "pno_sm100.cuh"
 #include "pno_tc.cuh"
 
@@ -271,7 +273,8 @@ int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, 
     g.x_tile = B * 128;
     g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
     g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
-    g.stages = 4;
+    g.stages = getenv("PNO_MIX_STAGES") ? atoi(getenv("PNO_MIX_STAGES")) : 4;   // diagnostics override
+    if (g.stages < 2 || g.stages > 4) g.stages = 4;
     while (g.stages > 2 && g.stages * g.stage_bytes + 1024 > 220 * 1024) --g.stages;
     g.smem_bytes = g.stages * g.stage_bytes + 1024;
     if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd: %d bytes of shared memory needed", g.smem_bytes);
