@@ -7,8 +7,14 @@
 //   warp 1      one thread issues tcgen05.mma kind::tf32 into two TMEM accumulators (mean, log-var), double buffered
 //   warps 6-21  epilogue (16 warps = 4 per scheduler; the noise generation makes this the issue-bound role): tcgen05.ld ->
 //               bias, clamp/exp, Philox noise, (d out / d lv for backward) -> shared-memory transpose -> coalesced global rows
-// A tile is (batch item b, 128 output channels, 128 pixels); tiles are statically strided over the persistent grid with the
+// A tile is (batch item b, 128 output channels, TN pixels); tiles are statically strided over the persistent grid with the
 // output-channel tile fastest so that the CTAs sharing an x tile run at the same time (L2 reuse).
+// TN = 128 by default (double-buffered accumulators).  TN = 256 (PNO_LOCAL_TN=256, single-pass mode only) halves the weight-tile
+// fill per output (384 -> 256 KB per 128x128 outputs) at the price of single-buffered accumulators (mean | log-var = 512 TMEM
+// columns); measured 193 vs 185 us at the headline shape: the kernel is bound by the epilogue's noise generation (Philox +
+// Box-Muller + exp per output element, ~9k cycles per 128x128 tile on 16 warps), not by the operand fill.
+#include <stdlib.h>
+
 #include "pno_sm100.cuh"
 #include "pno_tc.cuh"
 
@@ -19,7 +25,6 @@ namespace {
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 128 + kEpiWarps * 32;
 constexpr int TM = 128;          // output channels per tile (UMMA M)
-constexpr int TN = 128;          // pixels per tile (UMMA N)
 constexpr int TK = 32;           // input channels per stage (one 128-byte swizzle row)
 constexpr int TILE_BYTES = TM * TK * 4;   // 16 KB, same for A [128][32] and B [32][128]
 
@@ -33,12 +38,15 @@ struct LocalArgs {
     int n_tiles, p_tiles, o_tiles;
 };
 
-template <int NSPLIT>
+template <int NSPLIT, int TN>
 struct Cfg {
-    static constexpr int kStages = NSPLIT == 3 ? 2 : 4;
-    static constexpr int kOperandBytes = 3 * TILE_BYTES;                         // Am, Al, X
+    static constexpr int kXBytes = TK * TN * 4;                                  // X tile [TN/32 p-blocks][32 rows][128 B]
+    static constexpr int kOperandBytes = 2 * TILE_BYTES + kXBytes;               // Am, Al, X
     static constexpr int kStageBytes = kOperandBytes * (NSPLIT == 3 ? 2 : 1);    // + lo copies
+    static constexpr int kStages = (192 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (3xTF32)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    static constexpr int kAcc = TN == 128 ? 2 : 1;                               // accumulator buffers in tensor memory
+    static_assert(kStages >= 2, "stage does not fit");
 };
 
 __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-nearest on the 13 dropped mantissa bits
@@ -50,11 +58,11 @@ __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-neares
     return r;
 }
 
-template <int NSPLIT, bool NOISY, bool DLV>
+template <int NSPLIT, bool NOISY, bool DLV, int TN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
            const __grid_constant__ CUtensorMap tmWl) {
-    using C = Cfg<NSPLIT>;
+    using C = Cfg<NSPLIT, TN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bar_raw[C::kStages], bar_split[C::kStages], bar_empty[C::kStages];
@@ -97,10 +105,10 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     unsigned char* st = stage_ptr(stage);
-                    mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 3 : 2) * TILE_BYTES);
+                    mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 2 : 1) * TILE_BYTES + C::kXBytes);
                     tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
                     if (NOISY) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
-                    // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, 4} lands as [4 p-blocks][32 rows][128 B]
+                    // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, TN/32} lands as [TN/32 p-blocks][32 rows][128 B]
                     tma_load_3d(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -115,10 +123,10 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             const uint32_t bhi = sdesc_base(0, TK * 128, 512, SWIZZLE_128B_BASE32B).hi;
             int stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                mbar_wait(&bar_tempty[acc], ((it >> 1) & 1) ^ 1);
+                const int acc = it % C::kAcc;
+                mbar_wait(&bar_tempty[acc], ((it / C::kAcc) & 1) ^ 1);
                 tc_fence_after_sync();
-                const uint32_t d_m = tmem + acc * 256, d_l = d_m + 128;
+                const uint32_t d_m = tmem + acc * (2 * TN), d_l = d_m + TN;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
                     tc_fence_after_sync();
@@ -161,7 +169,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     const uint32_t hi = smem_u32(stage_ptr(stage)), lo = hi + C::kOperandBytes;
                     constexpr int kVec = TILE_BYTES / 16;
 #pragma unroll 4
-                    for (int i = t; i < 3 * kVec; i += 128) {
+                    for (int i = t; i < C::kOperandBytes / 16; i += 128) {
                         if (!NOISY && i >= kVec && i < 2 * kVec) continue;
                         const float4 v = lds128(hi + 16 * i);
                         const float4 h = tf32_hi(v);
@@ -177,23 +185,24 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     } else {
         // ================================ epilogue ================================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int cc = (warp - 6) >> 2;         // 32-column chunk of the 128-pixel tile
+        const int cc = (warp - 6) >> 2;         // this warp's quarter of the TN-pixel tile
+        constexpr int CW = TN / 4;              // columns per warp
         float4* sc = s_scratch[warp - 6];
         int it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
             const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
-            const int acc = it & 1;
+            const int acc = it % C::kAcc;
             const int o = ot * TM + q * 32 + lane;
             const float bias_m = a.bm ? a.bm[o] : 0.f;
             const float bias_l = (NOISY && a.bl) ? a.bl[o] : 0.f;
             // first row of this warp / Philox element of this thread's row
-            const size_t wrow = ((size_t)b * a.Co + ot * TM + q * 32) * a.HW + (size_t)pt * TN + cc * 32;
-            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN + cc * 32;
-            mbar_wait(&bar_tfull[acc], (it >> 1) & 1);
+            const size_t wrow = ((size_t)b * a.Co + ot * TM + q * 32) * a.HW + (size_t)pt * TN + cc * CW;
+            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN + cc * CW;
+            mbar_wait(&bar_tfull[acc], (it / C::kAcc) & 1);
             tc_fence_after_sync();
-            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * 256 + cc * 32), t_l = t_m + 128;
+            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * (2 * TN) + cc * CW), t_l = t_m + TN;
 #pragma unroll 1
-            for (int c = 0; c < 32; c += 16) {
+            for (int c = 0; c < CW; c += 16) {
                 float v[16], l[16];
                 tmem_ld16(t_m + c, v);
                 if (NOISY) tmem_ld16(t_l + c, l);
@@ -228,23 +237,24 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-template <int NSPLIT, bool NOISY, bool DLV>
+template <int NSPLIT, bool NOISY, bool DLV, int TN>
 int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
-    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NSPLIT>::kSmemBytes));
+    using C = Cfg<NSPLIT, TN>;
+    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    k_tc_local<NSPLIT, NOISY, DLV><<<grid, kThreads, Cfg<NSPLIT>::kSmemBytes, st>>>(a, tmX, tmWm, tmWl);
+    k_tc_local<NSPLIT, NOISY, DLV, TN><<<grid, kThreads, C::kSmemBytes, st>>>(a, tmX, tmWm, tmWl);
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
-template <int NSPLIT>
+template <int NSPLIT, int TN>
 int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
-    if (!a.noisy) return launch<NSPLIT, false, false>(a, tmX, tmWm, tmWl, st);
-    if (a.want_dlv) return launch<NSPLIT, true, true>(a, tmX, tmWm, tmWl, st);
-    return launch<NSPLIT, true, false>(a, tmX, tmWm, tmWl, st);
+    if (!a.noisy) return launch<NSPLIT, false, false, TN>(a, tmX, tmWm, tmWl, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true, TN>(a, tmX, tmWm, tmWl, st);
+    return launch<NSPLIT, true, false, TN>(a, tmX, tmWm, tmWl, st);
 }
 
 }  // namespace
@@ -252,7 +262,7 @@ int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW
 int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
                  const float* Wl, const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv,
                  cudaStream_t st) {
-    if (Ci % TK || Co % TM || HW % TN)
+    if (Ci % TK || Co % TM || HW % 128)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_fwd tiles Ci%%32 == 0, Co%%128 == 0, HW%%128 == 0 (got %d, %d, %d)", Ci, Co, HW);
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wm) | reinterpret_cast<uintptr_t>(Wl) |
          reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout_dlv)) & 15)
@@ -261,13 +271,16 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     a.B = B; a.Ci = Ci; a.Co = Co; a.HW = HW;
     a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;
     a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset;
+    // pixel-tile width (see the header comment): 128 unless PNO_LOCAL_TN=256 asks for the wide tile
+    const char* e_tn = getenv("PNO_LOCAL_TN");
+    const int TN = (e_tn && atoi(e_tn) == 256 && engine != PNO_ENGINE_TC_TF32X3 && HW % 256 == 0) ? 256 : 128;
     a.o_tiles = Co / TM; a.p_tiles = HW / TN; a.n_tiles = B * a.o_tiles * a.p_tiles;
     CUtensorMap tmX, tmWm, tmWl;
     int rc;
     {   // x as (p % 32, row = b*Ci + i, p / 32)
         const uint64_t dims[3] = {32, (uint64_t)B * Ci, (uint64_t)HW / 32};
         const uint64_t str[2] = {(uint64_t)HW * 4, 128};
-        const uint32_t box[3] = {32, TK, TN / 32};
+        const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
     {
@@ -277,6 +290,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         if ((rc = pno_encode_tmap(&tmWm, Wm, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmWl, Wl ? Wl : Wm, 2, dims, str, box, 1))) return rc;
     }
-    if (engine == PNO_ENGINE_TC_TF32X3) return launch_ns<3>(a, tmX, tmWm, tmWl, st);
-    return launch_ns<1>(a, tmX, tmWm, tmWl, st);
+    if (engine == PNO_ENGINE_TC_TF32X3) return launch_ns<3, 128>(a, tmX, tmWm, tmWl, st);
+    if (TN == 256) return launch_ns<1, 256>(a, tmX, tmWm, tmWl, st);
+    return launch_ns<1, 128>(a, tmX, tmWm, tmWl, st);
 }
