@@ -48,6 +48,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None          # wall-clock bounds of the timed region (rows outside are dropped)
 
     def __enter__(self):
         try:
@@ -62,7 +63,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *a):
         if self.proc:
@@ -73,10 +80,13 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.1)]
+        if not rows:                       # region shorter than one sampling period: fall back to the nearest samples
+            rows = [r for _, r in self.rows[-3:]]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].startswith("Active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].startswith("Active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -287,14 +297,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(args.warmup):
-        step_resident(i)
-        step_e2e(i)
-    launches0 = lib.pno_launch_count()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:        # nvidia-smi needs ~1 s to start: launched before the warm-up, rows filtered by time
+        for i in range(args.warmup):
+            step_resident(i)
+            step_e2e(i)
+        launches0 = lib.pno_launch_count()
+        clocks.mark_start()
         ms_total = timed(step_resident, args.steps)
         launches = lib.pno_launch_count() - launches0
         ms_e2e = timed(step_e2e, args.steps)
+        clocks.mark_end()
     ms_step = ms_total / args.steps
     fields = B * total_samples
     value = fields / (ms_step * 1e-3)
