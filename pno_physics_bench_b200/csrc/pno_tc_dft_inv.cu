@@ -57,21 +57,6 @@ __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long
 
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
-// Coalesced row store through a per-warp shared-memory transpose: on entry lane r holds 32 consecutive floats of row
-// (row0 + r); on exit every store instruction has written 4 rows x 128 contiguous bytes.  sc = 32 x 8 float4 per warp.
-__device__ __forceinline__ void warp_store_rows32(float4* sc, int lane, const float v[32], float* base, size_t row_stride) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) sc[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + (lane >> 3), ch = lane & 7;
-        const float4 t = sc[rr * 8 + (ch ^ (rr & 7))];
-        *reinterpret_cast<float4*>(base + (size_t)rr * row_stride + 4 * ch) = t;
-    }
-    __syncwarp();
-}
-
 template <int NSPLIT, int G, int ACT>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
@@ -85,6 +70,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+    (void)w4; (void)w5;
     PNO_TRACE_DECL();
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {

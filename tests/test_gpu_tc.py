@@ -197,3 +197,86 @@ def test_model_tensor_core_engines_against_oracle(engine, tol):
     assert rel_l2(y, yo) < tol and rel_l2(loss, lo) < tol
     for k, v in model.named_parameters():
         assert rel_l2(v.grad, p[k].grad) < 5 * tol, k
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# size-independent properties at the full BASELINE config-3 layer shape (B 64, C 256, 64x64, modes 20), where the oracle is
+# too slow to be the checker
+# ----------------------------------------------------------------------------------------------------------------------
+FULL = dict(B=64, C=256, H=64, W=64, m=20)
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
+def test_full_size_transform_pair(engine, tol):
+    """forward + inverse transform at the full shape: the tensor-core engines against the fp32 CUDA-core engine (itself
+    checked against the oracle at small sizes), and the pair reproduces a field made of conjugate-complete retained modes."""
+    lib = _lib.load()
+    B, C, H, W, m = (FULL[k] for k in ("B", "C", "H", "W", "m"))
+    M = 2 * m * m
+    plan = _lib.plan(H, W, m, m, torch.device(DEV, 0))
+    eng = _lib.ENGINES[engine]
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(B, C, H, W, device=DEV, generator=gen)
+    st = _lib.stream_ptr()
+
+    def pair(e, xin):
+        xr, xi = torch.empty(M, B, C, device=DEV), torch.empty(M, B, C, device=DEV)
+        out = torch.empty_like(xin)
+        _lib.check(lib.pno_dft_fwd(plan, e, xin.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st))
+        _lib.check(lib.pno_dft_inv(plan, e, xr.data_ptr(), xi.data_ptr(), B, C, 0, 0, _lib.ACT_NONE, out.data_ptr(), 0, st))
+        return out, xr, xi
+
+    y_ref, xr_ref, xi_ref = pair(_lib.ENGINE_FP32, x)
+    y, xr, xi = pair(eng, x)
+    assert rel_l2(xr, xr_ref) < tol and rel_l2(xi, xi_ref) < tol
+    assert rel_l2(y, y_ref) < tol
+    # a field built from retained modes whose conjugate partners are retained too (|kx| < m1, ky < m2) is a fixed point
+    hh = torch.arange(H, device=DEV, dtype=torch.float32).view(H, 1)
+    ww = torch.arange(W, device=DEV, dtype=torch.float32).view(1, W)
+    f = torch.cos(2 * torch.pi * (3 * hh / H + 5 * ww / W)) + 0.5 * torch.sin(2 * torch.pi * (-7 * hh / H + 11 * ww / W)) + 0.25
+    xf = f.expand(B, C, H, W).contiguous()
+    yf, _, _ = pair(eng, xf)
+    assert rel_l2(yf, xf) < tol
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
+def test_full_size_layer_is_linear_in_x_for_fixed_noise(engine, tol):
+    """For one weight sample (fixed Philox key) the sampled layer is linear: L(a x1 + b x2) = a L(x1) + b L(x2)."""
+    import pno_physics_bench_b200 as pno
+    B, C, H, W, m = (FULL[k] for k in ("B", "C", "H", "W", "m"))
+    torch.manual_seed(2)
+    layer = pno.SpectralConv2d_Probabilistic(C, C, m, m, engine=engine).to(DEV).train()
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x1 = torch.randn(B, C, H, W, device=DEV, generator=gen)
+    x2 = torch.randn(B, C, H, W, device=DEV, generator=gen)
+    with torch.no_grad():
+        outs = []
+        for xin in (x1, x2, 0.75 * x1 - 1.5 * x2):
+            with pno.noise_scope(77, 3):
+                outs.append(layer(xin, sample=True))
+    assert rel_l2(outs[2], 0.75 * outs[0] - 1.5 * outs[1]) < tol
+    # and the draw really is a sample: another key gives another output
+    with torch.no_grad(), pno.noise_scope(77, 4):
+        other = layer(x1, sample=True)
+    assert rel_l2(other, outs[0]) > 0.1
+
+
+def test_full_size_engines_agree_on_one_block():
+    """One PNO block at the headline shape: the single-pass engine stays within the reduced-precision budget of the
+    fp32-parity engine (same noise), and the MC moments are finite."""
+    import pno_physics_bench_b200 as pno
+    B, C, H, W, m = (FULL[k] for k in ("B", "C", "H", "W", "m"))
+    torch.manual_seed(4)
+    blk = pno.PNOBlock(C, C, m, m, activation="gelu", local_noise="activation", engine="tf32x3").to(DEV).train()
+    with torch.no_grad():
+        blk.w_log_var.weight.mul_(0.02)
+        blk.w_log_var.bias.fill_(-2.0)
+    x = torch.randn(B, C, H, W, device=DEV)
+    with torch.no_grad():
+        with pno.noise_scope(9, 1):
+            ref = blk(x, sample=True)
+        blk.engine = _lib.ENGINES["tf32"]
+        blk.conv.engine = blk.engine
+        with pno.noise_scope(9, 1):
+            fast = blk(x, sample=True)
+    assert torch.isfinite(ref).all() and rel_l2(fast, ref) < 2e-2
