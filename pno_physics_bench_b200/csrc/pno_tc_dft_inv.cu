@@ -38,6 +38,7 @@ struct InvGeom {
     int epi_warps, off_scratch;   // epilogue warps (8 or 16) and their transpose scratch (2 KB per warp)
     int nb1, nzt, nd2;            // buffer counts: B1 operand sets, Zt operand sets, stage-2 accumulators
     int b1_buf;                   // bytes of one B1 operand set
+    int add_stages, off_add, add_bytes;   // TMA-staged addend tiles (0 stages: the epilogue loads the addend with LDG)
     int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, b1_im, zt_one, zt_buf, smem_bytes;
     long long* dbg;   // optional per-CTA wait-cycle counters (pno_debug_set_buffer)
     int dbg_mma;      // diagnostics: the issuer also waits for its own batches (serialises the pipeline)
@@ -61,11 +62,13 @@ template <int NSPLIT, int G, int ACT>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __restrict__ tabB_g,
              const float* __restrict__ coef, const float* __restrict__ yr, const float* __restrict__ yi,
-             const float* __restrict__ addend, float* __restrict__ y, float* __restrict__ pre_act) {
+             const float* __restrict__ addend, float* __restrict__ y, float* __restrict__ pre_act,
+             const __grid_constant__ CUtensorMap tmAdd) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bar_b1_full[2], bar_b1_empty[2], bar_d1_full, bar_d1_empty;
     __shared__ __align__(8) uint64_t bar_zt_full[3], bar_zt_empty[3], bar_d2_full[3], bar_d2_empty[3];
+    __shared__ __align__(8) uint64_t bar_add_full[3], bar_add_empty[3];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,6 +87,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
             mbar_init(&bar_zt_empty[s], 1);
             mbar_init(&bar_d2_full[s], 1);
             mbar_init(&bar_d2_empty[s], g.epi_warps * 32);
+            mbar_init(&bar_add_full[s], 1);
+            mbar_init(&bar_add_empty[s], g.epi_warps * 32);
         }
         fence_mbar_init();
     }
@@ -118,7 +123,25 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     const int lw = small_h ? (((warp - 2) >> 2) * 2 + ((warp & 3) - 2)) : warp - 2;     // loader warp index 0..3
     const int part_lo = small_h ? (warp - 4) >> 2 : 0, part_hi = small_h ? part_lo + 1 : 2;   // accumulator halves of a transposer warp
 
-    if (warp == 1) {
+    if (warp == 0) {
+        // ================================ addend producer (TMA) ================================
+        // The local-branch tile of a 128-row output tile is W/32 swizzled [128 rows x 128 B] boxes; staging it with TMA two or
+        // three tiles ahead takes the addend off the epilogue's critical path (as LDG it was 26% of the epilogue's stall
+        // samples) and off the L1 miss-tracking budget.
+        if (lane == 0 && g.add_stages > 0 && addend != nullptr) {
+            int n = 0;
+            for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
+                for (int j = 0; j < g.TPG; ++j, ++n) {
+                    const int sa = n % g.add_stages;
+                    mbar_wait(&bar_add_empty[sa], ((n / g.add_stages) & 1) ^ 1);
+                    unsigned char* dst = smem + g.off_add + sa * g.add_bytes;
+                    const int row0 = (grp * G + j * g.IPT) * g.H;
+                    mbar_arrive_expect_tx(&bar_add_full[sa], g.add_bytes);
+                    for (int cb = 0; cb < g.W / 32; ++cb) tma_load_2d(dst + cb * 128 * 128, &tmAdd, &bar_add_full[sa], cb * 32, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
         // ================================ MMA issuer ================================
         // (a second issuer warp for stage 2 was measured: no gain in single-pass mode, slower in 3xTF32 mode)
         {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
@@ -368,16 +391,27 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 const size_t gofs = (tile_row0 + row) * g.W;
                 const size_t wofs = (tile_row0 + q * 32) * g.W;              // first row of this warp
                 const uint32_t ta = tmem_addr(tmem, q * 32, d2_col + db * g.W);
-                // the first addend chunk is fetched before the accumulator is ready, so DRAM latency hides behind the wait
+                // addend: staged by TMA (add_stages > 0) or fetched with LDG before the accumulator is ready
+                const bool staged = g.add_stages > 0 && addend != nullptr;
+                const int sa = staged ? nE % g.add_stages : 0;
+                const uint32_t add_s = smem_u32(smem + g.off_add) + sa * g.add_bytes + row * 128;
                 float4 a4[4];
                 auto fetch = [&](int c) {
+                    if (staged) {                  // swizzled [W/32][128 rows][128 B]: 16-byte chunk index XOR (row & 7)
+                        const uint32_t blk = add_s + (c >> 5) * (128 * 128);
+                        const int j0 = (c & 31) >> 2;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        a4[k] = addend ? __ldg(reinterpret_cast<const float4*>(addend + gofs + c + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k = 0; k < 4; ++k) a4[k] = lds128(blk + (((j0 + k) ^ (row & 7)) << 4));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            a4[k] = addend ? __ldg(reinterpret_cast<const float4*>(addend + gofs + c + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 };
+                if (staged) mbar_wait(&bar_add_full[sa], (nE / g.add_stages) & 1);
                 fetch(c_lo);
-                // ... and the chunk of the tile after this one is pulled into L2 now, so that its fetch is an L2 hit
-                if (addend) {
+                // ... and (LDG path) the chunk of the tile after this one is pulled into L2 now, so that its fetch is an L2 hit
+                if (addend && !staged) {
                     const size_t nxt_row0 = j + 1 < g.TPG ? tile_row0 + (size_t)g.IPT * g.H
                                                            : (size_t)(grp + gridDim.x) * G * g.H;
                     if (nxt_row0 + 128 <= (size_t)g.B * g.C * g.H) prefetch_l2(addend + (nxt_row0 + row) * g.W + c_lo);
@@ -398,6 +432,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     for (int k = 0; k < 4; ++k) {
                         v[4 * k] += a4[k].x; v[4 * k + 1] += a4[k].y; v[4 * k + 2] += a4[k].z; v[4 * k + 3] += a4[k].w;
                     }
+                    // the staged tile has been consumed by this thread (the adds above depend on the loaded values)
+                    if (staged && c + 16 >= c_hi) mbar_arrive(&bar_add_empty[sa]);
 #ifdef PNO_TRACE
                     { const long long t2 = clock64(); w0 += t2 - tq; tq = t2; }
 #endif
@@ -541,18 +577,25 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
         const int nb1_max = e_nb1 && atoi(e_nb1) == 2 ? 2 : 1, nzt_max = e_nzt && atoi(e_nzt) == 3 ? 3 : 2;
         // deepest buffering that fits: prefer 16 epilogue warps, then a second B1 set, then a third Zt set
         const int epi_max = (W % 64 == 0) ? 16 : 8;
+        const int add_bytes = 128 * W * 4;                 // one 128-row tile of the addend
+        const char* e_add = getenv("PNO_INV_ADD");         // tuning override: 0 = LDG addend
+        const int add_max = addend == nullptr ? 0 : (e_add ? atoi(e_add) : 3);
         int best = -1;
         for (int epi = epi_max; epi >= 8; epi -= 8)
             for (int nb1 = nb1_max; nb1 >= 1; --nb1)
                 for (int nzt = nzt_max; nzt >= 2; --nzt) {
                     const int off_zt = g.off_b1 + nb1 * g.b1_buf;
                     const int off_scratch = off_zt + nzt * g.zt_buf;
-                    const int bytes = off_scratch + epi * 2048 + 1024;
-                    if (bytes > 226 * 1024) continue;            // 227 KB minus the static barriers
-                    const int score = epi * 100 + nb1 * 10 + nzt;
-                    if (score > best) {
-                        best = score; ok = true;
-                        g.epi_warps = epi; g.nb1 = nb1; g.nzt = nzt; g.off_zt = off_zt; g.off_scratch = off_scratch; g.smem_bytes = bytes;
+                    const int off_add = pad_up(off_scratch + epi * 2048, 1024);
+                    for (int na = add_max; na >= 0; na = (na == 0 ? -1 : (na > 2 ? 2 : 0))) {      // 3, 2 or 0 staged addend tiles
+                        const int bytes = off_add + na * add_bytes + 1024;
+                        if (bytes > 226 * 1024) continue;            // 227 KB minus the static barriers
+                        const int score = epi * 100 + (na > 0 ? 50 : 0) + nb1 * 10 + nzt + na;
+                        if (score > best) {
+                            best = score; ok = true;
+                            g.epi_warps = epi; g.nb1 = nb1; g.nzt = nzt; g.off_zt = off_zt; g.off_scratch = off_scratch;
+                            g.off_add = off_add; g.add_stages = na; g.add_bytes = add_bytes; g.smem_bytes = bytes;
+                        }
                     }
                 }
     }
@@ -568,6 +611,14 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     int rc = inv_tables_get(p, &t);
     if (rc) return rc;
     const float* tabB = adjoint ? t->tabB_adj : t->tabB;
+    CUtensorMap tmAdd;
+    memset(&tmAdd, 0, sizeof(tmAdd));
+    if (g.add_stages > 0) {
+        const uint64_t dims[2] = {(uint64_t)W, (uint64_t)B * C * H};
+        const uint64_t str[1] = {(uint64_t)W * 4};
+        const uint32_t box[2] = {32, 128};
+        if ((rc = pno_encode_tmap(&tmAdd, addend, 2, dims, str, box, 1))) return rc;
+    }
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -576,7 +627,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     do {                                                                                                                   \
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<NS, GG, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes)); \
         k_tc_dft_inv<NS, GG, AC><<<grid, kFront + g.epi_warps * 32, g.smem_bytes, st>>>(g, t->tabA, tabB, p->coef, yr, yi, \
-                                                                                        addend, y, pre_act);               \
+                                                                                        addend, y, pre_act, tmAdd);        \
     } while (0)
 #define PNO_LAUNCH_INV_ACT(NS, GG)                           \
     do {                                                     \

@@ -36,7 +36,10 @@ struct LocalArgs {
     PhiloxKey key;
     uint64_t batch_offset;
     int n_tiles, p_tiles, o_tiles;
+    long long* dbg;   // optional event trace (PNO_TRACE builds)
 };
+
+#define TRACE(role, ev) PNO_TRACE_EV(a.dbg, role, ev)
 
 template <int NSPLIT, int TN>
 struct Cfg {
@@ -72,6 +75,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = a.Ci / TK;
+    PNO_TRACE_DECL();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -104,6 +108,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
+                    TRACE(3, 1);
                     unsigned char* st = stage_ptr(stage);
                     mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 2 : 1) * TILE_BYTES + C::kXBytes);
                     tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
@@ -125,10 +130,12 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
                 const int acc = it % C::kAcc;
                 mbar_wait(&bar_tempty[acc], ((it / C::kAcc) & 1) ^ 1);
+                TRACE(0, 1);
                 tc_fence_after_sync();
                 const uint32_t d_m = tmem + acc * (2 * TN), d_l = d_m + TN;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
+                    TRACE(0, 2);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(stage_ptr(stage));
                     const uint32_t am = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;                       // A tiles: K-major SW128
@@ -156,6 +163,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 mma_commit(&bar_tfull[acc], el);
+                TRACE(0, 3);
             }
         }
     } else if (warp < 6) {
@@ -199,6 +207,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             const size_t wrow = ((size_t)b * a.Co + ot * TM + q * 32) * a.HW + (size_t)pt * TN + cc * CW;
             const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN + cc * CW;
             mbar_wait(&bar_tfull[acc], (it / C::kAcc) & 1);
+            if (warp == 6) TRACE(2, 1);
             tc_fence_after_sync();
             const uint32_t t_m = tmem_addr(tmem, q * 32, acc * (2 * TN) + cc * CW), t_l = t_m + TN;
 #pragma unroll 1
@@ -230,6 +239,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             }
             tc_fence_before_sync();
             mbar_arrive(&bar_tempty[acc]);
+            if (warp == 6) TRACE(2, 2);
         }
     }
     tc_fence_before_sync();
@@ -270,6 +280,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     LocalArgs a;
     a.B = B; a.Ci = Ci; a.Co = Co; a.HW = HW;
     a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;
+    a.dbg = g_pno_debug_buffer;
     a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset;
     // pixel-tile width (see the header comment): 128 unless PNO_LOCAL_TN=256 asks for the wide tile
     const char* e_tn = getenv("PNO_LOCAL_TN");

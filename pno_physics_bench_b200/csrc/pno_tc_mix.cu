@@ -171,9 +171,17 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             for (int kb = 0; kb < g.KB; ++kb) {
                 const uint64_t quad = quad_n;       // Philox counters of the k-block held in the buffers
-                if (++kb_n == g.KB) { kb_n = 0; item_n += gridDim.x; }
-                const bool more = item_n < g.n_items;
-                if (more) locate(item_n, kb_n);
+                bool more = true;
+                if (++kb_n == g.KB) {                             // next k-block belongs to the next item: full address computation
+                    kb_n = 0;
+                    item_n += gridDim.x;
+                    more = item_n < g.n_items;
+                    if (more) locate(item_n, 0);
+                } else {                                          // same item: the streams just advance by TK input channels
+                    mu_n += (size_t)2 * TK * g.Co;
+                    if (SAMPLED) lv_n += (size_t)TK * g.Co;
+                    quad_n += (uint64_t)TK * g.Cop;
+                }
                 mbar_wait(&bar_raw[stage], phase);              // xhat landed => the stage is ours to fill
                 const uint32_t st = smem_u32(smem + (size_t)stage * g.stage_bytes);
                 float wr[2][4], wi[2][4];
