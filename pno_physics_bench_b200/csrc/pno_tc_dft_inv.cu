@@ -70,6 +70,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     __shared__ __align__(8) uint64_t bar_zt_full[3], bar_zt_empty[3], bar_d2_full[3], bar_d2_empty[3];
     __shared__ __align__(8) uint64_t bar_add_full[3], bar_add_empty[3];
     __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t s_witem[512];     // loader work items: part << 16 | first kx2 << 8 | first ky (no divisions in the hot loop)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
@@ -93,6 +94,14 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    {
+        const int kyb_n = g.m2 >> 2, kxb_n = g.K1 >> 3;
+        for (int w = threadIdx.x; w < 2 * kxb_n * kyb_n; w += blockDim.x) {
+            const int part = w / (kxb_n * kyb_n), r = w - part * kxb_n * kyb_n;
+            const int kxb = r / kyb_n, kyb = r - kxb * kyb_n;
+            s_witem[w] = (uint32_t)part << 16 | (uint32_t)(kxb * 8) << 8 | (uint32_t)(kyb * 4);
+        }
+    }
     // twiddle tables: the plan holds them as the exact shared-memory image (slab-swizzled), so this is a straight copy
     {
         // global images: tabA = (C hi, C lo, S hi, S lo), tabB = (hi, lo); shared: (C hi, [C lo], S hi, [S lo]) and (hi, [lo])
@@ -240,11 +249,10 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         unsigned char* b1 = smem + g.off_b1;
         int ng = 0;
         auto decode = [&](int w, int& part, int& kx2, int& ky) {
-            part = w / (kxb_n * kyb_n);
-            const int r = w - part * kxb_n * kyb_n;
-            const int kxb = r / kyb_n, kyb = r - kxb * kyb_n;
-            kx2 = kxb * 8 + lkx;
-            ky = kyb * 4 + lky;
+            const uint32_t e = s_witem[w];
+            part = e >> 16;
+            kx2 = ((e >> 8) & 0xFF) + lkx;
+            ky = (e & 0xFF) + lky;
         };
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x, ++ng) {
             const int img0 = grp * g.G;
@@ -383,17 +391,16 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
         float4* sc = reinterpret_cast<float4*>(smem + g.off_scratch) + ew * 128;
         const int c_lo = chunk * (g.W / n_chunks), c_hi = c_lo + g.W / n_chunks;
         int nE = 0;
+        int db = 0, dph = 0, sa = 0, aph = 0;            // accumulator / staged-addend ring positions and phases (no divisions)
         for (int grp = blockIdx.x; grp < g.n_groups; grp += gridDim.x) {
             const int img0 = grp * G;
             for (int j = 0; j < g.TPG; ++j, ++nE) {
-                const int db = nE % g.nd2;
                 const size_t tile_row0 = (size_t)(img0 + j * g.IPT) * g.H;     // rows of the [B*C*H][W] view are consecutive
                 const size_t gofs = (tile_row0 + row) * g.W;
                 const size_t wofs = (tile_row0 + q * 32) * g.W;              // first row of this warp
                 const uint32_t ta = tmem_addr(tmem, q * 32, d2_col + db * g.W);
                 // addend: staged by TMA (add_stages > 0) or fetched with LDG before the accumulator is ready
                 const bool staged = g.add_stages > 0 && addend != nullptr;
-                const int sa = staged ? nE % g.add_stages : 0;
                 const uint32_t add_s = smem_u32(smem + g.off_add) + sa * g.add_bytes + row * 128;
                 float4 a4[4];
                 auto fetch = [&](int c) {
@@ -408,7 +415,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                             a4[k] = addend ? __ldg(reinterpret_cast<const float4*>(addend + gofs + c + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 };
-                if (staged) mbar_wait(&bar_add_full[sa], (nE / g.add_stages) & 1);
+                if (staged) mbar_wait(&bar_add_full[sa], aph);
                 fetch(c_lo);
                 // ... and (LDG path) the chunk of the tile after this one is pulled into L2 now, so that its fetch is an L2 hit
                 if (addend && !staged) {
@@ -416,7 +423,7 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                                                            : (size_t)(grp + gridDim.x) * G * g.H;
                     if (nxt_row0 + 128 <= (size_t)g.B * g.C * g.H) prefetch_l2(addend + (nxt_row0 + row) * g.W + c_lo);
                 }
-                wait_t(&bar_d2_full[db], (nE / g.nd2) & 1, w2);
+                wait_t(&bar_d2_full[db], dph, w2);
                 if (ew == 0) TRACE(2, 1);
                 if (ew == g.epi_warps - 1) TRACE(4, 1);
                 tc_fence_after_sync();
@@ -452,6 +459,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 mbar_arrive(&bar_d2_empty[db]);
                 if (ew == 0) TRACE(2, 2);
                 if (ew == g.epi_warps - 1) TRACE(4, 2);
+                if (++db == g.nd2) { db = 0; dph ^= 1; }
+                if (staged && ++sa == g.add_stages) { sa = 0; aph ^= 1; }
             }
         }
     }

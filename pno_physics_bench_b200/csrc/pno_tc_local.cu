@@ -23,6 +23,7 @@ using namespace sm100;
 namespace {
 
 constexpr int kEpiWarps = 16;
+constexpr int kTileTab = 128;
 constexpr int kThreads = 64 + 128 + kEpiWarps * 32;
 constexpr int TM = 128;          // output channels per tile (UMMA M)
 constexpr int TK = 32;           // input channels per stage (one 128-byte swizzle row)
@@ -72,6 +73,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float4 s_scratch[kEpiWarps][128];
+    __shared__ int s_tile[kTileTab][3];      // (ot, pt, b) of this CTA's first kTileTab tiles: no divisions in the role loops
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = a.Ci / TK;
@@ -92,6 +94,12 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         tma_prefetch_desc(&tmWm);
         tma_prefetch_desc(&tmWl);
     }
+    for (int it = threadIdx.x; it < kTileTab; it += blockDim.x) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        s_tile[it][0] = tile % a.o_tiles;
+        s_tile[it][1] = (tile / a.o_tiles) % a.p_tiles;
+        s_tile[it][2] = tile / (a.o_tiles * a.p_tiles);
+    }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
@@ -103,9 +111,11 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
+            int stage = 0, phase = 0, itp = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++itp) {
+                int ot, pt, b;
+                if (itp < kTileTab) { ot = s_tile[itp][0]; pt = s_tile[itp][1]; b = s_tile[itp][2]; }
+                else { ot = tile % a.o_tiles; pt = (tile / a.o_tiles) % a.p_tiles; b = tile / (a.o_tiles * a.p_tiles); }
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     TRACE(3, 1);
@@ -198,7 +208,9 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         float4* sc = s_scratch[warp - 6];
         int it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const int ot = tile % a.o_tiles, pt = (tile / a.o_tiles) % a.p_tiles, b = tile / (a.o_tiles * a.p_tiles);
+            int ot, pt, b;
+            if (it < kTileTab) { ot = s_tile[it][0]; pt = s_tile[it][1]; b = s_tile[it][2]; }
+            else { ot = tile % a.o_tiles; pt = (tile / a.o_tiles) % a.p_tiles; b = tile / (a.o_tiles * a.p_tiles); }
             const int acc = it % C::kAcc;
             const int o = ot * TM + q * 32 + lane;
             const float bias_m = a.bm ? a.bm[o] : 0.f;
