@@ -172,7 +172,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             const uint32_t t1 = g.tab_one >> 4, bo1 = g.b2_one >> 4;
             int stage = 0, phase = 0;
             int n1 = 0;      // stage-1 tiles issued
-            int n2 = 0;      // stage-2 tiles issued
+            int n2 = 0;      // stage-2 batches issued
+            int i_slot = 0, i_sph = 0, i_bb = 0, i_bph = 0, i_tb = 0;   // ring positions / phases (no divisions in the issue loop)
             mbar_wait(&bar_tab, 0);
 
             auto issue_stage1 = [&]() {
@@ -210,10 +211,10 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             };
 
             auto issue_stage2 = [&]() {                         // one batch of TPB tiles
-                const int slot = n2 % g.nslot, bb = n2 % g.nb2;
-                mbar_wait(&bar_d2_empty[slot], ((n2 / g.nslot) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+                const int slot = i_slot, bb = i_bb;
+                mbar_wait(&bar_d2_empty[slot], i_sph ^ 1);   // the epilogue has drained this accumulator buffer
                 TRACE(0, 4);
-                mbar_wait(&bar_b2_full[bb], (n2 / g.nb2) & 1);
+                mbar_wait(&bar_b2_full[bb], i_bph);
                 TRACE(0, 2);
                 tc_fence_after_sync();
                 const uint32_t d_re = tmem + d2_base + slot * 2 * g.N2p, d_im = d_re + g.N2p;
@@ -246,6 +247,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 mma_commit(&bar_d2_full[slot], el);
                 TRACE(0, 3);
                 ++n2;
+                if (++i_slot == g.nslot) { i_slot = 0; i_sph ^= 1; }
+                if (++i_bb == g.nb2) { i_bb = 0; i_bph ^= 1; }
             };
 
             int my_tiles = 0;
@@ -263,7 +266,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (my_tiles > 0) issue_stage1();
                 for (int t = 0; t < my_tiles; ++t) {
                     if (t + 1 < my_tiles) issue_stage1();
-                    if ((t + 1) % g.TPB == 0) issue_stage2();
+                    if (++i_tb == g.TPB) { i_tb = 0; issue_stage2(); }
                 }
             }
         }
@@ -299,15 +302,14 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         const uint32_t col_off = (uint32_t)((hk >> 5) * b2_kb + ((hk & 3) << 2));
         const int chunk = (hk & 31) >> 2;
         int n = 0;
+        int tb_ = 0, bb = 0, bph = 0;           // tile within its stage-2 batch, B2 buffer and its phase (no divisions in the loop)
         for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
             for (int t = 0; t < g.TPS; ++t, ++n) {
                 const int buf = n & 1;
-                const int tb_ = n % g.TPB, batch = n / g.TPB;       // tile within its stage-2 batch
                 mbar_wait(&bar_d1_full[buf], (n >> 1) & 1);
                 if (warp == 8) TRACE(1, 1);
                 tc_fence_after_sync();
-                const int bb = batch % g.nb2;
-                if (tb_ == 0) mbar_wait(&bar_b2_empty[bb], ((batch / g.nb2) & 1) ^ 1);   // stage 2 of the batch that used this buffer is done
+                if (tb_ == 0) mbar_wait(&bar_b2_empty[bb], bph ^ 1);   // stage 2 of the batch that used this buffer is done
                 if (warp == 8) TRACE(1, 2);
                 const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p + im * g.m2);
                 const uint32_t dst0 = smem_u32(smem + g.off_b2) + bb * g.b2_bytes + im * NT * g.b2_one + col_off;
@@ -342,6 +344,10 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_b2_full[bb]);
                 if (warp == 8) TRACE(1, 4);
+                if (++tb_ == g.TPB) {
+                    tb_ = 0;
+                    if (++bb == g.nb2) { bb = 0; bph ^= 1; }
+                }
             }
         }
     } else if (warp < 22) {
@@ -355,16 +361,16 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         const bool active = row < 2 * g.m1;
         float* dst_plane = part ? xi : xr;
         const int bps = g.TPS / g.TPB;                   // batches per super tile
-        int nb = 0;
+        int slot = 0, sph = 0;
         for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
-            for (int k = 0; k < bps; ++k, ++nb) {
-                const int slot = nb % g.nslot;
-                mbar_wait(&bar_d2_full[slot], (nb / g.nslot) & 1);
+            const int simg0 = sup * bps * GB;                // first image of the super tile = b*C + c0 (one division per super tile)
+            const int sb = simg0 / g.C, sc0 = simg0 - sb * g.C;
+            for (int k = 0; k < bps; ++k) {
+                mbar_wait(&bar_d2_full[slot], sph);
                 if (warp == 16) TRACE(2, 1);
                 tc_fence_after_sync();
                 if (warp_active) {
-                    const int img0 = (sup * bps + k) * GB;       // first image = b*C + c0
-                    const int b = img0 / g.C, c0 = img0 % g.C;
+                    const int b = sb, c0 = sc0 + k * GB;         // a super tile never straddles a batch item (C % (bps*GB) == 0)
                     const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + part * g.N2p);
                     for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
                         float vals[8][4];
@@ -397,6 +403,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 tc_fence_before_sync();
                 mbar_arrive(&bar_d2_empty[slot]);
                 if (warp == 16) TRACE(2, 2);
+                if (++slot == g.nslot) { slot = 0; sph ^= 1; }
             }
         }
     }
