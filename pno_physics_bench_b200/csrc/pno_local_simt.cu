@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads) k_local_fwd(const float* __restrict_
 }
 
 // ---- reparameterisation epilogue shared by the thin kernels below ------------------------------------------------------
+template <bool kDlv = true>
 __device__ __forceinline__ void reparam4(const float m[4], const float l[4], const PhiloxKey& key, uint64_t e0, float v[4],
                                          float d[4]) {
     float z[4];
@@ -131,7 +132,7 @@ __device__ __forceinline__ void reparam4(const float m[4], const float l[4], con
         const float s_raw = fast_ex2(0.72134752044448170f * lvc);      // exp(lv/2), one MUFU
         const float s = fmaxf(s_raw, 1e-6f);
         v[p] = fmaf(z[p], s, m[p]);
-        d[p] = ((l[p] >= -10.f) && (l[p] <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[p] * s : 0.f;
+        if (kDlv) d[p] = ((l[p] >= -10.f) && (l[p] <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[p] * s : 0.f;
     }
 }
 
@@ -184,9 +185,14 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restr
         const size_t off = ((size_t)b * Co + o) * HW + p0;
         if (kNoise) {
             float v[4], d[4];
-            reparam4(m, l, key, ((batch_offset + b) * (uint64_t)Co + o) * (uint64_t)HW + p0, v, d);
+            const uint64_t e0 = ((batch_offset + b) * (uint64_t)Co + o) * (uint64_t)HW + p0;
+            if (dout_dlv) {
+                reparam4<true>(m, l, key, e0, v, d);
+                *reinterpret_cast<float4*>(dout_dlv + off) = make_float4(d[0], d[1], d[2], d[3]);
+            } else {
+                reparam4<false>(m, l, key, e0, v, d);       // inference: no d out / d log-var bookkeeping
+            }
             *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
-            if (dout_dlv) *reinterpret_cast<float4*>(dout_dlv + off) = make_float4(d[0], d[1], d[2], d[3]);
         } else {
             *reinterpret_cast<float4*>(out + off) = make_float4(m[0], m[1], m[2], m[3]);
         }
