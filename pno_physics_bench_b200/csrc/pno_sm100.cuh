@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -232,6 +234,14 @@ __host__ __device__ __forceinline__ uint32_t kslab_sw32_off(int r, int k, int R)
 }
 
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// pdl_wait(): everything the preceding kernel of the stream wrote is complete and visible after this returns (a no-op when the
+// kernel was launched without the PDL attribute).  Kernels call it after their prologue (barrier init, TMEM allocation, constant
+// tables) and before touching any activation / spectrum buffer; pdl_launch_dependents() lets the next kernel's CTAs be scheduled
+// on SMs this grid has vacated, so its prologue overlaps this grid's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- explicit shared-space accesses ----------------------------------------------------------------------------------------
 // Pointers derived from the dynamic shared-memory base are generic to the compiler (LD.E / ST.E with a window check per
 // access); the hot staging loops address shared memory by its 32-bit window offset instead (LDS / STS).
@@ -289,6 +299,26 @@ __device__ __forceinline__ void warp_store_rows16(float4* sc, int lane, const fl
 #define PNO_TRACE_EV(dbg, role, ev) do {} while (0)
 #endif
 
+
+// ---- host: launch, optionally with the programmatic-stream-serialization attribute (PNO_PDL=1) -------------------------------
+// Measured on B200 at the headline shape: no gain (20.77k vs 20.75k fields/s) -- every kernel here owns a whole SM (shared memory,
+// TMEM), so a dependent CTA can only start when its predecessor has left and only the ~us prologue overlaps.  Off by default.
+#include <stdlib.h>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pno_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool pdl = getenv("PNO_PDL") && atoi(getenv("PNO_PDL")) == 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- host: tensor maps --------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).

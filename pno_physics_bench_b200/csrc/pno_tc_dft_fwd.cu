@@ -116,6 +116,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                        // x (the previous kernel's output) is complete from here on
 
     constexpr int NT = NSPLIT == 3 ? 2 : 1;            // hi (+ lo) copies of every operand
     // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then nslot buffers of 2*N2p (re | im), one batch each
@@ -571,10 +573,10 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     const int grid = g.n_super < sms ? g.n_super : sms;
     if (x3) {
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        k_tc_dft_fwd<3><<<grid, kThreads, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
+        PNO_CUDA(pno_launch(k_tc_dft_fwd<3>, grid, kThreads, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
     } else {
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        k_tc_dft_fwd<1><<<grid, kThreads - 32, g.smem_bytes, st>>>(g, p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo);
+        PNO_CUDA(pno_launch(k_tc_dft_fwd<1>, grid, kThreads - 32, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
     }
     PNO_LAUNCH_CHECK();
     return PNO_OK;

@@ -123,6 +123,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                    // spectrum and addend (previous kernels' outputs) are complete from here on
     const int d2_col = 2 * g.N1;
     // role of the front warps 2..9
     const bool small_h = g.H <= 64;
@@ -635,8 +637,8 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
 #define PNO_LAUNCH_INV(NS, GG, AC)                                                                                         \
     do {                                                                                                                   \
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_inv<NS, GG, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes)); \
-        k_tc_dft_inv<NS, GG, AC><<<grid, kFront + g.epi_warps * 32, g.smem_bytes, st>>>(g, t->tabA, tabB, p->coef, yr, yi, \
-                                                                                        addend, y, pre_act, tmAdd);        \
+        PNO_CUDA(pno_launch(k_tc_dft_inv<NS, GG, AC>, grid, kFront + g.epi_warps * 32, g.smem_bytes, st, g,                 \
+                            (const float*)t->tabA, tabB, (const float*)p->coef, yr, yi, addend, y, pre_act, tmAdd));       \
     } while (0)
 #define PNO_LAUNCH_INV_ACT(NS, GG)                           \
     do {                                                     \

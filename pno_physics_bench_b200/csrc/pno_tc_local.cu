@@ -105,6 +105,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                     // x (the previous kernel's output) is complete from here on
 
     auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
 
@@ -267,7 +269,7 @@ int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, 
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    k_tc_local<NSPLIT, NOISY, DLV, TN><<<grid, kThreads, C::kSmemBytes, st>>>(a, tmX, tmWm, tmWl);
+    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN>, grid, kThreads, C::kSmemBytes, st, a, tmX, tmWm, tmWl));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }

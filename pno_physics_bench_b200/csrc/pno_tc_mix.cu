@@ -71,6 +71,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                     // the spectrum written by the forward transform is complete from here on
     const int acc_cols = 2 * g.B;                   // Dre | Dim
     const int x_off = NW * W_TILE;                  // byte offset of the xhat tiles inside a stage
 
@@ -303,7 +305,7 @@ int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, 
 #define PNO_LAUNCH_MIX(NS, SM)                                                                                          \
     do {                                                                                                               \
         PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<NS, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
-        k_tc_mix_fwd<NS, SM><<<grid, kThreads, g.smem_bytes, st>>>(g, tmXr, tmXi);                                     \
+        PNO_CUDA(pno_launch(k_tc_mix_fwd<NS, SM>, grid, kThreads, g.smem_bytes, st, g, tmXr, tmXi));                                     \
     } while (0)
     if (x3 && sampled) PNO_LAUNCH_MIX(3, true);
     else if (x3) PNO_LAUNCH_MIX(3, false);
