@@ -204,13 +204,14 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restr
 // are combined through shared memory and the channel-group-0 threads run the reparameterisation epilogue.
 // grid (ceil(HW/4/64), B), HW % 4 == 0
 constexpr int kProjQuads = 64, kProjGroups = 4;
-template <bool kNoise>
-__global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __restrict__ x, int Ci, int Co, int HW,
+template <bool kNoise, int CO>          // CO = Co at compile time: no per-channel branches, so the 8 loads of an unrolled step batch
+__global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __restrict__ x, int Ci, int /*Co*/, int HW,
                                                              const float* __restrict__ Wm, const float* __restrict__ bm,
                                                              const float* __restrict__ Wl, const float* __restrict__ bl,
                                                              PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
                                                              float* __restrict__ dout_dlv) {
     extern __shared__ float sw[];          // [2][Co][Ci] weights, then [groups-1][quads][2*4*4] partial sums
+    constexpr int Co = CO;
     float* red = sw + 2 * Co * Ci;
     const int b = blockIdx.y;
     for (int e = threadIdx.x; e < Co * Ci; e += kThreads) {
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __rest
     const int quad = threadIdx.x % kProjQuads, grp = threadIdx.x / kProjQuads;
     const int p0 = (blockIdx.x * kProjQuads + quad) * 4;
     const bool live = p0 < HW;
-    float m[4][4] = {}, l[4][4] = {};
+    float m[CO][4] = {}, l[CO][4] = {};
     if (live) {
         const int per = (Ci + kProjGroups - 1) / kProjGroups;
         const int i0 = grp * per, i1 = min(Ci, i0 + per);
@@ -231,14 +232,12 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __rest
             const float4 t = __ldg(reinterpret_cast<const float4*>(xb + (size_t)i * HW));
             const float xv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (o < Co) {
-                    const float wm = sw[o * Ci + i], wl = sw[(Co + o) * Ci + i];
+            for (int o = 0; o < CO; ++o) {
+                const float wm = sw[o * Ci + i], wl = kNoise ? sw[(Co + o) * Ci + i] : 0.f;
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        m[o][p] = fmaf(wm, xv[p], m[o][p]);
-                        if (kNoise) l[o][p] = fmaf(wl, xv[p], l[o][p]);
-                    }
+                for (int p = 0; p < 4; ++p) {
+                    m[o][p] = fmaf(wm, xv[p], m[o][p]);
+                    if (kNoise) l[o][p] = fmaf(wl, xv[p], l[o][p]);
                 }
             }
         }
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __rest
     if (grp > 0) {
         float* r = red + ((size_t)(grp - 1) * kProjQuads + quad) * 32;
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
+        for (int o = 0; o < CO; ++o)
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 r[o * 4 + p] = m[o][p];
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __rest
     for (int gg = 0; gg < kProjGroups - 1; ++gg) {
         const float* r = red + ((size_t)gg * kProjQuads + quad) * 32;
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
+        for (int o = 0; o < CO; ++o)
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 m[o][p] += r[o * 4 + p];
@@ -266,8 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __rest
             }
     }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        if (o >= Co) break;
+    for (int o = 0; o < CO; ++o) {
         const float bias_m = bm ? bm[o] : 0.f, bias_l = (kNoise && bl) ? bl[o] : 0.f;
         const size_t off = ((size_t)b * Co + o) * HW + p0;
         float mm[4], ll[4];
@@ -306,8 +304,10 @@ int simt_local_fwd(const float* x, int B, int Ci, int Co, int HW, const float* W
     if (aligned && Co <= 4 && proj_smem <= 48 * 1024) {   // projection-shaped: streaming read
         dim3 g((HW / 4 + kProjQuads - 1) / kProjQuads, B);
         const size_t smem = proj_smem;
-        if (Wl) k_local_thin_out<true><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
-        else k_local_thin_out<false><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
+#define PNO_PROJ(NZ, CO_) k_local_thin_out<NZ, CO_><<<g, kThreads, smem, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv)
+        if (Wl) { if (Co == 1) PNO_PROJ(true, 1); else if (Co == 2) PNO_PROJ(true, 2); else if (Co == 3) PNO_PROJ(true, 3); else PNO_PROJ(true, 4); }
+        else { if (Co == 1) PNO_PROJ(false, 1); else if (Co == 2) PNO_PROJ(false, 2); else if (Co == 3) PNO_PROJ(false, 3); else PNO_PROJ(false, 4); }
+#undef PNO_PROJ
         PNO_LAUNCH_CHECK();
         return PNO_OK;
     }
