@@ -594,7 +594,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
         int best = -1;
         for (int epi = epi_max; epi >= 8; epi -= 8)
             for (int nb1 = nb1_max; nb1 >= 1; --nb1)
-                for (int nzt = nzt_max; nzt >= 2; --nzt) {
+                for (int nzt = nzt_max; nzt >= 1; --nzt) {      // a single Zt set is the last resort (128x128 grids with 32 modes)
                     const int off_zt = g.off_b1 + nb1 * g.b1_buf;
                     const int off_scratch = off_zt + nzt * g.zt_buf;
                     const int off_add = pad_up(off_scratch + epi * 2048, 1024);

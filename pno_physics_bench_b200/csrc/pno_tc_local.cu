@@ -229,22 +229,25 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 float v[16], l[16];
                 tmem_ld16(t_m + c, v);
                 if (NOISY) tmem_ld16(t_l + c, l);
-                tmem_ld_wait();
                 if (NOISY) {
+                    // the noise does not depend on the accumulators: it is generated while the TMEM loads are in flight
+                    float z[16];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float4 z4 = philox_quad_normals(a.key, ((e_row + c) >> 2) + k);
-                        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+                        z[4 * k] = z4.x; z[4 * k + 1] = z4.y; z[4 * k + 2] = z4.z; z[4 * k + 3] = z4.w;
+                    }
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float lv = l[4 * k + j] + bias_l;
-                            const float s_raw = fast_ex2(0.72134752044448170f * fminf(fmaxf(lv, -10.f), 10.f));
-                            const float s = fmaxf(s_raw, 1e-6f);
-                            v[4 * k + j] = fmaf(z[j], s, v[4 * k + j] + bias_m);
-                            if (DLV) l[4 * k + j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        const float lv = l[j] + bias_l;
+                        const float s_raw = fast_ex2(0.72134752044448170f * fminf(fmaxf(lv, -10.f), 10.f));
+                        const float s = fmaxf(s_raw, 1e-6f);
+                        v[j] = fmaf(z[j], s, v[j] + bias_m);
+                        if (DLV) l[j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;
                     }
                 } else {
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += bias_m;
                 }
