@@ -27,7 +27,7 @@ constexpr int TK = 32;           // input channels per stage
 constexpr int W_TILE = TM * TK * 4;      // 16 KB
 
 struct MixGeom {
-    int B, Ci, Co, m1m2, Cop, n_modes, o_tiles, n_items, KB;
+    int B, Bp, Ci, Co, m1m2, Cop, n_modes, o_tiles, n_items, KB;   // Bp = B rounded up to 16 (MMA N, TMA box rows)
     int x_tile;        // B * 128 bytes
     int stage_bytes, stages, smem_bytes;
     const float *mu1, *mu2, *lv1, *lv2;
@@ -73,7 +73,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
     const uint32_t tmem = tmem_slot;
     pdl_launch_dependents();
     pdl_wait();                                     // the spectrum written by the forward transform is complete from here on
-    const int acc_cols = 2 * g.B;                   // Dre | Dim
+    const int acc_cols = 2 * g.Bp;                  // Dre | Dim (columns >= B are padding: rows of the next mode / zero fill)
     const int x_off = NW * W_TILE;                  // byte offset of the xhat tiles inside a stage
 
     if (warp == 0) {
@@ -96,15 +96,15 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         // ================================ MMA issuer ================================
         {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
-            const uint32_t idesc = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K);
-            const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.B, MAJOR_K, MAJOR_K, 1, 0);
+            const uint32_t idesc = make_idesc(FMT_TF32, TM, g.Bp, MAJOR_K, MAJOR_K);
+            const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.Bp, MAJOR_K, MAJOR_K, 1, 0);
             const uint32_t dhi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
             int stage = 0, phase = 0, it = 0;
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&bar_tempty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
-                const uint32_t d_re = tmem + acc * acc_cols, d_im = d_re + g.B;
+                const uint32_t d_re = tmem + acc * acc_cols, d_im = d_re + g.Bp;
                 for (int kb = 0; kb < g.KB; ++kb) {
                     mbar_wait(&bar_ready[stage], phase);
                     tc_fence_after_sync();
@@ -248,12 +248,14 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
             for (int b0 = 0; b0 < g.B; b0 += 16) {
                 float vr[16], vi[16];
                 tmem_ld16(ta + b0, vr);
-                tmem_ld16(ta + g.B + b0, vi);
+                tmem_ld16(ta + g.Bp + b0, vi);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    dr[(size_t)(b0 + j) * g.Co] = vr[j];
-                    di[(size_t)(b0 + j) * g.Co] = vi[j];
+                    if (b0 + j < g.B) {             // warp-uniform: skips the padding columns when B is not a multiple of 16
+                        dr[(size_t)(b0 + j) * g.Co] = vr[j];
+                        di[(size_t)(b0 + j) * g.Co] = vi[j];
+                    }
                 }
             }
             tc_fence_before_sync();
@@ -269,18 +271,18 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
 
 int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
                const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st) {
-    if (B % 16 || B < 16 || B > 128 || Ci % TK || Co % TM)
-        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd tiles B%%16 == 0, 16 <= B <= 128, Ci%%32 == 0, Co%%128 == 0 (got %d, %d, %d)", B, Ci, Co);
+    if (B < 1 || B > 128 || Ci % TK || Co % TM)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd tiles 1 <= B <= 128, Ci%%32 == 0, Co%%128 == 0 (got %d, %d, %d)", B, Ci, Co);
     if ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(xi) | reinterpret_cast<uintptr_t>(mu1) |
          reinterpret_cast<uintptr_t>(mu2) | reinterpret_cast<uintptr_t>(lv1) | reinterpret_cast<uintptr_t>(lv2)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd needs 16-byte aligned tensors");
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
     MixGeom g;
     memset(&g, 0, sizeof(g));
-    g.B = B; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
+    g.B = B; g.Bp = (B + 15) / 16 * 16; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
     g.o_tiles = Co / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = Ci / TK;
     g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = yr; g.yi = yi; g.key = key;
-    g.x_tile = B * 128;
+    g.x_tile = g.Bp * 128;
     g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
     g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
     g.stages = getenv("PNO_MIX_STAGES") ? atoi(getenv("PNO_MIX_STAGES")) : 4;   // diagnostics override
@@ -293,7 +295,7 @@ int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, 
     {
         const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)p->M * B};
         const uint64_t str[1] = {(uint64_t)Ci * 4};
-        const uint32_t box[2] = {TK, (uint32_t)B};
+        const uint32_t box[2] = {TK, (uint32_t)g.Bp};      // rows past mode*B + B: the next mode's rows, or zero fill past the end
         if ((rc = pno_encode_tmap(&tmXr, xr, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmXi, xi, 2, dims, str, box, 1))) return rc;
     }

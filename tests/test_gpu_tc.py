@@ -139,7 +139,8 @@ def _mix(xr, xi, layer, sampled, engine):
 
 @pytest.mark.parametrize("engine,tol", [("tf32x3", 5e-6), ("tf32", 2e-3)])   # fp32 CUDA-core sums of 512 terms are ~2e-6 themselves
 @pytest.mark.parametrize("sampled", [False, True])
-@pytest.mark.parametrize("shape", [(16, 128, 128, 4, 4), (64, 256, 256, 20, 20), (32, 64, 256, 5, 3), (128, 128, 128, 2, 2)])
+@pytest.mark.parametrize("shape", [(16, 128, 128, 4, 4), (64, 256, 256, 20, 20), (32, 64, 256, 5, 3), (128, 128, 128, 2, 2),
+                                   (2, 128, 128, 3, 4), (20, 64, 128, 2, 2)])       # batch smaller than / not a multiple of the MMA N step
 def test_mix_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
     import pno_physics_bench_b200 as pno
     b, ci, co, m1, m2 = shape
