@@ -356,3 +356,39 @@ def test_batch_sharding_draws_the_same_activation_noise():
         with pno.noise_scope(11, 2, 2):
             tail = model(x[2:].contiguous(), sample=True)
     assert rel_l2(tail, full[2:]) < 1e-6
+
+
+def test_mc_statistics_match_reference_with_independent_noise():
+    """P14 (statistical): with INDEPENDENT noise streams (ours: in-kernel Philox; oracle: torch.randn) the MC predictive mean
+    and std of a small model agree within sampling error."""
+    torch.manual_seed(8)
+    model = pno.ProbabilisticNeuralOperator(input_dim=3, hidden_dim=8, num_layers=2, modes=4).to(DEV)
+    with torch.no_grad():                       # keep activation noise in the unclamped regime so that statistics are well behaved
+        for conv in [*model.linear_log_var, model.lift_log_var, model.project_log_var]:
+            conv.weight.mul_(0.02)
+            conv.bias.fill_(-2.0)
+    x = torch.randn(2, 3, 16, 16, device=DEV)
+    S = 768
+    mean, std = model.predict_with_uncertainty(x, num_samples=S, seed=31337)
+    p = {k: v.detach().cpu().contiguous() for k, v in model.state_dict().items()}
+
+    class TorchNoise:
+        def __init__(self):
+            self.g = torch.Generator().manual_seed(99)
+
+        def activation(self, site, shape, dtype=torch.float32):
+            return torch.randn(tuple(shape), generator=self.g, dtype=dtype)
+
+        def spectral(self, site, ci, co, m1, m2, dtype=torch.float32):
+            return (torch.randn(2, ci, co, m1, m2, generator=self.g, dtype=dtype),
+                    torch.randn(2, ci, co, m1, m2, generator=self.g, dtype=dtype))
+
+    noise = TorchNoise()
+    with torch.no_grad():
+        ys = torch.stack([orc.pno_forward(p, x.cpu(), noise, True, True, "gelu") for _ in range(S)])
+    m_ref, s_ref = ys.mean(0), ys.std(0)
+    se = (s_ref ** 2 / S + std.cpu() ** 2 / S).sqrt()            # standard error of the difference of two independent MC means
+    z = ((mean.cpu() - m_ref) / se).abs()
+    assert float(z.max()) < 5.5 and float((z > 3).float().mean()) < 0.02
+    ratio = std.cpu() / s_ref
+    assert float((ratio - 1).abs().mean()) < 0.05 and float((ratio - 1).abs().max()) < 0.25

@@ -281,3 +281,26 @@ def test_full_size_engines_agree_on_one_block():
         with pno.noise_scope(9, 1):
             fast = blk(x, sample=True)
     assert torch.isfinite(ref).all() and rel_l2(fast, ref) < 2e-2
+
+
+def test_local_branch_wide_tile_variant(monkeypatch):
+    """The optional 256-pixel-tile variant of the local-branch kernel (PNO_LOCAL_TN=256) computes the same thing."""
+    b, ci, co, h, w = 2, 64, 128, 16, 32
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(b, ci, h, w, generator=gen).to(DEV)
+    wm = (torch.randn(co, ci, generator=gen) / ci ** 0.5).to(DEV)
+    wl = (torch.randn(co, ci, generator=gen) * 0.05).to(DEV)
+    bm, bl = torch.randn(co, generator=gen).to(DEV), (torch.randn(co, generator=gen) - 3).to(DEV)
+    lib = _lib.load()
+    outs = []
+    for tn in ("128", "256"):
+        monkeypatch.setenv("PNO_LOCAL_TN", tn)
+        out = torch.empty(b, co, h, w, device=DEV)
+        _lib.check(lib.pno_local_fwd(_lib.ENGINES["tf32"], x.data_ptr(), b, ci, co, h * w, wm.data_ptr(), bm.data_ptr(), wl.data_ptr(),
+                                     bl.data_ptr(), 5, 1, 2, 0, out.data_ptr(), 0, _lib.stream_ptr()))
+        outs.append(out)
+    ref = torch.empty(b, co, h, w, device=DEV)
+    _lib.check(lib.pno_local_fwd(_lib.ENGINE_FP32, x.data_ptr(), b, ci, co, h * w, wm.data_ptr(), bm.data_ptr(), wl.data_ptr(),
+                                 bl.data_ptr(), 5, 1, 2, 0, ref.data_ptr(), 0, _lib.stream_ptr()))
+    assert rel_l2(outs[0], ref) < 5e-3 and rel_l2(outs[1], ref) < 5e-3
+    assert rel_l2(outs[1], outs[0]) < 1e-6
