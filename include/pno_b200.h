@@ -22,6 +22,16 @@
  *     separate arrays;
  *   - noise is a counter-based Philox4x32-10 stream keyed by (seed, sample_idx, site, element) -- see
  *     oracle/philox.py for the normative definition; nothing depends on launch geometry or GPU count.
+ *
+ * Tuning / diagnostic environment variables (read by the host side of the library; none is needed in normal use):
+ *   PNO_PDL=1            launch the tensor-core kernels with programmatic stream serialization (measured: no gain)
+ *   PNO_LOCAL_TN=256     256-pixel tiles in the single-pass local-branch kernel (measured slower than the default 128)
+ *   PNO_INV_NB1=2, PNO_INV_NZT=3, PNO_INV_ND2=n, PNO_INV_ADD=0|2|3   buffer counts of the inverse-transform kernel
+ *   PNO_FWD_STAGES=n, PNO_FWD_KPS=1|2                                ring depth / stage size of the forward-transform kernel
+ *   PNO_MIX_STAGES=2..4                                              ring depth of the channel-mix kernel
+ *   PNO_DEBUG_MMA=1      (PNO_TRACE builds) serialise the inverse kernel's MMA batches to time them
+ * A library built with `make EXTRA=-DPNO_TRACE` records per-role event timelines of CTA 0 into the pno_debug_set_buffer() buffer
+ * (tools/trace_*.py); production builds compile all of that away.
  */
 #ifndef PNO_B200_H
 #define PNO_B200_H
