@@ -21,7 +21,7 @@ using namespace sm100;
 namespace {
 
 constexpr int kGen = 512;        // generator threads
-constexpr int kThreads = 64 + kGen + 128;
+constexpr int kThreads = 64 + kGen + 128 + 32;   // + a second MMA issuer warp (3xTF32 only: one issuer per accumulator)
 constexpr int TM = 128;          // output channels per item
 constexpr int TK = 32;           // input channels per stage
 constexpr int W_TILE = TM * TK * 4;      // 16 KB
@@ -56,10 +56,10 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&bar_raw[s], 1);
             mbar_init(&bar_ready[s], kGen);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], NSPLIT == 3 ? 2 : 1);      // one commit per issuer warp
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bar_tfull[s], 1);
+            mbar_init(&bar_tfull[s], NSPLIT == 3 ? 2 : 1);
             mbar_init(&bar_tempty[s], 128);
         }
         fence_mbar_init();
@@ -92,9 +92,12 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+    } else if (warp == 1 || warp == 2 + kGen / 32 + 4) {
+        // ================================ MMA issuer(s) ================================
+        // single pass: warp 1 issues everything.  3xTF32: 48 MMAs per k-block at >= ~53 issue cycles each outrun the generators, so
+        // warp 1 issues the Dre accumulator and the extra warp the Dim accumulator.
+        const bool do_re = NSPLIT != 3 || warp == 1, do_im = NSPLIT != 3 || warp != 1;
+        if (NSPLIT == 3 || warp == 1) {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
             const uint32_t idesc = make_idesc(FMT_TF32, TM, g.Bp, MAJOR_K, MAJOR_K);
             const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.Bp, MAJOR_K, MAJOR_K, 1, 0);
@@ -118,19 +121,26 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t first = (kb | ks) ? 1u : 0u;
                         const uint32_t o = ks * 2;              // 32 bytes per K step
-                        mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first, el);
-                        mma_tf32(d_re, wim + o, dhi, xim + o, dhi, idesc_n, 1u, el);
-                        mma_tf32(d_im, wim + o, dhi, xre + o, dhi, idesc, first, el);
-                        mma_tf32(d_im, wre + o, dhi, xim + o, dhi, idesc, 1u, el);
+                        if (do_re) {
+                            mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first, el);
+                            mma_tf32(d_re, wim + o, dhi, xim + o, dhi, idesc_n, 1u, el);
+                        }
+                        if (do_im) {
+                            mma_tf32(d_im, wim + o, dhi, xre + o, dhi, idesc, first, el);
+                            mma_tf32(d_im, wre + o, dhi, xim + o, dhi, idesc, 1u, el);
+                        }
                         if (NSPLIT == 3) {
-                            mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u, el);
-                            mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
-                            mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, idesc_n, 1u, el);
-                            mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, idesc_n, 1u, el);
-                            mma_tf32(d_im, wim_l + o, dhi, xre + o, dhi, idesc, 1u, el);
-                            mma_tf32(d_im, wim + o, dhi, xre_l + o, dhi, idesc, 1u, el);
-                            mma_tf32(d_im, wre_l + o, dhi, xim + o, dhi, idesc, 1u, el);
-                            mma_tf32(d_im, wre + o, dhi, xim_l + o, dhi, idesc, 1u, el);
+                            if (do_re) {
+                                mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, idesc_n, 1u, el);
+                                mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, idesc_n, 1u, el);
+                            } else {
+                                mma_tf32(d_im, wim_l + o, dhi, xre + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_im, wim + o, dhi, xre_l + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_im, wre_l + o, dhi, xim + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_im, wre + o, dhi, xim_l + o, dhi, idesc, 1u, el);
+                            }
                         }
                     }
                     mma_commit(&bar_empty[stage], el);
