@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller (torch's caching allocator); the library never frees
- *     caller memory and allocates only the small twiddle tables a plan owns;
+ *     caller memory and allocates only the small twiddle tables a plan owns (plus, for the 3xTF32 engine, one grow-only scratch
+ *     per stream holding the tf32 hi / lo parts of the two 1x1 weight matrices of pno_local_fwd: 16 bytes per weight);
  *   - `stream` is a cudaStream_t passed as void*; every launch goes on it; no hidden synchronisation;
  *   - every function returns 0 on success, a negative PNO_E_* code otherwise; pno_last_error() gives the message
  *     (thread-local);

@@ -65,7 +65,8 @@ __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-neares
 template <int NSPLIT, bool NOISY, bool DLV, int TN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
-           const __grid_constant__ CUtensorMap tmWl) {
+           const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmWmLo,
+           const __grid_constant__ CUtensorMap tmWlLo) {
     using C = Cfg<NSPLIT, TN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,6 +94,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmWm);
         tma_prefetch_desc(&tmWl);
+        tma_prefetch_desc(&tmWmLo);
+        tma_prefetch_desc(&tmWlLo);
     }
     for (int it = threadIdx.x; it < kTileTab; it += blockDim.x) {
         const int tile = blockIdx.x + it * gridDim.x;
@@ -122,9 +125,15 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     TRACE(3, 1);
                     unsigned char* st = stage_ptr(stage);
-                    mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 2 : 1) * TILE_BYTES + C::kXBytes);
+                    // 3xTF32: the weights arrive pre-split (tmWm / tmWl = hi parts, tmWmLo / tmWlLo = lo parts, k_split_weights);
+                    // only the x tile is split on the fly
+                    mbar_arrive_expect_tx(&bar_raw[stage], (NSPLIT == 3 ? 2 : 1) * (NOISY ? 2 : 1) * TILE_BYTES + C::kXBytes);
                     tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
                     if (NOISY) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
+                    if (NSPLIT == 3) {
+                        tma_load_2d(st + C::kOperandBytes, &tmWmLo, &bar_raw[stage], kb * TK, ot * TM);
+                        if (NOISY) tma_load_2d(st + C::kOperandBytes + TILE_BYTES, &tmWlLo, &bar_raw[stage], kb * TK, ot * TM);
+                    }
                     // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, TN/32} lands as [TN/32 p-blocks][32 rows][128 B]
                     tma_load_3d(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -189,8 +198,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     const uint32_t hi = smem_u32(stage_ptr(stage)), lo = hi + C::kOperandBytes;
                     constexpr int kVec = TILE_BYTES / 16;
 #pragma unroll 4
-                    for (int i = t; i < C::kOperandBytes / 16; i += 128) {
-                        if (!NOISY && i >= kVec && i < 2 * kVec) continue;
+                    for (int i = 2 * kVec + t; i < C::kOperandBytes / 16; i += 128) {       // the x tile (weights are pre-split)
                         const float4 v = lds128(hi + 16 * i);
                         const float4 h = tf32_hi(v);
                         sts128(hi + 16 * i, h);
@@ -264,24 +272,62 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// hi / lo tf32 parts of the two 1x1 weight matrices for the 3xTF32 engine: out = [Wm hi][Wl hi][Wm lo][Wl lo], each n floats
+__global__ void k_split_weights(const float* __restrict__ wm, const float* __restrict__ wl, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a_ = wm[i], b_ = wl ? wl[i] : 0.f;
+    const float ah = __uint_as_float((__float_as_uint(a_) + 0x1000u) & 0xFFFFE000u);
+    const float bh = __uint_as_float((__float_as_uint(b_) + 0x1000u) & 0xFFFFE000u);
+    out[i] = ah;
+    out[n + i] = bh;
+    out[2 * n + i] = a_ - ah;
+    out[3 * n + i] = b_ - bh;
+}
+
+// Library-owned scratch for the split weights: one grow-only buffer per (device, stream) so that calls on different streams
+// never share it (calls on one stream are ordered).  A handful of entries at most; never freed before process exit.
+struct SplitScratch { int dev; cudaStream_t st; float* buf; size_t floats; };
+static SplitScratch g_split[16];
+static int g_nsplit = 0;
+static float* split_scratch(int dev, cudaStream_t st, size_t floats) {
+    for (int i = 0; i < g_nsplit; ++i)
+        if (g_split[i].dev == dev && g_split[i].st == st) {
+            if (g_split[i].floats < floats) {
+                cudaFree(g_split[i].buf);
+                if (cudaMalloc(&g_split[i].buf, floats * 4) != cudaSuccess) { g_split[i].floats = 0; return nullptr; }
+                g_split[i].floats = floats;
+            }
+            return g_split[i].buf;
+        }
+    if (g_nsplit == 16) return nullptr;
+    SplitScratch& e = g_split[g_nsplit];
+    e.dev = dev; e.st = st; e.floats = floats;
+    if (cudaMalloc(&e.buf, floats * 4) != cudaSuccess) return nullptr;
+    ++g_nsplit;
+    return e.buf;
+}
+
 template <int NSPLIT, bool NOISY, bool DLV, int TN>
-int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
+int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
+           const CUtensorMap& tmWlLo, cudaStream_t st) {
     using C = Cfg<NSPLIT, TN>;
     PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN>, grid, kThreads, C::kSmemBytes, st, a, tmX, tmWm, tmWl));
+    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN>, grid, kThreads, C::kSmemBytes, st, a, tmX, tmWm, tmWl, tmWmLo, tmWlLo));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
 template <int NSPLIT, int TN>
-int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, cudaStream_t st) {
-    if (!a.noisy) return launch<NSPLIT, false, false, TN>(a, tmX, tmWm, tmWl, st);
-    if (a.want_dlv) return launch<NSPLIT, true, true, TN>(a, tmX, tmWm, tmWl, st);
-    return launch<NSPLIT, true, false, TN>(a, tmX, tmWm, tmWl, st);
+int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
+              const CUtensorMap& tmWlLo, cudaStream_t st) {
+    if (!a.noisy) return launch<NSPLIT, false, false, TN>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true, TN>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    return launch<NSPLIT, true, false, TN>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
 }
 
 }  // namespace
@@ -311,14 +357,28 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
+    CUtensorMap tmWmLo, tmWlLo;
     {
         const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
         const uint64_t str[1] = {(uint64_t)Ci * 4};
         const uint32_t box[2] = {TK, TM};
-        if ((rc = pno_encode_tmap(&tmWm, Wm, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWl, Wl ? Wl : Wm, 2, dims, str, box, 1))) return rc;
+        const float *wm_hi = Wm, *wl_hi = Wl ? Wl : Wm, *wm_lo = Wm, *wl_lo = Wm;
+        if (engine == PNO_ENGINE_TC_TF32X3) {          // split the weights once per call (tiny) instead of once per pixel tile
+            int dev = 0;
+            PNO_CUDA(cudaGetDevice(&dev));
+            const size_t n = (size_t)Co * Ci;
+            float* sc = split_scratch(dev, st, 4 * n);
+            if (!sc) PNO_FAIL(PNO_E_CUDA, "tc_local_fwd: cannot allocate the split-weight scratch (%zu bytes)", 16 * n);
+            k_split_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wm, Wl, (int)n, sc);
+            PNO_LAUNCH_CHECK();
+            wm_hi = sc; wl_hi = sc + n; wm_lo = sc + 2 * n; wl_lo = sc + 3 * n;
+        }
+        if ((rc = pno_encode_tmap(&tmWm, wm_hi, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWl, wl_hi, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWmLo, wm_lo, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWlLo, wl_lo, 2, dims, str, box, 1))) return rc;
     }
-    if (engine == PNO_ENGINE_TC_TF32X3) return launch_ns<3, 128>(a, tmX, tmWm, tmWl, st);
-    if (TN == 256) return launch_ns<1, 256>(a, tmX, tmWm, tmWl, st);
-    return launch_ns<1, 128>(a, tmX, tmWm, tmWl, st);
+    if (engine == PNO_ENGINE_TC_TF32X3) return launch_ns<3, 128>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    if (TN == 256) return launch_ns<1, 256>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    return launch_ns<1, 128>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
 }
