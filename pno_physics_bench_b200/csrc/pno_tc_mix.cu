@@ -47,7 +47,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kMaxStages = 4;
     constexpr int NW = NSPLIT == 3 ? 4 : 2;         // W tiles per stage
-    __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_ready[kMaxStages], bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_ready[kMaxStages], bar_empty[kMaxStages], bar_free[kMaxStages];
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
 
@@ -56,6 +56,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&bar_raw[s], 1);
             mbar_init(&bar_ready[s], kGen);
+            mbar_init(&bar_free[s], 1);
             mbar_init(&bar_empty[s], NSPLIT == 3 ? 2 : 1);      // one commit per issuer warp
         }
         for (int s = 0; s < 2; ++s) {
@@ -84,6 +85,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 const int mode = item / g.o_tiles;
                 for (int kb = 0; kb < g.KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_arrive(&bar_free[stage]);                 // the generators may fill the W tiles while the xhat tiles are in flight
                     unsigned char* st = smem + (size_t)stage * g.stage_bytes + x_off;
                     mbar_arrive_expect_tx(&bar_raw[stage], 2 * g.x_tile);
                     tma_load_2d(st, &tmXr, &bar_raw[stage], kb * TK, mode * g.B);
@@ -110,6 +112,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 const uint32_t d_re = tmem + acc * acc_cols, d_im = d_re + g.Bp;
                 for (int kb = 0; kb < g.KB; ++kb) {
                     mbar_wait(&bar_ready[stage], phase);
+                    if (NSPLIT != 3) mbar_wait(&bar_raw[stage], phase);   // xhat tiles landed (3xTF32: the generators already waited)
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(smem + (size_t)stage * g.stage_bytes);
                     // low descriptor words of the operand tiles of this stage (all K-major SW128: LBO 16, SBO 1024)
@@ -194,7 +197,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     if (SAMPLED) lv_n += (size_t)TK * g.Co;
                     quad_n += (uint64_t)TK * g.Cop;
                 }
-                mbar_wait(&bar_raw[stage], phase);              // xhat landed => the stage is ours to fill
+                mbar_wait(&bar_free[stage], phase);             // the MMAs that read this stage are done: its W tiles are ours to fill
                 const uint32_t st = smem_u32(smem + (size_t)stage * g.stage_bytes);
                 float wr[2][4], wi[2][4];
 #pragma unroll
@@ -229,6 +232,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 }
                 // ---- xhat tiles: hi in place, lo behind (layout-agnostic elementwise pass) ----
                 if (NSPLIT == 3) {
+                    mbar_wait(&bar_raw[stage], phase);          // xhat tiles landed
                     const uint32_t xh = st + x_off, xl = st + x_off + 2 * g.x_tile;
                     for (int i = t; i < 2 * g.x_tile / 16; i += kGen) {
                         const float4 v = lds128(xh + 16 * i);
