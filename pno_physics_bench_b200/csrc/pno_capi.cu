@@ -152,9 +152,12 @@ extern "C" int pno_mix_bwd_dx(const pno_plan_t* p, int engine, const float* gr, 
     if (rc) return rc;
     if ((rc = check_lv(lv1, lv2, "pno_mix_bwd_dx"))) return rc;
     if (!gr || !gi || !mu1 || !mu2 || !dxr || !dxi) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dx: null pointer");
-    (void)engine;   // backward kernels run on the fp32 engine in this version
-    return simt_mix_bwd_dx(p, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, make_key(seed, sample_idx, site), dxr, dxi,
-                           as_stream(stream));
+    const PhiloxKey key = make_key(seed, sample_idx, site);
+    if (engine != PNO_ENGINE_FP32) {
+        rc = tc_mix_bwd_dx(p, engine, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, as_stream(stream));
+        if (rc != PNO_E_UNSUPPORTED) return rc;
+    }
+    return simt_mix_bwd_dx(p, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, as_stream(stream));
 }
 
 extern "C" int pno_mix_bwd_dw(const pno_plan_t* p, int engine, const float* xr, const float* xi, const float* gr,

@@ -246,6 +246,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // Pointers derived from the dynamic shared-memory base are generic to the compiler (LD.E / ST.E with a window check per
 // access); the hot staging loops address shared memory by its 32-bit window offset instead (LDS / STS).
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, const float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }

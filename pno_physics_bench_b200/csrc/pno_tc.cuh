@@ -11,6 +11,8 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
                const float* addend, int act, float* y, float* pre_act, cudaStream_t st);
 int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
                const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st);
+int tc_mix_bwd_dx(const pno_plan* p, int engine, const float* gr, const float* gi, int B, int Ci, int Co, const float* mu1,
+                  const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* dxr, float* dxi, cudaStream_t st);
 int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
                  const float* Wl, const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv,
                  cudaStream_t st);

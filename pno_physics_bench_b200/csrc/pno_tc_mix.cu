@@ -11,6 +11,9 @@
 //                 is computed): mu/lv -> Philox/Box-Muller -> W = mu + sigma*eps -> (tf32 hi/lo) -> K-major SW128 tiles
 //                 [128 o][32 i]; they also split the xhat tiles into hi/lo (3xTF32)
 //   warps 18-21   epilogue: TMEM -> yhat[mode][b][o] (coalesced over o)
+// The same kernel with BWD = true is the input-gradient pass  dxhat[mode][b][i] = sum_o ghat[mode][b][o] * conj(W[mode][i][o])
+// (W re-sampled from the same Philox counters, never stored): the reduction runs over o, the 128-row tiles over i, the generated
+// tiles are [128 i][32 o] (o is contiguous in the parameter arrays, so no transposition) and the MMA sign pattern conjugates W.
 #include <stdlib.h>
 
 #include "pno_sm100.cuh"
@@ -28,6 +31,7 @@ constexpr int W_TILE = TM * TK * 4;      // 16 KB
 
 struct MixGeom {
     int B, Bp, Ci, Co, m1m2, Cop, n_modes, o_tiles, n_items, KB;   // Bp = B rounded up to 16 (MMA N, TMA box rows)
+    int MD;            // channels of the output ("row") side: Co forward, Ci backward; o_tiles = MD / 128, KB = (other side) / 32
     int x_tile;        // B * 128 bytes
     int stage_bytes, stages, smem_bytes;
     const float *mu1, *mu2, *lv1, *lv2;
@@ -40,7 +44,7 @@ __device__ __forceinline__ float4 tf32_rn4(const float4 v) { return make_float4(
 __device__ __forceinline__ float4 sub4(const float4 a, const float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
 // stage layout, NSPLIT == 1: [Wre][Wim][Xre][Xim];  NSPLIT == 3: [Wre hi][Wim hi][Wre lo][Wim lo][Xre hi][Xim hi][Xre lo][Xim lo]
-template <int NSPLIT, bool SAMPLED>
+template <int NSPLIT, bool SAMPLED, bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __grid_constant__ CUtensorMap tmXi) {
     extern __shared__ unsigned char smem_raw[];
@@ -124,25 +128,33 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t first = (kb | ks) ? 1u : 0u;
                         const uint32_t o = ks * 2;              // 32 bytes per K step
+                        // forward:  Dre = Wre Xre - Wim Xim ,  Dim = Wim Xre + Wre Xim
+                        // backward: Dre = Wre Gre + Wim Gim ,  Dim = Wre Gim - Wim Gre        (conj W)
+                        const uint32_t id_re2 = BWD ? idesc : idesc_n;          // sign of the Wim term of Dre
+                        const uint32_t a_im1 = BWD ? wre : wim, a_im2 = BWD ? wim : wre;        // A operands of the two Dim terms
+                        const uint32_t a_im1l = BWD ? wre_l : wim_l, a_im2l = BWD ? wim_l : wre_l;
+                        const uint32_t b_im1 = BWD ? xim : xre, b_im2 = BWD ? xre : xim;        // and their B operands
+                        const uint32_t b_im1l = BWD ? xim_l : xre_l, b_im2l = BWD ? xre_l : xim_l;
+                        const uint32_t id_im2 = BWD ? idesc_n : idesc;          // sign of the second Dim term
                         if (do_re) {
                             mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first, el);
-                            mma_tf32(d_re, wim + o, dhi, xim + o, dhi, idesc_n, 1u, el);
+                            mma_tf32(d_re, wim + o, dhi, xim + o, dhi, id_re2, 1u, el);
                         }
                         if (do_im) {
-                            mma_tf32(d_im, wim + o, dhi, xre + o, dhi, idesc, first, el);
-                            mma_tf32(d_im, wre + o, dhi, xim + o, dhi, idesc, 1u, el);
+                            mma_tf32(d_im, a_im1 + o, dhi, b_im1 + o, dhi, idesc, first, el);
+                            mma_tf32(d_im, a_im2 + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
                         }
                         if (NSPLIT == 3) {
                             if (do_re) {
                                 mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u, el);
                                 mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, idesc_n, 1u, el);
-                                mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, idesc_n, 1u, el);
+                                mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, id_re2, 1u, el);
+                                mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, id_re2, 1u, el);
                             } else {
-                                mma_tf32(d_im, wim_l + o, dhi, xre + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_im, wim + o, dhi, xre_l + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_im, wre_l + o, dhi, xim + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_im, wre + o, dhi, xim_l + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_im, a_im1l + o, dhi, b_im1 + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_im, a_im1 + o, dhi, b_im1l + o, dhi, idesc, 1u, el);
+                                mma_tf32(d_im, a_im2l + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
+                                mma_tf32(d_im, a_im2 + o, dhi, b_im2l + o, dhi, id_im2, 1u, el);
                             }
                         }
                     }
@@ -156,7 +168,9 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         // ================================ generators ================================
         // thread = (o pair p, quad iq of 4 consecutive i): one Philox call per (i, o pair) feeds (re, im) of o and o+1
         const int t = threadIdx.x - 64;             // 0..511
-        const int p = t & 63, iq = t >> 6;
+        // forward:  p = output-channel pair (64 per tile), iq = quad of 4 consecutive i (8 per k-block)
+        // backward: p = o pair inside the k-block (16),    iq = quad of 4 consecutive i rows of the tile (32)
+        const int p = BWD ? (t & 15) : (t & 63), iq = BWD ? (t >> 4) : (t >> 6);
         float4 bm[4];                               // mu of (o, o+1) at the 4 i of this thread, next k-block in flight
         float2 bl[4];                               // log_var of (o, o+1)
         const float* mu_n = nullptr;                // addresses of the k-block the buffers hold / will hold
@@ -166,11 +180,12 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
             const int mode = item / g.o_tiles, ot = item - mode * g.o_tiles;
             const int blk = mode >= g.m1m2;
             const int mb = mode - blk * g.m1m2;
-            const int i0 = kb * TK + iq * 4;
-            const size_t base = ((size_t)mb * g.Ci + i0) * g.Co + ot * TM + 2 * p;
+            const int i0 = BWD ? ot * TM + iq * 4 : kb * TK + iq * 4;         // first of this thread's 4 consecutive i
+            const int o0 = BWD ? kb * TK + 2 * p : ot * TM + 2 * p;           // its (even) output channel
+            const size_t base = ((size_t)mb * g.Ci + i0) * g.Co + o0;
             mu_n = (blk ? g.mu2 : g.mu1) + 2 * base;
             lv_n = SAMPLED ? (blk ? g.lv2 : g.lv1) + base : nullptr;
-            quad_n = ((uint64_t)mode * g.Ci + i0) * g.Cop + ((ot * TM) >> 1) + p;
+            quad_n = ((uint64_t)mode * g.Ci + i0) * g.Cop + (o0 >> 1);
         };
         auto fetch = [&](int j) {
             bm[j] = __ldg(reinterpret_cast<const float4*>(mu_n + (size_t)2 * j * g.Co));
@@ -192,7 +207,11 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     item_n += gridDim.x;
                     more = item_n < g.n_items;
                     if (more) locate(item_n, 0);
-                } else {                                          // same item: the streams just advance by TK input channels
+                } else if (BWD) {                                 // same item: the streams advance by TK output channels
+                    mu_n += 2 * TK;
+                    if (SAMPLED) lv_n += TK;
+                    quad_n += TK / 2;
+                } else {                                          // same item: the streams advance by TK input channels
                     mu_n += (size_t)2 * TK * g.Co;
                     if (SAMPLED) lv_n += (size_t)TK * g.Co;
                     quad_n += (uint64_t)TK * g.Cop;
@@ -213,6 +232,25 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                         wr[1][j] = fmaf(s1, z.z, wr[1][j]); wi[1][j] = fmaf(s1, z.w, wi[1][j]);
                     }
                 }
+                if (BWD) {
+                    // tile rows = i (iq*4 + j), columns = o: this thread owns the 8-byte pair (o, o+1) of four rows
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = iq * 4 + j;
+                        const uint32_t off = row * 128 + ((((p >> 1) ^ (row & 7)) << 4) | ((p & 1) << 3));
+                        const float2 vr = make_float2(wr[0][j], wr[1][j]), vi = make_float2(wi[0][j], wi[1][j]);
+                        if (NSPLIT == 3) {
+                            const float2 hr = make_float2(tf32_rn(vr.x), tf32_rn(vr.y)), hi = make_float2(tf32_rn(vi.x), tf32_rn(vi.y));
+                            sts64(st + off, hr);
+                            sts64(st + W_TILE + off, hi);
+                            sts64(st + 2 * W_TILE + off, make_float2(vr.x - hr.x, vr.y - hr.y));
+                            sts64(st + 3 * W_TILE + off, make_float2(vi.x - hi.x, vi.y - hi.y));
+                        } else {
+                            sts64(st + off, vr);
+                            sts64(st + W_TILE + off, vi);
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {
                     const int row = 2 * p + r2;
@@ -229,6 +267,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                         sts128(st + off, vr);
                         sts128(st + W_TILE + off, vi);
                     }
+                }
                 }
                 // ---- xhat tiles: hi in place, lo behind (layout-agnostic elementwise pass) ----
                 if (NSPLIT == 3) {
@@ -256,8 +295,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
             mbar_wait(&bar_tfull[acc], (it >> 1) & 1);
             tc_fence_after_sync();
             const int o = ot * TM + q * 32 + lane;
-            float* dr = g.yr + (size_t)mode * g.B * g.Co + o;
-            float* di = g.yi + (size_t)mode * g.B * g.Co + o;
+            float* dr = g.yr + (size_t)mode * g.B * g.MD + o;
+            float* di = g.yi + (size_t)mode * g.B * g.MD + o;
             const uint32_t ta = tmem_addr(tmem, q * 32, acc * acc_cols);
             for (int b0 = 0; b0 < g.B; b0 += 16) {
                 float vr[16], vi[16];
@@ -267,8 +306,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (b0 + j < g.B) {             // warp-uniform: skips the padding columns when B is not a multiple of 16
-                        dr[(size_t)(b0 + j) * g.Co] = vr[j];
-                        di[(size_t)(b0 + j) * g.Co] = vi[j];
+                        dr[(size_t)(b0 + j) * g.MD] = vr[j];
+                        di[(size_t)(b0 + j) * g.MD] = vi[j];
                     }
                 }
             }
@@ -283,19 +322,25 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
 
 }  // namespace
 
-int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
-               const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st) {
-    if (B < 1 || B > 128 || Ci % TK || Co % TM)
-        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd tiles 1 <= B <= 128, Ci%%32 == 0, Co%%128 == 0 (got %d, %d, %d)", B, Ci, Co);
-    if ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(xi) | reinterpret_cast<uintptr_t>(mu1) |
+// Shared launcher.  in_r / in_i: spectra [mode][b][KD] (KD = channels of the reduction side), out_r / out_i: [mode][b][MD].
+static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r, const float* in_i, int B, int Ci, int Co,
+                      const float* mu1, const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* out_r,
+                      float* out_i, cudaStream_t st) {
+    const int KD = bwd ? Co : Ci, MD = bwd ? Ci : Co;
+    const char* who = bwd ? "tc_mix_bwd_dx" : "tc_mix_fwd";
+    if (B < 1 || B > 128 || KD % TK || MD % TM || Co % 2)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "%s tiles 1 <= B <= 128, reduction channels %%32 == 0, output channels %%128 == 0 (got %d, %d, %d)",
+                 who, B, KD, MD);
+    if ((reinterpret_cast<uintptr_t>(in_r) | reinterpret_cast<uintptr_t>(in_i) | reinterpret_cast<uintptr_t>(mu1) |
          reinterpret_cast<uintptr_t>(mu2) | reinterpret_cast<uintptr_t>(lv1) | reinterpret_cast<uintptr_t>(lv2)) & 15)
-        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd needs 16-byte aligned tensors");
+        PNO_FAIL(PNO_E_UNSUPPORTED, "%s needs 16-byte aligned tensors", who);
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
     MixGeom g;
     memset(&g, 0, sizeof(g));
     g.B = B; g.Bp = (B + 15) / 16 * 16; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
-    g.o_tiles = Co / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = Ci / TK;
-    g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = yr; g.yi = yi; g.key = key;
+    g.MD = MD;
+    g.o_tiles = MD / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = KD / TK;
+    g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = out_r; g.yi = out_i; g.key = key;
     g.x_tile = g.Bp * 128;
     g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
     g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
@@ -303,31 +348,48 @@ int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, 
     if (g.stages < 2 || g.stages > 4) g.stages = 4;
     while (g.stages > 2 && g.stages * g.stage_bytes + 1024 > 220 * 1024) --g.stages;
     g.smem_bytes = g.stages * g.stage_bytes + 1024;
-    if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_fwd: %d bytes of shared memory needed", g.smem_bytes);
+    if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "%s: %d bytes of shared memory needed", who, g.smem_bytes);
     CUtensorMap tmXr, tmXi;
     int rc;
     {
-        const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)p->M * B};
-        const uint64_t str[1] = {(uint64_t)Ci * 4};
+        const uint64_t dims[2] = {(uint64_t)KD, (uint64_t)p->M * B};
+        const uint64_t str[1] = {(uint64_t)KD * 4};
         const uint32_t box[2] = {TK, (uint32_t)g.Bp};      // rows past mode*B + B: the next mode's rows, or zero fill past the end
-        if ((rc = pno_encode_tmap(&tmXr, xr, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmXi, xi, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmXr, in_r, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmXi, in_i, 2, dims, str, box, 1))) return rc;
     }
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = g.n_items < sms ? g.n_items : sms;
     const bool sampled = lv1 != nullptr;
-#define PNO_LAUNCH_MIX(NS, SM)                                                                                          \
-    do {                                                                                                               \
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<NS, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
-        PNO_CUDA(pno_launch(k_tc_mix_fwd<NS, SM>, grid, kThreads, g.smem_bytes, st, g, tmXr, tmXi));                                     \
+#define PNO_LAUNCH_MIX(NS, SM, BW)                                                                                          \
+    do {                                                                                                                   \
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<NS, SM, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
+        PNO_CUDA(pno_launch(k_tc_mix_fwd<NS, SM, BW>, grid, kThreads, g.smem_bytes, st, g, tmXr, tmXi));                   \
     } while (0)
-    if (x3 && sampled) PNO_LAUNCH_MIX(3, true);
-    else if (x3) PNO_LAUNCH_MIX(3, false);
-    else if (sampled) PNO_LAUNCH_MIX(1, true);
-    else PNO_LAUNCH_MIX(1, false);
+#define PNO_LAUNCH_MIX_DIR(NS, SM)               \
+    do {                                         \
+        if (bwd) PNO_LAUNCH_MIX(NS, SM, true);   \
+        else PNO_LAUNCH_MIX(NS, SM, false);      \
+    } while (0)
+    if (x3 && sampled) PNO_LAUNCH_MIX_DIR(3, true);
+    else if (x3) PNO_LAUNCH_MIX_DIR(3, false);
+    else if (sampled) PNO_LAUNCH_MIX_DIR(1, true);
+    else PNO_LAUNCH_MIX_DIR(1, false);
+#undef PNO_LAUNCH_MIX_DIR
 #undef PNO_LAUNCH_MIX
     PNO_LAUNCH_CHECK();
     return PNO_OK;
+}
+
+int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
+               const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st) {
+    return mix_launch(p, engine, false, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, st);
+}
+
+// dxhat[mode][b][i] = sum_o ghat[mode][b][o] * conj(W[mode][i][o])      (reference: autograd of models.py:33-35, 93-94)
+int tc_mix_bwd_dx(const pno_plan* p, int engine, const float* gr, const float* gi, int B, int Ci, int Co, const float* mu1,
+                  const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* dxr, float* dxi, cudaStream_t st) {
+    return mix_launch(p, engine, true, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, st);
 }

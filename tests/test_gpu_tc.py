@@ -200,6 +200,44 @@ def test_model_tensor_core_engines_against_oracle(engine, tol):
         assert rel_l2(v.grad, p[k].grad) < 5 * tol, k
 
 
+def _mix_bwd_dx(gr, gi, layer, sampled, engine):
+    lib = _lib.load()
+    m, b, co = gr.shape
+    ci = layer.in_channels
+    plan = _lib.plan(64, 64, layer.modes1, layer.modes2, gr.device)
+    n = [t.detach().permute(2, 3, 0, 1) for t in (layer.weights1, layer.weights2, layer.weights1_log_var, layer.weights2_log_var)]
+    dxr = torch.full((m, b, ci), float("nan"), device=gr.device)
+    dxi = torch.full((m, b, ci), float("nan"), device=gr.device)
+    _lib.check(lib.pno_mix_bwd_dx(plan, _lib.ENGINES[engine], gr.data_ptr(), gi.data_ptr(), b, ci, co, n[0].data_ptr(),
+                                  n[1].data_ptr(), n[2].data_ptr() if sampled else 0, n[3].data_ptr() if sampled else 0,
+                                  777, 3, 9, dxr.data_ptr(), dxi.data_ptr(), _lib.stream_ptr()), "pno_mix_bwd_dx")
+    torch.cuda.synchronize()
+    return dxr, dxi
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 5e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("sampled", [False, True])
+@pytest.mark.parametrize("shape", [(16, 128, 128, 4, 4), (64, 256, 256, 20, 20), (20, 128, 64, 2, 2), (3, 256, 32, 3, 4)])
+def test_mix_backward_dx_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
+    """Input gradient of the channel mix (W re-sampled in-kernel, conjugated): tensor-core engines vs the fp32 CUDA-core kernel,
+    which the layer-level tests pin to the oracle's autograd."""
+    import pno_physics_bench_b200 as pno
+    b, ci, co, m1, m2 = shape
+    gen = torch.Generator().manual_seed(sum(shape) + 1)
+    layer = pno.SpectralConv2d_Probabilistic(ci, co, m1, m2)
+    with torch.no_grad():
+        for w_, lv in ((layer.weights1, layer.weights1_log_var), (layer.weights2, layer.weights2_log_var)):
+            w_.copy_(torch.complex(torch.randn(w_.shape, generator=gen), torch.randn(w_.shape, generator=gen)) / co ** 0.5)
+            lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 6)
+    layer = layer.to(DEV)
+    m = 2 * m1 * m2
+    gr = torch.randn(m, b, co, generator=gen).to(DEV)
+    gi = torch.randn(m, b, co, generator=gen).to(DEV)
+    rr, ri = _mix_bwd_dx(gr, gi, layer, sampled, "fp32")
+    tr, ti = _mix_bwd_dx(gr, gi, layer, sampled, engine)
+    assert rel_l2(tr, rr) < tol and rel_l2(ti, ri) < tol, (rel_l2(tr, rr), rel_l2(ti, ri))
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # size-independent properties at the full BASELINE config-3 layer shape (B 64, C 256, 64x64, modes 20), where the oracle is
 # too slow to be the checker
