@@ -297,6 +297,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # per-kernel roofline first: each kernel timed alone (L2 flushed), before the long timed region heats the part into its power cap
+    roof = None
+    if rank == 0:
+        roof = layer_roofline(args.engine, device)
+    if world > 1:
+        dist.barrier()
     with ClockSampler(local) as clocks:        # nvidia-smi needs ~1 s to start: launched before the warm-up, rows filtered by time
         for i in range(args.warmup):
             step_resident(i)
@@ -320,9 +326,8 @@ def main():
         model.set_engine(args.engine)
         strict = {"engine": "tf32x3", "value": round(fields / (ms_strict * 1e-3), 2), "unit": UNIT,
                   "ms_per_step": round(ms_strict, 3), "parity": "rel-L2 <= 1e-5 vs the fp32 reference (tests/test_gpu_tc.py)"}
-    roof = base = None
+    base = None
     if rank == 0:
-        roof = layer_roofline(args.engine, device)
         if strict is not None:
             ks = block_kernel_times("tf32x3", device, iters=3)
             strict["block_kernels_us"] = {n: v["us"] for n, v in ks.items()}
