@@ -77,6 +77,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// shared -> global tile store (bulk async group of the issuing thread); the shared tile must have been made visible to the
+// async proxy (fence_proxy_async_smem by the writers, then a barrier) before this is issued
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -178,6 +190,21 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_
         "setp.ne.b32 q, %7, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: A is 128 lanes x 8 consecutive 32-bit columns of tensor memory (e.g. the accumulator of an
+// earlier MMA; its column address must be a multiple of 4 - measured, tools/micro/mma_ts.cu), read as fp32 truncated to tf32.
+// MMAs of one thread execute in issue order, so an MMA may consume the accumulator of the one issued before it.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t elected = 1u) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
         : "memory");
 }
 

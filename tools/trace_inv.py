@@ -16,7 +16,7 @@ plan = _lib.plan(H, W, m, m, torch.device("cuda", 0))
 yr, yi = torch.randn(M, B, C, device="cuda"), torch.randn(M, B, C, device="cuda")
 add = torch.randn(B, C, H, W, device="cuda")
 y = torch.empty_like(add)
-dbg = torch.zeros(4096 + 5 * 512, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(4096 + 6 * 512, dtype=torch.int64, device="cuda")
 for rep in range(2):
     dbg.zero_()
     lib.pno_debug_set_buffer(dbg.data_ptr())
@@ -26,11 +26,11 @@ for rep in range(2):
     lib.pno_debug_set_buffer(0)
 names = {0: {1: "I b1_full", 2: "I d1_empty", 3: "I S1 issued", 4: "I zt_full", 5: "I d2_empty", 6: "I S2 issued"},
          1: {1: "T d1_full", 2: "T zt_empty", 3: "T tile done", 4: "T arrived", 5: "T tmem loaded"},
-         2: {1: "E d2_full", 2: "E done"}, 3: {1: "L b1_empty", 2: "L loaded", 3: "L arrived"},
+         2: {1: "E d2_full", 2: "E done", 3: "E add_full"}, 5: {1: "P tile complete", 2: "P store read out", 3: "P load issued"}, 3: {1: "L b1_empty", 2: "L loaded", 3: "L arrived"},
          4: {1: "E' d2_full", 2: "E' done"}}
 ev = []
 d = dbg.cpu()
-for role in range(5):
+for role in range(6):
     for n in range(512):
         v = int(d[4096 + role * 512 + n])
         if v:
