@@ -310,6 +310,17 @@ __device__ __forceinline__ void warp_store_rows16(float4* sc, int lane, const fl
     __syncwarp();
 }
 
+// Each lane stores its own run of 16 consecutive floats (64 B) with two 256-bit stores: every store instruction writes 32 whole
+// sectors (one per lane) and no shared memory is touched.
+__device__ __forceinline__ void lane_store16(float* dst, const float v[16]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+                 "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                 : "memory");
+}
+
 }  // namespace sm100
 
 // ---- diagnostics (compiled in only with -DPNO_TRACE: `make EXTRA=-DPNO_TRACE`) -------------------------------------------

@@ -687,7 +687,8 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     g.IPT = 128 / H;
     const int nbuf = x3 ? 2 : 1;          // hi (+ lo)
     bool ok = false;
-    const int epi_max = (W % 64 == 0) ? 16 : 8;
+    const char* e_epi = getenv("PNO_INV_EPI");         // tuning override: 8 = narrow epilogue
+    const int epi_max = (W % 64 == 0 && !(e_epi && atoi(e_epi) == 8)) ? 16 : 8;
     const int add_bytes = 128 * W * 4;                 // one 128-row tile of the addend
     const char* e_add = getenv("PNO_INV_ADD");         // tuning override: 0 = LDG addend
     const int add_max = addend == nullptr ? 0 : (e_add ? atoi(e_add) : 3);

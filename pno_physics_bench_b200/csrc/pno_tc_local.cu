@@ -22,9 +22,10 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kEpiWarps = 16;
 constexpr int kTileTab = 128;
-constexpr int kThreads = 64 + 128 + kEpiWarps * 32;
+// CTA: warp 0 TMA, warp 1 MMA issuer, (3xTF32 only) warps 2-5 x-tile splitter, then EW epilogue warps
+constexpr int epi0(int nsplit) { return nsplit == 3 ? 6 : 2; }
+constexpr int threads_for(int nsplit, int ew) { return (epi0(nsplit) + ew) * 32; }
 constexpr int TM = 128;          // output channels per tile (UMMA M)
 constexpr int TK = 32;           // input channels per stage (one 128-byte swizzle row)
 constexpr int TILE_BYTES = TM * TK * 4;   // 16 KB, same for A [128][32] and B [32][128]
@@ -42,12 +43,12 @@ struct LocalArgs {
 
 #define TRACE(role, ev) PNO_TRACE_EV(a.dbg, role, ev)
 
-template <int NSPLIT, int TN>
+template <int NSPLIT, int TN, int EW>
 struct Cfg {
     static constexpr int kXBytes = TK * TN * 4;                                  // X tile [TN/32 p-blocks][32 rows][128 B]
     static constexpr int kOperandBytes = 2 * TILE_BYTES + kXBytes;               // Am, Al, X
     static constexpr int kStageBytes = kOperandBytes * (NSPLIT == 3 ? 2 : 1);    // + lo copies
-    static constexpr int kStages = (192 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (3xTF32)
+    static constexpr int kStages = (224 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (3xTF32)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
     static constexpr int kAcc = TN == 128 ? 2 : 1;                               // accumulator buffers in tensor memory
     static_assert(kStages >= 2, "stage does not fit");
@@ -62,18 +63,18 @@ __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-neares
     return r;
 }
 
-template <int NSPLIT, bool NOISY, bool DLV, int TN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW>
+__global__ void __launch_bounds__(threads_for(NSPLIT, EW), 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
            const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmWmLo,
            const __grid_constant__ CUtensorMap tmWlLo) {
-    using C = Cfg<NSPLIT, TN>;
+    using C = Cfg<NSPLIT, TN, EW>;
+    constexpr int kEpi0 = epi0(NSPLIT);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bar_raw[C::kStages], bar_split[C::kStages], bar_empty[C::kStages];
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float4 s_scratch[kEpiWarps][128];
     __shared__ int s_tile[kTileTab][3];      // (ot, pt, b) of this CTA's first kTileTab tiles: no divisions in the role loops
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,7 +89,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], kEpiWarps * 32);
+            mbar_init(&bar_tempty[s], EW * 32);
         }
         fence_mbar_init();
         tma_prefetch_desc(&tmX);
@@ -187,7 +188,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 TRACE(0, 3);
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < kEpi0) {
         // ================================ hi/lo splitter (3xTF32) ================================
         if (NSPLIT == 3) {
             const int t = threadIdx.x - 64;   // 0..127
@@ -212,11 +213,13 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         }
     } else {
         // ================================ epilogue ================================
+        // A tile is NP passes of 16 pixel columns per lane quarter; the EW / 4 warps of a quarter take the passes of the tile
+        // stream round-robin (pass s = it * NP + p goes to warp s % (EW/4)), so any warp count divides the work evenly
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int cc = (warp - 6) >> 2;         // this warp's quarter of the TN-pixel tile
-        constexpr int CW = TN / 4;              // columns per warp
-        float4* sc = s_scratch[warp - 6];
-        int it = 0;
+        const int kq = (warp - kEpi0) >> 2;     // index of this warp among the warps of its quarter
+        constexpr int EWQ = EW / 4, NP = TN / 16;
+        static_assert(EW % 4 == 0 && NP >= EWQ, "every epilogue warp needs a pass in every tile");
+        int it = 0, base = 0;                   // base = (it * NP) % EWQ
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
             int ot, pt, b;
             if (it < kTileTab) { ot = s_tile[it][0]; pt = s_tile[it][1]; b = s_tile[it][2]; }
@@ -225,15 +228,17 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             const int o = ot * TM + q * 32 + lane;
             const float bias_m = a.bm ? a.bm[o] : 0.f;
             const float bias_l = (NOISY && a.bl) ? a.bl[o] : 0.f;
-            // first row of this warp / Philox element of this thread's row
-            const size_t wrow = ((size_t)b * a.Co + ot * TM + q * 32) * a.HW + (size_t)pt * TN + cc * CW;
-            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN + cc * CW;
+            // output row / first Philox element of this thread
+            const size_t wrow = ((size_t)b * a.Co + o) * a.HW + (size_t)pt * TN;      // this lane's row
+            const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN;
             mbar_wait(&bar_tfull[acc], (it / C::kAcc) & 1);
-            if (warp == 6) TRACE(2, 1);
+            if (warp == kEpi0) TRACE(2, 1);
             tc_fence_after_sync();
-            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * (2 * TN) + cc * CW), t_l = t_m + TN;
+            const uint32_t t_m = tmem_addr(tmem, q * 32, acc * (2 * TN)), t_l = t_m + TN;
+            int p0 = kq - base;
+            if (p0 < 0) p0 += EWQ;
 #pragma unroll 1
-            for (int c = 0; c < CW; c += 16) {
+            for (int c = p0 * 16; c < TN; c += EWQ * 16) {
                 float v[16], l[16];
                 tmem_ld16(t_m + c, v);
                 if (NOISY) tmem_ld16(t_l + c, l);
@@ -259,12 +264,16 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += bias_m;
                 }
-                warp_store_rows16(sc, lane, v, a.out + wrow + c, a.HW);
-                if (NOISY && DLV) warp_store_rows16(sc, lane, l, a.dlv + wrow + c, a.HW);
+                // each lane owns one output row: 64 contiguous bytes per pass, stored from registers as two 256-bit stores
+                // (whole sectors; measured faster than a shared-memory transpose, which competes with the MMA operand reads)
+                lane_store16(a.out + wrow + c, v);
+                if (NOISY && DLV) lane_store16(a.dlv + wrow + c, l);
             }
+            base += NP % EWQ;
+            if (base >= EWQ) base -= EWQ;
             tc_fence_before_sync();
             mbar_arrive(&bar_tempty[acc]);
-            if (warp == 6) TRACE(2, 2);
+            if (warp == kEpi0) TRACE(2, 2);
         }
     }
     tc_fence_before_sync();
@@ -308,26 +317,27 @@ static float* split_scratch(int dev, cudaStream_t st, size_t floats) {
     return e.buf;
 }
 
-template <int NSPLIT, bool NOISY, bool DLV, int TN>
+template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16>
 int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
            const CUtensorMap& tmWlLo, cudaStream_t st) {
-    using C = Cfg<NSPLIT, TN>;
-    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    using C = Cfg<NSPLIT, TN, EW>;
+    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN>, grid, kThreads, C::kSmemBytes, st, a, tmX, tmWm, tmWl, tmWmLo, tmWlLo));
+    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN, EW>, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl,
+                        tmWmLo, tmWlLo));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
-template <int NSPLIT, int TN>
+template <int NSPLIT, int TN, int EW>
 int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
               const CUtensorMap& tmWlLo, cudaStream_t st) {
-    if (!a.noisy) return launch<NSPLIT, false, false, TN>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    if (a.want_dlv) return launch<NSPLIT, true, true, TN>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    return launch<NSPLIT, true, false, TN>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    return launch<NSPLIT, true, false, TN, EW>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
 }
 
 }  // namespace
@@ -378,7 +388,13 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         if ((rc = pno_encode_tmap(&tmWmLo, wm_lo, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmWlLo, wl_lo, 2, dims, str, box, 1))) return rc;
     }
-    if (engine == PNO_ENGINE_TC_TF32X3) return launch_ns<3, 128>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    if (TN == 256) return launch_ns<1, 256>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    return launch_ns<1, 128>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    // Epilogue warps: measured on B200 at the headline shape (single pass): 4 warps 177 us, 8 warps 163, 16 warps 177, 24 warps
+    // 196 -- two per scheduler keep up with the tensor pipe, more only take issue slots and power from it.  PNO_LOCAL_EW=16
+    // selects the wide epilogue (tuning).
+    const char* e_ew = getenv("PNO_LOCAL_EW");
+    const bool wide = e_ew && atoi(e_ew) == 16;
+    if (engine == PNO_ENGINE_TC_TF32X3)
+        return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    if (TN == 256) return launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
 }
