@@ -77,6 +77,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// pull one box of a 3-D tensor map into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1) : "memory");
+}
 // shared -> global tile store (bulk async group of the issuing thread); the shared tile must have been made visible to the
 // async proxy (fence_proxy_async_smem by the writers, then a barrier) before this is issued
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {

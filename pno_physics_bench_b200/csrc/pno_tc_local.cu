@@ -5,14 +5,17 @@
 //               [128 o][32 i] (K-major A operands) into a multi-stage shared-memory ring
 //   warps 2-5   (3xTF32 only) split every staged tile into tf32 hi (in place) + lo (second buffer)
 //   warp 1      one thread issues tcgen05.mma kind::tf32 into two TMEM accumulators (mean, log-var), double buffered
-//   warps 6-21  epilogue (16 warps = 4 per scheduler; the noise generation makes this the issue-bound role): tcgen05.ld ->
-//               bias, clamp/exp, Philox noise, (d out / d lv for backward) -> shared-memory transpose -> coalesced global rows
+//   then EW epilogue warps (8 by default = 2 per scheduler): tcgen05.ld -> bias, clamp/exp, Philox noise, (d out / d lv for
+//               backward) -> each lane stores its own output row straight from registers with 256-bit stores
 // A tile is (batch item b, 128 output channels, TN pixels); tiles are statically strided over the persistent grid with the
-// output-channel tile fastest so that the CTAs sharing an x tile run at the same time (L2 reuse).
+// output-channel tile fastest so that the CTAs sharing an x tile run at the same time (L2 reuse); the producer also pulls the x
+// boxes of its next tile into L2 one tile ahead.
 // TN = 128 by default (double-buffered accumulators).  TN = 256 (PNO_LOCAL_TN=256, single-pass mode only) halves the weight-tile
-// fill per output (384 -> 256 KB per 128x128 outputs) at the price of single-buffered accumulators (mean | log-var = 512 TMEM
-// columns); measured 193 vs 185 us at the headline shape: the kernel is bound by the epilogue's noise generation (Philox +
-// Box-Muller + exp per output element, ~9k cycles per 128x128 tile on 16 warps), not by the operand fill.
+// fill per output at the price of single-buffered accumulators (mean | log-var = 512 TMEM columns); measured slower.
+// What bounds it (measured on B200, headline shape, ablations of the epilogue): without noise generation the kernel still takes
+// 136 of its 164 us -- the MMA side is shared-memory-bandwidth bound (a 128x128x8 SS MMA reads 8 KB per 64 tensor cycles = the
+// full 128 B/clk, and the TMA stage fills write another 48 KB per 64 KB of operand reads); TMEM loads and the global stores cost
+// nothing measurable; more than 8 epilogue warps only slow the issuer down (4 warps 177 us, 8: 163, 16: 177, 24: 196).
 #include <stdlib.h>
 
 #include "pno_sm100.cuh"
@@ -33,6 +36,7 @@ constexpr int TILE_BYTES = TM * TK * 4;   // 16 KB, same for A [128][32] and B [
 struct LocalArgs {
     int B, Ci, Co, HW;
     int noisy, want_dlv;
+    int prefetch;           // L2 prefetch of the next tile's x boxes
     const float *bm, *bl;
     float *out, *dlv;
     PhiloxKey key;
@@ -122,7 +126,17 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 int ot, pt, b;
                 if (itp < kTileTab) { ot = s_tile[itp][0]; pt = s_tile[itp][1]; b = s_tile[itp][2]; }
                 else { ot = tile % a.o_tiles; pt = (tile / a.o_tiles) % a.p_tiles; b = tile / (a.o_tiles * a.p_tiles); }
+                // x tiles of this CTA's NEXT tile are pulled into L2 one tile ahead: the stage fills then see L2 latency instead
+                // of HBM latency (the ring holds only kStages stages, too few bytes in flight to cover ~1.5 us of HBM latency)
+                int npt = 0, nb = 0;
+                const int ntile = tile + gridDim.x;
+                const bool pf = a.prefetch && ntile < a.n_tiles;
+                if (pf) {
+                    if (itp + 1 < kTileTab) { npt = s_tile[itp + 1][1]; nb = s_tile[itp + 1][2]; }
+                    else { npt = (ntile / a.o_tiles) % a.p_tiles; nb = ntile / (a.o_tiles * a.p_tiles); }
+                }
                 for (int kb = 0; kb < KB; ++kb) {
+                    if (pf) tma_prefetch_l2_3d(&tmX, 0, nb * a.Ci + kb * TK, npt * (TN / 32));
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     TRACE(3, 1);
                     unsigned char* st = stage_ptr(stage);
@@ -354,6 +368,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     a.B = B; a.Ci = Ci; a.Co = Co; a.HW = HW;
     a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;
     a.dbg = g_pno_debug_buffer;
+    a.prefetch = getenv("PNO_LOCAL_PREFETCH") ? atoi(getenv("PNO_LOCAL_PREFETCH")) : 1;
     a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset;
     // pixel-tile width (see the header comment): 128 unless PNO_LOCAL_TN=256 asks for the wide tile
     const char* e_tn = getenv("PNO_LOCAL_TN");
@@ -395,6 +410,6 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     const bool wide = e_ew && atoi(e_ew) == 16;
     if (engine == PNO_ENGINE_TC_TF32X3)
         return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    if (TN == 256) return launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+    if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
     return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
 }
