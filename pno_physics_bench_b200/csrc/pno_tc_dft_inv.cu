@@ -743,6 +743,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     // ---- transposer path (3xTF32, or no tensor-memory geometry fits) ----
     for (int G = 8; G >= g.IPT && G >= 4 && !ok; G >>= 1) {
         if (C % G || (G * m2) % 16 || G * m2 > 256 || 2 * G * m2 + 2 * W > 512) continue;
+        if (getenv("PNO_INV_G") && atoi(getenv("PNO_INV_G")) != G) continue;      // tuning override
         g.ts = 0; g.zs = m2; g.n_lw = 4; g.rowsA = H; g.d2_stride = W;
         g.G = G; g.N1 = G * m2; g.TPG = G / g.IPT;
         g.tabA_one = g.S1 * H * 32;
