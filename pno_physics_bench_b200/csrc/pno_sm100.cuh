@@ -41,8 +41,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
+    // (measured: a shorter retry path -- clock read once per 256 retries -- makes the waiters spin faster and the kernels
+    //  3-5% SLOWER; the clock read doubles as back-off)
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#ifdef PNO_WAIT_SLEEP
+        __nanosleep(PNO_WAIT_SLEEP);
+#endif
         if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug, not a slow kernel -> fail loudly, do not hang
             printf("pno_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
             __trap();
