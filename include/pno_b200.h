@@ -160,6 +160,29 @@ int pno_mc_accumulate(const float* y, uint64_t n, double* sum, double* sumsq, vo
 int pno_mc_finalize(const double* sum, const double* sumsq, uint64_t n, uint32_t S, float* mean, float* std,
                     void* stream);
 
+/* ---- loss / calibration epilogue on device ----------------------------------------------------------
+ * One pass over (mean, spread, target), n elements each; spread_kind 0: spread is the predictive std, 1: spread is log_var
+ * (std = exp(0.5 log_var), training/losses.py:60).  ADDS into acc (double, device), so batches accumulate on device and
+ * PNOTrainer.evaluate needs no per-batch host copies (training/trainer.py:540-552).  Layout of acc (L = n_levels,
+ * A = n_alphas, NB = n_bins):
+ *   [0] n   [1] sum |mean-target|   [2] sum (mean-target)^2   [3] sum Gaussian NLL, std clamped at 1e-6 (losses.py:97-117,
+ *   metrics.py:295-324)   [4] sum std   [5] sum std^2   [6] sum std*|mean-target|
+ *   [7 .. 7+L)        count(|mean-target| <= z_levels[l] * std)        (metrics.py:99-128, losses.py:119-149)
+ *   [7+L .. 7+L+A)    sum interval score for (alphas[a], z_alphas[a])  (metrics.py:130-159)
+ *   [7+L+A .. +3 NB)  per ECE bin b = (bin_edges[b], bin_edges[b+1]]: count, sum confidence, count(|e|/(std+1e-8) <= 1)
+ *                     with confidence = clamp(1 - 2 pdf(|e|/(std+1e-8)), 0, 1)                  (metrics.py:32-97)
+ * z_levels / alphas / z_alphas are HOST arrays (copied by value), bin_edges is a DEVICE array of NB+1 floats. */
+#define PNO_UQ_MAX_LEVELS 8
+#define PNO_UQ_MAX_ALPHAS 4
+#define PNO_UQ_MAX_BINS 64
+int pno_uq_stats(const float* mean, const float* spread, const float* target, uint64_t n, int spread_kind,
+                 const float* z_levels, int n_levels, const float* alphas, const float* z_alphas, int n_alphas,
+                 const float* bin_edges, int n_bins, double* acc, void* stream);
+/* Gradient of  g[0] * sum (mean-target)^2 + g[1] * sum nll  (g: 2 doubles on device) w.r.t. mean and log_var
+ * (log_var / dlog_var may be NULL: MSE only).  The coverage term of the loss is piecewise constant (losses.py:140-143). */
+int pno_loss_data_bwd(const float* mean, const float* log_var, const float* target, uint64_t n, const double* g,
+                      float* dmean, float* dlog_var, void* stream);
+
 /* Diagnostics: device buffer (>= 148*16 int64) into which the tensor-core kernels dump per-CTA barrier-wait cycle counters
  * (NULL switches it off, the default).  Used by tools/phase_times.py to find the stage a pipeline is waiting on. */
 int pno_debug_set_buffer(void* device_ptr);

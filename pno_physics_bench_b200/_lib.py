@@ -50,6 +50,8 @@ SIGNATURES = {
     "pno_kl_bwd": (_int, [_vp, _vp, _u64, _vp, _int, _vp, _vp, _vp]),
     "pno_mc_accumulate": (_int, [_vp, _u64, _vp, _vp, _vp]),
     "pno_mc_finalize": (_int, [_vp, _vp, _u64, _u32, _vp, _vp, _vp]),
+    "pno_uq_stats": (_int, [_vp, _vp, _vp, _u64, _int, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp]),
+    "pno_loss_data_bwd": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "pno_debug_set_buffer": (_int, [_vp]),
     "pno_selftest_umma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

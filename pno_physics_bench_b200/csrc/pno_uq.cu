@@ -1,0 +1,173 @@
+// Loss / calibration epilogue on device: one pass over (mean, spread, target) produces every
+// sufficient statistic that the reference's losses (training/losses.py:97-149) and CalibrationMetrics
+// (metrics.py:32-170, 295-392) reduce to, as fp64 sums that are additive over batches -- so PNOTrainer.evaluate never copies
+// predictions to the host (trainer.py:540-552 does, per batch) and the metrics are one small read at the end.
+//   pno_uq_stats          the statistics (layout in include/pno_b200.h)
+//   pno_loss_data_bwd     gradient of  g_se * sum (mean-target)^2 + g_nll * sum nll  w.r.t. mean and log_var
+#include "pno_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxLevels = PNO_UQ_MAX_LEVELS, kMaxAlphas = PNO_UQ_MAX_ALPHAS, kMaxBins = PNO_UQ_MAX_BINS;
+
+struct UqArgs {
+    const float *mean, *spread, *target;
+    unsigned long long n;
+    int spread_kind, n_levels, n_alphas, n_bins;
+    float z_levels[kMaxLevels];
+    float alphas[kMaxAlphas], z_alphas[kMaxAlphas];
+    const float* bin_edges;     // n_bins + 1 boundaries (device), bins are (edge[b], edge[b+1]] like metrics.py:69-75
+    double* acc;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_uq_stats(const UqArgs a) {
+    __shared__ float s_edges[kMaxBins + 1];
+    __shared__ unsigned int s_cnt[kMaxBins], s_hit[kMaxBins];
+    __shared__ float s_conf[kMaxBins];
+    __shared__ double s_red[kThreads / 32];
+    for (int i = threadIdx.x; i < kMaxBins; i += kThreads) { s_cnt[i] = 0; s_hit[i] = 0; s_conf[i] = 0.f; }
+    for (int i = threadIdx.x; i <= a.n_bins && a.n_bins > 0; i += kThreads) s_edges[i] = a.bin_edges[i];
+    __syncthreads();
+
+    double d_ae = 0, d_se = 0, d_nll = 0, d_s = 0, d_s2 = 0, d_sae = 0, d_is[kMaxAlphas];
+    unsigned long long cnt[kMaxLevels];
+#pragma unroll
+    for (int k = 0; k < kMaxLevels; ++k) cnt[k] = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxAlphas; ++k) d_is[k] = 0;
+    unsigned long long n_mine = 0;
+
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < a.n;
+         i += (unsigned long long)gridDim.x * kThreads) {
+        const float mu = a.mean[i], t = a.target[i], sp = a.spread[i];
+        const float sd = a.spread_kind ? expf(0.5f * sp) : sp;         // losses.py:60 std = exp(0.5 log_var)
+        const float err = fabsf(mu - t);                               // metrics.py:121
+        const float d = t - mu;
+        const float se = d * d;
+        // Gaussian NLL, std clamped at 1e-6 (losses.py:104-115, metrics.py:312-323)
+        const float sc = fmaxf(sd, 1e-6f);
+        const float nll = 0.5f * (1.8378770664093453f + 2.f * logf(sc) + se / (sc * sc));
+        ++n_mine;
+        d_ae += err; d_se += se; d_nll += nll; d_s += sd; d_s2 += (double)sd * sd; d_sae += (double)sd * err;
+#pragma unroll
+        for (int k = 0; k < kMaxLevels; ++k)
+            if (k < a.n_levels) cnt[k] += err <= a.z_levels[k] * sd;   // metrics.py:122-125, losses.py:140-143
+#pragma unroll
+        for (int k = 0; k < kMaxAlphas; ++k)
+            if (k < a.n_alphas) {                                      // metrics.py:147-158
+                const float lower = mu - a.z_alphas[k] * sd, upper = mu + a.z_alphas[k] * sd;
+                const float pen = 2.f / a.alphas[k];
+                d_is[k] += (upper - lower) + pen * fmaxf(lower - t, 0.f) + pen * fmaxf(t - upper, 0.f);
+            }
+        if (a.n_bins > 0) {                                            // metrics.py:58-83
+            const float zn = err / (sd + 1e-8f);
+            const float pdf = expf(-(zn * zn) / 2.f - 0.91893853320467274f);
+            const float conf = fminf(fmaxf(1.f - 2.f * pdf, 0.f), 1.f);
+            int b = (int)ceilf(conf * a.n_bins) - 1;                   // first guess, then the reference's own comparisons
+            b = max(0, min(a.n_bins - 1, b));
+            while (b > 0 && !(conf > s_edges[b])) --b;
+            while (b < a.n_bins - 1 && !(conf <= s_edges[b + 1])) ++b;
+            if (conf > s_edges[b] && conf <= s_edges[b + 1]) {
+                atomicAdd(&s_cnt[b], 1u);
+                atomicAdd(&s_conf[b], conf);
+                if (zn <= 1.0f) atomicAdd(&s_hit[b], 1u);
+            }
+        }
+    }
+
+    // block reduction of the scalar slots, one double atomic per block and slot
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto block_add = [&](double v, int slot) {
+        v = warp_sum(v);
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double w = lane < kThreads / 32 ? s_red[lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0 && w != 0.0) atomicAdd(&a.acc[slot], w);
+        }
+        __syncthreads();
+    };
+    block_add((double)n_mine, 0);
+    block_add(d_ae, 1);
+    block_add(d_se, 2);
+    block_add(d_nll, 3);
+    block_add(d_s, 4);
+    block_add(d_s2, 5);
+    block_add(d_sae, 6);
+    for (int k = 0; k < a.n_levels; ++k) block_add((double)cnt[k], 7 + k);
+    for (int k = 0; k < a.n_alphas; ++k) block_add(d_is[k], 7 + a.n_levels + k);
+    const int base = 7 + a.n_levels + a.n_alphas;
+    for (int b = threadIdx.x; b < a.n_bins; b += kThreads)
+        if (s_cnt[b]) {
+            atomicAdd(&a.acc[base + 3 * b], (double)s_cnt[b]);
+            atomicAdd(&a.acc[base + 3 * b + 1], (double)s_conf[b]);
+            atomicAdd(&a.acc[base + 3 * b + 2], (double)s_hit[b]);
+        }
+}
+
+__global__ void __launch_bounds__(kThreads) k_loss_data_bwd(const float* __restrict__ mean, const float* __restrict__ lv,
+                                                           const float* __restrict__ target, unsigned long long n,
+                                                           const double* __restrict__ g, float* __restrict__ dmean,
+                                                           float* __restrict__ dlv) {
+    const float g_se = (float)g[0], g_nll = (float)g[1];
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * kThreads) {
+        const float mu = mean[i], t = target[i];
+        const float d = mu - t;
+        float gm = g_se * 2.f * d, gl = 0.f;
+        if (lv) {
+            const float sd = expf(0.5f * lv[i]);
+            const float sc = fmaxf(sd, 1e-6f);
+            const float iv = 1.f / (sc * sc);
+            gm += g_nll * d * iv;                                       // d nll / d mean = (mean - t) / var
+            // d nll / d log_var = 0.5 (1 - (t - mean)^2 / var) through std = exp(lv / 2); zero where the clamp is active
+            if (sd >= 1e-6f) gl = g_nll * 0.5f * (1.f - d * d * iv);
+        }
+        dmean[i] = gm;
+        if (dlv) dlv[i] = gl;
+    }
+}
+
+}  // namespace
+
+extern "C" int pno_uq_stats(const float* mean, const float* spread, const float* target, uint64_t n, int spread_kind,
+                            const float* z_levels, int n_levels, const float* alphas, const float* z_alphas, int n_alphas,
+                            const float* bin_edges, int n_bins, double* acc, void* stream) {
+    if (!mean || !spread || !target || !acc) PNO_FAIL(PNO_E_INVALID, "pno_uq_stats: null pointer");
+    if (n_levels < 0 || n_levels > kMaxLevels || n_alphas < 0 || n_alphas > kMaxAlphas || n_bins < 0 || n_bins > kMaxBins)
+        PNO_FAIL(PNO_E_INVALID, "pno_uq_stats: at most %d coverage levels, %d interval levels, %d bins", kMaxLevels, kMaxAlphas,
+                 kMaxBins);
+    if ((n_levels && !z_levels) || (n_alphas && (!alphas || !z_alphas)) || (n_bins && !bin_edges))
+        PNO_FAIL(PNO_E_INVALID, "pno_uq_stats: missing level / bin arrays");
+    if (n == 0) return PNO_OK;
+    UqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mean = mean; a.spread = spread; a.target = target; a.n = n; a.spread_kind = spread_kind;
+    a.n_levels = n_levels; a.n_alphas = n_alphas; a.n_bins = n_bins; a.bin_edges = bin_edges; a.acc = acc;
+    for (int k = 0; k < n_levels; ++k) a.z_levels[k] = z_levels[k];           // host arrays (a handful of floats)
+    for (int k = 0; k < n_alphas; ++k) { a.alphas[k] = alphas[k]; a.z_alphas[k] = z_alphas[k]; }
+    const unsigned long long want = (n + kThreads - 1) / kThreads;
+    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    k_uq_stats<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+extern "C" int pno_loss_data_bwd(const float* mean, const float* log_var, const float* target, uint64_t n, const double* g,
+                                 float* dmean, float* dlog_var, void* stream) {
+    if (!mean || !target || !g || !dmean) PNO_FAIL(PNO_E_INVALID, "pno_loss_data_bwd: null pointer");
+    if (n == 0) return PNO_OK;
+    const unsigned long long want = (n + kThreads - 1) / kThreads;
+    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    k_loss_data_bwd<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(mean, log_var, target, n, g, dmean, dlog_var);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}

@@ -129,19 +129,31 @@ class PNOTrainer:
         return self.training_history
 
     def evaluate(self, loader, num_samples: int = 100) -> Dict[str, float]:
-        """trainer.py:499-575 (loss part): MC predictive mean/std with S=100, MSE and NLL."""
+        """trainer.py:499-575: MC predictive mean/std with S=100 per batch, the loss on (mean, 2 log(std + 1e-8)) and the
+        CalibrationMetrics report.  Predictions stay on the device: every batch adds its sufficient statistics to one fp64
+        vector (`metrics.UQAccumulator`), read once at the end -- the reference copies every batch to the host and
+        concatenates (trainer.py:548-556).  Returns the reference's keys plus 'mse' / 'nll'."""
+        from ..metrics import UQAccumulator
         self.model.eval()
-        se = nll = 0.0
-        count = 0
+        acc = UQAccumulator(device=self.device)
+        total_loss = None
+        total_samples = 0
         with torch.no_grad():
             for inputs, targets in loader:
                 inputs, targets = inputs.to(self.device), targets.to(self.device)
                 mean, std = self.model.predict_with_uncertainty(inputs, num_samples=num_samples)
-                std = std.clamp(min=1e-6)
-                se = se + ((mean - targets) ** 2).sum()
-                nll = nll + (0.5 * (1.8378770664093453 + 2 * torch.log(std) + (targets - mean) ** 2 / std ** 2)).sum()
-                count += targets.numel()
-        return {"mse": float(se) / max(count, 1), "nll": float(nll) / max(count, 1)}
+                losses = self.loss_fn((mean, 2 * torch.log(std + 1e-8)), targets, self.model)      # trainer.py:533-538
+                batch = inputs.shape[0]
+                total_loss = losses["total"].detach() * batch if total_loss is None else total_loss + losses["total"].detach() * batch
+                total_samples += batch
+                acc.update(mean, std, targets)
+        if total_samples == 0:
+            return {}
+        m = acc.compute()
+        out = {"test_loss": float(total_loss) / total_samples, "rmse": m["rmse"], "mae": m["mae"]}
+        out.update(m)
+        out["mse"] = m["rmse"] ** 2
+        return out
 
     # ------------------------------------------------------------------------------------------------------------------
     def save_checkpoint(self, path, metadata: Optional[dict] = None):

@@ -230,7 +230,30 @@ def gen_losses():
     print("loss_cases.npz", {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
 
 
+def gen_metrics():
+    """CalibrationMetrics of the reference (metrics.py:21-392) on seeded (prediction, std, target) fields."""
+    from pno_physics_bench.metrics import CalibrationMetrics
+    cm = CalibrationMetrics(device="cpu")
+    g = torch.Generator().manual_seed(SEED + 7)
+    out = {}
+    cases = {"calibrated": (1.0, 1.0), "overconfident": (0.4, 1.0), "underconfident": (2.5, 1.0), "tiny_std": (1e-7, 1e-3)}
+    for name, (std_scale, err_scale) in cases.items():
+        target = torch.randn(3, 1, 16, 16, generator=g)
+        true_std = 0.2 + 0.3 * torch.rand(3, 1, 16, 16, generator=g)
+        pred = target + err_scale * true_std * torch.randn(3, 1, 16, 16, generator=g)
+        std = std_scale * true_std
+        m = cm.compute_all_metrics(pred, std, target)
+        out[name + ".pred"], out[name + ".std"], out[name + ".target"] = pred.numpy(), std.numpy(), target.numpy()
+        for k, v in m.items():
+            out[name + ".m." + k] = np.float64(v)
+        out[name + ".m.coverage_at_0.68"] = np.float64(cm.coverage_at_confidence(pred, std, target, 0.68))
+        out[name + ".m.ece_10bins"] = np.float64(cm.expected_calibration_error(pred, std, target, num_bins=10))
+    np.savez_compressed(os.path.join(HERE, "metrics_cases.npz"), **out)
+    print("metrics_cases.npz", {k: float(v) for k, v in out.items() if ".m." in k and k.startswith("calibrated")})
+
+
 if __name__ == "__main__":
     gen_layers()
     gen_model()
     gen_losses()
+    gen_metrics()

@@ -139,3 +139,21 @@ def test_mode_limits_raise():
         orc.spectral_conv_fft(x, w, w)
     with pytest.raises(RuntimeError):
         orc.spectral_conv_dense(x, w, w)
+
+
+METRIC_CASES = ["calibrated", "overconfident", "underconfident", "tiny_std"]
+
+
+@pytest.mark.parametrize("name", METRIC_CASES)
+def test_calibration_metrics_against_reference(golden, name):
+    """oracle uq_stats / uq_metrics vs the reference's CalibrationMetrics (metrics.py:21-392)."""
+    g = golden("metrics_cases.npz")
+    pred, std, tgt = g[name + ".pred"], g[name + ".std"], g[name + ".target"]
+    m = orc.uq_metrics(pred, std, tgt)
+    for k, v in m.items():
+        ref = float(g[f"{name}.m.{k}"])
+        assert abs(v - ref) <= 2e-6 * max(1.0, abs(ref)), (k, v, ref)
+    s = orc.uq_stats(pred, std, tgt, z_levels=[orc._ndtri(0.5 + 0.68 / 2)], n_bins=10)
+    assert abs(s[7] / s[0] - float(g[name + ".m.coverage_at_0.68"])) < 1e-7
+    ece10 = orc.uq_metrics_from_stats(s, levels=(0.68,), alphas=(), n_bins=10)["ece"]
+    assert abs(ece10 - float(g[name + ".m.ece_10bins"])) < 2e-6
