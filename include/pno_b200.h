@@ -156,6 +156,11 @@ int pno_kl_bwd(const float* mu, const float* lv, uint64_t n, const float* gscale
 
 /* ---- MC predictive moments (models.py:361-368) ----------------------------------------------------------------- */
 int pno_mc_accumulate(const float* y, uint64_t n, double* sum, double* sumsq, void* stream);
+/* One forward pass of UncertaintyDecomposer.decompose (uncertainty.py:57-73): p = mean + sqrt(exp(log_var) + 1e-8) * eps with
+ * eps = Philox normal of (seed, sample_idx, site, flat element index); sum += p, sumsq += p^2, sum_avar += exp(log_var);
+ * pred_out (optional) receives p.  log_var == NULL: p = mean, aleatoric variance 0 (uncertainty.py:75-77). */
+int pno_mc_accumulate_decompose(const float* mean, const float* log_var, uint64_t n, uint64_t seed, uint32_t sample_idx,
+                                uint32_t site, double* sum, double* sumsq, double* sum_avar, float* pred_out, void* stream);
 /* mean = sum/S; std = sqrt((sumsq - S mean^2)/(S-1)) (unbiased; S == 1 -> NaN like torch.std) */
 int pno_mc_finalize(const double* sum, const double* sumsq, uint64_t n, uint32_t S, float* mean, float* std,
                     void* stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "pno_kl_fwd": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "pno_kl_bwd": (_int, [_vp, _vp, _u64, _vp, _int, _vp, _vp, _vp]),
     "pno_mc_accumulate": (_int, [_vp, _u64, _vp, _vp, _vp]),
+    "pno_mc_accumulate_decompose": (_int, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "pno_mc_finalize": (_int, [_vp, _vp, _u64, _u32, _vp, _vp, _vp]),
     "pno_uq_stats": (_int, [_vp, _vp, _vp, _u64, _int, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp]),
     "pno_loss_data_bwd": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),

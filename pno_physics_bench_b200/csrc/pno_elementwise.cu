@@ -115,6 +115,30 @@ __global__ void k_mc_accumulate(const float* __restrict__ y, uint64_t n, double*
     }
 }
 
+// uncertainty.py:57-73: prediction = mean + sqrt(exp(lv) + 1e-8) * eps with eps from this repo's Philox stream (element = flat
+// index), accumulated with its square and the aleatoric variance exp(lv); optionally also written out (return_samples)
+__global__ void k_mc_accumulate_decompose(const float* __restrict__ mean, const float* __restrict__ lv, uint64_t n, PhiloxKey key,
+                                          double* __restrict__ s1, double* __restrict__ s2, double* __restrict__ sa,
+                                          float* __restrict__ pred) {
+    const uint64_t nq = (n + 3) >> 2;
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < nq; q += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 z4 = lv ? philox_quad_normals(key, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const uint64_t i = q * 4 + l;
+            if (i < n) {
+                const float var = lv ? expf(lv[i]) : 0.f;
+                const float p = lv ? mean[i] + sqrtf(var + 1e-8f) * z[l] : mean[i];
+                s1[i] += (double)p;
+                s2[i] += (double)p * (double)p;
+                sa[i] += (double)var;
+                if (pred) pred[i] = p;
+            }
+        }
+    }
+}
+
 __global__ void k_mc_finalize(const double* __restrict__ s1, const double* __restrict__ s2, uint64_t n, uint32_t S,
                               float* __restrict__ mean, float* __restrict__ sd) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -196,6 +220,17 @@ extern "C" int pno_mc_accumulate(const float* y, uint64_t n, double* sum, double
     if (n == 0) return PNO_OK;
     if (!y || !sum || !sumsq) PNO_FAIL(PNO_E_INVALID, "pno_mc_accumulate: null pointer");
     k_mc_accumulate<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(y, n, sum, sumsq);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+extern "C" int pno_mc_accumulate_decompose(const float* mean, const float* log_var, uint64_t n, uint64_t seed, uint32_t sample_idx,
+                                          uint32_t site, double* sum, double* sumsq, double* sum_avar, float* pred_out,
+                                          void* stream) {
+    if (n == 0) return PNO_OK;
+    if (!mean || !sum || !sumsq || !sum_avar) PNO_FAIL(PNO_E_INVALID, "pno_mc_accumulate_decompose: null pointer");
+    k_mc_accumulate_decompose<<<grid_for((n + 3) / 4), kThreads, 0, as_stream(stream)>>>(mean, log_var, n, make_key(seed, sample_idx, site),
+                                                                                       sum, sumsq, sum_avar, pred_out);
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }

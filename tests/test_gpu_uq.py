@@ -121,3 +121,81 @@ def test_trainer_evaluate_reports_the_reference_metrics_without_host_copies():
         assert k in out and math.isfinite(out[k]), k
     assert 0.0 <= out["coverage_50"] <= out["coverage_99"] <= 1.0
     assert abs(out["mse"] - out["rmse"] ** 2) < 1e-9
+
+
+# ---- the other MC-loop callers on the device-side MC driver ------------------------------------------
+from pno_physics_bench_b200 import functional as F_  # noqa: E402
+from pno_physics_bench_b200.uncertainty import UncertaintyDecomposer, VariationalEnsemble  # noqa: E402
+
+
+class _Heteroscedastic(torch.nn.Module):
+    """Returns (mean, log_var) like the models uncertainty.py:63-73 is written for."""
+
+    def forward(self, x, sample=True):
+        return x.mean(1, keepdim=True) * 0.5, (x[:, :1] * 0.3 - 1.0)
+
+
+def test_decompose_matches_the_reference_formulas_with_injected_noise():
+    torch.manual_seed(1)
+    x = torch.randn(3, 2, 8, 12, device=DEV)
+    S, seed = 7, 4242
+    model = _Heteroscedastic()
+    alea, epi, samples = UncertaintyDecomposer().decompose(model, x, S, return_samples=True, seed=seed)
+    mean, lv = model(x)
+    preds = torch.stack([mean + torch.sqrt(torch.exp(lv) + 1e-8) * F_.materialize_activation_noise(seed, s, 0xFFFE, mean.shape)
+                         for s in range(S)])                                   # uncertainty.py:66-73
+    assert torch.allclose(samples, preds, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(epi, preds.var(dim=0).sqrt(), rtol=2e-5, atol=1e-7)   # :84-85
+    assert torch.allclose(alea, torch.exp(lv).sqrt(), rtol=1e-6, atol=1e-7)     # :88-89
+    a2, e2 = UncertaintyDecomposer().decompose(model, x, S, seed=seed)
+    assert torch.equal(a2, alea) and torch.equal(e2, epi)
+
+
+def test_decompose_on_a_pno_keeps_the_reference_gate_and_can_sample_the_posterior():
+    torch.manual_seed(2)
+    model = pno.ProbabilisticNeuralOperator(3, 32, 2, 8).to(DEV)
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    alea, epi = UncertaintyDecomposer().decompose(model, x, 5, seed=9)
+    assert not model.training                      # the reference leaves the model in eval() (uncertainty.py:49)
+    assert float(epi.abs().max()) == 0.0 and float(alea.abs().max()) == 0.0      # eval-mode passes are deterministic
+    model.train()
+    alea, epi = UncertaintyDecomposer().decompose(model, x, 6, seed=9, sample_weights=True)
+    assert model.training                          # a sampled run restores the previous mode
+    _, std = model.predict_with_uncertainty(x, num_samples=6, seed=9)
+    assert torch.allclose(epi, std, rtol=1e-6, atol=1e-7) and float(epi.mean()) > 0
+    assert float(alea.abs().max()) == 0.0          # the PNO forward returns a tensor: no variance output (uncertainty.py:75-77)
+
+
+def test_variational_ensemble_matches_the_reference_formulas():
+    torch.manual_seed(3)
+    models = [pno.ProbabilisticNeuralOperator(3, 32, 1, 8) for _ in range(3)]
+    ens = VariationalEnsemble(models, num_samples_per_model=4)
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    mean, total, dec = ens.predict(x, sample_weights=True, seed=77)
+    # the same passes, stacked and reduced like ensemble_methods.py:340-375
+    per_model = []
+    for mi, m in enumerate(models):
+        m.train()
+        with torch.no_grad():
+            ys = []
+            for s in range(4):
+                with pno.noise_scope(77, mi * 4 + s, 0):
+                    ys.append(m(x, sample=True))
+        m.eval()
+        per_model.append(torch.stack(ys))
+    allp = torch.cat(per_model)
+    means = torch.stack([p.mean(0) for p in per_model])
+    stds = torch.stack([p.std(0) for p in per_model])
+    alea, epis = (stds ** 2).mean(0), means.var(0)
+    assert torch.allclose(mean, allp.mean(0), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(dec["aleatoric"], alea.sqrt(), rtol=2e-4, atol=1e-6)
+    assert torch.allclose(dec["epistemic"], epis.sqrt(), rtol=2e-4, atol=1e-6)
+    assert torch.allclose(total, (alea + epis).sqrt(), rtol=2e-4, atol=1e-6)
+    mean2, total2, none = ens.predict(x, decompose_uncertainty=False, sample_weights=True, seed=77)
+    assert none is None and torch.allclose(total2, allp.std(0), rtol=2e-4, atol=1e-6)
+    # reference behaviour (eval mode): deterministic passes, so no within-model spread; the models still differ
+    with torch.no_grad():
+        det = torch.stack([m(x, sample=False) for m in models])
+    _, t0, d0 = ens.predict(x, seed=77)
+    assert float(d0["aleatoric"].abs().max()) == 0.0
+    assert torch.allclose(t0, det.var(0).sqrt(), rtol=2e-4, atol=1e-6)
