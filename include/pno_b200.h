@@ -188,6 +188,16 @@ int pno_uq_stats(const float* mean, const float* spread, const float* target, ui
 int pno_loss_data_bwd(const float* mean, const float* log_var, const float* target, uint64_t n, const double* g,
                       float* dmean, float* dlog_var, void* stream);
 
+/* ---- optimiser step of the trainer (training/trainer.py:283-291: clip_grad_norm_, AdamW.step) without host syncs ---- */
+/* *acc (double, device) += sum of squares of n gradient values */
+int pno_sumsq_accumulate(const float* grad, uint64_t n, double* acc, void* stream);
+/* torch.optim.AdamW semantics (decoupled weight decay, bias correction by step >= 1, denom = sqrt(v_hat) + eps) on one
+ * flat tensor; the gradient is first scaled by min(1, max_norm / (sqrt(*grad_sumsq) + 1e-6)) (torch clip_grad_norm_) when
+ * grad_sumsq != NULL and max_norm > 0, and written back clipped when write_clipped_grad != 0. */
+int pno_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, uint32_t step, const double* grad_sumsq, float max_norm,
+                   int write_clipped_grad, void* stream);
+
 /* Diagnostics: device buffer (>= 148*16 int64) into which the tensor-core kernels dump per-CTA barrier-wait cycle counters
  * (NULL switches it off, the default).  Used by tools/phase_times.py to find the stage a pipeline is waiting on. */
 int pno_debug_set_buffer(void* device_ptr);

@@ -19,6 +19,7 @@ ENGINES = {"fp32": ENGINE_FP32, "tf32x3": ENGINE_TC_TF32X3, "tf32": ENGINE_TC_TF
 
 _c_float_p = ctypes.c_void_p      # device pointers travel as integers
 _u64, _u32, _int, _vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p
+_f32 = ctypes.c_float
 
 # name -> (restype, argtypes); must list every symbol include/pno_b200.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
@@ -53,6 +54,8 @@ SIGNATURES = {
     "pno_mc_finalize": (_int, [_vp, _vp, _u64, _u32, _vp, _vp, _vp]),
     "pno_uq_stats": (_int, [_vp, _vp, _vp, _u64, _int, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp]),
     "pno_loss_data_bwd": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "pno_sumsq_accumulate": (_int, [_vp, _u64, _vp, _vp]),
+    "pno_adamw_step": (_int, [_vp, _vp, _vp, _vp, _u64, _f32, _f32, _f32, _f32, _f32, _u32, _vp, _f32, _int, _vp]),
     "pno_debug_set_buffer": (_int, [_vp]),
     "pno_selftest_umma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

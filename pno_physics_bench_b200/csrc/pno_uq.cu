@@ -171,3 +171,106 @@ extern "C" int pno_loss_data_bwd(const float* mean, const float* log_var, const 
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Optimiser step of the trainer (training/trainer.py:283-291: clip_grad_norm_ then AdamW.step) without host syncs:
+//   pno_sumsq_accumulate   acc (double, device) += sum g^2                         -> global gradient norm
+//   pno_adamw_step         clip coefficient from the device-side norm, decoupled weight decay, Adam moments, update
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(kThreads) k_sumsq(const float* __restrict__ g, unsigned long long n, double* __restrict__ acc) {
+    __shared__ double s_red[kThreads / 32];
+    double s = 0.0;
+    const unsigned long long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * kThreads) {
+        const float4 v = g4[i];
+        s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    for (unsigned long long i = (n4 << 2) + blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * kThreads)
+        s += (double)g[i] * g[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double w = threadIdx.x < kThreads / 32 ? s_red[threadIdx.x] : 0.0;
+        w = warp_sum(w);
+        if (threadIdx.x == 0 && w != 0.0) atomicAdd(acc, w);
+    }
+}
+
+struct AdamArgs {
+    float lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, max_norm;
+};
+
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float clip) {
+    g *= clip;
+    p *= 1.f - a.lr * a.weight_decay;                                   // decoupled weight decay (torch AdamW)
+    m = fmaf(1.f - a.beta1, g - m, m);                                  // m.lerp_(g, 1 - beta1)
+    v = fmaf(a.beta2, v, (1.f - a.beta2) * g * g);
+    const float denom = sqrtf(v) / a.bias_c2_sqrt + a.eps;
+    p -= (a.lr / a.bias_c1) * (m / denom);
+    return g;
+}
+
+__global__ void __launch_bounds__(kThreads) k_adamw(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, unsigned long long n, const AdamArgs a,
+                                                   const double* __restrict__ gsumsq, int write_grad) {
+    // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1 (torch/nn/utils/clip_grad.py)
+    float clip = 1.f;
+    if (gsumsq && a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / ((float)sqrt(*gsumsq) + 1e-6f));
+    const unsigned long long n4 = n >> 2;
+    float4 *p4 = reinterpret_cast<float4*>(p), *g4 = reinterpret_cast<float4*>(g), *m4 = reinterpret_cast<float4*>(m),
+           *v4 = reinterpret_cast<float4*>(v);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * kThreads) {
+        float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+        gg.x = adam_one(pp.x, gg.x, mm.x, vv.x, a, clip);
+        gg.y = adam_one(pp.y, gg.y, mm.y, vv.y, a, clip);
+        gg.z = adam_one(pp.z, gg.z, mm.z, vv.z, a, clip);
+        gg.w = adam_one(pp.w, gg.w, mm.w, vv.w, a, clip);
+        p4[i] = pp; m4[i] = mm; v4[i] = vv;
+        if (write_grad) g4[i] = gg;
+    }
+    for (unsigned long long i = (n4 << 2) + blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * kThreads) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        const float gg = adam_one(pp, g[i], mm, vv, a, clip);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+        if (write_grad) g[i] = gg;
+    }
+}
+
+}  // namespace
+
+extern "C" int pno_sumsq_accumulate(const float* g, uint64_t n, double* acc, void* stream) {
+    if (n == 0) return PNO_OK;
+    if (!g || !acc) PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate: null pointer");
+    if (reinterpret_cast<uintptr_t>(g) & 15) PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate: gradient must be 16-byte aligned");
+    const unsigned long long want = (n / 4 + kThreads - 1) / kThreads + 1;
+    const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
+    k_sumsq<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, n, acc);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+extern "C" int pno_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, uint32_t step, const double* grad_sumsq, float max_norm,
+                              int write_clipped_grad, void* stream) {
+    if (n == 0) return PNO_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || step == 0) PNO_FAIL(PNO_E_INVALID, "pno_adamw_step: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+         reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+        PNO_FAIL(PNO_E_INVALID, "pno_adamw_step: tensors must be 16-byte aligned");
+    AdamArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+    a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    const unsigned long long want = (n / 4 + kThreads - 1) / kThreads + 1;
+    const int grid = (int)(want < 148ull * 16 ? want : 148ull * 16);
+    k_adamw<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a, grad_sumsq,
+                                                                      write_clipped_grad);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}

@@ -1,0 +1,96 @@
+"""Optimiser step of the trainer on device kernels (`pno_sumsq_accumulate`, `pno_adamw_step`, csrc/pno_uq.cu).
+
+`FusedAdamW` has torch.optim.AdamW's update rule (decoupled weight decay, bias correction, `sqrt(v_hat) + eps`) and state
+(`step`, `exp_avg`, `exp_avg_sq`), and folds `torch.nn.utils.clip_grad_norm_` (reference training/trainer.py:283-288) into
+the same pass: one reduction launch per tensor for the global gradient norm, one update launch per tensor that reads the norm
+from device memory -- no host sync, two passes over the 10 GB of parameter / gradient / moment state of the cfg-2 model instead
+of torch's clip (norm + scale) and multi-pass foreach update.  Complex parameters are updated through their real view in
+storage order (the spectral weights are permuted views of kernel-native storage)."""
+from typing import Optional
+
+import torch
+
+from .. import _lib
+
+
+def _storage_order(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """Flat view of a dense (non-overlapping, gap-free) real tensor in memory order, or None."""
+    dims = sorted((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1)
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return None
+        expect *= sz
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+
+
+def _real(t):
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 max_grad_norm: Optional[float] = None, write_clipped_grads: bool = False):
+        if lr < 0 or eps < 0 or weight_decay < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
+            raise ValueError("invalid AdamW hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.max_grad_norm = max_grad_norm
+        self.write_clipped_grads = write_clipped_grads      # leave .grad scaled like clip_grad_norm_ does (one more write)
+        self._gsq = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        stream = _lib.stream_ptr()
+        work = []
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                _lib.require_cuda(p, "parameter")
+                if _real(p).dtype != torch.float32:
+                    raise RuntimeError(f"FusedAdamW: float32 / complex64 parameters only, got {p.dtype}")
+                pf = _storage_order(_real(p))
+                if pf is None:
+                    raise RuntimeError("FusedAdamW: parameter storage must be dense")
+                g = p.grad
+                if g.stride() != p.stride() or g.dtype != p.dtype:
+                    g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(p.grad)
+                    if self.write_clipped_grads:
+                        p.grad = g
+                gf = _storage_order(_real(g))
+                state = self.state[p]
+                if not state:
+                    state["step"] = torch.tensor(0.0)
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                work.append((group, state, pf, gf, _storage_order(_real(state["exp_avg"])),
+                             _storage_order(_real(state["exp_avg_sq"]))))
+        if not work:
+            return loss
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        if clip:
+            dev = work[0][2].device
+            if self._gsq is None or self._gsq.device != dev:
+                self._gsq = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._gsq.zero_()
+            for _, _, _, gf, _, _ in work:
+                _lib.check(lib.pno_sumsq_accumulate(_lib.ptr(gf), gf.numel(), _lib.ptr(self._gsq), stream), "pno_sumsq_accumulate")
+        for group, state, pf, gf, mf, vf in work:
+            state["step"] += 1
+            b1, b2 = group["betas"]
+            _lib.check(lib.pno_adamw_step(_lib.ptr(pf), _lib.ptr(gf), _lib.ptr(mf), _lib.ptr(vf), pf.numel(), group["lr"], b1, b2,
+                                          group["eps"], group["weight_decay"], int(state["step"]),
+                                          _lib.ptr(self._gsq) if clip else None, float(self.max_grad_norm) if clip else 0.0,
+                                          int(self.write_clipped_grads), stream), "pno_adamw_step")
+        return loss
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm of the last step (device scalar; what clip_grad_norm_ returns)."""
+        if self._gsq is None:
+            raise RuntimeError("FusedAdamW.grad_norm() before a clipped step")
+        return self._gsq.sqrt().float()[0]

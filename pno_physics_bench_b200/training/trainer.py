@@ -14,6 +14,7 @@ import torch.nn as nn
 from .. import functional as F_
 from ..distributed import allreduce_gradients, shared_seed, world
 from .losses import ELBOLoss
+from .optim import FusedAdamW
 
 logger = logging.getLogger(__name__)
 
@@ -27,8 +28,10 @@ class PNOTrainer:
         self.device = torch.device(device if device is not None else "cuda")
         self.model = model.to(self.device)
         self.loss_fn = loss_fn if loss_fn is not None else ELBOLoss(kl_weight=kl_weight, num_samples=num_samples)
-        self.optimizer = optimizer if optimizer is not None else torch.optim.AdamW(
-            self.model.parameters(), lr=1e-3, weight_decay=1e-4)
+        # default optimiser: the reference's AdamW(lr 1e-3, weight decay 1e-4) (trainer.py:71-75) as the device-side fused step,
+        # with the gradient clipping of trainer.py:283-288 folded in; a user-supplied optimiser takes the reference's path
+        self.optimizer = optimizer if optimizer is not None else FusedAdamW(
+            self.model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=gradient_clipping)
         self.scheduler = scheduler
         self.gradient_clipping = gradient_clipping
         self.mixed_precision = mixed_precision      # accepted for signature compatibility; the kernels choose their
@@ -55,7 +58,8 @@ class PNOTrainer:
             losses = self.loss_fn(outputs, targets, self.model)
             losses["total"].backward()
         allreduce_gradients(self.model.parameters(), self.group)
-        if self.gradient_clipping:
+        fused_clip = isinstance(self.optimizer, FusedAdamW) and self.optimizer.max_grad_norm == self.gradient_clipping
+        if self.gradient_clipping and not fused_clip:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.gradient_clipping)
         self.optimizer.step()
         self.global_step += 1

@@ -199,3 +199,43 @@ def test_variational_ensemble_matches_the_reference_formulas():
     _, t0, d0 = ens.predict(x, seed=77)
     assert float(d0["aleatoric"].abs().max()) == 0.0
     assert torch.allclose(t0, det.var(0).sqrt(), rtol=2e-4, atol=1e-6)
+
+
+# ---- optimiser step on device (trainer.py:283-291) ----------------------------------------------------------------------
+from pno_physics_bench_b200.training import FusedAdamW  # noqa: E402
+
+
+@pytest.mark.parametrize("max_norm", [0.05, 1e9, None])
+def test_fused_adamw_matches_torch_adamw_with_clipping(max_norm):
+    torch.manual_seed(4)
+
+    def make():
+        torch.manual_seed(11)
+        native = torch.randn(4, 6, 5, 7, dtype=torch.cfloat, device=DEV)              # kernel-native storage [m1,m2,Ci,Co]
+        return [torch.nn.Parameter(native.permute(2, 3, 0, 1)),                        # logical [Ci,Co,m1,m2] view, like the model
+                torch.nn.Parameter(torch.randn(13, 9, device=DEV)),                    # ragged (117 elements)
+                torch.nn.Parameter(torch.randn(1027, device=DEV))]
+
+    ours, ref = make(), make()
+    opt_o = FusedAdamW(ours, lr=3e-3, weight_decay=1e-2, max_grad_norm=max_norm)
+    opt_r = torch.optim.AdamW(ref, lr=3e-3, weight_decay=1e-2)
+    for step in range(4):
+        torch.manual_seed(100 + step)
+        grads = [torch.randn_like(p) * (10.0 if step == 1 else 0.1) for p in ours]
+        for p, q, g in zip(ours, ref, grads):
+            p.grad = g.clone().contiguous() if step % 2 else g.clone()                 # also a gradient with other strides
+            q.grad = g.clone()
+        if max_norm is not None:
+            want_norm = torch.nn.utils.clip_grad_norm_(ref, max_norm)
+        opt_o.step()
+        opt_r.step()
+        if max_norm is not None:
+            assert torch.allclose(opt_o.grad_norm(), want_norm, rtol=1e-6)
+        for p, q in zip(ours, ref):
+            assert torch.allclose(torch.view_as_real(p) if p.is_complex() else p, torch.view_as_real(q) if q.is_complex() else q,
+                                  rtol=2e-6, atol=2e-7), step
+    for p, q in zip(ours, ref):
+        so, sr = opt_o.state[p], opt_r.state[q]
+        assert int(so["step"]) == int(sr["step"]) == 4
+        assert torch.allclose(torch.view_as_real(so["exp_avg"]) if p.is_complex() else so["exp_avg"],
+                              torch.view_as_real(sr["exp_avg"]) if p.is_complex() else sr["exp_avg"], rtol=1e-5, atol=1e-8)
