@@ -143,6 +143,14 @@ int pno_spectral_bwd(const pno_plan_t* plan, int engine, const float* x, const f
 int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
                   const float* Wl, const float* bl, uint64_t seed, uint32_t sample_idx, uint32_t site,
                   uint64_t batch_offset, float* out, float* dout_dlv, void* stream);
+/* Backward of pno_local_fwd on the tensor-core engines (autograd of models.py:298-303): with dYm = g and dYl = g * dout_dlv,
+ *   dx = Wm^T dYm + Wl^T dYl ([B,Ci,HW]);  dw = [sum_b dYm x^T ; sum_b dYl x^T] ([2Co][Ci] stacked, [Co][Ci] when Wl == NULL);
+ *   db = [sum dYm ; sum dYl] per output channel.  dx / dw / db may each be NULL.  Shapes: Co % 128 == 0, Ci in {128, 256},
+ * HW % 128 == 0, else PNO_E_UNSUPPORTED (as for PNO_ENGINE_FP32): the caller then uses plain library GEMMs.
+ * workspace: pno_local_bwd_workspace_bytes(...) bytes (the stacked gradient [B][2Co][HW] and the stacked transposed weights). */
+size_t pno_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy);
+int pno_local_bwd(int engine, const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW,
+                  const float* Wm, const float* Wl, float* dx, float* dw, float* db, void* workspace, void* stream);
 
 /* gz = g * act'(pre_act)  (backward of models.py:306) */
 int pno_act_bwd(const float* pre_act, const float* g, uint64_t n, int act, float* gz, void* stream);

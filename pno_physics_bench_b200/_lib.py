@@ -46,6 +46,8 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp]),
     "pno_local_fwd": (_int, [_int, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u64, _vp, _vp,
                              _vp]),
+    "pno_local_bwd_workspace_bytes": (ctypes.c_size_t, [_int, _int, _int, _int, _int]),
+    "pno_local_bwd": (_int, [_int, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pno_act_bwd": (_int, [_vp, _vp, _u64, _int, _vp, _vp]),
     "pno_kl_fwd": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "pno_kl_bwd": (_int, [_vp, _vp, _u64, _vp, _int, _vp, _vp, _vp]),

@@ -230,6 +230,20 @@ extern "C" int pno_spectral_bwd(const pno_plan_t* p, int engine, const float* x,
     return PNO_OK;
 }
 
+extern "C" size_t pno_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy) {
+    if (B <= 0 || Ci <= 0 || Co <= 0 || HW <= 0) return 0;
+    return tc_local_bwd_workspace_bytes(B, Ci, Co, HW, noisy);
+}
+
+extern "C" int pno_local_bwd(int engine, const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW,
+                             const float* Wm, const float* Wl, float* dx, float* dw, float* db, void* workspace, void* stream) {
+    if (B <= 0 || Ci <= 0 || Co <= 0 || HW <= 0) PNO_FAIL(PNO_E_INVALID, "pno_local_bwd: non-positive size");
+    if (!x || !g || !Wm || !workspace) PNO_FAIL(PNO_E_INVALID, "pno_local_bwd: null pointer");
+    if (engine == PNO_ENGINE_FP32)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "pno_local_bwd runs on the tensor-core engines; the fp32 engine leaves these GEMMs to the caller");
+    return tc_local_bwd(engine, x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, workspace, as_stream(stream));
+}
+
 extern "C" int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
                              const float* Wl, const float* bl, uint64_t seed, uint32_t sample_idx, uint32_t site,
                              uint64_t batch_offset, float* out, float* dout_dlv, void* stream) {

@@ -16,3 +16,7 @@ int tc_mix_bwd_dx(const pno_plan* p, int engine, const float* gr, const float* g
 int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
                  const float* Wl, const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv,
                  cudaStream_t st);
+// backward of the local branch (pno_tc_local_bwd.cu): dx, stacked weight gradients dw = [dWm; dWl] ([rows][Ci]) and bias sums db
+size_t tc_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy);
+int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW, const float* Wm,
+                 const float* Wl, float* dx, float* dw, float* db, void* workspace, cudaStream_t st);

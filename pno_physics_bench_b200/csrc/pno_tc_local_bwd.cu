@@ -1,0 +1,268 @@
+// Backward of the local branch (the two 1x1 convs + reparameterisation, reference models.py:298-303 through autograd) on the
+// tensor cores.  With  dYm = g  and  dYl = g * d out/d lv  (saved by the forward kernel):
+//   dx[b]   = Wm^T dYm[b] + Wl^T dYl[b]                     -> ONE GEMM over the stacked gradient G2 = [dYm; dYl] ([B][2Co][HW])
+//                                                              with the stacked transposed weights: the forward kernel
+//                                                              (k_tc_local, no noise) runs it unchanged
+//   dWm, dWl = sum_b dY{m,l}[b] x[b]^T                       -> k_tc_local_dw below: D[2Co][Ci] = G2 . x^T, reduction over the
+//                                                              B*HW pixels split across the CTAs of the grid
+//   dbm, dbl = row sums of G2                                -> k_local_bwd_prep (which also builds G2)
+//
+// k_tc_local_dw: work item = (128-row tile of G2, slice of the pixel range); both operands are K-major (pixels contiguous)
+// straight from the NCHW tensors by TMA ([32 px][128 | Ci rows] SWIZZLE_128B boxes), accumulated in one [128 x Ci] TMEM tile
+// over the whole slice, then added to the output with float atomics (at most ~74 contributions per element).
+//   warp 0 TMA producer; warp 1 MMA issuer; warps 2-9 (3xTF32) hi/lo splitter; warps 10-13 epilogue.
+#include <stdlib.h>
+
+#include "pno_sm100.cuh"
+#include "pno_tc.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TM = 128, TK = 32;
+constexpr int A_BYTES = TM * TK * 4;          // 16 KB
+constexpr int kSplitWarps = 8;
+constexpr int kThreads = (2 + kSplitWarps + 4) * 32;
+
+struct DwArgs {
+    int Ci, rows, HW, B;          // rows = rows of G2 per batch item (Co or 2 Co)
+    int m_tiles, k_splits;        // work items = m_tiles * k_splits
+    int kb_total;                 // B * HW / 32 pixel blocks
+    int stages, stage_bytes, b_bytes;
+    float* dw;                    // [rows][Ci], zero-initialised by the caller
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_local_dw(const DwArgs a, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar_raw[4], bar_split[4], bar_empty[4], bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&bar_raw[s], 1);
+            mbar_init(&bar_split[s], kSplitWarps * 32);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_done, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmG);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const bool has_work = (int)blockIdx.x < a.m_tiles * a.k_splits;
+    const int mt = blockIdx.x % a.m_tiles, ks = blockIdx.x / a.m_tiles;
+    // pixel blocks [kb0, kb1) of this slice (contiguous in (b, p))
+    const int kb0 = (int)((long long)a.kb_total * ks / a.k_splits), kb1 = (int)((long long)a.kb_total * (ks + 1) / a.k_splits);
+    const int kb_per_img = a.HW / TK;
+
+    if (has_work && warp == 0) {
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                unsigned char* st = smem + (size_t)stage * a.stage_bytes;
+                const int b = kb / kb_per_img, p0 = (kb - b * kb_per_img) * TK;
+                mbar_arrive_expect_tx(&bar_raw[stage], A_BYTES + a.b_bytes);
+                tma_load_2d(st, &tmG, &bar_raw[stage], p0, b * a.rows + mt * TM);
+                tma_load_2d(st + A_BYTES, &tmX, &bar_raw[stage], p0, b * a.Ci);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (has_work && warp == 1) {
+        const uint32_t el = lane == 0;
+        const uint32_t idesc = make_idesc(FMT_TF32, TM, a.Ci, MAJOR_K, MAJOR_K);
+        const uint32_t dhi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
+        const uint32_t lo = (A_BYTES + a.b_bytes) >> 4;          // hi tile -> its lo copy (3xTF32)
+        int stage = 0, phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t s0 = smem_u32(smem + (size_t)stage * a.stage_bytes);
+            const uint32_t ad = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;
+            const uint32_t bd = sdesc_base(s0 + A_BYTES, 16, 1024, SWIZZLE_128B).lo;
+#pragma unroll
+            for (int k = 0; k < TK / 8; ++k) {
+                const uint32_t first = (kb != kb0 || k) ? 1u : 0u;
+                mma_tf32(tmem, ad + 2 * k, dhi, bd + 2 * k, dhi, idesc, first, el);
+                if (NSPLIT == 3) {
+                    mma_tf32(tmem, ad + lo + 2 * k, dhi, bd + 2 * k, dhi, idesc, 1u, el);
+                    mma_tf32(tmem, ad + 2 * k, dhi, bd + lo + 2 * k, dhi, idesc, 1u, el);
+                }
+            }
+            mma_commit(&bar_empty[stage], el);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&bar_done, el);
+    } else if (has_work && warp < 2 + kSplitWarps) {
+        if (NSPLIT == 3) {
+            const int t = threadIdx.x - 64;
+            const int n16 = (A_BYTES + a.b_bytes) / 16;
+            int stage = 0, phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&bar_raw[stage], phase);
+                const uint32_t hi = smem_u32(smem + (size_t)stage * a.stage_bytes), lw = hi + A_BYTES + a.b_bytes;
+#pragma unroll 4
+                for (int i = t; i < n16; i += kSplitWarps * 32) {
+                    const float4 v = lds128(hi + 16 * i);
+                    float4 h;
+                    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                    sts128(hi + 16 * i, h);
+                    sts128(lw + 16 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar_split[stage]);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (has_work && warp >= 2 + kSplitWarps) {
+        const int q = warp & 3;
+        mbar_wait(&bar_done, 0);
+        tc_fence_after_sync();
+        float* dst = a.dw + (size_t)(mt * TM + q * 32 + lane) * a.Ci;
+        for (int c = 0; c < a.Ci; c += 16) {
+            float v[16];
+            tmem_ld16(tmem_addr(tmem, q * 32, c), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + c + j, v[j]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// G2[b][o][p] = g[b][o][p], G2[b][Co+o][p] = g[b][o][p] * dlv[b][o][p]; db[o] += row sums (dbm), db[Co+o] (dbl).
+// One block per (b, o) row.  noisy == 0: only the bias sums (G2 is g itself).
+__global__ void __launch_bounds__(256) k_local_bwd_prep(const float* __restrict__ g, const float* __restrict__ dlv, int Co, int HW,
+                                                        int noisy, float* __restrict__ g2, float* __restrict__ db) {
+    __shared__ float s_red[2][8];
+    const int row = blockIdx.x;                 // b * Co + o
+    const int b = row / Co, o = row - b * Co;
+    const float4* gs = reinterpret_cast<const float4*>(g + (size_t)row * HW);
+    const float4* ls = noisy ? reinterpret_cast<const float4*>(dlv + (size_t)row * HW) : nullptr;
+    float4* d0 = noisy ? reinterpret_cast<float4*>(g2 + ((size_t)b * 2 * Co + o) * HW) : nullptr;
+    float4* d1 = noisy ? reinterpret_cast<float4*>(g2 + ((size_t)b * 2 * Co + Co + o) * HW) : nullptr;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = threadIdx.x; i < HW / 4; i += 256) {
+        const float4 v = gs[i];
+        s0 += (v.x + v.y) + (v.z + v.w);
+        if (noisy) {
+            const float4 l = ls[i];
+            const float4 w = make_float4(v.x * l.x, v.y * l.y, v.z * l.z, v.w * l.w);
+            s1 += (w.x + w.y) + (w.z + w.w);
+            d0[i] = v;
+            d1[i] = w;
+        }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, of);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, of);
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = s0; s_red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2 && db) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_red[threadIdx.x][w];
+        if (threadIdx.x == 0) atomicAdd(db + o, s);
+        else if (noisy) atomicAdd(db + Co + o, s);
+    }
+}
+
+// wcat[i][o] = Wm[o][i], wcat[i][Co + o] = Wl[o][i]   ([Ci][2 Co]; [Ci][Co] when Wl == NULL)
+__global__ void k_wcat(const float* __restrict__ wm, const float* __restrict__ wl, int Ci, int Co, float* __restrict__ wcat) {
+    const int n = Ci * Co, ld = wl ? 2 * Co : Co;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int o = e / Ci, i = e - o * Ci;
+        wcat[(size_t)i * ld + o] = wm[e];
+        if (wl) wcat[(size_t)i * ld + Co + o] = wl[e];
+    }
+}
+
+}  // namespace
+
+size_t tc_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy) {
+    const size_t g2 = noisy ? (size_t)B * 2 * Co * HW * 4 : 0;
+    return g2 + (size_t)Ci * (noisy ? 2 : 1) * Co * 4 + 1024;
+}
+
+int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW, const float* Wm,
+                 const float* Wl, float* dx, float* dw, float* db, void* workspace, cudaStream_t st) {
+    const int noisy = Wl != nullptr;
+    const int rows = noisy ? 2 * Co : Co;
+    if (Co % TM || Ci % 128 || Ci > 256 || HW % 128 || rows % 32)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_bwd tiles Co%%128 == 0, Ci in {128, 256}, HW%%128 == 0 (got %d, %d, %d)", Co, Ci, HW);
+    if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "tc_local_bwd: d out / d log_var is needed when Wl is given");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dout_dlv) |
+         reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_bwd needs 16-byte aligned tensors");
+    float* g2 = noisy ? static_cast<float*>(workspace) : const_cast<float*>(g);
+    float* wcat = static_cast<float*>(workspace) + (noisy ? (size_t)B * 2 * Co * HW : 0);
+    if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
+    if (noisy || db) {
+        k_local_bwd_prep<<<B * Co, 256, 0, st>>>(g, dout_dlv, Co, HW, noisy, g2, db);
+        PNO_LAUNCH_CHECK();
+    }
+    int rc;
+    if (dx) {        // dx = [Wm^T | Wl^T] G2: the forward kernel without noise, "input channels" = rows of G2
+        k_wcat<<<(Ci * Co + 255) / 256, 256, 0, st>>>(Wm, Wl, Ci, Co, wcat);
+        PNO_LAUNCH_CHECK();
+        PhiloxKey key = make_key(0, 0, 0);
+        if ((rc = tc_local_fwd(engine, g2, B, rows, Ci, HW, wcat, nullptr, nullptr, nullptr, key, 0, dx, nullptr, st))) return rc;
+    }
+    if (dw) {
+        const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
+        DwArgs a;
+        memset(&a, 0, sizeof(a));
+        a.Ci = Ci; a.rows = rows; a.HW = HW; a.B = B; a.dw = dw;
+        a.m_tiles = rows / TM;
+        int dev = 0, sms = 148;
+        PNO_CUDA(cudaGetDevice(&dev));
+        PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        a.kb_total = (int)((long long)B * HW / TK);
+        a.k_splits = sms / a.m_tiles;
+        if (a.k_splits > a.kb_total) a.k_splits = a.kb_total;
+        if (a.k_splits < 1) a.k_splits = 1;
+        a.b_bytes = Ci * TK * 4;
+        a.stage_bytes = (A_BYTES + a.b_bytes) * (x3 ? 2 : 1);
+        a.stages = (200 * 1024) / a.stage_bytes;
+        if (a.stages > 4) a.stages = 4;
+        const int smem = a.stages * a.stage_bytes + 1024;
+        CUtensorMap tmG, tmX;
+        {
+            const uint64_t dims[2] = {(uint64_t)HW, (uint64_t)B * rows};
+            const uint64_t str[1] = {(uint64_t)HW * 4};
+            const uint32_t box[2] = {TK, TM};
+            if ((rc = pno_encode_tmap(&tmG, g2, 2, dims, str, box, 1))) return rc;
+        }
+        {
+            const uint64_t dims[2] = {(uint64_t)HW, (uint64_t)B * Ci};
+            const uint64_t str[1] = {(uint64_t)HW * 4};
+            const uint32_t box[2] = {TK, (uint32_t)Ci};
+            if ((rc = pno_encode_tmap(&tmX, x, 2, dims, str, box, 1))) return rc;
+        }
+        PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
+        const int grid = a.m_tiles * a.k_splits;
+        if (x3) {
+            PNO_CUDA(cudaFuncSetAttribute(k_tc_local_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PNO_CUDA(pno_launch(k_tc_local_dw<3>, grid, kThreads, smem, st, a, tmG, tmX));
+        } else {
+            PNO_CUDA(cudaFuncSetAttribute(k_tc_local_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PNO_CUDA(pno_launch(k_tc_local_dw<1>, grid, kThreads, smem, st, a, tmG, tmX));
+        }
+        PNO_LAUNCH_CHECK();
+    }
+    return PNO_OK;
+}

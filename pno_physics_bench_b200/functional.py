@@ -174,17 +174,34 @@ class _LocalFn(torch.autograd.Function):
                                      out.data_ptr(), _lib.ptr(dlv), _lib.stream_ptr()), "pno_local_fwd")
         if needs_grad:
             ctx.save_for_backward(x, wm_c, wl_c, dlv)
-            ctx.meta = (b, ci, co, hw, noisy, wm.shape, bm is not None, bl is not None)
+            ctx.meta = (b, ci, co, hw, noisy, wm.shape, bm is not None, bl is not None, engine)
         return out
 
     @staticmethod
     def backward(ctx, g):
         # Plain GEMMs and reductions on the 1x1 weights: left to cuBLAS through torch (not on the spectral path).
         x, wm, wl, dlv = ctx.saved_tensors
-        b, ci, co, hw, noisy, wshape, has_bm, has_bl = ctx.meta
+        b, ci, co, hw, noisy, wshape, has_bm, has_bl, engine = ctx.meta
+        ni = ctx.needs_input_grad
+        # tensor-core engines: dx, [dWm; dWl] and the bias sums from pno_local_bwd (csrc/pno_tc_local_bwd.cu)
+        if engine != _lib.ENGINE_FP32 and co % 128 == 0 and ci in (128, 256) and hw % 128 == 0:
+            lib = _lib.load()
+            gc = g.contiguous()
+            rows = 2 * co if noisy else co
+            dx = torch.empty_like(x) if ni[0] else None
+            want_w = ni[1] or (noisy and ni[3])
+            dw = torch.empty(rows, ci, dtype=torch.float32, device=x.device) if want_w else None
+            want_b = (ni[2] and has_bm) or (noisy and ni[4] and has_bl)
+            db = torch.empty(rows, dtype=torch.float32, device=x.device) if want_b else None
+            ws = torch.empty(lib.pno_local_bwd_workspace_bytes(b, ci, co, hw, int(noisy)) // 4 + 4, dtype=torch.float32, device=x.device)
+            _lib.check(lib.pno_local_bwd(engine, x.data_ptr(), gc.data_ptr(), _lib.ptr(dlv), b, ci, co, hw, wm.data_ptr(),
+                                         _lib.ptr(wl), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), ws.data_ptr(), _lib.stream_ptr()),
+                       "pno_local_bwd")
+            return (dx, dw[:co].reshape(wshape) if ni[1] else None, db[:co] if (ni[2] and has_bm) else None,
+                    dw[co:].reshape(wshape) if (noisy and ni[3]) else None, db[co:] if (noisy and ni[4] and has_bl) else None,
+                    None, None, None, None, None, None)
         g2 = g.contiguous().reshape(b, co, hw)
         x2 = x.reshape(b, ci, hw)
-        ni = ctx.needs_input_grad
         dx = dwm = dbm = dwl = dbl = None
         glv = g2 * dlv.reshape(b, co, hw) if noisy else None
         if ni[0]:
@@ -247,6 +264,29 @@ class _KLFn(torch.autograd.Function):
 
 def kl_divergence(*params):
     return _KLFn.apply(*params)
+
+
+def kl_grad_accumulate_(params, gscale):
+    """In-place form of `_KLFn.backward` for a training loop that owns the step: adds gscale * dKL/d(mu, log_var) straight into
+    the existing `.grad` buffers (one kernel per block) instead of letting autograd materialise a second gradient per
+    parameter and add the two (4 full-size adds per layer).  params = (mu_0, lv_0, ...); gscale: 0-d float32 CUDA tensor."""
+    lib = _lib.load()
+    gs = gscale.detach().to(torch.float32).contiguous()
+    for k in range(0, len(params), 2):
+        mu_p, lv_p = params[k], params[k + 1]
+        mu, _ = native_spectral(mu_p.detach())
+        lv, _ = native_spectral(lv_p.detach())
+        grads, fresh = [], False
+        for p in (mu_p, lv_p):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+            gn, view = native_spectral(p.grad)
+            if not view:                       # a gradient in another layout: re-home it in the parameter's layout
+                p.grad = torch.empty_like(p, memory_format=torch.preserve_format).copy_(p.grad)
+                gn, view = native_spectral(p.grad)
+            grads.append(gn)
+        _lib.check(lib.pno_kl_bwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), gs.data_ptr(), 1, grads[0].data_ptr(),
+                                  grads[1].data_ptr(), _lib.stream_ptr()), "pno_kl_bwd")
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -353,3 +353,9 @@ class ProbabilisticNeuralOperator(nn.Module):
         return F_.kl_divergence(*params)
 
     compute_kl_divergence = kl_divergence          # the name training/losses.py:75 looks for
+
+    def kl_params(self):
+        params = []
+        for layer in self.fourier_layers:
+            params += [layer.weights1, layer.weights1_log_var, layer.weights2, layer.weights2_log_var]
+        return params

@@ -55,8 +55,16 @@ class PNOTrainer:
         self.optimizer.zero_grad()
         with F_.noise_scope(self.seed, self.global_step, batch_offset):
             outputs = self.model(inputs, sample=True, return_kl=True)
+            kl_leaf = None
+            if isinstance(outputs, tuple) and len(outputs) == 3 and hasattr(self.model, "kl_params"):
+                # the KL term enters the loss as a leaf: its gradient w.r.t. the weights is analytic and is added straight
+                # into the .grad buffers below, scaled by d total / d kl (whatever the loss does with it)
+                kl_leaf = outputs[2].detach().requires_grad_(True)
+                outputs = (outputs[0], outputs[1], kl_leaf)
             losses = self.loss_fn(outputs, targets, self.model)
             losses["total"].backward()
+            if kl_leaf is not None and kl_leaf.grad is not None:
+                F_.kl_grad_accumulate_(self.model.kl_params(), kl_leaf.grad)
         allreduce_gradients(self.model.parameters(), self.group)
         fused_clip = isinstance(self.optimizer, FusedAdamW) and self.optimizer.max_grad_norm == self.gradient_clipping
         if self.gradient_clipping and not fused_clip:

@@ -51,7 +51,8 @@ def _local_case(b, ci, co, h, w, noisy, engine, gen):
 
 @pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
 @pytest.mark.parametrize("noisy", [False, True])
-@pytest.mark.parametrize("shape", [(2, 32, 128, 16, 16), (3, 256, 256, 64, 64), (1, 64, 384, 8, 48)])
+@pytest.mark.parametrize("shape", [(2, 32, 128, 16, 16), (3, 256, 256, 64, 64), (1, 64, 384, 8, 48), (5, 128, 256, 16, 32),
+                                   (2, 256, 128, 8, 16)])
 def test_local_branch_tensor_core_vs_cuda_core(engine, tol, noisy, shape):
     b, ci, co, h, w = shape
     ref_out, ref_g = _local_case(b, ci, co, h, w, noisy, "fp32", torch.Generator().manual_seed(sum(shape)))
