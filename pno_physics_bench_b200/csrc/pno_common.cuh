@@ -79,11 +79,16 @@ __host__ __device__ __forceinline__ PhiloxKey make_key(uint64_t seed, uint32_t s
     return k;
 }
 
+// PNO_PHILOX_ROUNDS exists to MEASURE what the round count costs; the normative stream is 10 rounds
+// (oracle/philox.py) and every parity test assumes it.
+#ifndef PNO_PHILOX_ROUNDS
+#define PNO_PHILOX_ROUNDS 10
+#endif
 __device__ __forceinline__ uint4 philox_quad_bits(const PhiloxKey& key, uint64_t q) {
     uint32_t c0 = (uint32_t)q, c1 = (uint32_t)(q >> 32), c2 = key.sample, c3 = key.site;
     uint32_t k0 = key.k0, k1 = key.k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PNO_PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;

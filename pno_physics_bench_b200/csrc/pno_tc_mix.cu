@@ -25,6 +25,11 @@ namespace {
 
 constexpr int kGen = 512;        // generator threads
 constexpr int kThreads = 64 + kGen + 128 + 32;   // + a second MMA issuer warp (3xTF32 only: one issuer per accumulator)
+// single pass: the second issuer warp is not launched.  Register cap: each scheduler owns 16 K registers, so 22-23 warps (6 on
+// some schedulers) allow 80 per thread, and only <= 20 warps would allow 96 -- the generators (24 registers of prefetched
+// mu / log_var) sit right at the cap: small additions to their loop spill and cost 20-50% (measured: an L2 prefetch added to
+// the loop took the kernel from 206 to 245 us, 3xTF32 from 245 to 326-358 us).
+constexpr int threads_for(int nsplit) { return nsplit == 3 ? kThreads : kThreads - 32; }
 constexpr int TM = 128;          // output channels per item
 constexpr int TK = 32;           // input channels per stage
 constexpr int W_TILE = TM * TK * 4;      // 16 KB
@@ -34,6 +39,7 @@ struct MixGeom {
     int MD;            // channels of the output ("row") side: Co forward, Ci backward; o_tiles = MD / 128, KB = (other side) / 32
     int x_tile;        // B * 128 bytes
     int stage_bytes, stages, smem_bytes;
+    int raw_off, raw_bytes;       // RAW mode: two staging buffers [mu 32 KB][log_var 16 KB] behind the operand stages
     const float *mu1, *mu2, *lv1, *lv2;
     float *yr, *yi;
     PhiloxKey key;
@@ -44,15 +50,21 @@ __device__ __forceinline__ float4 tf32_rn4(const float4 v) { return make_float4(
 __device__ __forceinline__ float4 sub4(const float4 a, const float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
 // stage layout, NSPLIT == 1: [Wre][Wim][Xre][Xim];  NSPLIT == 3: [Wre hi][Wim hi][Wre lo][Wim lo][Xre hi][Xim hi][Xre lo][Xim lo]
-template <int NSPLIT, bool SAMPLED, bool BWD>
-__global__ void __launch_bounds__(kThreads, 1)
-k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __grid_constant__ CUtensorMap tmXi) {
+// RAW (single pass, sampled): the mu / log_var tiles of a k-block are staged in shared memory by TMA, two k-blocks deep,
+// instead of being prefetched into generator registers one k-block deep.  That takes 24 registers off the generators (which sit
+// at the 80-register cap) and puts 96 KB per SM in flight against HBM latency instead of 48 KB.
+template <int NSPLIT, bool SAMPLED, bool BWD, bool RAW>
+__global__ void __launch_bounds__(threads_for(NSPLIT), 1)
+k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __grid_constant__ CUtensorMap tmXi,
+             const __grid_constant__ CUtensorMap tmMu1, const __grid_constant__ CUtensorMap tmMu2,
+             const __grid_constant__ CUtensorMap tmLv1, const __grid_constant__ CUtensorMap tmLv2) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kMaxStages = 4;
     constexpr int NW = NSPLIT == 3 ? 4 : 2;         // W tiles per stage
     __shared__ __align__(8) uint64_t bar_raw[kMaxStages], bar_ready[kMaxStages], bar_empty[kMaxStages], bar_free[kMaxStages];
     __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_rawfull[2], bar_rawempty[2];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,6 +78,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_tfull[s], NSPLIT == 3 ? 2 : 1);
             mbar_init(&bar_tempty[s], 128);
+            mbar_init(&bar_rawfull[s], 1);
+            mbar_init(&bar_rawempty[s], kGen);
         }
         fence_mbar_init();
         tma_prefetch_desc(&tmXr);
@@ -84,10 +98,21 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int stage = 0, phase = 0;
+            int stage = 0, phase = 0, rs = 0, rph = 0;
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int mode = item / g.o_tiles;
                 for (int kb = 0; kb < g.KB; ++kb) {
+                    if (RAW) {
+                        // weight tiles of this k-block: rows = reduction-side... forward: 32 i rows x 128 o; backward: 128 i rows x 32 o
+                        const int ot = item - mode * g.o_tiles, blk = mode >= g.m1m2, mb = mode - blk * g.m1m2;
+                        const int row0 = mb * g.Ci + (BWD ? ot * TM : kb * TK), col0 = BWD ? kb * TK : ot * TM;
+                        mbar_wait(&bar_rawempty[rs], rph ^ 1);
+                        unsigned char* rw = smem + g.raw_off + (size_t)rs * g.raw_bytes;
+                        mbar_arrive_expect_tx(&bar_rawfull[rs], SAMPLED ? 3 * W_TILE : 2 * W_TILE);
+                        tma_load_2d(rw, blk ? &tmMu2 : &tmMu1, &bar_rawfull[rs], 2 * col0, row0);
+                        if (SAMPLED) tma_load_2d(rw + 2 * W_TILE, blk ? &tmLv2 : &tmLv1, &bar_rawfull[rs], col0, row0);
+                        if (++rs == 2) { rs = 0; rph ^= 1; }
+                    }
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     mbar_arrive(&bar_free[stage]);                 // the generators may fill the W tiles while the xhat tiles are in flight
                     unsigned char* st = smem + (size_t)stage * g.stage_bytes + x_off;
@@ -194,10 +219,12 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         int item_n = blockIdx.x, kb_n = 0;
         if (item_n < g.n_items) {
             locate(item_n, 0);
+            if (!RAW) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) fetch(j);
+                for (int j = 0; j < 4; ++j) fetch(j);
+            }
         }
-        int stage = 0, phase = 0;
+        int stage = 0, phase = 0, rs = 0, rph = 0;
         for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             for (int kb = 0; kb < g.KB; ++kb) {
                 const uint64_t quad = quad_n;       // Philox counters of the k-block held in the buffers
@@ -216,14 +243,22 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     if (SAMPLED) lv_n += (size_t)TK * g.Co;
                     quad_n += (uint64_t)TK * g.Cop;
                 }
+                uint32_t raw_mu = 0, raw_lv = 0;
+                if (RAW) {
+                    mbar_wait(&bar_rawfull[rs], rph);           // mu / log_var tiles of this k-block landed
+                    const uint32_t rw = smem_u32(smem + g.raw_off + (size_t)rs * g.raw_bytes);
+                    // forward: [32 i rows][128 o complex]; backward: [128 i rows][32 o complex]; this thread: rows iq*4 + j, o pair p
+                    raw_mu = rw + (BWD ? iq * 4 * 256 : iq * 4 * 1024) + p * 16;
+                    raw_lv = rw + 2 * W_TILE + (BWD ? iq * 4 * 128 : iq * 4 * 512) + p * 8;
+                }
                 mbar_wait(&bar_free[stage], phase);             // the MMAs that read this stage are done: its W tiles are ours to fill
                 const uint32_t st = smem_u32(smem + (size_t)stage * g.stage_bytes);
                 float wr[2][4], wi[2][4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 m4 = bm[j];
-                    const float2 l2 = bl[j];
-                    if (more) fetch(j);                          // refill the slot just consumed: next k-block's loads in flight
+                    const float4 m4 = RAW ? lds128(raw_mu + j * (BWD ? 256 : 1024)) : bm[j];
+                    const float2 l2 = RAW ? (SAMPLED ? lds64(raw_lv + j * (BWD ? 128 : 512)) : make_float2(0.f, 0.f)) : bl[j];
+                    if (!RAW && more) fetch(j);                  // refill the slot just consumed: next k-block's loads in flight
                     wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
                     if (SAMPLED) {
                         const float4 z = philox_quad_normals(g.key, quad + (uint64_t)j * g.Cop);
@@ -282,6 +317,10 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_ready[stage]);
+                if (RAW) {
+                    mbar_arrive(&bar_rawempty[rs]);             // (the loads above completed: their values were consumed)
+                    if (++rs == 2) { rs = 0; rph ^= 1; }
+                }
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -348,6 +387,16 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     if (g.stages < 2 || g.stages > 4) g.stages = 4;
     while (g.stages > 2 && g.stages * g.stage_bytes + 1024 > 220 * 1024) --g.stages;
     g.smem_bytes = g.stages * g.stage_bytes + 1024;
+    // RAW mode (see the kernel): single pass with sampled weights; two operand stages + two 48 KB mu / log_var staging buffers
+    const bool sampled = lv1 != nullptr;
+    const char* e_raw = getenv("PNO_MIX_RAW");          // tuning override: 0 = register-prefetched weights
+    const bool raw = !x3 && sampled && !(e_raw && atoi(e_raw) == 0) && 2 * g.stage_bytes + 2 * 3 * W_TILE + 1024 <= 225 * 1024;
+    if (raw) {
+        g.stages = 2;
+        g.raw_off = g.stages * g.stage_bytes;
+        g.raw_bytes = 3 * W_TILE;
+        g.smem_bytes = g.raw_off + 2 * g.raw_bytes + 1024;
+    }
     if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "%s: %d bytes of shared memory needed", who, g.smem_bytes);
     CUtensorMap tmXr, tmXi;
     int rc;
@@ -358,25 +407,39 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
         if ((rc = pno_encode_tmap(&tmXr, in_r, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmXi, in_i, 2, dims, str, box, 1))) return rc;
     }
+    CUtensorMap tmMu1, tmMu2, tmLv1, tmLv2;
+    memset(&tmMu1, 0, sizeof(tmMu1)); memset(&tmMu2, 0, sizeof(tmMu2)); memset(&tmLv1, 0, sizeof(tmLv1)); memset(&tmLv2, 0, sizeof(tmLv2));
+    if (raw) {      // mu: [m1m2*Ci rows][2*Co floats], log_var: [m1m2*Ci rows][Co floats]; unswizzled boxes
+        const uint64_t rows = (uint64_t)g.m1m2 * Ci;
+        const uint64_t dmu[2] = {(uint64_t)2 * Co, rows}, dlv[2] = {(uint64_t)Co, rows};
+        const uint64_t smu[1] = {(uint64_t)2 * Co * 4}, slv[1] = {(uint64_t)Co * 4};
+        const uint32_t bmu[2] = {bwd ? 2u * TK : 2u * TM, bwd ? (uint32_t)TM : (uint32_t)TK};
+        const uint32_t blv[2] = {bwd ? (uint32_t)TK : (uint32_t)TM, bwd ? (uint32_t)TM : (uint32_t)TK};
+        if ((rc = pno_encode_tmap(&tmMu1, mu1, 2, dmu, smu, bmu, 0))) return rc;
+        if ((rc = pno_encode_tmap(&tmMu2, mu2, 2, dmu, smu, bmu, 0))) return rc;
+        if ((rc = pno_encode_tmap(&tmLv1, lv1, 2, dlv, slv, blv, 0))) return rc;
+        if ((rc = pno_encode_tmap(&tmLv2, lv2, 2, dlv, slv, blv, 0))) return rc;
+    }
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = g.n_items < sms ? g.n_items : sms;
-    const bool sampled = lv1 != nullptr;
-#define PNO_LAUNCH_MIX(NS, SM, BW)                                                                                          \
-    do {                                                                                                                   \
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<NS, SM, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
-        PNO_CUDA(pno_launch(k_tc_mix_fwd<NS, SM, BW>, grid, kThreads, g.smem_bytes, st, g, tmXr, tmXi));                   \
+#define PNO_LAUNCH_MIX(NS, SM, BW, RW)                                                                                          \
+    do {                                                                                                                       \
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_mix_fwd<NS, SM, BW, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
+        PNO_CUDA(pno_launch(k_tc_mix_fwd<NS, SM, BW, RW>, grid, threads_for(NS), g.smem_bytes, st, g, tmXr, tmXi, tmMu1, tmMu2, \
+                            tmLv1, tmLv2));                                                                                    \
     } while (0)
-#define PNO_LAUNCH_MIX_DIR(NS, SM)               \
-    do {                                         \
-        if (bwd) PNO_LAUNCH_MIX(NS, SM, true);   \
-        else PNO_LAUNCH_MIX(NS, SM, false);      \
+#define PNO_LAUNCH_MIX_DIR(NS, SM, RW)               \
+    do {                                             \
+        if (bwd) PNO_LAUNCH_MIX(NS, SM, true, RW);   \
+        else PNO_LAUNCH_MIX(NS, SM, false, RW);      \
     } while (0)
-    if (x3 && sampled) PNO_LAUNCH_MIX_DIR(3, true);
-    else if (x3) PNO_LAUNCH_MIX_DIR(3, false);
-    else if (sampled) PNO_LAUNCH_MIX_DIR(1, true);
-    else PNO_LAUNCH_MIX_DIR(1, false);
+    if (x3 && sampled) PNO_LAUNCH_MIX_DIR(3, true, false);
+    else if (x3) PNO_LAUNCH_MIX_DIR(3, false, false);
+    else if (raw) PNO_LAUNCH_MIX_DIR(1, true, true);
+    else if (sampled) PNO_LAUNCH_MIX_DIR(1, true, false);
+    else PNO_LAUNCH_MIX_DIR(1, false, false);
 #undef PNO_LAUNCH_MIX_DIR
 #undef PNO_LAUNCH_MIX
     PNO_LAUNCH_CHECK();
