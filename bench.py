@@ -259,6 +259,9 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # NCCL's banner ("NCCL version ...", printed to stdout when NCCL_DEBUG=VERSION/INFO is set in the environment) must not
+        # share stdout with the one JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     from pno_physics_bench_b200 import _lib
     lib = _lib.load()
