@@ -260,9 +260,18 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         # NCCL's banner ("NCCL version ...", printed to stdout when NCCL_DEBUG=VERSION/INFO is set in the environment) must not
-        # share stdout with the one JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
+        # share stdout with the one JSON line of the contract: stdout points at stderr while the communicator is created
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from pno_physics_bench_b200 import _lib
     lib = _lib.load()
     model = build_model(args.engine, device)
