@@ -171,6 +171,11 @@ extern "C" int pno_mix_bwd_dw(const pno_plan_t* p, int engine, const float* xr, 
     if ((dmu1 == nullptr) != (dmu2 == nullptr) || (dlv1 == nullptr) != (dlv2 == nullptr))
         PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dw: gradient outputs must be given per pair");
     (void)engine;
+    if (engine != PNO_ENGINE_FP32) {
+        rc = tc_mix_bwd_dw(p, engine, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, make_key(seed, sample_idx, site), dmu1, dmu2, dlv1, dlv2,
+                           as_stream(stream));
+        if (rc != PNO_E_UNSUPPORTED) return rc;   // shapes the tensor-core kernel does not tile run on CUDA cores
+    }
     return simt_mix_bwd_dw(p, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, make_key(seed, sample_idx, site), dmu1, dmu2, dlv1,
                            dlv2, as_stream(stream));
 }

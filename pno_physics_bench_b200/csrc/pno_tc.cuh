@@ -20,3 +20,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
 size_t tc_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy);
 int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW, const float* Wm,
                  const float* Wl, float* dx, float* dw, float* db, void* workspace, cudaStream_t st);
+// weight gradient of the channel mix (pno_tc_mix_dw.cu)
+int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* xi, const float* gr, const float* gi, int B, int Ci,
+                  int Co, const float* lv1, const float* lv2, PhiloxKey key, float* dmu1, float* dmu2, float* dlv1, float* dlv2,
+                  cudaStream_t st);

@@ -239,6 +239,47 @@ def test_mix_backward_dx_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
     assert rel_l2(tr, rr) < tol and rel_l2(ti, ri) < tol, (rel_l2(tr, rr), rel_l2(ti, ri))
 
 
+def _mix_bwd_dw(xr, xi, gr, gi, layer, sampled, engine):
+    lib = _lib.load()
+    m, b, ci = xr.shape
+    co = gr.shape[2]
+    m1, m2 = layer.modes1, layer.modes2
+    plan = _lib.plan(64, 64, m1, m2, gr.device)
+    lv = [t.detach().permute(2, 3, 0, 1) for t in (layer.weights1_log_var, layer.weights2_log_var)]
+    dmu = [torch.full((m1, m2, ci, co, 2), float("nan"), device=gr.device) for _ in range(2)]
+    dlv = [torch.full((m1, m2, ci, co), float("nan"), device=gr.device) for _ in range(2)]
+    _lib.check(lib.pno_mix_bwd_dw(plan, _lib.ENGINES[engine], xr.data_ptr(), xi.data_ptr(), gr.data_ptr(), gi.data_ptr(), b, ci, co,
+                                  lv[0].data_ptr() if sampled else 0, lv[1].data_ptr() if sampled else 0, 777, 3, 9,
+                                  dmu[0].data_ptr(), dmu[1].data_ptr(), dlv[0].data_ptr() if sampled else 0,
+                                  dlv[1].data_ptr() if sampled else 0, _lib.stream_ptr()), "pno_mix_bwd_dw")
+    torch.cuda.synchronize()
+    return dmu + (dlv if sampled else [])
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 5e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("sampled", [False, True])
+@pytest.mark.parametrize("shape", [(32, 256, 256, 6, 5), (5, 128, 256, 3, 4), (64, 128, 128, 2, 2), (12, 256, 128, 4, 4)])
+def test_mix_backward_dw_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
+    """Weight gradient of the channel mix (dmu and, with the noise re-drawn, dlv): tensor-core kernel vs the fp32 CUDA-core
+    kernel, which the layer-level tests pin to the oracle's autograd.  Ragged batches exercise the TMA zero fill."""
+    import pno_physics_bench_b200 as pno
+    b, ci, co, m1, m2 = shape
+    gen = torch.Generator().manual_seed(sum(shape) + 2)
+    layer = pno.SpectralConv2d_Probabilistic(ci, co, m1, m2)
+    with torch.no_grad():
+        for lv in (layer.weights1_log_var, layer.weights2_log_var):
+            lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 6)
+    layer = layer.to(DEV)
+    m = 2 * m1 * m2
+    xr, xi = torch.randn(m, b, ci, generator=gen).to(DEV), torch.randn(m, b, ci, generator=gen).to(DEV)
+    gr, gi = torch.randn(m, b, co, generator=gen).to(DEV), torch.randn(m, b, co, generator=gen).to(DEV)
+    ref = _mix_bwd_dw(xr, xi, gr, gi, layer, sampled, "fp32")
+    got = _mix_bwd_dw(xr, xi, gr, gi, layer, sampled, engine)
+    for a_, b_ in zip(got, ref):
+        assert not torch.isnan(a_).any()
+        assert rel_l2(a_, b_) < tol, rel_l2(a_, b_)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # size-independent properties at the full BASELINE config-3 layer shape (B 64, C 256, 64x64, modes 20), where the oracle is
 # too slow to be the checker
