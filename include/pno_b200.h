@@ -197,14 +197,19 @@ int pno_loss_data_bwd(const float* mean, const float* log_var, const float* targ
                       float* dmean, float* dlog_var, void* stream);
 
 /* ---- optimiser step of the trainer (training/trainer.py:283-291: clip_grad_norm_, AdamW.step) without host syncs ---- */
-/* *acc (double, device) += sum of squares of n gradient values */
-int pno_sumsq_accumulate(const float* grad, uint64_t n, double* acc, void* stream);
+/* kl_kind (both calls): 0 = none; 1 / 2 = the tensor is a spectral mean (re, im parts) / log-variance whose KL gradient
+ * (models.py:100-104) is ANALYTIC in the parameter itself -- *kl_gscale * p, resp. *kl_gscale * (-0.5 (1 - exp(p))) -- and is
+ * added to the data gradient on the fly instead of being materialised and accumulated by a separate pass (kl_gscale: one float
+ * on the device = d loss / d KL). */
+/* *acc (double, device) += sum of squares of the n (total) gradient values */
+int pno_sumsq_accumulate(const float* grad, uint64_t n, double* acc, const float* param, int kl_kind, const float* kl_gscale,
+                         void* stream);
 /* torch.optim.AdamW semantics (decoupled weight decay, bias correction by step >= 1, denom = sqrt(v_hat) + eps) on one
  * flat tensor; the gradient is first scaled by min(1, max_norm / (sqrt(*grad_sumsq) + 1e-6)) (torch clip_grad_norm_) when
  * grad_sumsq != NULL and max_norm > 0, and written back clipped when write_clipped_grad != 0. */
 int pno_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, uint32_t step, const double* grad_sumsq, float max_norm,
-                   int write_clipped_grad, void* stream);
+                   int write_clipped_grad, int kl_kind, const float* kl_gscale, void* stream);
 
 /* Diagnostics: device buffer (>= 148*16 int64) into which the tensor-core kernels dump per-CTA barrier-wait cycle counters
  * (NULL switches it off, the default).  Used by tools/phase_times.py to find the stage a pipeline is waiting on. */

@@ -179,18 +179,33 @@ extern "C" int pno_loss_data_bwd(const float* mean, const float* log_var, const 
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 
-__global__ void __launch_bounds__(kThreads) k_sumsq(const float* __restrict__ g, unsigned long long n, double* __restrict__ acc) {
+// analytic KL gradient of a spectral parameter (models.py:100-104), added to the data gradient on the fly:
+//   kind 1 (mean, re / im parts): gs * p          kind 2 (log-variance): gs * (-0.5 (1 - exp(p)))
+__device__ __forceinline__ float kl_extra(float p, int kind, float gs) {
+    return kind == 1 ? gs * p : gs * (-0.5f * (1.0f - expf(p)));
+}
+
+__global__ void __launch_bounds__(kThreads) k_sumsq(const float* __restrict__ g, unsigned long long n, double* __restrict__ acc,
+                                                   const float* __restrict__ p, int kl_kind, const float* __restrict__ kl_gscale) {
     __shared__ double s_red[kThreads / 32];
     double s = 0.0;
     const unsigned long long n4 = n >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float gs = kl_kind ? *kl_gscale : 0.f;
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * kThreads) {
-        const float4 v = g4[i];
+        float4 v = g4[i];
+        if (kl_kind) {
+            const float4 q = reinterpret_cast<const float4*>(p)[i];
+            v.x += kl_extra(q.x, kl_kind, gs); v.y += kl_extra(q.y, kl_kind, gs);
+            v.z += kl_extra(q.z, kl_kind, gs); v.w += kl_extra(q.w, kl_kind, gs);
+        }
         s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
     }
     for (unsigned long long i = (n4 << 2) + blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * kThreads)
-        s += (double)g[i] * g[i];
+         i += (unsigned long long)gridDim.x * kThreads) {
+        const float v = g[i] + (kl_kind ? kl_extra(p[i], kl_kind, gs) : 0.f);
+        s += (double)v * v;
+    }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -203,9 +218,12 @@ __global__ void __launch_bounds__(kThreads) k_sumsq(const float* __restrict__ g,
 
 struct AdamArgs {
     float lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, max_norm;
+    int kl_kind;
+    float kl_gs;          // filled in the kernel from device memory
 };
 
 __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float clip) {
+    if (a.kl_kind) g += kl_extra(p, a.kl_kind, a.kl_gs);
     g *= clip;
     p *= 1.f - a.lr * a.weight_decay;                                   // decoupled weight decay (torch AdamW)
     m = fmaf(1.f - a.beta1, g - m, m);                                  // m.lerp_(g, 1 - beta1)
@@ -216,8 +234,10 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(kThreads) k_adamw(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, unsigned long long n, const AdamArgs a,
-                                                   const double* __restrict__ gsumsq, int write_grad) {
+                                                   float* __restrict__ v, unsigned long long n, AdamArgs a,
+                                                   const double* __restrict__ gsumsq, int write_grad,
+                                                   const float* __restrict__ kl_gscale) {
+    a.kl_gs = a.kl_kind ? *kl_gscale : 0.f;
     // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1 (torch/nn/utils/clip_grad.py)
     float clip = 1.f;
     if (gsumsq && a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / ((float)sqrt(*gsumsq) + 1e-6f));
@@ -244,33 +264,38 @@ __global__ void __launch_bounds__(kThreads) k_adamw(float* __restrict__ p, float
 
 }  // namespace
 
-extern "C" int pno_sumsq_accumulate(const float* g, uint64_t n, double* acc, void* stream) {
+extern "C" int pno_sumsq_accumulate(const float* g, uint64_t n, double* acc, const float* param, int kl_kind, const float* kl_gscale,
+                                    void* stream) {
     if (n == 0) return PNO_OK;
     if (!g || !acc) PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate: null pointer");
+    if (kl_kind < 0 || kl_kind > 2 || (kl_kind && (!param || !kl_gscale || (reinterpret_cast<uintptr_t>(param) & 15))))
+        PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate: kl_kind in {0, 1, 2}; kinds 1 / 2 need the (16-byte aligned) parameter and the scale");
     if (reinterpret_cast<uintptr_t>(g) & 15) PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate: gradient must be 16-byte aligned");
     const unsigned long long want = (n / 4 + kThreads - 1) / kThreads + 1;
     const int grid = (int)(want < 148ull * 8 ? want : 148ull * 8);
-    k_sumsq<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, n, acc);
+    k_sumsq<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, n, acc, param, kl_kind, kl_gscale);
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
 extern "C" int pno_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, uint32_t step, const double* grad_sumsq, float max_norm,
-                              int write_clipped_grad, void* stream) {
+                              int write_clipped_grad, int kl_kind, const float* kl_gscale, void* stream) {
     if (n == 0) return PNO_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || step == 0) PNO_FAIL(PNO_E_INVALID, "pno_adamw_step: bad arguments");
+    if (kl_kind < 0 || kl_kind > 2 || (kl_kind && !kl_gscale)) PNO_FAIL(PNO_E_INVALID, "pno_adamw_step: kl_kind in {0, 1, 2}, kinds 1 / 2 need the scale");
     if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
          reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
         PNO_FAIL(PNO_E_INVALID, "pno_adamw_step: tensors must be 16-byte aligned");
     AdamArgs a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+    a.kl_kind = kl_kind; a.kl_gs = 0.f;
     a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     const unsigned long long want = (n / 4 + kThreads - 1) / kThreads + 1;
     const int grid = (int)(want < 148ull * 16 ? want : 148ull * 16);
     k_adamw<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a, grad_sumsq,
-                                                                      write_clipped_grad);
+                                                                      write_clipped_grad, kl_gscale);
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }

@@ -37,6 +37,19 @@ class FusedAdamW(torch.optim.Optimizer):
         self.max_grad_norm = max_grad_norm
         self.write_clipped_grads = write_clipped_grads      # leave .grad scaled like clip_grad_norm_ does (one more write)
         self._gsq = None
+        self._kl = {}            # id(param) -> 1 (spectral mean) / 2 (spectral log-variance)
+        self._kl_gscale = None
+
+    def set_analytic_kl(self, kl_params, gscale):
+        """For the next step(): the KL term's gradient w.r.t. the spectral weights is added inside the optimiser kernels
+        (it is analytic in the parameter: gs * mu, gs * (-0.5 (1 - exp(lv))), models.py:100-104) instead of being materialised
+        and accumulated into .grad by a separate pass.  kl_params = (mu_0, lv_0, mu_1, lv_1, ...); gscale: 0-d float32 CUDA
+        tensor (d loss / d KL).  `.grad` then holds the data-term gradient only."""
+        self._kl = {}
+        for k in range(0, len(kl_params), 2):
+            self._kl[id(kl_params[k])] = 1
+            self._kl[id(kl_params[k + 1])] = 2
+        self._kl_gscale = gscale.detach().to(torch.float32).contiguous()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -49,7 +62,7 @@ class FusedAdamW(torch.optim.Optimizer):
         work = []
         for group in self.param_groups:
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None and not self._kl.get(id(p), 0):
                     continue
                 _lib.require_cuda(p, "parameter")
                 if _real(p).dtype != torch.float32:
@@ -57,6 +70,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 pf = _storage_order(_real(p))
                 if pf is None:
                     raise RuntimeError("FusedAdamW: parameter storage must be dense")
+                kind = self._kl.get(id(p), 0)
+                if p.grad is None and kind:
+                    p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
                 g = p.grad
                 if g.stride() != p.stride() or g.dtype != p.dtype:
                     g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(p.grad)
@@ -69,7 +85,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 work.append((group, state, pf, gf, _storage_order(_real(state["exp_avg"])),
-                             _storage_order(_real(state["exp_avg_sq"]))))
+                             _storage_order(_real(state["exp_avg_sq"])), kind))
         if not work:
             return loss
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
@@ -78,15 +94,18 @@ class FusedAdamW(torch.optim.Optimizer):
             if self._gsq is None or self._gsq.device != dev:
                 self._gsq = torch.zeros(1, dtype=torch.float64, device=dev)
             self._gsq.zero_()
-            for _, _, _, gf, _, _ in work:
-                _lib.check(lib.pno_sumsq_accumulate(_lib.ptr(gf), gf.numel(), _lib.ptr(self._gsq), stream), "pno_sumsq_accumulate")
-        for group, state, pf, gf, mf, vf in work:
+            for _, _, pf, gf, _, _, kind in work:
+                _lib.check(lib.pno_sumsq_accumulate(_lib.ptr(gf), gf.numel(), _lib.ptr(self._gsq), _lib.ptr(pf) if kind else None, kind,
+                                                    _lib.ptr(self._kl_gscale) if kind else None, stream), "pno_sumsq_accumulate")
+        for group, state, pf, gf, mf, vf, kind in work:
             state["step"] += 1
             b1, b2 = group["betas"]
             _lib.check(lib.pno_adamw_step(_lib.ptr(pf), _lib.ptr(gf), _lib.ptr(mf), _lib.ptr(vf), pf.numel(), group["lr"], b1, b2,
                                           group["eps"], group["weight_decay"], int(state["step"]),
                                           _lib.ptr(self._gsq) if clip else None, float(self.max_grad_norm) if clip else 0.0,
-                                          int(self.write_clipped_grads), stream), "pno_adamw_step")
+                                          int(self.write_clipped_grads), kind, _lib.ptr(self._kl_gscale) if kind else None, stream),
+                       "pno_adamw_step")
+        self._kl, self._kl_gscale = {}, None          # one step only: the scale belongs to this step's loss
         return loss
 
     def grad_norm(self) -> torch.Tensor:

@@ -64,7 +64,10 @@ class PNOTrainer:
             losses = self.loss_fn(outputs, targets, self.model)
             losses["total"].backward()
             if kl_leaf is not None and kl_leaf.grad is not None:
-                F_.kl_grad_accumulate_(self.model.kl_params(), kl_leaf.grad)
+                if isinstance(self.optimizer, FusedAdamW):      # identical on every rank: added after the gradient all-reduce
+                    self.optimizer.set_analytic_kl(self.model.kl_params(), kl_leaf.grad)     # added inside the optimiser kernels
+                else:
+                    F_.kl_grad_accumulate_(self.model.kl_params(), kl_leaf.grad)
         allreduce_gradients(self.model.parameters(), self.group)
         fused_clip = isinstance(self.optimizer, FusedAdamW) and self.optimizer.max_grad_norm == self.gradient_clipping
         if self.gradient_clipping and not fused_clip:

@@ -239,3 +239,34 @@ def test_fused_adamw_matches_torch_adamw_with_clipping(max_norm):
         assert int(so["step"]) == int(sr["step"]) == 4
         assert torch.allclose(torch.view_as_real(so["exp_avg"]) if p.is_complex() else so["exp_avg"],
                               torch.view_as_real(sr["exp_avg"]) if p.is_complex() else sr["exp_avg"], rtol=1e-5, atol=1e-8)
+
+
+def test_fused_adamw_adds_the_analytic_kl_gradient_in_kernel():
+    """set_analytic_kl: same update as materialising kl_weight * dKL/d(mu, lv) into .grad first (models.py:100-104)."""
+    def make():
+        torch.manual_seed(21)
+        mu = torch.nn.Parameter(torch.randn(3, 5, 4, 6, dtype=torch.cfloat, device=DEV).permute(2, 3, 0, 1))
+        lv = torch.nn.Parameter((torch.rand(3, 5, 4, 6, device=DEV) * 4 - 6).permute(2, 3, 0, 1))
+        other = torch.nn.Parameter(torch.randn(33, device=DEV))
+        return [mu, lv, other]
+
+    ours, ref = make(), make()
+    opt_o = FusedAdamW(ours, lr=1e-2, weight_decay=1e-3, max_grad_norm=0.5)
+    opt_r = torch.optim.AdamW(ref, lr=1e-2, weight_decay=1e-3)
+    gs = torch.tensor(3e-2, device=DEV)
+    for step in range(3):
+        torch.manual_seed(50 + step)
+        grads = [torch.randn_like(p) for p in ours]
+        for p, q, g in zip(ours, ref, grads):
+            p.grad, q.grad = g.clone(), g.clone()
+        with torch.no_grad():
+            ref[0].grad += gs * ref[0]                                          # d KL / d mu = mu (re and im parts)
+            ref[1].grad += gs * (-0.5 * (1 - torch.exp(ref[1])))                # d KL / d lv
+        want_norm = torch.nn.utils.clip_grad_norm_(ref, 0.5)
+        opt_o.set_analytic_kl(ours[:2], gs)
+        opt_o.step()
+        opt_r.step()
+        assert torch.allclose(opt_o.grad_norm(), want_norm, rtol=2e-6)
+        for p, q in zip(ours, ref):
+            assert torch.allclose(torch.view_as_real(p) if p.is_complex() else p, torch.view_as_real(q) if q.is_complex() else q,
+                                  rtol=2e-6, atol=2e-7), step
