@@ -84,6 +84,10 @@ class FusedAdamW(torch.optim.Optimizer):
                     state["step"] = torch.tensor(0.0)
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                for key in ("exp_avg", "exp_avg_sq"):          # e.g. loaded from a reference (torch.optim.AdamW) checkpoint:
+                    t = state[key]                             # same values, but laid out for the logical shape
+                    if t.stride() != p.stride() or t.dtype != p.dtype or t.device != p.device:
+                        state[key] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(t)
                 work.append((group, state, pf, gf, _storage_order(_real(state["exp_avg"])),
                              _storage_order(_real(state["exp_avg_sq"])), kind))
         if not work:

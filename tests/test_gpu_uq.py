@@ -270,3 +270,32 @@ def test_fused_adamw_adds_the_analytic_kl_gradient_in_kernel():
         for p, q in zip(ours, ref):
             assert torch.allclose(torch.view_as_real(p) if p.is_complex() else p, torch.view_as_real(q) if q.is_complex() else q,
                                   rtol=2e-6, atol=2e-7), step
+
+
+def test_fused_adamw_continues_from_a_torch_adamw_state_dict():
+    """Reference checkpoints carry torch.optim.AdamW state (training/trainer.py:452): moments in logical-shape layout."""
+    torch.manual_seed(31)
+    native = torch.randn(2, 3, 4, 5, dtype=torch.cfloat, device=DEV)
+    ours = [torch.nn.Parameter(native.clone().permute(2, 3, 0, 1)), torch.nn.Parameter(torch.randn(7, 3, device=DEV))]
+    ref = [torch.nn.Parameter(native.permute(2, 3, 0, 1).contiguous()), torch.nn.Parameter(ours[1].detach().clone())]
+    opt_r = torch.optim.AdamW(ref, lr=2e-3, weight_decay=1e-2)
+    grads = [[torch.randn_like(p) for p in ref] for _ in range(4)]
+    for step in range(2):
+        for q, g in zip(ref, grads[step]):
+            q.grad = g.clone()
+        opt_r.step()
+    with torch.no_grad():
+        for p, q in zip(ours, ref):
+            p.copy_(q)
+    opt_o = FusedAdamW(ours, lr=2e-3, weight_decay=1e-2)
+    import copy
+    opt_o.load_state_dict(copy.deepcopy(opt_r.state_dict()))      # (a checkpoint from disk: no tensors shared with opt_r)
+    for step in range(2, 4):
+        for p, q, g in zip(ours, ref, grads[step]):
+            p.grad, q.grad = g.clone(), g.clone()
+        opt_o.step()
+        opt_r.step()
+    for p, q in zip(ours, ref):
+        assert torch.allclose(torch.view_as_real(p) if p.is_complex() else p, torch.view_as_real(q) if q.is_complex() else q,
+                              rtol=2e-6, atol=2e-7)
+    assert int(opt_o.state[ours[0]]["step"]) == 4
