@@ -63,6 +63,28 @@ def test_local_branch_tensor_core_vs_cuda_core(engine, tol, noisy, shape):
         assert rel_l2(a_, b_) < (10 * tol if engine == "tf32x3" else 0.2)
 
 
+def test_full_size_inverse_every_tile_is_right(monkeypatch):
+    """Single pass, full cfg-3 shape, repeated launches: stage 2 reads Z from tensor memory behind stage 1 with no barrier in
+    between (in-order MMA pipe) and y leaves by TMA store from the staged addend buffers.  A protocol race would corrupt
+    single 128-row tiles, which a whole-tensor rel-L2 could hide: check the worst element against the CUDA-core kernel, and
+    the tensor-memory form against the transposer form."""
+    b, c, h, w, m1, m2 = 64, 256, 64, 64, 20, 20
+    gen = torch.Generator().manual_seed(99)
+    m = 2 * m1 * m2
+    yr = (torch.randn(m, b, c, generator=gen) / 8).to(DEV)
+    yi = (torch.randn(m, b, c, generator=gen) / 8).to(DEV)
+    add = torch.randn(b, c, h, w, generator=gen).to(DEV)
+    ref, _ = _dft_inv(yr, yi, h, w, m1, m2, "fp32", 0, add, 1)
+    scale = float(ref.abs().max())
+    for rep in range(3):
+        got, _ = _dft_inv(yr, yi, h, w, m1, m2, "tf32", 0, add, 1)
+        assert not torch.isnan(got).any()
+        assert float((got - ref).abs().max()) < 4e-3 * scale, rep
+    monkeypatch.setenv("PNO_INV_TS", "0")
+    old, _ = _dft_inv(yr, yi, h, w, m1, m2, "tf32", 0, add, 1)
+    assert float((got - old).abs().max()) < 4e-3 * scale
+
+
 def _dft_fwd(x, m1, m2, engine, grad_scale=0):
     lib = _lib.load()
     b, c, h, w = x.shape
