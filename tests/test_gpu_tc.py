@@ -180,6 +180,12 @@ def test_mix_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
     rr, ri = _mix(xr, xi, layer, sampled, "fp32")
     tr, ti = _mix(xr, xi, layer, sampled, engine)
     assert rel_l2(tr, rr) < tol and rel_l2(ti, ri) < tol, (rel_l2(tr, rr), rel_l2(ti, ri))
+    # a pipeline race (TMA-staged weight tiles, operand rings) would corrupt single (mode, 128-channel) tiles that the
+    # whole-tensor norm can hide: bound the worst element too, over repeated launches
+    scale = float(rr.abs().max())
+    for _ in range(2):
+        tr, ti = _mix(xr, xi, layer, sampled, engine)
+        assert float((tr - rr).abs().max()) < 20 * tol * scale and float((ti - ri).abs().max()) < 20 * tol * scale
 
 
 @pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 2e-2)])
