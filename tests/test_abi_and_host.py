@@ -143,3 +143,26 @@ def test_losses_match_reference(golden):
         assert abs(float(res[k]) - float(g["tensor." + k])) < 1e-6, k
     with pytest.raises(ValueError):
         PNOLoss()((mean,), tgt)
+
+
+def test_metrics_host_logic_matches_the_oracle(golden):
+    """Host side of the calibration report (metrics.py mirror): quantiles and the metrics computed from the statistics vector."""
+    import numpy as np
+    import torch
+    from oracle import pno_oracle as orc
+    from pno_physics_bench_b200 import metrics as M
+    from scipy import stats
+    for p in (1e-6, 0.01, 0.3, 0.5, 0.75, 0.975, 0.995, 0.99995):       # the levels in use are 0.75 .. 0.995
+        assert abs(M.norm_ppf(p) - stats.norm.ppf(p)) < 1e-11 * max(1.0, abs(stats.norm.ppf(p)))
+    g = golden("metrics_cases.npz")
+    acc = M.UQAccumulator(device="cpu")
+    z = [orc._ndtri(0.5 + lv / 2) for lv in acc.levels]
+    stats_vec = orc.uq_stats(g["calibrated.pred"], g["calibrated.std"], g["calibrated.target"], z, acc.alphas, acc.num_bins)
+    acc.acc = torch.from_numpy(stats_vec)
+    got = acc.compute()
+    for k, v in got.items():
+        ref = float(g["calibrated.m." + k])
+        assert abs(v - ref) <= 2e-6 * max(1.0, abs(ref)), (k, v, ref)
+    assert abs(acc.ece(acc.stats(), "l2") ** 2 - sum(
+        (abs(h / c - s / c) ** 2) * (c / stats_vec[0])
+        for c, s, h in np.asarray(stats_vec[7 + len(acc.levels) + len(acc.alphas):]).reshape(-1, 3) if c > 0)) < 1e-12
