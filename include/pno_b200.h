@@ -27,7 +27,13 @@
  * Tuning / diagnostic environment variables (read by the host side of the library; none is needed in normal use):
  *   PNO_PDL=1            launch the tensor-core kernels with programmatic stream serialization (measured: no gain)
  *   PNO_LOCAL_TN=256     256-pixel tiles in the single-pass local-branch kernel (measured slower than the default 128)
- *   PNO_INV_NB1=2, PNO_INV_NZT=3, PNO_INV_ND2=n, PNO_INV_ADD=0|2|3   buffer counts of the inverse-transform kernel
+ *   PNO_LOCAL_EW=16      16 epilogue warps in the local-branch kernel instead of 8 (measured slower)
+ *   PNO_LOCAL_PREFETCH=0 no L2 prefetch of the next tile's x boxes
+ *   PNO_INV_NB1=2, PNO_INV_NZT=3, PNO_INV_ND2=n, PNO_INV_ADD=0|2|3|4 buffer counts of the inverse-transform kernel
+ *   PNO_INV_TS=0         single pass: transposer path instead of stage 2 from tensor memory
+ *   PNO_INV_TMAOUT=0     global store instructions instead of the in-place TMA tile store
+ *   PNO_INV_G=4|8, PNO_INV_EPI=8, PNO_INV_CAP=kb                     channel-group size, epilogue warps, shared-memory budget
+ *   PNO_MIX_RAW=0        single pass: register-prefetched mu / log_var instead of the TMA-staged tiles
  *   PNO_FWD_STAGES=n, PNO_FWD_KPS=1|2                                ring depth / stage size of the forward-transform kernel
  *   PNO_MIX_STAGES=2..4                                              ring depth of the channel-mix kernel
  *   PNO_DEBUG_MMA=1      (PNO_TRACE builds) serialise the inverse kernel's MMA batches to time them
