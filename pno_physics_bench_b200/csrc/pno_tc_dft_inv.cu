@@ -498,9 +498,10 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                             a4[k] = addend ? __ldg(reinterpret_cast<const float4*>(addend + gofs + c + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 };
-                if (staged) mbar_wait(&bar_add_full[sa], aph);
-                if (ew == 0) TRACE(2, 3);
-                fetch(c_lo);
+                // A staged addend is waited for AFTER the accumulator: the TMA that fills it completes in many partial
+                // transactions and each one wakes every warp parked on the barrier (~11 retries per wait, 12% of all executed
+                // instructions of the kernel); by the time stage 2 of the tile is done the tile landed long ago.
+                if (!staged) fetch(c_lo);
                 // ... and (LDG path) the chunk of the tile after this one is pulled into L2 now, so that its fetch is an L2 hit
                 if (addend && !staged) {
                     const size_t nxt_row0 = j + 1 < g.TPG ? tile_row0 + (size_t)g.IPT * g.H
@@ -511,6 +512,11 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                 if (ew == 0) TRACE(2, 1);
                 if (ew == g.epi_warps - 1) TRACE(4, 1);
                 tc_fence_after_sync();
+                if (staged) {
+                    mbar_wait(&bar_add_full[sa], aph);
+                    if (ew == 0) TRACE(2, 3);
+                    fetch(c_lo);
+                }
 #pragma unroll 1
                 for (int c = c_lo; c < c_hi; c += 16) {
                     float v[16];
