@@ -181,6 +181,55 @@ __global__ void __launch_bounds__(256) k_local_bwd_prep(const float* __restrict_
     }
 }
 
+// Lift-shaped layers (Ci <= 4, e.g. the 3 -> C lift of models.py:288-290): the weight gradient is a handful of dot products per
+// (b, o) row and the pass is a pure streaming read of g and d out / d lv.  One block per (b, o) row:
+//   dw[o][i] += sum_p g x_i ; dw[Co + o][i] += sum_p g dlv x_i ; db[o] += sum_p g ; db[Co + o] += sum_p g dlv
+__global__ void __launch_bounds__(256) k_local_thin_in_bwd(const float* __restrict__ x, const float* __restrict__ g,
+                                                           const float* __restrict__ dlv, int Ci, int Co, int HW, int noisy,
+                                                           float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float s_red[10][8];
+    const int row = blockIdx.x;
+    const int b = row / Co, o = row - b * Co;
+    const float4* gs = reinterpret_cast<const float4*>(g + (size_t)row * HW);
+    const float4* ls = noisy ? reinterpret_cast<const float4*>(dlv + (size_t)row * HW) : nullptr;
+    float acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+    for (int i4 = threadIdx.x; i4 < HW / 4; i4 += 256) {
+        const float4 gv = gs[i4];
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (noisy) {
+            const float4 l = ls[i4];
+            wv = make_float4(gv.x * l.x, gv.y * l.y, gv.z * l.z, gv.w * l.w);
+        }
+        acc[8] += (gv.x + gv.y) + (gv.z + gv.w);
+        acc[9] += (wv.x + wv.y) + (wv.z + wv.w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < Ci) {
+                const float4 xv = reinterpret_cast<const float4*>(x + ((size_t)b * Ci + i) * HW)[i4];
+                acc[i] += gv.x * xv.x + gv.y * xv.y + gv.z * xv.z + gv.w * xv.w;
+                acc[4 + i] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], of);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_red[threadIdx.x][w];
+        const int k = threadIdx.x;
+        if (k < 4) { if (k < Ci && dw) atomicAdd(dw + (size_t)o * Ci + k, s); }
+        else if (k < 8) { if (k - 4 < Ci && dw && noisy) atomicAdd(dw + (size_t)(Co + o) * Ci + (k - 4), s); }
+        else if (k == 8) { if (db) atomicAdd(db + o, s); }
+        else if (db && noisy) atomicAdd(db + Co + o, s);
+    }
+}
+
 // wcat[i][o] = Wm[o][i], wcat[i][Co + o] = Wl[o][i]   ([Ci][2 Co]; [Ci][Co] when Wl == NULL)
 __global__ void k_wcat(const float* __restrict__ wm, const float* __restrict__ wl, int Ci, int Co, float* __restrict__ wcat) {
     const int n = Ci * Co, ld = wl ? 2 * Co : Co;
@@ -194,6 +243,7 @@ __global__ void k_wcat(const float* __restrict__ wm, const float* __restrict__ w
 }  // namespace
 
 size_t tc_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy) {
+    if (Ci <= 4) return 1024;                   // lift-shaped layers stream g / dlv directly (no stacked gradient)
     const size_t g2 = noisy ? (size_t)B * 2 * Co * HW * 4 : 0;
     return g2 + (size_t)Ci * (noisy ? 2 : 1) * Co * 4 + 1024;
 }
@@ -202,6 +252,16 @@ int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_d
                  const float* Wl, float* dx, float* dw, float* db, void* workspace, cudaStream_t st) {
     const int noisy = Wl != nullptr;
     const int rows = noisy ? 2 * Co : Co;
+    if (Ci <= 4 && dx == nullptr && HW % 4 == 0 && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) |
+                                                      reinterpret_cast<uintptr_t>(dout_dlv)) & 15)) {
+        // lift-shaped layer: streaming dot products (no input gradient: x is data)
+        if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "tc_local_bwd: d out / d log_var is needed when Wl is given");
+        if (dw) PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
+        if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
+        k_local_thin_in_bwd<<<B * Co, 256, 0, st>>>(x, g, dout_dlv, Ci, Co, HW, noisy, dw, db);
+        PNO_LAUNCH_CHECK();
+        return PNO_OK;
+    }
     if (Co % TM || Ci % 128 || Ci > 256 || HW % 128 || rows % 32)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_bwd tiles Co%%128 == 0, Ci in {128, 256}, HW%%128 == 0 (got %d, %d, %d)", Co, Ci, HW);
     if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "tc_local_bwd: d out / d log_var is needed when Wl is given");
