@@ -152,7 +152,8 @@ int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, con
 /* Backward of pno_local_fwd on the tensor-core engines (autograd of models.py:298-303): with dYm = g and dYl = g * dout_dlv,
  *   dx = Wm^T dYm + Wl^T dYl ([B,Ci,HW]);  dw = [sum_b dYm x^T ; sum_b dYl x^T] ([2Co][Ci] stacked, [Co][Ci] when Wl == NULL);
  *   db = [sum dYm ; sum dYl] per output channel.  dx / dw / db may each be NULL.  Shapes: Co % 128 == 0, Ci in {128, 256},
- * HW % 128 == 0; or a lift-shaped layer (Ci <= 4, dx == NULL, HW % 4 == 0: streaming dot products); else PNO_E_UNSUPPORTED (as for PNO_ENGINE_FP32): the caller then uses plain library GEMMs.
+ * HW % 128 == 0; or a lift-shaped layer (Ci <= 4, dx == NULL, HW % 4 == 0: streaming dot products); or a projection-shaped
+ * layer (Co <= 4, HW % 4 == 0: one pass over x); else PNO_E_UNSUPPORTED (as for PNO_ENGINE_FP32): the caller then uses plain library GEMMs.
  * workspace: pno_local_bwd_workspace_bytes(...) bytes (the stacked gradient [B][2Co][HW] and the stacked transposed weights;
  * 1 KB for lift-shaped layers).  A lift-shaped call with dx != NULL is PNO_E_UNSUPPORTED. */
 size_t pno_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy);

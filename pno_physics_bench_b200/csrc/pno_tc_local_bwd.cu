@@ -230,6 +230,67 @@ __global__ void __launch_bounds__(256) k_local_thin_in_bwd(const float* __restri
     }
 }
 
+// Projection-shaped layers (Co <= 4, e.g. the C -> 1 heads of models.py:309-314): one block per (b, i) row of x computes
+//   dx[b][i][p] = sum_o Wm[o][i] g[b][o][p] + Wl[o][i] g[b][o][p] dlv[b][o][p]      (streaming write)
+//   dw[o][i] += sum_p g x ;  dw[Co + o][i] += sum_p g dlv x                         (one pass over x);  db from the i == 0 rows
+template <int CO>
+__global__ void __launch_bounds__(256) k_local_thin_out_bwd(const float* __restrict__ x, const float* __restrict__ g,
+                                                            const float* __restrict__ dlv, const float* __restrict__ wm,
+                                                            const float* __restrict__ wl, int Ci, int HW, int noisy,
+                                                            float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float s_red[4 * CO][8];
+    const int row = blockIdx.x;
+    const int b = row / Ci, i = row - b * Ci;
+    float wmi[CO], wli[CO], acc[4 * CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+        wmi[o] = wm[(size_t)o * Ci + i];
+        wli[o] = noisy ? wl[(size_t)o * Ci + i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * CO; ++k) acc[k] = 0.f;
+    const float4* xs = reinterpret_cast<const float4*>(x + (size_t)row * HW);
+    float4* dxs = dx ? reinterpret_cast<float4*>(dx + (size_t)row * HW) : nullptr;
+    for (int p4 = threadIdx.x; p4 < HW / 4; p4 += 256) {
+        const float4 xv = xs[p4];
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            const float4 gv = reinterpret_cast<const float4*>(g + ((size_t)b * CO + o) * HW)[p4];
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (noisy) {
+                const float4 l = reinterpret_cast<const float4*>(dlv + ((size_t)b * CO + o) * HW)[p4];
+                wv = make_float4(gv.x * l.x, gv.y * l.y, gv.z * l.z, gv.w * l.w);
+            }
+            d.x += wmi[o] * gv.x + wli[o] * wv.x; d.y += wmi[o] * gv.y + wli[o] * wv.y;
+            d.z += wmi[o] * gv.z + wli[o] * wv.z; d.w += wmi[o] * gv.w + wli[o] * wv.w;
+            acc[o] += gv.x * xv.x + gv.y * xv.y + gv.z * xv.z + gv.w * xv.w;
+            acc[CO + o] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+            acc[2 * CO + o] += (gv.x + gv.y) + (gv.z + gv.w);
+            acc[3 * CO + o] += (wv.x + wv.y) + (wv.z + wv.w);
+        }
+        if (dxs) dxs[p4] = d;
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * CO; ++k) {
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], of);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 * CO) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_red[threadIdx.x][w];
+        const int kind = threadIdx.x / CO, o = threadIdx.x % CO;
+        if (kind == 0) { if (dw) atomicAdd(dw + (size_t)o * Ci + i, s); }
+        else if (kind == 1) { if (dw && noisy) atomicAdd(dw + (size_t)(CO + o) * Ci + i, s); }
+        else if (i == 0 && db) {                       // bias sums once per batch item
+            if (kind == 2) atomicAdd(db + o, s);
+            else if (noisy) atomicAdd(db + CO + o, s);
+        }
+    }
+}
+
 // wcat[i][o] = Wm[o][i], wcat[i][Co + o] = Wl[o][i]   ([Ci][2 Co]; [Ci][Co] when Wl == NULL)
 __global__ void k_wcat(const float* __restrict__ wm, const float* __restrict__ wl, int Ci, int Co, float* __restrict__ wcat) {
     const int n = Ci * Co, ld = wl ? 2 * Co : Co;
@@ -243,7 +304,7 @@ __global__ void k_wcat(const float* __restrict__ wm, const float* __restrict__ w
 }  // namespace
 
 size_t tc_local_bwd_workspace_bytes(int B, int Ci, int Co, int HW, int noisy) {
-    if (Ci <= 4) return 1024;                   // lift-shaped layers stream g / dlv directly (no stacked gradient)
+    if (Ci <= 4 || Co <= 4) return 1024;                   // lift-shaped layers stream g / dlv directly (no stacked gradient)
     const size_t g2 = noisy ? (size_t)B * 2 * Co * HW * 4 : 0;
     return g2 + (size_t)Ci * (noisy ? 2 : 1) * Co * 4 + 1024;
 }
@@ -259,6 +320,18 @@ int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_d
         if (dw) PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
         if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
         k_local_thin_in_bwd<<<B * Co, 256, 0, st>>>(x, g, dout_dlv, Ci, Co, HW, noisy, dw, db);
+        PNO_LAUNCH_CHECK();
+        return PNO_OK;
+    }
+    if (Co <= 4 && HW % 4 == 0 && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dout_dlv) |
+                                     reinterpret_cast<uintptr_t>(dx)) & 15)) {
+        // projection-shaped layer: one pass over x
+        if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "tc_local_bwd: d out / d log_var is needed when Wl is given");
+        if (dw) PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
+        if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
+#define PNO_PROJ_BWD(CO_) k_local_thin_out_bwd<CO_><<<B * Ci, 256, 0, st>>>(x, g, dout_dlv, Wm, Wl, Ci, HW, noisy, dx, dw, db)
+        if (Co == 1) PNO_PROJ_BWD(1); else if (Co == 2) PNO_PROJ_BWD(2); else if (Co == 3) PNO_PROJ_BWD(3); else PNO_PROJ_BWD(4);
+#undef PNO_PROJ_BWD
         PNO_LAUNCH_CHECK();
         return PNO_OK;
     }

@@ -185,7 +185,8 @@ class _LocalFn(torch.autograd.Function):
         ni = ctx.needs_input_grad
         # tensor-core engines: dx, [dWm; dWl] and the bias sums from pno_local_bwd (csrc/pno_tc_local_bwd.cu)
         lift_shaped = ci <= 4 and not ni[0] and hw % 4 == 0        # e.g. the 3 -> C lift: streaming dot products, no dx
-        if engine != _lib.ENGINE_FP32 and ((co % 128 == 0 and ci in (128, 256) and hw % 128 == 0) or lift_shaped):
+        proj_shaped = co <= 4 and hw % 4 == 0                      # e.g. the C -> 1 heads: one streaming pass over x
+        if engine != _lib.ENGINE_FP32 and ((co % 128 == 0 and ci in (128, 256) and hw % 128 == 0) or lift_shaped or proj_shaped):
             lib = _lib.load()
             gc = g.contiguous()
             rows = 2 * co if noisy else co

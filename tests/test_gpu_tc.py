@@ -108,6 +108,29 @@ def test_lift_shaped_backward_vs_torch(noisy, shape):
         assert rel_l2(a_, b_) < 2e-5, rel_l2(a_, b_)
 
 
+@pytest.mark.parametrize("noisy", [False, True])
+@pytest.mark.parametrize("shape", [(4, 256, 1, 32, 32), (2, 64, 3, 8, 12), (3, 96, 4, 16, 16)])
+def test_projection_shaped_backward_vs_torch(noisy, shape):
+    """dx, weight and bias gradients of a projection-shaped 1x1 conv pair (Co <= 4): the streaming kernel of pno_local_bwd
+    against the fp32 engine's torch path."""
+    from pno_physics_bench_b200 import functional as F_
+    b, ci, co, h, w = shape
+
+    def case(engine):
+        gen = torch.Generator().manual_seed(sum(shape) + 3)
+        x = torch.randn(b, ci, h, w, generator=gen).to(DEV).requires_grad_(True)
+        wm = (torch.randn(co, ci, 1, 1, generator=gen) / ci ** 0.5).to(DEV).requires_grad_(True)
+        bm = torch.randn(co, generator=gen).to(DEV).requires_grad_(True)
+        wl = (torch.randn(co, ci, 1, 1, generator=gen) * 0.1).to(DEV).requires_grad_(True) if noisy else None
+        bl = (torch.randn(co, generator=gen) - 3).to(DEV).requires_grad_(True) if noisy else None
+        out = F_.local_branch(x, wm, bm, wl, bl, seed=5, sample_idx=1, site=13, engine=_lib.ENGINES[engine])
+        out.backward(torch.randn(out.shape, generator=torch.Generator().manual_seed(2)).to(DEV))
+        return [t.grad.clone() for t in (x, wm, bm) + ((wl, bl) if noisy else ())]
+
+    for a_, b_ in zip(case("tf32x3"), case("fp32")):
+        assert rel_l2(a_, b_) < 2e-5, rel_l2(a_, b_)
+
+
 def _dft_fwd(x, m1, m2, engine, grad_scale=0):
     lib = _lib.load()
     b, c, h, w = x.shape
