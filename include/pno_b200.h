@@ -63,13 +63,23 @@ enum {
 
 enum { PNO_ACT_NONE = 0, PNO_ACT_GELU = 1, PNO_ACT_RELU = 2 };   /* models.py:224-229 (exact-erf GELU) */
 
-/* arithmetic engines.  The tensor-core engines tile the shapes documented in each kernel file (the BASELINE configs);
- * a stage whose shape they do not tile runs on the CUDA-core engine instead (same results to fp32 accuracy). */
+/* arithmetic engines.  The tensor-core engines tile the shapes documented in each kernel file (the BASELINE configs).  A stage
+ * whose shape a tensor-core engine does not tile FAILS with PNO_E_UNSUPPORTED -- unless the caller ORs
+ * PNO_ENGINE_ALLOW_FALLBACK into the engine argument, in which case that stage runs on the CUDA-core fp32 engine instead (same
+ * results to fp32 accuracy).  pno_stage_counts() tells which engine actually ran each stage.  1x1 convs with <= 8 input or <= 4
+ * output channels (the lift / projection heads) are streaming CUDA-core kernels under every engine: there is no GEMM in them. */
 enum {
     PNO_ENGINE_FP32 = 0,      /* fp32 FMA on CUDA cores: any shape, reference-grade fp32 (rel-L2 <= 1e-5)      */
     PNO_ENGINE_TC_TF32X3 = 1, /* tcgen05 tensor cores, error-compensated 3xTF32 (rel-L2 <= 1e-5)                */
-    PNO_ENGINE_TC_TF32 = 2    /* tcgen05 tensor cores, single-pass TF32 operands / fp32 accumulate: the reduced-
+    PNO_ENGINE_TC_TF32 = 2,   /* tcgen05 tensor cores, single-pass TF32 operands / fp32 accumulate: the reduced-
                                  precision mode (rel-L2 ~1e-3, inside the 2e-2 budget of the bf16-compute mode)   */
+    PNO_ENGINE_ALLOW_FALLBACK = 0x100   /* flag: opt into the CUDA-core fallback for shapes the engine does not tile */
+};
+
+/* stages whose engine is dispatched (index into pno_stage_counts) */
+enum {
+    PNO_STAGE_DFT_FWD = 0, PNO_STAGE_DFT_INV = 1, PNO_STAGE_MIX_FWD = 2, PNO_STAGE_MIX_BWD_DX = 3, PNO_STAGE_MIX_BWD_DW = 4,
+    PNO_STAGE_LOCAL_FWD = 5, PNO_STAGE_LOCAL_BWD = 6, PNO_N_STAGES = 7
 };
 
 typedef struct pno_plan pno_plan_t;
@@ -80,6 +90,22 @@ const char* pno_last_error(void);
 int pno_check_device(void);
 /* number of CUDA kernels this library has launched in this process (monotonic; bench.py reports deltas) */
 uint64_t pno_launch_count(void);
+/* out[2*stage + 0] / out[2*stage + 1] = successful calls of `stage` that ran on CUDA cores / on the tensor cores since the process
+ * started (monotonic; PNO_N_STAGES pairs).  Tests assert on deltas that the tensor-core kernel really ran. */
+int pno_stage_counts(uint64_t* out);
+/* Host-only query (no CUDA call, works without a GPU): 1 if `engine` (PNO_ENGINE_TC_*) runs `stage` on its tensor-core kernel
+ * for a [B, Ci|Co, H, W] problem with (m1, m2) retained modes -- every variant of the stage the block path uses (with / without
+ * addend and pre-activation output, mean / sampled weights) -- else 0.  Answered by the tilings' own validation code. */
+int pno_engine_supports(int stage, int engine, int H, int W, int m1, int m2, int B, int Ci, int Co);
+/* Device-resident noise key for CUDA-graph replay (reference models.py:361-364 is a host loop over samples; here one captured
+ * forward is replayed S times).  While device_key != NULL (per host thread) every stochastic entry point records that pointer in
+ * its launches, and the kernels read (seed low word, seed high word, sample_idx) = device_key[0..2] at RUN time instead of using
+ * their by-value seed / sample_idx arguments; `site` and batch_offset stay by-value.  NULL restores the by-value behaviour. */
+int pno_set_dynamic_noise(const uint32_t* device_key);
+/* device_key[0..3] = (seed low, seed high, sample_idx, 0) written by a one-thread kernel on `stream` (no host buffer to keep
+ * alive); pno_noise_key_advance adds delta to device_key[2] (captured at the end of a graphed forward: next sample). */
+int pno_noise_key_write(uint32_t* device_key, uint64_t seed, uint32_t sample_idx, void* stream);
+int pno_noise_key_advance(uint32_t* device_key, uint32_t delta, void* stream);
 
 /* Plan = twiddle tables for one (H, W, m1, m2) on the current device.  Immutable after creation. */
 int pno_plan_create(int H, int W, int m1, int m2, pno_plan_t** plan);

@@ -18,6 +18,90 @@ void pno_set_error(const char* fmt, ...) {
 
 unsigned long long g_pno_launches = 0;
 long long* g_pno_debug_buffer = nullptr;
+thread_local const uint32_t* g_pno_dyn_key = nullptr;
+
+// which engine ran each stage: g_stage_counts[stage][0 = CUDA cores, 1 = tensor cores] (pno_stage_counts)
+static unsigned long long g_stage_counts[PNO_N_STAGES][2];
+
+extern "C" int pno_stage_counts(uint64_t* out) {
+    if (!out) PNO_FAIL(PNO_E_INVALID, "pno_stage_counts: null output");
+    for (int s = 0; s < PNO_N_STAGES; ++s) {
+        out[2 * s] = g_stage_counts[s][0];
+        out[2 * s + 1] = g_stage_counts[s][1];
+    }
+    return PNO_OK;
+}
+
+thread_local int g_pno_dry_run = 0;
+
+// Host-only (no CUDA call): would `engine` run `stage` on its tensor-core kernel at this shape?  The tilings' own validation code
+// answers (dry run), so this can never disagree with what a launch would do.
+extern "C" int pno_engine_supports(int stage, int engine, int H, int W, int m1, int m2, int B, int Ci, int Co) {
+    const int eng = engine & 0xFF;
+    if (eng == PNO_ENGINE_FP32) return 0;
+    if (eng != PNO_ENGINE_TC_TF32X3 && eng != PNO_ENGINE_TC_TF32) return 0;
+    if (H <= 0 || W <= 0 || m1 <= 0 || m2 <= 0 || B <= 0 || Ci <= 0 || Co <= 0 || m1 > H || m2 > W / 2 + 1) return 0;
+    pno_plan plan;
+    memset(&plan, 0, sizeof(plan));
+    plan.H = H; plan.W = W; plan.m1 = m1; plan.m2 = m2; plan.M = 2 * m1 * m2;
+    float* const d = reinterpret_cast<float*>(uintptr_t(4096));      // aligned stand-in for every device pointer
+    const PhiloxKey key = make_key(0, 0, 0);
+    g_pno_dry_run = 1;
+    bool ok = true;
+    switch (stage) {
+    case PNO_STAGE_DFT_FWD:
+        ok = tc_dft_fwd(&plan, eng, d, B, Ci, 0, d, d, nullptr) == PNO_OK;
+        break;
+    case PNO_STAGE_DFT_INV:      // bare layer, block epilogue (addend), block epilogue kept for backward (addend + pre-activation)
+        ok = tc_dft_inv(&plan, eng, d, d, B, Co, 0, nullptr, PNO_ACT_NONE, d, nullptr, nullptr) == PNO_OK &&
+             tc_dft_inv(&plan, eng, d, d, B, Co, 0, d, PNO_ACT_GELU, d, nullptr, nullptr) == PNO_OK &&
+             tc_dft_inv(&plan, eng, d, d, B, Co, 0, d, PNO_ACT_GELU, d, d, nullptr) == PNO_OK;
+        break;
+    case PNO_STAGE_MIX_FWD:      // mean weights and sampled weights
+        ok = tc_mix_fwd(&plan, eng, d, d, B, Ci, Co, d, d, nullptr, nullptr, key, d, d, nullptr) == PNO_OK &&
+             tc_mix_fwd(&plan, eng, d, d, B, Ci, Co, d, d, d, d, key, d, d, nullptr) == PNO_OK;
+        break;
+    case PNO_STAGE_MIX_BWD_DX:
+        ok = tc_mix_bwd_dx(&plan, eng, d, d, B, Ci, Co, d, d, d, d, key, d, d, nullptr) == PNO_OK;
+        break;
+    case PNO_STAGE_MIX_BWD_DW:
+        ok = tc_mix_bwd_dw(&plan, eng, d, d, d, d, B, Ci, Co, d, d, key, d, d, d, d, nullptr) == PNO_OK;
+        break;
+    case PNO_STAGE_LOCAL_FWD:
+        ok = Ci > 8 && Co > 4 && tc_local_fwd(eng, d, B, Ci, Co, H * W, d, d, d, d, key, 0, d, d, nullptr) == PNO_OK;
+        break;
+    case PNO_STAGE_LOCAL_BWD:
+        ok = Ci > 4 && Co > 4 && tc_local_bwd(eng, d, d, d, B, Ci, Co, H * W, d, d, d, d, d, d, nullptr) == PNO_OK;
+        break;
+    default:
+        ok = false;
+    }
+    g_pno_dry_run = 0;
+    return ok ? 1 : 0;
+}
+
+extern "C" int pno_set_dynamic_noise(const uint32_t* device_key) {
+    g_pno_dyn_key = device_key;
+    return PNO_OK;
+}
+
+// Engine dispatch of one stage.  `engine` = PNO_ENGINE_* code, optionally ORed with PNO_ENGINE_ALLOW_FALLBACK.  A tensor-core
+// engine whose tiling does not cover the shape fails with PNO_E_UNSUPPORTED unless the caller opted into the CUDA-core
+// fallback; either way the stage counters record which engine actually ran.
+template <typename TC, typename SIMT>
+static int dispatch(int engine, int stage, const char* who, TC tc, SIMT simt) {
+    const int eng = engine & 0xFF;
+    if (eng != PNO_ENGINE_FP32 && eng != PNO_ENGINE_TC_TF32X3 && eng != PNO_ENGINE_TC_TF32)
+        PNO_FAIL(PNO_E_INVALID, "%s: unknown engine %d", who, eng);
+    if (eng != PNO_ENGINE_FP32) {
+        const int rc = tc(eng);
+        if (rc == PNO_OK) { ++g_stage_counts[stage][1]; return rc; }
+        if (rc != PNO_E_UNSUPPORTED || !(engine & PNO_ENGINE_ALLOW_FALLBACK)) return rc;
+    }
+    const int rc = simt();
+    if (rc == PNO_OK) ++g_stage_counts[stage][0];
+    return rc;
+}
 
 extern "C" int pno_debug_set_buffer(void* device_ptr) {
     g_pno_debug_buffer = static_cast<long long*>(device_ptr);
@@ -106,11 +190,9 @@ extern "C" int pno_dft_fwd(const pno_plan_t* p, int engine, const float* x, int 
     int rc = check_common(p, B, C, C, "pno_dft_fwd");
     if (rc) return rc;
     if (!x || !xr || !xi) PNO_FAIL(PNO_E_INVALID, "pno_dft_fwd: null pointer");
-    if (engine != PNO_ENGINE_FP32) {
-        rc = tc_dft_fwd(p, engine, x, B, C, grad_scale, xr, xi, as_stream(stream));
-        if (rc != PNO_E_UNSUPPORTED) return rc;
-    }
-    return simt_dft_fwd(p, x, B, C, grad_scale, xr, xi, as_stream(stream));
+    return dispatch(engine, PNO_STAGE_DFT_FWD, "pno_dft_fwd",
+                    [&](int eng) { return tc_dft_fwd(p, eng, x, B, C, grad_scale, xr, xi, as_stream(stream)); },
+                    [&]() { return simt_dft_fwd(p, x, B, C, grad_scale, xr, xi, as_stream(stream)); });
 }
 
 extern "C" int pno_dft_inv(const pno_plan_t* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
@@ -118,11 +200,9 @@ extern "C" int pno_dft_inv(const pno_plan_t* p, int engine, const float* yr, con
     int rc = check_common(p, B, C, C, "pno_dft_inv");
     if (rc) return rc;
     if (!yr || !yi || !y) PNO_FAIL(PNO_E_INVALID, "pno_dft_inv: null pointer");
-    if (engine != PNO_ENGINE_FP32) {
-        rc = tc_dft_inv(p, engine, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream));
-        if (rc != PNO_E_UNSUPPORTED) return rc;
-    }
-    return simt_dft_inv(p, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream));
+    return dispatch(engine, PNO_STAGE_DFT_INV, "pno_dft_inv",
+                    [&](int eng) { return tc_dft_inv(p, eng, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream)); },
+                    [&]() { return simt_dft_inv(p, yr, yi, B, C, adjoint, addend, act, y, pre_act, as_stream(stream)); });
 }
 
 static int check_lv(const float* lv1, const float* lv2, const char* who) {
@@ -138,11 +218,9 @@ extern "C" int pno_mix_fwd(const pno_plan_t* p, int engine, const float* xr, con
     if ((rc = check_lv(lv1, lv2, "pno_mix_fwd"))) return rc;
     if (!xr || !xi || !mu1 || !mu2 || !yr || !yi) PNO_FAIL(PNO_E_INVALID, "pno_mix_fwd: null pointer");
     const PhiloxKey key = make_key(seed, sample_idx, site);
-    if (engine != PNO_ENGINE_FP32) {
-        rc = tc_mix_fwd(p, engine, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
-        if (rc != PNO_E_UNSUPPORTED) return rc;
-    }
-    return simt_mix_fwd(p, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream));
+    return dispatch(engine, PNO_STAGE_MIX_FWD, "pno_mix_fwd",
+                    [&](int eng) { return tc_mix_fwd(p, eng, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream)); },
+                    [&]() { return simt_mix_fwd(p, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, as_stream(stream)); });
 }
 
 extern "C" int pno_mix_bwd_dx(const pno_plan_t* p, int engine, const float* gr, const float* gi, int B, int Ci, int Co,
@@ -153,11 +231,9 @@ extern "C" int pno_mix_bwd_dx(const pno_plan_t* p, int engine, const float* gr, 
     if ((rc = check_lv(lv1, lv2, "pno_mix_bwd_dx"))) return rc;
     if (!gr || !gi || !mu1 || !mu2 || !dxr || !dxi) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dx: null pointer");
     const PhiloxKey key = make_key(seed, sample_idx, site);
-    if (engine != PNO_ENGINE_FP32) {
-        rc = tc_mix_bwd_dx(p, engine, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, as_stream(stream));
-        if (rc != PNO_E_UNSUPPORTED) return rc;
-    }
-    return simt_mix_bwd_dx(p, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, as_stream(stream));
+    return dispatch(engine, PNO_STAGE_MIX_BWD_DX, "pno_mix_bwd_dx",
+                    [&](int eng) { return tc_mix_bwd_dx(p, eng, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, as_stream(stream)); },
+                    [&]() { return simt_mix_bwd_dx(p, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, as_stream(stream)); });
 }
 
 extern "C" int pno_mix_bwd_dw(const pno_plan_t* p, int engine, const float* xr, const float* xi, const float* gr,
@@ -170,14 +246,14 @@ extern "C" int pno_mix_bwd_dw(const pno_plan_t* p, int engine, const float* xr, 
     if (!xr || !xi || !gr || !gi) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dw: null pointer");
     if ((dmu1 == nullptr) != (dmu2 == nullptr) || (dlv1 == nullptr) != (dlv2 == nullptr))
         PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dw: gradient outputs must be given per pair");
-    (void)engine;
-    if (engine != PNO_ENGINE_FP32) {
-        rc = tc_mix_bwd_dw(p, engine, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, make_key(seed, sample_idx, site), dmu1, dmu2, dlv1, dlv2,
-                           as_stream(stream));
-        if (rc != PNO_E_UNSUPPORTED) return rc;   // shapes the tensor-core kernel does not tile run on CUDA cores
-    }
-    return simt_mix_bwd_dw(p, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, make_key(seed, sample_idx, site), dmu1, dmu2, dlv1,
-                           dlv2, as_stream(stream));
+    const PhiloxKey key = make_key(seed, sample_idx, site);
+    return dispatch(engine, PNO_STAGE_MIX_BWD_DW, "pno_mix_bwd_dw",
+                    [&](int eng) {
+                        return tc_mix_bwd_dw(p, eng, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, key, dmu1, dmu2, dlv1, dlv2, as_stream(stream));
+                    },
+                    [&]() {
+                        return simt_mix_bwd_dw(p, xr, xi, gr, gi, B, Ci, Co, lv1, lv2, key, dmu1, dmu2, dlv1, dlv2, as_stream(stream));
+                    });
 }
 
 extern "C" int pno_spectral_fwd(const pno_plan_t* p, int engine, const float* x, int B, int Ci, int Co, const float* mu1,
@@ -244,9 +320,17 @@ extern "C" int pno_local_bwd(int engine, const float* x, const float* g, const f
                              const float* Wm, const float* Wl, float* dx, float* dw, float* db, void* workspace, void* stream) {
     if (B <= 0 || Ci <= 0 || Co <= 0 || HW <= 0) PNO_FAIL(PNO_E_INVALID, "pno_local_bwd: non-positive size");
     if (!x || !g || !Wm || !workspace) PNO_FAIL(PNO_E_INVALID, "pno_local_bwd: null pointer");
-    if (engine == PNO_ENGINE_FP32)
-        PNO_FAIL(PNO_E_UNSUPPORTED, "pno_local_bwd runs on the tensor-core engines; the fp32 engine leaves these GEMMs to the caller");
-    return tc_local_bwd(engine, x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, workspace, as_stream(stream));
+    // lift- (Ci <= 4, no dx) and projection-shaped (Co <= 4) layers are streaming CUDA-core kernels whatever the engine
+    const bool thin = HW % 4 == 0 && ((Ci <= 4 && dx == nullptr) || Co <= 4);
+    if (thin) {
+        const int rc = tc_local_bwd(PNO_ENGINE_TC_TF32X3, x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, workspace, as_stream(stream));
+        if (rc == PNO_OK) { ++g_stage_counts[PNO_STAGE_LOCAL_BWD][0]; return rc; }
+        if (rc != PNO_E_UNSUPPORTED) return rc;       // (misaligned thin layers take the general kernels below)
+        return simt_local_bwd(x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, as_stream(stream));
+    }
+    return dispatch(engine, PNO_STAGE_LOCAL_BWD, "pno_local_bwd",
+                    [&](int eng) { return tc_local_bwd(eng, x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, workspace, as_stream(stream)); },
+                    [&]() { return simt_local_bwd(x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, as_stream(stream)); });
 }
 
 extern "C" int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm,
@@ -256,10 +340,14 @@ extern "C" int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, 
     if (!x || !Wm || !out) PNO_FAIL(PNO_E_INVALID, "pno_local_fwd: null pointer");
     if (B > 65535) PNO_FAIL(PNO_E_INVALID, "pno_local_fwd: batch %d exceeds the grid limit", B);
     const PhiloxKey key = make_key(seed, sample_idx, site);
-    if (engine != PNO_ENGINE_FP32) {
-        const int rc = tc_local_fwd(engine, x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv,
-                                    as_stream(stream));
-        if (rc != PNO_E_UNSUPPORTED) return rc;   // shapes the tensor-core kernel does not tile run on CUDA cores
+    // lift- (Ci <= 8) and projection-shaped (Co <= 4) layers are streaming CUDA-core kernels whatever the engine: there is no
+    // GEMM in them to put on the tensor cores
+    if (Ci <= 8 || Co <= 4) {
+        const int rc = simt_local_fwd(x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv, as_stream(stream));
+        if (rc == PNO_OK) ++g_stage_counts[PNO_STAGE_LOCAL_FWD][0];
+        return rc;
     }
-    return simt_local_fwd(x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv, as_stream(stream));
+    return dispatch(engine, PNO_STAGE_LOCAL_FWD, "pno_local_fwd",
+                    [&](int eng) { return tc_local_fwd(eng, x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv, as_stream(stream)); },
+                    [&]() { return simt_local_fwd(x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv, as_stream(stream)); });
 }

@@ -68,14 +68,32 @@ __device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ft
 // ---------------------------------------------------------------------------------------------------------------------
 struct PhiloxKey {
     uint32_t k0, k1, sample, site;
+    // Device-resident key (pno_set_dynamic_noise): when non-NULL the kernel reads (seed lo, seed hi, sample_idx) from these three
+    // words at run time instead of the by-value fields above, so that a captured CUDA graph of a sampled forward can be replayed
+    // for every MC sample / training step without re-recording its launch arguments.
+    const uint32_t* dyn;
 };
 
-__host__ __device__ __forceinline__ PhiloxKey make_key(uint64_t seed, uint32_t sample, uint32_t site) {
+extern thread_local int g_pno_dry_run;               // pno_engine_supports: validate the shape / geometry only
+extern thread_local const uint32_t* g_pno_dyn_key;   // set by pno_set_dynamic_noise (this host thread), NULL by default
+
+static inline PhiloxKey make_key(uint64_t seed, uint32_t sample, uint32_t site) {
     PhiloxKey k;
     k.k0 = (uint32_t)seed;
     k.k1 = (uint32_t)(seed >> 32);
     k.sample = sample;
     k.site = site;
+    k.dyn = g_pno_dyn_key;
+    return k;
+}
+
+// every kernel that draws noise calls this once (per thread, before its main loop)
+__device__ __forceinline__ PhiloxKey resolve_key(PhiloxKey k) {
+    if (k.dyn != nullptr) {
+        k.k0 = __ldg(k.dyn);
+        k.k1 = __ldg(k.dyn + 1);
+        k.sample = __ldg(k.dyn + 2);
+    }
     return k;
 }
 
@@ -184,3 +202,5 @@ int simt_mix_bwd_dw(const pno_plan* p, const float* xr, const float* xi, const f
                     float* dlv2, cudaStream_t st);
 int simt_local_fwd(const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm, const float* Wl,
                    const float* bl, PhiloxKey key, uint64_t batch_offset, float* out, float* dout_dlv, cudaStream_t st);
+int simt_local_bwd(const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW, const float* Wm,
+                   const float* Wl, float* dx, float* dw, float* db, cudaStream_t st);

@@ -5,7 +5,8 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__global__ void k_normal_activation(PhiloxKey key, uint64_t first, uint64_t n, float* __restrict__ out) {
+__global__ void k_normal_activation(PhiloxKey key_in, uint64_t first, uint64_t n, float* __restrict__ out) {
+    const PhiloxKey key = resolve_key(key_in);
     // one thread per quad overlapping [first, first+n)
     const uint64_t q0 = first >> 2;
     const uint64_t nq = ((first + n + 3) >> 2) - q0;
@@ -21,8 +22,9 @@ __global__ void k_normal_activation(PhiloxKey key, uint64_t first, uint64_t n, f
     }
 }
 
-__global__ void k_normal_spectral(PhiloxKey key, int Ci, int Co, int m1, int m2, float* __restrict__ ere,
+__global__ void k_normal_spectral(PhiloxKey key_in, int Ci, int Co, int m1, int m2, float* __restrict__ ere,
                                   float* __restrict__ eim) {
+    const PhiloxKey key = resolve_key(key_in);
     const int Cop = (Co + 1) / 2, m1m2 = m1 * m2;
     const uint64_t nq = (uint64_t)2 * m1m2 * Ci * Cop;
     for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < nq; q += (uint64_t)gridDim.x * blockDim.x) {
@@ -45,7 +47,8 @@ __global__ void k_normal_spectral(PhiloxKey key, int Ci, int Co, int m1, int m2,
     }
 }
 
-__global__ void k_bits(PhiloxKey key, uint64_t q0, uint64_t nq, uint32_t* __restrict__ out) {
+__global__ void k_bits(PhiloxKey key_in, uint64_t q0, uint64_t nq, uint32_t* __restrict__ out) {
+    const PhiloxKey key = resolve_key(key_in);
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < nq; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 x = philox_quad_bits(key, q0 + t);
         reinterpret_cast<uint4*>(out)[t] = x;
@@ -117,9 +120,10 @@ __global__ void k_mc_accumulate(const float* __restrict__ y, uint64_t n, double*
 
 // uncertainty.py:57-73: prediction = mean + sqrt(exp(lv) + 1e-8) * eps with eps from this repo's Philox stream (element = flat
 // index), accumulated with its square and the aleatoric variance exp(lv); optionally also written out (return_samples)
-__global__ void k_mc_accumulate_decompose(const float* __restrict__ mean, const float* __restrict__ lv, uint64_t n, PhiloxKey key,
+__global__ void k_mc_accumulate_decompose(const float* __restrict__ mean, const float* __restrict__ lv, uint64_t n, PhiloxKey key_in,
                                           double* __restrict__ s1, double* __restrict__ s2, double* __restrict__ sa,
                                           float* __restrict__ pred) {
+    const PhiloxKey key = resolve_key(key_in);
     const uint64_t nq = (n + 3) >> 2;
     for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < nq; q += (uint64_t)gridDim.x * blockDim.x) {
         const float4 z4 = lv ? philox_quad_normals(key, q) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -153,6 +157,12 @@ __global__ void k_mc_finalize(const double* __restrict__ s1, const double* __res
     }
 }
 
+// device-resident noise key (pno_set_dynamic_noise): key[0..1] = seed, key[2] = sample_idx (+= advance when only_advance)
+__global__ void k_noise_key(uint32_t* key, uint32_t k0, uint32_t k1, uint32_t sample, int only_advance) {
+    if (only_advance) { key[2] += sample; return; }
+    key[0] = k0; key[1] = k1; key[2] = sample; key[3] = 0u;
+}
+
 inline int grid_for(uint64_t n) {
     uint64_t g = (n + kThreads - 1) / kThreads;
     const uint64_t cap = 148ull * 16;
@@ -178,6 +188,20 @@ extern "C" int pno_philox_normal_spectral(uint64_t seed, uint32_t sample_idx, ui
     const uint64_t nq = (uint64_t)2 * m1 * m2 * Ci * ((Co + 1) / 2);
     k_normal_spectral<<<grid_for(nq), kThreads, 0, as_stream(stream)>>>(make_key(seed, sample_idx, site), Ci, Co, m1, m2,
                                                                         eps_re, eps_im);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+extern "C" int pno_noise_key_write(uint32_t* device_key, uint64_t seed, uint32_t sample_idx, void* stream) {
+    if (!device_key) PNO_FAIL(PNO_E_INVALID, "pno_noise_key_write: null key buffer");
+    k_noise_key<<<1, 1, 0, as_stream(stream)>>>(device_key, (uint32_t)seed, (uint32_t)(seed >> 32), sample_idx, 0);
+    PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+extern "C" int pno_noise_key_advance(uint32_t* device_key, uint32_t delta, void* stream) {
+    if (!device_key) PNO_FAIL(PNO_E_INVALID, "pno_noise_key_advance: null key buffer");
+    k_noise_key<<<1, 1, 0, as_stream(stream)>>>(device_key, 0u, 0u, delta, 1);
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }

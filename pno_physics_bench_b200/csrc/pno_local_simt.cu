@@ -18,8 +18,9 @@ template <bool kNoise>
 __global__ void __launch_bounds__(kThreads) k_local_fwd(const float* __restrict__ x, int Ci, int Co, int HW,
                                                         const float* __restrict__ Wm, const float* __restrict__ bm,
                                                         const float* __restrict__ Wl, const float* __restrict__ bl,
-                                                        PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
+                                                        PhiloxKey key_in, uint64_t batch_offset, float* __restrict__ out,
                                                         float* __restrict__ dout_dlv) {
+    const PhiloxKey key = resolve_key(key_in);
     __shared__ __align__(16) float sx[KC][LD], swm[KC][LD], swl[kNoise ? KC : 1][LD];
     const int p_base = blockIdx.x * TP, o_base = blockIdx.y * TO, b = blockIdx.z;
     const int tid = threadIdx.x, to = tid >> 4, tp = tid & 15;
@@ -143,8 +144,9 @@ template <bool kNoise, int CIM>          // CIM: compile-time bound on Ci (4 or 
 __global__ void __launch_bounds__(kThreads) k_local_thin_in(const float* __restrict__ x, int Ci, int Co, int HW,
                                                             const float* __restrict__ Wm, const float* __restrict__ bm,
                                                             const float* __restrict__ Wl, const float* __restrict__ bl,
-                                                            PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
+                                                            PhiloxKey key_in, uint64_t batch_offset, float* __restrict__ out,
                                                             float* __restrict__ dout_dlv) {
+    const PhiloxKey key = resolve_key(key_in);
     __shared__ float swm[kLiftChunk][CIM], swl[kLiftChunk][CIM], sbm[kLiftChunk], sbl[kLiftChunk];
     const int o_base = blockIdx.y * kLiftChunk, b = blockIdx.z;
     for (int e = threadIdx.x; e < kLiftChunk * CIM; e += kThreads) {
@@ -208,8 +210,9 @@ template <bool kNoise, int CO>          // CO = Co at compile time: no per-chann
 __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __restrict__ x, int Ci, int /*Co*/, int HW,
                                                              const float* __restrict__ Wm, const float* __restrict__ bm,
                                                              const float* __restrict__ Wl, const float* __restrict__ bl,
-                                                             PhiloxKey key, uint64_t batch_offset, float* __restrict__ out,
+                                                             PhiloxKey key_in, uint64_t batch_offset, float* __restrict__ out,
                                                              float* __restrict__ dout_dlv) {
+    const PhiloxKey key = resolve_key(key_in);
     extern __shared__ float sw[];          // [2][Co][Ci] weights, then [groups-1][quads][2*4*4] partial sums
     constexpr int Co = CO;
     float* red = sw + 2 * Co * Ci;
@@ -282,6 +285,109 @@ __global__ void __launch_bounds__(kThreads) k_local_thin_out(const float* __rest
     }
 }
 
+
+// ---- general-shape backward of the local branch on CUDA cores (fp32 engine, and any shape the tensor-core tilings do not cover) ----
+// G[b][r][p] = g[b][r][p] for r < Co, g[b][r-Co][p] * dlv[b][r-Co][p] for r >= Co (the stacked upstream gradient dYm | dYl).
+__device__ __forceinline__ float stacked_grad(const float* __restrict__ g, const float* __restrict__ dlv, int Co, int HW, int b,
+                                              int r, int p) {
+    if (r < Co) return g[((size_t)b * Co + r) * HW + p];
+    const size_t o = ((size_t)b * Co + (r - Co)) * HW + p;
+    return g[o] * dlv[o];
+}
+
+constexpr int BT = 64, BK = 16, BLD = BT + 4;
+
+// dx[b][i][p] = sum_r Wcat[r][i] G[b][r][p]   (Wcat = [Wm; Wl], rows x Ci).   grid (ceil(HW/64), ceil(Ci/64), B)
+__global__ void __launch_bounds__(kThreads) k_local_bwd_dx(const float* __restrict__ g, const float* __restrict__ dlv,
+                                                           const float* __restrict__ Wm, const float* __restrict__ Wl, int Ci,
+                                                           int Co, int HW, int rows, float* __restrict__ dx) {
+    __shared__ float sG[BK][BLD], sW[BK][BLD];
+    const int p_base = blockIdx.x * BT, i_base = blockIdx.y * BT, b = blockIdx.z;
+    const int tid = threadIdx.x, ti = tid >> 4, tp = tid & 15;
+    float acc[4][4] = {};
+    for (int r0 = 0; r0 < rows; r0 += BK) {
+        for (int e = tid; e < BK * BT; e += kThreads) {
+            const int k = e / BT, c = e - k * BT;
+            const int r = r0 + k, p = p_base + c, i = i_base + c;
+            sG[k][c] = (r < rows && p < HW) ? stacked_grad(g, dlv, Co, HW, b, r, p) : 0.f;
+            sW[k][c] = (r < rows && i < Ci) ? (r < Co ? Wm[(size_t)r * Ci + i] : Wl[(size_t)(r - Co) * Ci + i]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float wv[4], gv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { wv[a] = sW[k][ti * 4 + a]; gv[a] = sG[k][tp * 4 + a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(wv[a], gv[c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i_base + ti * 4 + a;
+        if (i >= Ci) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int p = p_base + tp * 4 + c;
+            if (p < HW) dx[((size_t)b * Ci + i) * HW + p] = acc[a][c];
+        }
+    }
+}
+
+// dw[r][i] += sum over this block's slice of (b, p) of G[b][r][p] x[b][i][p];  db[r] += sum G[b][r][p]  (blocks with blockIdx.y == 0).
+// grid (ceil(rows/64), ceil(Ci/64), n_split); the slice is a range of 16-pixel chunks of the flattened (b, chunk) index.
+__global__ void __launch_bounds__(kThreads) k_local_bwd_dw(const float* __restrict__ x, const float* __restrict__ g,
+                                                           const float* __restrict__ dlv, int B, int Ci, int Co, int HW, int rows,
+                                                           int chunks_per_b, int chunks_per_split, float* __restrict__ dw,
+                                                           float* __restrict__ db) {
+    __shared__ float sG[BT][BK + 1], sX[BT][BK + 1];
+    const int r_base = blockIdx.x * BT, i_base = blockIdx.y * BT;
+    const int tid = threadIdx.x, tr = tid >> 4, ti = tid & 15;
+    const int total = B * chunks_per_b;
+    const int c_lo = blockIdx.z * chunks_per_split, c_hi = min(total, c_lo + chunks_per_split);
+    float acc[4][4] = {};
+    float bsum[4] = {};
+    for (int ch = c_lo; ch < c_hi; ++ch) {
+        const int b = ch / chunks_per_b, p0 = (ch - b * chunks_per_b) * BK;
+        for (int e = tid; e < BT * BK; e += kThreads) {
+            const int row = e / BK, k = e - row * BK;
+            const int p = p0 + k, r = r_base + row, i = i_base + row;
+            sG[row][k] = (r < rows && p < HW) ? stacked_grad(g, dlv, Co, HW, b, r, p) : 0.f;
+            sX[row][k] = (i < Ci && p < HW) ? x[((size_t)b * Ci + i) * HW + p] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float gv[4], xv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { gv[a] = sG[tr * 4 + a][k]; xv[a] = sX[ti * 4 + a][k]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                bsum[a] += gv[a];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(gv[a], xv[c], acc[a][c]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = r_base + tr * 4 + a;
+        if (r >= rows) continue;
+        if (dw) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i_base + ti * 4 + c;
+                if (i < Ci) atomicAdd(dw + (size_t)r * Ci + i, acc[a][c]);
+            }
+        }
+        if (db && blockIdx.y == 0 && ti == 0) atomicAdd(db + r, bsum[a]);
+    }
+}
+
 }  // namespace
 
 int simt_local_fwd(const float* x, int B, int Ci, int Co, int HW, const float* Wm, const float* bm, const float* Wl,
@@ -317,5 +423,35 @@ int simt_local_fwd(const float* x, int B, int Ci, int Co, int HW, const float* W
     else
         k_local_fwd<false><<<grid, kThreads, 0, st>>>(x, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv);
     PNO_LAUNCH_CHECK();
+    return PNO_OK;
+}
+
+// Backward of simt_local_fwd for any shape (see pno_local_bwd in include/pno_b200.h): dx, dw = [dWm; dWl], db = [dbm; dbl].
+int simt_local_bwd(const float* x, const float* g, const float* dout_dlv, int B, int Ci, int Co, int HW, const float* Wm,
+                   const float* Wl, float* dx, float* dw, float* db, cudaStream_t st) {
+    const int noisy = Wl != nullptr;
+    const int rows = noisy ? 2 * Co : Co;
+    if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "pno_local_bwd: d out / d log_var is needed when Wl is given");
+    if (B > 65535) PNO_FAIL(PNO_E_INVALID, "pno_local_bwd: batch %d exceeds the grid limit", B);
+    if (dx) {
+        dim3 grid((HW + BT - 1) / BT, (Ci + BT - 1) / BT, B);
+        k_local_bwd_dx<<<grid, kThreads, 0, st>>>(g, dout_dlv, Wm, Wl, Ci, Co, HW, rows, dx);
+        PNO_LAUNCH_CHECK();
+    }
+    if (dw || db) {
+        if (dw) PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
+        if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
+        const int chunks_per_b = (HW + BK - 1) / BK;
+        const int total = B * chunks_per_b;
+        const int tiles = ((rows + BT - 1) / BT) * ((Ci + BT - 1) / BT);
+        int n_split = (4 * 148 + tiles - 1) / tiles;
+        if (n_split > total) n_split = total;
+        if (n_split > 65535) n_split = 65535;
+        const int per = (total + n_split - 1) / n_split;
+        n_split = (total + per - 1) / per;
+        dim3 grid((rows + BT - 1) / BT, (Ci + BT - 1) / BT, n_split);
+        k_local_bwd_dw<<<grid, kThreads, 0, st>>>(x, g, dout_dlv, B, Ci, Co, HW, rows, chunks_per_b, per, dw, db);
+        PNO_LAUNCH_CHECK();
+    }
     return PNO_OK;
 }

@@ -77,9 +77,11 @@ __device__ __forceinline__ void load_weights4(const MixArgs& a, int mode, int i,
 }
 
 // yhat[mode][b][o] = sum_i xhat[mode][b][i] * W[i][o].   grid (M, ceil(Co/T)); b tiles looped inside.
-__global__ void __launch_bounds__(kThreads) k_mix_fwd(const MixArgs a, const float* __restrict__ xr,
+__global__ void __launch_bounds__(kThreads) k_mix_fwd(const MixArgs a_in, const float* __restrict__ xr,
                                                       const float* __restrict__ xi, float* __restrict__ yr,
                                                       float* __restrict__ yi) {
+    MixArgs a = a_in;
+    a.key = resolve_key(a_in.key);
     __shared__ __align__(16) float sxr[KC][LD], sxi[KC][LD], swr[KC][LD], swi[KC][LD];
     const int mode = blockIdx.x, o_base = blockIdx.y * T;
     const int tid = threadIdx.x, tb = tid >> 4, to = tid & 15;
@@ -145,9 +147,11 @@ __global__ void __launch_bounds__(kThreads) k_mix_fwd(const MixArgs a, const flo
 }
 
 // dxhat[mode][b][i] = sum_o ghat[mode][b][o] * conj(W[i][o]).   grid (M, ceil(Ci/T))
-__global__ void __launch_bounds__(kThreads) k_mix_bwd_dx(const MixArgs a, const float* __restrict__ gr,
+__global__ void __launch_bounds__(kThreads) k_mix_bwd_dx(const MixArgs a_in, const float* __restrict__ gr,
                                                          const float* __restrict__ gi, float* __restrict__ dxr,
                                                          float* __restrict__ dxi) {
+    MixArgs a = a_in;
+    a.key = resolve_key(a_in.key);
     __shared__ __align__(16) float sgr[KC][LD], sgi[KC][LD], swr[KC][LD], swi[KC][LD];
     const int mode = blockIdx.x, i_base = blockIdx.y * T;
     const int tid = threadIdx.x, tb = tid >> 4, ti = tid & 15;
@@ -214,11 +218,13 @@ __global__ void __launch_bounds__(kThreads) k_mix_bwd_dx(const MixArgs a, const 
 
 // dmu[mode][i][o] = sum_b conj(xhat[mode][b][i]) ghat[mode][b][o];  dlv = 0.5 s (eps_re Re + eps_im Im)
 // grid (M, ceil(Ci/T) * ceil(Co/T))
-__global__ void __launch_bounds__(kThreads) k_mix_bwd_dw(const MixArgs a, const float* __restrict__ xr,
+__global__ void __launch_bounds__(kThreads) k_mix_bwd_dw(const MixArgs a_in, const float* __restrict__ xr,
                                                          const float* __restrict__ xi, const float* __restrict__ gr,
                                                          const float* __restrict__ gi, float* __restrict__ dmu1,
                                                          float* __restrict__ dmu2, float* __restrict__ dlv1,
                                                          float* __restrict__ dlv2) {
+    MixArgs a = a_in;
+    a.key = resolve_key(a_in.key);
     __shared__ __align__(16) float sxr[KC][LD], sxi[KC][LD], sgr[KC][LD], sgi[KC][LD];
     const int mode = blockIdx.x;
     const int ntile_o = (a.Co + T - 1) / T;

@@ -539,6 +539,7 @@ int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int 
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
     g.dbg = g_pno_debug_buffer;
     if ((reinterpret_cast<uintptr_t>(x) & 15)) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd needs a 16-byte aligned input");
+    if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
 
     void* tv = nullptr;
     int rc = tc_tables_get(p, &tv);

@@ -795,6 +795,7 @@ int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, 
     if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(pre_act) |
          reinterpret_cast<uintptr_t>(yr) | reinterpret_cast<uintptr_t>(yi)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv needs 16-byte aligned tensors");
+    if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     g.n_groups = B * C / g.G;
     if (getenv("PNO_INV_PAD")) g.smem_bytes += atoi(getenv("PNO_INV_PAD")) * 1024;   // diagnostics: shrink the L1 carve-out
     g.dbg = g_pno_debug_buffer;

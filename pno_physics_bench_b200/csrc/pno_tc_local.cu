@@ -231,6 +231,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         // stream round-robin (pass s = it * NP + p goes to warp s % (EW/4)), so any warp count divides the work evenly
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int kq = (warp - kEpi0) >> 2;     // index of this warp among the warps of its quarter
+        const PhiloxKey key = resolve_key(a.key);
         constexpr int EWQ = EW / 4, NP = TN / 16;
         static_assert(EW % 4 == 0 && NP >= EWQ, "every epilogue warp needs a pass in every tile");
         int it = 0, base = 0;                   // base = (it * NP) % EWQ
@@ -261,7 +262,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     float z[16];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float4 z4 = philox_quad_normals(a.key, ((e_row + c) >> 2) + k);
+                        const float4 z4 = philox_quad_normals(key, ((e_row + c) >> 2) + k);
                         z[4 * k] = z4.x; z[4 * k + 1] = z4.y; z[4 * k + 2] = z4.z; z[4 * k + 3] = z4.w;
                     }
                     tmem_ld_wait();
@@ -364,6 +365,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wm) | reinterpret_cast<uintptr_t>(Wl) |
          reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout_dlv)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_fwd needs 16-byte aligned tensors");
+    if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     LocalArgs a;
     a.B = B; a.Ci = Ci; a.Co = Co; a.HW = HW;
     a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;

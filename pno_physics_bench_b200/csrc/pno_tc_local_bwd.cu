@@ -316,6 +316,7 @@ int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_d
     if (Ci <= 4 && dx == nullptr && HW % 4 == 0 && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) |
                                                       reinterpret_cast<uintptr_t>(dout_dlv)) & 15)) {
         // lift-shaped layer: streaming dot products (no input gradient: x is data)
+        if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
         if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "tc_local_bwd: d out / d log_var is needed when Wl is given");
         if (dw) PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
         if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
@@ -326,6 +327,7 @@ int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_d
     if (Co <= 4 && HW % 4 == 0 && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dout_dlv) |
                                      reinterpret_cast<uintptr_t>(dx)) & 15)) {
         // projection-shaped layer: one pass over x
+        if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
         if (noisy && !dout_dlv) PNO_FAIL(PNO_E_INVALID, "tc_local_bwd: d out / d log_var is needed when Wl is given");
         if (dw) PNO_CUDA(cudaMemsetAsync(dw, 0, (size_t)rows * Ci * 4, st));
         if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));
@@ -341,6 +343,7 @@ int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_d
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dout_dlv) |
          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(workspace)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_bwd needs 16-byte aligned tensors");
+    if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     float* g2 = noisy ? static_cast<float*>(workspace) : const_cast<float*>(g);
     float* wcat = static_cast<float*>(workspace) + (noisy ? (size_t)B * 2 * Co * HW : 0);
     if (db) PNO_CUDA(cudaMemsetAsync(db, 0, (size_t)rows * 4, st));

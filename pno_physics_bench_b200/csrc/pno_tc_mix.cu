@@ -193,6 +193,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         // ================================ generators ================================
         // thread = (o pair p, quad iq of 4 consecutive i): one Philox call per (i, o pair) feeds (re, im) of o and o+1
         const int t = threadIdx.x - 64;             // 0..511
+        const PhiloxKey key = resolve_key(g.key);   // (seed, sample) from device memory under pno_set_dynamic_noise
         // forward:  p = output-channel pair (64 per tile), iq = quad of 4 consecutive i (8 per k-block)
         // backward: p = o pair inside the k-block (16),    iq = quad of 4 consecutive i rows of the tile (32)
         const int p = BWD ? (t & 15) : (t & 63), iq = BWD ? (t >> 4) : (t >> 6);
@@ -261,7 +262,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     if (!RAW && more) fetch(j);                  // refill the slot just consumed: next k-block's loads in flight
                     wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
                     if (SAMPLED) {
-                        const float4 z = philox_quad_normals(g.key, quad + (uint64_t)j * g.Cop);
+                        const float4 z = philox_quad_normals(key, quad + (uint64_t)j * g.Cop);
                         const float s0 = fast_ex2(0.72134752044448170f * l2.x), s1 = fast_ex2(0.72134752044448170f * l2.y);   // exp(lv/2)
                         wr[0][j] = fmaf(s0, z.x, wr[0][j]); wi[0][j] = fmaf(s0, z.y, wi[0][j]);
                         wr[1][j] = fmaf(s1, z.z, wr[1][j]); wi[1][j] = fmaf(s1, z.w, wi[1][j]);
@@ -398,6 +399,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
         g.smem_bytes = g.raw_off + 2 * g.raw_bytes + 1024;
     }
     if (g.smem_bytes > 225 * 1024) PNO_FAIL(PNO_E_UNSUPPORTED, "%s: %d bytes of shared memory needed", who, g.smem_bytes);
+    if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     CUtensorMap tmXr, tmXi;
     int rc;
     {

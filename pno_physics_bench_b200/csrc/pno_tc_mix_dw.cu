@@ -155,6 +155,7 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
     } else {
         // ================================ epilogue: lane = input channel i, 32 of the 128 output channels per warp ================
         const int q = warp & 3, cw = (warp - 6) >> 2;
+        const PhiloxKey key = resolve_key(g.key);
         int n = 0;
         for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n) {
             const int mode = item / per_mode, r = item - mode * per_mode;
@@ -194,7 +195,7 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
                     float d[16];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {        // one Philox call: (eps_re, eps_im) of o and o + 1
-                        const float4 z = philox_quad_normals(g.key, quad0 + (c >> 1) + k);
+                        const float4 z = philox_quad_normals(key, quad0 + (c >> 1) + k);
                         const float s0 = 0.5f * fast_ex2(0.72134752044448170f * l[2 * k]);
                         const float s1 = 0.5f * fast_ex2(0.72134752044448170f * l[2 * k + 1]);
                         d[2 * k] = s0 * fmaf(z.x, re[2 * k], z.y * im[2 * k]);
@@ -237,6 +238,7 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
     g.stages = (200 * 1024) / g.stage_bytes;
     if (g.stages > 3) g.stages = 3;
     if (g.stages < 1) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_bwd_dw: batch %d needs %d bytes of shared memory per stage", B, g.stage_bytes);
+    if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     g.lv1 = lv1; g.lv2 = lv2; g.dmu1 = dmu1; g.dmu2 = dmu2; g.dlv1 = dlv1; g.dlv2 = dlv2; g.key = key;
     const int smem = g.stages * g.stage_bytes + 1024;
     CUtensorMap tmXr, tmXi, tmGr, tmGi;

@@ -38,8 +38,9 @@ def mc_shard(num_samples, group=None):
 
 def shared_seed(seed, device, group=None):
     """The Philox seed of one MC pass / training step: the caller's, or a fresh one drawn on rank 0, same on all ranks."""
-    if seed is None:
-        seed = F_.fresh_seed()
+    if seed is not None:
+        return int(seed)            # an explicit seed is the caller's promise that every rank passes the same one: no exchange
+    seed = F_.fresh_seed()
     if _active(group):
         t = torch.tensor([int(seed) & (2 ** 62 - 1)], dtype=torch.int64, device=device)
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
@@ -50,6 +51,11 @@ def shared_seed(seed, device, group=None):
 def allreduce_moments(s1, s2, group=None):
     """Sum the per-rank moment buffers in place (one fused NCCL all-reduce of [2, ...] fp64)."""
     if not _active(group):
+        return
+    # the two buffers are the halves of one [2, ...] allocation wherever this package creates them: reduce it in place
+    if (s2.data_ptr() == s1.data_ptr() + s1.numel() * s1.element_size() and s1.is_contiguous() and s2.is_contiguous()):
+        buf = torch.as_strided(s1, (2 * s1.numel(),), (1,))
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         return
     buf = torch.stack([s1, s2])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)

@@ -87,6 +87,10 @@ class _SpectralConvFn(torch.autograd.Function):
         lib = _lib.load()
         ci, co, m1, m2 = w1.shape
         _check_x(x, ci)
+        for name, t, dt in (("weights1", w1, torch.complex64), ("weights2", w2, torch.complex64),
+                            ("weights1_log_var", lv1, torch.float32), ("weights2_log_var", lv2, torch.float32),
+                            ("addend", addend, torch.float32)):
+            _lib.require_param(t, x, name, dt)
         x = x.contiguous()
         b, _, h, w = x.shape
         plan = _lib.plan(h, w, m1, m2, x.device)
@@ -100,9 +104,10 @@ class _SpectralConvFn(torch.autograd.Function):
         y = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
         pre = torch.empty_like(y) if (needs_grad and act != _lib.ACT_NONE) else None
         ws = torch.empty(lib.pno_spectral_workspace_bytes(plan, b, ci, co) // 4, dtype=torch.float32, device=x.device)
-        _lib.check(lib.pno_spectral_fwd(plan, engine, x.data_ptr(), b, ci, co, n1.data_ptr(), n2.data_ptr(), _lib.ptr(l1),
-                                        _lib.ptr(l2), seed, sample_idx, site, _lib.ptr(add), act, y.data_ptr(),
-                                        _lib.ptr(pre), ws.data_ptr(), _lib.stream_ptr()), "pno_spectral_fwd")
+        with _lib.on_device(x):
+            _lib.check(lib.pno_spectral_fwd(plan, engine, x.data_ptr(), b, ci, co, n1.data_ptr(), n2.data_ptr(), _lib.ptr(l1),
+                                            _lib.ptr(l2), seed, sample_idx, site, _lib.ptr(add), act, y.data_ptr(),
+                                            _lib.ptr(pre), ws.data_ptr(), _lib.stream_ptr(x.device)), "pno_spectral_fwd")
         if needs_grad:
             xhat = ws[: 2 * 2 * m1 * m2 * b * ci].clone() if any(ctx.needs_input_grad[1:5]) else None
             ctx.save_for_backward(x, n1, n2, l1, l2, pre, xhat)
@@ -117,8 +122,9 @@ class _SpectralConvFn(torch.autograd.Function):
         g = g.contiguous()
         if act != _lib.ACT_NONE:
             gz = torch.empty_like(g)
-            _lib.check(lib.pno_act_bwd(pre.data_ptr(), g.data_ptr(), g.numel(), act, gz.data_ptr(), _lib.stream_ptr()),
-                       "pno_act_bwd")
+            with _lib.on_device(g):
+                _lib.check(lib.pno_act_bwd(pre.data_ptr(), g.data_ptr(), g.numel(), act, gz.data_ptr(),
+                                           _lib.stream_ptr(g.device)), "pno_act_bwd")
         else:
             gz = g
         need_x, need_w, need_lv = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2], \
@@ -131,10 +137,11 @@ class _SpectralConvFn(torch.autograd.Function):
         dlv1 = torch.empty(m1, m2, ci, co, dtype=torch.float32, device=dev) if need_lv else None
         dlv2 = torch.empty(m1, m2, ci, co, dtype=torch.float32, device=dev) if need_lv else None
         ws = torch.empty(lib.pno_spectral_workspace_bytes(plan, b, ci, co) // 4, dtype=torch.float32, device=dev)
-        _lib.check(lib.pno_spectral_bwd(plan, engine, x.data_ptr(), _lib.ptr(xhat), gz.data_ptr(), b, ci, co,
-                                        n1.data_ptr(), n2.data_ptr(), _lib.ptr(l1), _lib.ptr(l2), seed, sample_idx, site,
-                                        _lib.ptr(dx), _lib.ptr(dmu1), _lib.ptr(dmu2), _lib.ptr(dlv1), _lib.ptr(dlv2),
-                                        ws.data_ptr(), _lib.stream_ptr()), "pno_spectral_bwd")
+        with _lib.on_device(x):
+            _lib.check(lib.pno_spectral_bwd(plan, engine, x.data_ptr(), _lib.ptr(xhat), gz.data_ptr(), b, ci, co,
+                                            n1.data_ptr(), n2.data_ptr(), _lib.ptr(l1), _lib.ptr(l2), seed, sample_idx, site,
+                                            _lib.ptr(dx), _lib.ptr(dmu1), _lib.ptr(dmu2), _lib.ptr(dlv1), _lib.ptr(dlv2),
+                                            ws.data_ptr(), _lib.stream_ptr(x.device)), "pno_spectral_bwd")
 
         def logical(t):
             return t.permute(2, 3, 0, 1) if t is not None else None
@@ -159,6 +166,13 @@ class _LocalFn(torch.autograd.Function):
     def forward(ctx, x, wm, bm, wl, bl, seed, sample_idx, site, batch_offset, engine, grad_mode):
         lib = _lib.load()
         _lib.require_cuda(x, "input")
+        if x.dtype != torch.float32:
+            # reference: nn.Conv2d with float32 weights raises RuntimeError for a half / double input
+            raise RuntimeError(f"expected a float32 input, got {x.dtype}")
+        if x.dim() < 3 or x.size(1) != wm.shape[1]:
+            raise RuntimeError(f"expected an input with {wm.shape[1]} channels, got shape {tuple(x.shape)}")
+        for name, t in (("weight", wm), ("bias", bm), ("log_var weight", wl), ("log_var bias", bl)):
+            _lib.require_param(t, x, name)
         x = x.contiguous()
         b, ci = x.shape[0], x.shape[1]
         hw = x.numel() // (b * ci)
@@ -169,9 +183,10 @@ class _LocalFn(torch.autograd.Function):
         dlv = torch.empty_like(out) if (noisy and needs_grad) else None
         wm_c = wm.detach().reshape(co, ci).contiguous()
         wl_c = wl.detach().reshape(co, ci).contiguous() if noisy else None
-        _lib.check(lib.pno_local_fwd(engine, x.data_ptr(), b, ci, co, hw, wm_c.data_ptr(), _lib.ptr(bm),
-                                     _lib.ptr(wl_c), _lib.ptr(bl) if noisy else 0, seed, sample_idx, site, batch_offset,
-                                     out.data_ptr(), _lib.ptr(dlv), _lib.stream_ptr()), "pno_local_fwd")
+        with _lib.on_device(x):
+            _lib.check(lib.pno_local_fwd(engine, x.data_ptr(), b, ci, co, hw, wm_c.data_ptr(), _lib.ptr(bm),
+                                         _lib.ptr(wl_c), _lib.ptr(bl) if noisy else 0, seed, sample_idx, site, batch_offset,
+                                         out.data_ptr(), _lib.ptr(dlv), _lib.stream_ptr(x.device)), "pno_local_fwd")
         if needs_grad:
             ctx.save_for_backward(x, wm_c, wl_c, dlv)
             ctx.meta = (b, ci, co, hw, noisy, wm.shape, bm is not None, bl is not None, engine)
@@ -179,47 +194,28 @@ class _LocalFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        # Plain GEMMs and reductions on the 1x1 weights: left to cuBLAS through torch (not on the spectral path).
+        """dx, [dWm; dWl] and the bias sums from pno_local_bwd: tensor-core kernels where the engine tiles the shape
+        (csrc/pno_tc_local_bwd.cu), streaming kernels for lift- / projection-shaped layers, CUDA-core GEMM kernels for the fp32
+        engine and fallback shapes (csrc/pno_local_simt.cu).  No torch / cuBLAS GEMM is involved."""
         x, wm, wl, dlv = ctx.saved_tensors
         b, ci, co, hw, noisy, wshape, has_bm, has_bl, engine = ctx.meta
         ni = ctx.needs_input_grad
-        # tensor-core engines: dx, [dWm; dWl] and the bias sums from pno_local_bwd (csrc/pno_tc_local_bwd.cu)
-        lift_shaped = ci <= 4 and not ni[0] and hw % 4 == 0        # e.g. the 3 -> C lift: streaming dot products, no dx
-        proj_shaped = co <= 4 and hw % 4 == 0                      # e.g. the C -> 1 heads: one streaming pass over x
-        if engine != _lib.ENGINE_FP32 and ((co % 128 == 0 and ci in (128, 256) and hw % 128 == 0) or lift_shaped or proj_shaped):
-            lib = _lib.load()
-            gc = g.contiguous()
-            rows = 2 * co if noisy else co
-            dx = torch.empty_like(x) if ni[0] else None
-            want_w = ni[1] or (noisy and ni[3])
-            dw = torch.empty(rows, ci, dtype=torch.float32, device=x.device) if want_w else None
-            want_b = (ni[2] and has_bm) or (noisy and ni[4] and has_bl)
-            db = torch.empty(rows, dtype=torch.float32, device=x.device) if want_b else None
-            ws = torch.empty(lib.pno_local_bwd_workspace_bytes(b, ci, co, hw, int(noisy)) // 4 + 4, dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        gc = g.contiguous()
+        rows = 2 * co if noisy else co
+        dx = torch.empty_like(x) if ni[0] else None
+        want_w = ni[1] or (noisy and ni[3])
+        dw = torch.empty(rows, ci, dtype=torch.float32, device=x.device) if want_w else None
+        want_b = (ni[2] and has_bm) or (noisy and ni[4] and has_bl)
+        db = torch.empty(rows, dtype=torch.float32, device=x.device) if want_b else None
+        ws = torch.empty(lib.pno_local_bwd_workspace_bytes(b, ci, co, hw, int(noisy)) // 4 + 4, dtype=torch.float32, device=x.device)
+        with _lib.on_device(x):
             _lib.check(lib.pno_local_bwd(engine, x.data_ptr(), gc.data_ptr(), _lib.ptr(dlv), b, ci, co, hw, wm.data_ptr(),
-                                         _lib.ptr(wl), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), ws.data_ptr(), _lib.stream_ptr()),
-                       "pno_local_bwd")
-            return (dx, dw[:co].reshape(wshape) if ni[1] else None, db[:co] if (ni[2] and has_bm) else None,
-                    dw[co:].reshape(wshape) if (noisy and ni[3]) else None, db[co:] if (noisy and ni[4] and has_bl) else None,
-                    None, None, None, None, None, None)
-        g2 = g.contiguous().reshape(b, co, hw)
-        x2 = x.reshape(b, ci, hw)
-        dx = dwm = dbm = dwl = dbl = None
-        glv = g2 * dlv.reshape(b, co, hw) if noisy else None
-        if ni[0]:
-            dx = torch.matmul(wm.t(), g2)
-            if noisy:
-                dx = dx + torch.matmul(wl.t(), glv)
-            dx = dx.reshape(x.shape)
-        if ni[1]:
-            dwm = torch.einsum("bop,bip->oi", g2, x2).reshape(wshape)
-        if ni[2] and has_bm:
-            dbm = g2.sum(dim=(0, 2))
-        if noisy and ni[3]:
-            dwl = torch.einsum("bop,bip->oi", glv, x2).reshape(wshape)
-        if noisy and ni[4] and has_bl:
-            dbl = glv.sum(dim=(0, 2))
-        return dx, dwm, dbm, dwl, dbl, None, None, None, None, None, None
+                                         _lib.ptr(wl), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), ws.data_ptr(),
+                                         _lib.stream_ptr(x.device)), "pno_local_bwd")
+        return (dx, dw[:co].reshape(wshape) if ni[1] else None, db[:co] if (ni[2] and has_bm) else None,
+                dw[co:].reshape(wshape) if (noisy and ni[3]) else None, db[co:] if (noisy and ni[4] and has_bl) else None,
+                None, None, None, None, None, None)
 
 
 def local_branch(x, wm, bm, wl=None, bl=None, *, seed=0, sample_idx=0, site=0, batch_offset=0, engine=_lib.ENGINE_FP32):
@@ -244,8 +240,9 @@ class _KLFn(torch.autograd.Function):
             mu, _ = native_spectral(params[k].detach())
             lv, _ = native_spectral(params[k + 1].detach())
             natives += [mu, lv]
-            _lib.check(lib.pno_kl_fwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), acc.data_ptr(), _lib.stream_ptr()),
-                       "pno_kl_fwd")
+            with _lib.on_device(mu):
+                _lib.check(lib.pno_kl_fwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), acc.data_ptr(),
+                                          _lib.stream_ptr(mu.device)), "pno_kl_fwd")
         ctx.save_for_backward(*natives)
         return acc.to(torch.float32)
 
@@ -258,8 +255,9 @@ class _KLFn(torch.autograd.Function):
         for k in range(0, len(natives), 2):
             mu, lv = natives[k], natives[k + 1]
             dmu, dlv = torch.empty_like(mu), torch.empty_like(lv)
-            _lib.check(lib.pno_kl_bwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), gs.data_ptr(), 0, dmu.data_ptr(),
-                                      dlv.data_ptr(), _lib.stream_ptr()), "pno_kl_bwd")
+            with _lib.on_device(mu):
+                _lib.check(lib.pno_kl_bwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), gs.data_ptr(), 0, dmu.data_ptr(),
+                                          dlv.data_ptr(), _lib.stream_ptr(mu.device)), "pno_kl_bwd")
             grads += [dmu.permute(2, 3, 0, 1), dlv.permute(2, 3, 0, 1)]
         return tuple(grads)
 
@@ -287,8 +285,9 @@ def kl_grad_accumulate_(params, gscale):
                 p.grad = torch.empty_like(p, memory_format=torch.preserve_format).copy_(p.grad)
                 gn, view = native_spectral(p.grad)
             grads.append(gn)
-        _lib.check(lib.pno_kl_bwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), gs.data_ptr(), 1, grads[0].data_ptr(),
-                                  grads[1].data_ptr(), _lib.stream_ptr()), "pno_kl_bwd")
+        with _lib.on_device(mu):
+            _lib.check(lib.pno_kl_bwd(mu.data_ptr(), lv.data_ptr(), lv.numel(), gs.data_ptr(), 1, grads[0].data_ptr(),
+                                      grads[1].data_ptr(), _lib.stream_ptr(mu.device)), "pno_kl_bwd")
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -297,16 +296,18 @@ def kl_grad_accumulate_(params, gscale):
 def mc_accumulate(y, s1, s2):
     lib = _lib.load()
     y = y.contiguous()
-    _lib.check(lib.pno_mc_accumulate(y.data_ptr(), y.numel(), s1.data_ptr(), s2.data_ptr(), _lib.stream_ptr()),
-               "pno_mc_accumulate")
+    with _lib.on_device(y):
+        _lib.check(lib.pno_mc_accumulate(y.data_ptr(), y.numel(), s1.data_ptr(), s2.data_ptr(), _lib.stream_ptr(y.device)),
+                   "pno_mc_accumulate")
 
 
 def mc_finalize(s1, s2, num_samples):
     lib = _lib.load()
     mean = torch.empty(s1.shape, dtype=torch.float32, device=s1.device)
     std = torch.empty_like(mean)
-    _lib.check(lib.pno_mc_finalize(s1.data_ptr(), s2.data_ptr(), s1.numel(), num_samples, mean.data_ptr(), std.data_ptr(),
-                                   _lib.stream_ptr()), "pno_mc_finalize")
+    with _lib.on_device(s1):
+        _lib.check(lib.pno_mc_finalize(s1.data_ptr(), s2.data_ptr(), s1.numel(), num_samples, mean.data_ptr(), std.data_ptr(),
+                                       _lib.stream_ptr(s1.device)), "pno_mc_finalize")
     return mean, std
 
 

@@ -27,19 +27,25 @@ noise_scope = F_.noise_scope
 
 _ACT_CODES = {"gelu": _lib.ACT_GELU, "relu": _lib.ACT_RELU}
 
-# Default arithmetic engine of every module: the fp32-parity tensor-core engine (error-compensated 3xTF32, rel-L2 <= 1e-5 against
-# the reference's fp32 path).  Kernels whose tilings do not cover a shape run that stage on the CUDA-core fp32 engine.
-# "tf32" is the reduced-precision mode (rel-L2 ~1e-3, the bf16-compute class of BASELINE.json); "fp32" forces CUDA cores.
-DEFAULT_ENGINE = "tf32x3"
+# Default arithmetic engine of every module: "auto" = the fp32-parity tensor-core engine (error-compensated 3xTF32, rel-L2 <= 1e-5
+# against the reference's fp32 path) for every stage whose shape its tiling covers, the fp32 CUDA-core engine for the others (both
+# are reference-grade fp32, so the dispatch is invisible in the results; `_lib.stage_counts()` shows which ran).
+# Explicit engines are STRICT: "tf32x3" / "tf32" raise when a stage's shape is not tiled by the tensor-core kernels instead of
+# silently computing it elsewhere ("tf32x3+fallback" / "tf32+fallback" opt into the fallback).  "tf32" is the reduced-precision
+# mode (rel-L2 ~1e-3, the bf16-compute class of BASELINE.json); "fp32" forces CUDA cores.
+DEFAULT_ENGINE = "auto"
 
 
-def _engine_code(engine):
+def _engine_code(engine, allow_fallback=False):
     if isinstance(engine, int):
-        return engine
+        return engine | (_lib.ENGINE_ALLOW_FALLBACK if allow_fallback and (engine & 0xFF) != _lib.ENGINE_FP32 else 0)
     try:
-        return _lib.ENGINES[engine]
+        code = _lib.ENGINES[engine]
     except KeyError:
         raise ValueError(f"engine must be one of {sorted(_lib.ENGINES)}, got {engine!r}") from None
+    if allow_fallback and code != _lib.ENGINE_FP32:
+        code |= _lib.ENGINE_ALLOW_FALLBACK
+    return code
 
 
 def _spectral_param(values):
@@ -227,11 +233,14 @@ class ProbabilisticNeuralOperator(nn.Module):
             layer.noise_site = 1 + 3 * l
 
     # -- configuration ------------------------------------------------------------------------------------------------
-    def set_engine(self, engine):
-        """'fp32' (CUDA cores, any shape), 'tf32x3' (tcgen05, fp32-grade) or 'tf32' (tcgen05, reduced precision)."""
-        self.engine = _engine_code(engine)
+    def set_engine(self, engine, allow_fallback=False):
+        """'auto' (default), 'fp32' (CUDA cores, any shape), 'tf32x3' (tcgen05, fp32-grade) or 'tf32' (tcgen05, reduced
+        precision).  The explicit tensor-core engines raise for shapes their tilings do not cover unless allow_fallback=True."""
+        self.engine = _engine_code(engine, allow_fallback)
         for layer in self.fourier_layers:
             layer.engine = self.engine
+        from .graphs import drop_graphs
+        drop_graphs(self)
         return self
 
     # -- pieces -------------------------------------------------------------------------------------------------------
@@ -303,12 +312,15 @@ class ProbabilisticNeuralOperator(nn.Module):
         return mean, std
 
     def predict_with_uncertainty(self, x: torch.Tensor, num_samples: int = 100, seed: Optional[int] = None,
-                                 group=None):
+                                 group=None, shard_samples: bool = True, use_graph: Optional[bool] = None):
         """models.py:344-379: S sampled forwards under train()+no_grad; mean and unbiased std over the samples.
 
-        The moments are accumulated on device (no [S,B,1,H,W] stack).  With torch.distributed initialised (or `group`
-        given) the S samples are sharded across ranks by GLOBAL sample index and the two moment buffers are all-reduced
-        over NCCL, so every rank returns the same (mean, std) for any number of GPUs."""
+        The moments are accumulated on device (no [S,B,1,H,W] stack).  The sample loop replays ONE captured CUDA graph of the
+        forward (graphs.MCForwardGraph; `use_graph=False` runs the eager loop, None = graph when this rank draws >= 4 samples).
+        With torch.distributed initialised (or `group` given) and shard_samples=True the S samples are sharded across ranks by
+        GLOBAL sample index and the two moment buffers are all-reduced over NCCL, so every rank returns the same (mean, std)
+        for any number of GPUs -- this requires the SAME x on every rank; pass shard_samples=False
+        when each rank holds its own batch (data-parallel evaluation)."""
         if not isinstance(x, torch.Tensor):
             raise TypeError(f"Expected torch.Tensor, got {type(x)}")
         if num_samples <= 0:
@@ -320,21 +332,30 @@ class ProbabilisticNeuralOperator(nn.Module):
         self.train()
         try:
             with torch.no_grad():
-                seed = shared_seed(seed, x.device, group)
-                first, count = mc_shard(num_samples, group)
-                s1 = s2 = None
-                for s in range(first, first + count):
-                    with F_.noise_scope(seed, s, 0):
-                        y = self.forward(x, sample=True)
-                    if s1 is None:
-                        s1 = torch.zeros(y.shape, dtype=torch.float64, device=y.device)
-                        s2 = torch.zeros_like(s1)
-                    F_.mc_accumulate(y, s1, s2)
-                if s1 is None:      # this rank drew no samples: contribute zeros of the right shape
-                    shape = (x.shape[0], 1) + tuple(x.shape[2:])
-                    s1 = torch.zeros(shape, dtype=torch.float64, device=x.device)
-                    s2 = torch.zeros_like(s1)
-                allreduce_moments(s1, s2, group)
+                if shard_samples:
+                    seed = shared_seed(seed, x.device, group)
+                    first, count = mc_shard(num_samples, group)
+                else:
+                    seed = F_.fresh_seed() if seed is None else int(seed)
+                    first, count = 0, num_samples
+                graph = count >= 4 if use_graph is None else bool(use_graph)
+                if graph and count > 0:
+                    self._validate(x)
+                    s1, s2 = self._mc_graph_for(x).run(x, seed, first, count)
+                else:
+                    s1 = s2 = None
+                    for s in range(first, first + count):
+                        with F_.noise_scope(seed, s, 0):
+                            y = self.forward(x, sample=True)
+                        if s1 is None:
+                            moments = torch.zeros((2,) + tuple(y.shape), dtype=torch.float64, device=y.device)
+                            s1, s2 = moments[0], moments[1]
+                        F_.mc_accumulate(y, s1, s2)
+                    if s1 is None:      # this rank drew no samples: contribute zeros of the right shape
+                        moments = torch.zeros((2, x.shape[0], 1) + tuple(x.shape[2:]), dtype=torch.float64, device=x.device)
+                        s1, s2 = moments[0], moments[1]
+                if shard_samples:
+                    allreduce_moments(s1, s2, group)
                 mean, std = F_.mc_finalize(s1, s2, num_samples)
         except torch.cuda.OutOfMemoryError as e:
             raise RuntimeError(f"CUDA out of memory during uncertainty estimation. "
@@ -344,6 +365,10 @@ class ProbabilisticNeuralOperator(nn.Module):
         finally:
             self.train(was_training)
         return mean, std
+
+    def _mc_graph_for(self, x):
+        from .graphs import mc_graph_for
+        return mc_graph_for(self, x)
 
     def kl_divergence(self) -> torch.Tensor:
         """models.py:381-389: fourier layers only; one fused reduction over all blocks."""

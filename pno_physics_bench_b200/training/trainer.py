@@ -91,20 +91,51 @@ class PNOTrainer:
                 cb.on_batch_end(batch_idx, losses, self)
         return {k: float(v) / max(count, 1) for k, v in sums.items()}
 
+    def _allreduce_sums(self, t):
+        """Sum an additive statistics vector over the data-parallel group (no-op on one rank)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def _validate_epoch(self, loader) -> Dict[str, float]:
-        """trainer.py:321-397: predict_with_uncertainty(S=num_samples) -> (mean, 2 log std) -> loss."""
+        """trainer.py:321-397: predict_with_uncertainty(S=num_samples) -> (mean, 2 log std) -> loss, plus `ece` / `coverage_90`.
+
+        Data-parallel runs shard the validation DATA like the training data, so every rank draws all S samples of its own batches
+        (shard_samples=False) and the additive sums (losses x batch, sample count, calibration statistics) are all-reduced once
+        at the end of the epoch."""
+        from ..metrics import UQAccumulator
         self.model.eval()
-        sums, count = {}, 0
+        keys, sums, count = None, None, 0
+        acc = UQAccumulator(confidence_levels=(0.9,), alphas=(), device=self.device)
         with torch.no_grad():
             for inputs, targets in loader:
                 inputs, targets = inputs.to(self.device), targets.to(self.device)
-                mean, std = self.model.predict_with_uncertainty(inputs, num_samples=self.num_samples)
-                losses = self.loss_fn((mean, 2 * torch.log(std.clamp(min=1e-6))), targets, self.model)
+                mean, std = self.model.predict_with_uncertainty(inputs, num_samples=self.num_samples, group=self.group,
+                                                                shard_samples=False)
+                losses = self.loss_fn((mean, 2 * torch.log(std)), targets, self.model)          # trainer.py:346
                 bs = inputs.shape[0]
-                for k, v in losses.items():
-                    sums[k] = sums.get(k, 0.0) + v.detach() * bs
+                if keys is None:
+                    keys = sorted(losses)
+                    sums = torch.zeros(len(keys) + 1, dtype=torch.float64, device=self.device)
+                sums[:-1] += torch.stack([losses[k].detach().double().reshape(()) for k in keys]) * bs
                 count += bs
-        return {k: float(v) / max(count, 1) for k, v in sums.items()}
+                acc.update(mean, std, targets)
+        if keys is None:
+            return {}
+        sums[-1] = count
+        self._allreduce_sums(sums)
+        if acc.acc is not None:
+            self._allreduce_sums(acc.acc)
+        host = sums.cpu().tolist()
+        out = {k: host[i] / max(host[-1], 1.0) for i, k in enumerate(keys)}
+        try:
+            m = acc.compute()
+            out["ece"] = m["ece"]                                                            # trainer.py:383-391
+            out["coverage_90"] = m["coverage_90"]
+        except Exception as e:      # noqa: BLE001  (the reference logs and carries on)
+            logger.warning("Failed to compute uncertainty metrics: %s", e)
+        return out
 
     def fit(self, train_loader, val_loader=None, epochs: int = 100, save_dir: Optional[str] = None,
             resume_from: Optional[str] = None) -> Dict[str, List[float]]:
@@ -156,7 +187,8 @@ class PNOTrainer:
         with torch.no_grad():
             for inputs, targets in loader:
                 inputs, targets = inputs.to(self.device), targets.to(self.device)
-                mean, std = self.model.predict_with_uncertainty(inputs, num_samples=num_samples)
+                mean, std = self.model.predict_with_uncertainty(inputs, num_samples=num_samples, group=self.group,
+                                                                shard_samples=False)
                 losses = self.loss_fn((mean, 2 * torch.log(std + 1e-8)), targets, self.model)      # trainer.py:533-538
                 batch = inputs.shape[0]
                 total_loss = losses["total"].detach() * batch if total_loss is None else total_loss + losses["total"].detach() * batch
@@ -164,6 +196,11 @@ class PNOTrainer:
                 acc.update(mean, std, targets)
         if total_samples == 0:
             return {}
+        # data-parallel evaluation: each rank saw its own shard of the loader; the statistics are additive
+        tot = self._allreduce_sums(torch.stack([total_loss.double().reshape(()),
+                                                torch.tensor(float(total_samples), dtype=torch.float64, device=self.device)]))
+        self._allreduce_sums(acc.acc)
+        total_loss, total_samples = float(tot[0]), float(tot[1])
         m = acc.compute()
         out = {"test_loss": float(total_loss) / total_samples, "rmse": m["rmse"], "mae": m["mae"]}
         out.update(m)
@@ -182,6 +219,10 @@ class PNOTrainer:
             "training_history": self.training_history,
             "optimizer_state_dict": self.optimizer.state_dict(),
             "metadata": metadata or {},
+            # additive keys (the reference loader ignores them): the noise of step k is keyed by (seed, k), so a resumed run must
+            # continue the step count under the same seed instead of replaying the keys of steps 0..k
+            "global_step": self.global_step,
+            "noise_seed": self.seed,
         }
         if self.scheduler is not None:
             ckpt["scheduler_state_dict"] = self.scheduler.state_dict()
@@ -194,6 +235,8 @@ class PNOTrainer:
             self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
         if self.scheduler is not None and "scheduler_state_dict" in ckpt:
             self.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+        self.global_step = ckpt.get("global_step", self.global_step)
+        self.seed = ckpt.get("noise_seed", self.seed)
         self.current_epoch = ckpt.get("epoch", 0)
         self.best_val_loss = ckpt.get("best_val_loss", float("inf"))
         self.training_history = ckpt.get("training_history", self.training_history)
