@@ -1,14 +1,21 @@
 #!/usr/bin/env python
 """Headline benchmark: MC-sample fields/s of `predict_with_uncertainty` at 64x64, hidden 256, modes 20 (BASELINE.json
-config 3: batch 64, S MC samples), on N B200s of one node, plus the spectral-conv roofline and a CPU baseline.
+config 3: batch 64, S MC samples), on N B200s of one node, plus the spectral-conv roofline, the other BASELINE configs, the
+reference's own eager path on the same B200 and on the host CPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--engine fp32|tf32x3|tf32] [--mc-samples S]
-    python bench.py --impl reference ...        # the reference's algorithm (oracle port) on the host CPU cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--engine tf32x3|tf32|fp32] [--mc-samples S]
+    python bench.py --scaling strong --mc-samples-total 100     # config 3 as written: S = 100 in total, sharded over the ranks
+    python bench.py --workload train_cfg2                       # data-parallel PNOTrainer step (batch 32 per GPU) as the timed step
+    python bench.py --impl reference ...                        # the UNMODIFIED reference (baseline/_ref) on the host CPU cores
 
-A "step" is one `predict_with_uncertainty(x, num_samples=S*N)` over one batch of 64 synthetic fields: S samples per
-GPU (weak scaling: per-GPU work fixed), parameters replicated, one NCCL all-reduce of the two moment buffers per step.
-`value` = N*S*64 / (max-over-ranks CUDA-event time per step), inputs resident in HBM.  `e2e` = the same call from
-pinned host memory (H2D of x, D2H of mean and std inside the timed region).  One JSON line on stdout (rank 0).
+A "step" is one `predict_with_uncertainty(x, num_samples=S*N)` over one batch of 64 synthetic fields: S samples per GPU (weak
+scaling: per-GPU work fixed), parameters replicated, one NCCL all-reduce of the two moment buffers per step.
+`value` = N*S*64 / (max-over-ranks CUDA-event time per step), inputs resident in HBM.  `e2e` = the same call from pinned host
+memory (H2D of x, D2H of mean and std inside the timed region).  One JSON line on stdout (rank 0).
+
+The headline engine is `tf32x3`, the fp32-PARITY engine (error-compensated 3xTF32, rel-L2 <= 1e-5 against the reference's
+fp32 path: tests/test_gpu_baseline_shapes.py).  The reduced-precision `tf32` engine (north_star's <= 2e-2 mode) is measured with
+the same steps / warm-up and reported under `reduced_precision`.
 """
 import argparse
 import json
@@ -26,6 +33,7 @@ import torch  # noqa: E402
 CFG = dict(B=64, C=256, H=64, W=64, modes=20, layers=4, in_dim=3)
 METRIC = "MC-sample fields/sec at 64^2 hid256 modes20 (predict_with_uncertainty, batch 64)"
 UNIT = "fields/s"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def log(*a):
@@ -48,7 +56,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
-        self.t0 = self.t1 = None          # wall-clock bounds of the timed region (rows outside are dropped)
+        self.marks = {}
 
     def __enter__(self):
         try:
@@ -65,11 +73,8 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def mark_start(self):
-        self.t0 = time.time()
-
-    def mark_end(self):
-        self.t1 = time.time()
+    def mark(self, name):
+        self.marks[name] = time.time()
 
     def __exit__(self, *a):
         if self.proc:
@@ -79,10 +84,11 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
-        rows = [r for t, r in self.rows if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.1)]
+    def summary(self, start="start", end="end"):
+        t0, t1 = self.marks.get(start), self.marks.get(end)
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.1)]
         if not rows:                       # region shorter than one sampling period: fall back to the nearest samples
-            rows = [r for _, r in self.rows[-3:]]
+            rows = [r for t, r in self.rows if t1 is None or t <= t1 + 0.3][-3:]
         sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -98,9 +104,26 @@ def build_model(engine, device):
     return model.to(device)
 
 
+def event_time(fn, iters, warmup=2, flush=None):
+    """mean CUDA-event milliseconds of fn() on torch's current stream (the stream the library launches on)."""
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts)
+
+
 def block_kernel_times(engine, device, iters=5):
-    """CUDA-event time (on torch's current stream, the stream the kernels are launched on) of each of the four kernels of
-    one PNO block at the cfg-3 shape, L2 flushed before every launch, with each kernel's ALGORITHMIC HBM bytes:
+    """CUDA-event time of each of the four kernels of one PNO block at the cfg-3 shape, L2 flushed before every launch, with each
+    kernel's ALGORITHMIC HBM bytes:
       local   : x read + local written (+ the two 1x1 weight matrices)
       dft_fwd : x read + truncated spectrum written
       mix     : spectrum read + spectrum written + mu (8 B) + log_var (4 B) per weight     <- SURVEY.md 8(d) parameter term
@@ -121,14 +144,20 @@ def block_kernel_times(engine, device, iters=5):
     bm, bl = torch.zeros(C, device=device), torch.full((C,), -3.0, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
     st, eng = _lib.stream_ptr(), _lib.ENGINES[engine]
+    it = [0]
+
+    def call(rc):
+        _lib.check(rc, "kernel")
+        it[0] += 1
+
     calls = {
-        "local": lambda it: lib.pno_local_fwd(eng, x.data_ptr(), B, C, C, H * W, wm.data_ptr(), bm.data_ptr(), wl.data_ptr(),
-                                              bl.data_ptr(), 1234, it, 2, 0, loc.data_ptr(), 0, st),
-        "dft_fwd": lambda it: lib.pno_dft_fwd(plan, eng, x.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st),
-        "mix": lambda it: lib.pno_mix_fwd(plan, eng, xr.data_ptr(), xi.data_ptr(), B, C, C, mu1.data_ptr(), mu2.data_ptr(),
-                                          lv1.data_ptr(), lv2.data_ptr(), 1234, it, 1, yr.data_ptr(), yi.data_ptr(), st),
-        "dft_inv": lambda it: lib.pno_dft_inv(plan, eng, yr.data_ptr(), yi.data_ptr(), B, C, 0, loc.data_ptr(), _lib.ACT_GELU,
-                                              y.data_ptr(), 0, st),
+        "local": lambda: call(lib.pno_local_fwd(eng, x.data_ptr(), B, C, C, H * W, wm.data_ptr(), bm.data_ptr(), wl.data_ptr(),
+                                                 bl.data_ptr(), 1234, it[0], 2, 0, loc.data_ptr(), 0, st)),
+        "dft_fwd": lambda: call(lib.pno_dft_fwd(plan, eng, x.data_ptr(), B, C, 0, xr.data_ptr(), xi.data_ptr(), st)),
+        "mix": lambda: call(lib.pno_mix_fwd(plan, eng, xr.data_ptr(), xi.data_ptr(), B, C, C, mu1.data_ptr(), mu2.data_ptr(),
+                                            lv1.data_ptr(), lv2.data_ptr(), 1234, it[0], 1, yr.data_ptr(), yi.data_ptr(), st)),
+        "dft_inv": lambda: call(lib.pno_dft_inv(plan, eng, yr.data_ptr(), yi.data_ptr(), B, C, 0, loc.data_ptr(), _lib.ACT_GELU,
+                                                y.data_ptr(), 0, st)),
     }
     act = 4.0 * B * C * H * W            # one fp32 activation tensor
     spec = 4.0 * M * B * C * 2           # one truncated spectrum (re + im planes)
@@ -136,17 +165,7 @@ def block_kernel_times(engine, device, iters=5):
               "dft_inv": spec + 2 * act}
     out = {}
     for name, fn in calls.items():
-        ts = []
-        for it in range(iters + 2):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(fn(it), name)
-            e1.record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                ts.append(e0.elapsed_time(e1) * 1e3)
-        us = sum(ts) / len(ts)
+        us = event_time(fn, iters, 2, flush) * 1e3
         out[name] = {"us": round(us, 1), "bytes": nbytes[name], "gbs": round(nbytes[name] / us / 1e3, 1)}
     return out
 
@@ -160,6 +179,12 @@ def ncu_traffic(kernel):
     return None
 
 
+KERNEL_NAMES = {"local": "k_tc_local (1x1 mean + log-var convs + reparameterised noise)",
+                "dft_fwd": "k_tc_dft_fwd (pruned forward transform)",
+                "mix": "k_tc_mix_fwd (weight sampling + per-mode complex channel mix)",
+                "dft_inv": "k_tc_dft_inv (pruned inverse transform + local add + GELU)"}
+
+
 def layer_roofline(engine, device):
     """Roofline of the dominant kernel of the block (the slowest of the four) + the whole spectral layer / block."""
     k = block_kernel_times(engine, device)
@@ -169,13 +194,10 @@ def layer_roofline(engine, device):
     layer_bytes = 4.0 * B * C * H * W * 2 + 12.0 * C * C * 2 * m * m        # x in + y out + mu + log_var
     layer_us = k["dft_fwd"]["us"] + k["mix"]["us"] + k["dft_inv"]["us"]
     block_us = layer_us + k["local"]["us"]
-    names = {"local": "k_tc_local (1x1 mean + log-var convs + reparameterised noise)",
-             "dft_fwd": "k_tc_dft_fwd (pruned forward transform)",
-             "mix": "k_tc_mix_fwd (weight sampling + per-mode complex channel mix)",
-             "dft_inv": "k_tc_dft_inv (pruned inverse transform + local add + GELU)"}
     return {"bound": "hbm", "achieved": k[top]["gbs"], "peak": hbm, "unit": "GB/s", "frac": round(k[top]["gbs"] / hbm, 4),
-            "traffic": ncu_traffic(top), "peak_source": src, "kernel": names[top], "kernel_us": k[top]["us"],
-            "algorithmic_bytes": k[top]["bytes"],
+            "traffic": ncu_traffic(top), "peak_source": src, "kernel": KERNEL_NAMES[top], "kernel_us": k[top]["us"],
+            "algorithmic_bytes": k[top]["bytes"], "engine": engine,
+            "timed": "each kernel alone, L2 flushed before every launch, right AFTER the timed region (loop clocks: `clocks_kernels`)",
             "kernels": {n: {"us": v["us"], "gbs": v["gbs"], "frac": round(v["gbs"] / hbm, 4), "traffic": ncu_traffic(n)}
                         for n, v in k.items()},
             "layer": {"us": round(layer_us, 1), "algorithmic_bytes": layer_bytes,
@@ -183,34 +205,69 @@ def layer_roofline(engine, device):
             "block_us": round(block_us, 1)}
 
 
-def cpu_baseline(sample_b=64, threads=None, reps=1):
-    """The reference's algorithm (oracle/pno_oracle.py, pinned to the reference by tests/golden) on the host cores:
-    ONE MC sample of the full cfg-3 batch (weight sampling does not shrink with the batch, so the batch is not reduced);
-    the MC loop is strictly linear in S, so fields/s of one sample is fields/s of the loop."""
-    from oracle import pno_oracle as orc
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference itself (baseline/_ref = `pip install --target` of the unmodified /root/reference)
+# ----------------------------------------------------------------------------------------------------------------------
+def import_reference():
+    """The reference's own `pno_physics_bench.models` from baseline/_ref, or None when the install is not in the tree."""
+    if not os.path.isdir(os.path.join(REF_DIR, "pno_physics_bench")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import contextlib
+    import io
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):          # the package prints a warning about matplotlib on import
+            from pno_physics_bench import models as ref_models
+        return ref_models
+    except Exception as e:                                       # noqa: BLE001
+        log(f"bench: reference import failed: {e}")
+        return None
+
+
+def cpu_baseline(threads=None, reps=1):
+    """The reference's own `predict_with_uncertainty` (unmodified models.py from baseline/_ref; the oracle port when the install is
+    absent) on the host cores: ONE MC sample of the full cfg-3 batch (weight sampling does not shrink with the batch, so the batch
+    is not reduced); the MC loop is strictly linear in S, so fields/s of one sample is fields/s of the loop."""
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    import pno_physics_bench_b200 as pno
-    torch.manual_seed(0)
-    model = pno.ProbabilisticNeuralOperator(CFG["in_dim"], CFG["C"], CFG["layers"], CFG["modes"])
-    p = {k: v.detach().contiguous() for k, v in model.state_dict().items()}
-    x = torch.randn(sample_b, CFG["in_dim"], CFG["H"], CFG["W"])
-
-    class TorchNoise:            # the reference draws with torch.randn_like; time that, not the numpy Philox restatement
-        def activation(self, site, shape, dtype=torch.float32):
-            return torch.randn(tuple(shape), dtype=dtype)
-
-        def spectral(self, site, ci, co, m1, m2, dtype=torch.float32):
-            return torch.randn(2, ci, co, m1, m2, dtype=dtype), torch.randn(2, ci, co, m1, m2, dtype=dtype)
-
+    B = CFG["B"]
+    torch.manual_seed(1)
+    x = torch.randn(B, CFG["in_dim"], CFG["H"], CFG["W"])
+    ref = import_reference()
     best = float("inf")
-    with torch.no_grad():
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            orc.pno_forward(p, x, TorchNoise(), True, True, "gelu")
-            best = min(best, time.perf_counter() - t0)
-    return {"value": round(sample_b / best, 3), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"1 MC sample x {sample_b} fields of the cfg-3 model ({best:.2f} s, torch CPU, {threads} threads)"}
+    if ref is not None:
+        torch.manual_seed(0)
+        model = ref.ProbabilisticNeuralOperator(CFG["in_dim"], CFG["C"], CFG["layers"], CFG["modes"])
+        model.train()
+        with torch.no_grad():
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                model(x, sample=True)          # one iteration of the loop body of predict_with_uncertainty (models.py:361-364)
+                best = min(best, time.perf_counter() - t0)
+        kind, what = "reference", "unmodified reference models.py (baseline/_ref)"
+    else:
+        from oracle import pno_oracle as orc
+        import pno_physics_bench_b200 as pno
+        torch.manual_seed(0)
+        model = pno.ProbabilisticNeuralOperator(CFG["in_dim"], CFG["C"], CFG["layers"], CFG["modes"])
+        p = {k: v.detach().contiguous() for k, v in model.state_dict().items()}
+
+        class TorchNoise:            # the reference draws with torch.randn_like; time that, not the numpy Philox restatement
+            def activation(self, site, shape, dtype=torch.float32):
+                return torch.randn(tuple(shape), dtype=dtype)
+
+            def spectral(self, site, ci, co, m1, m2, dtype=torch.float32):
+                return torch.randn(2, ci, co, m1, m2, dtype=dtype), torch.randn(2, ci, co, m1, m2, dtype=dtype)
+
+        with torch.no_grad():
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                orc.pno_forward(p, x, TorchNoise(), True, True, "gelu")
+                best = min(best, time.perf_counter() - t0)
+        kind, what = "port", "oracle port of the reference algorithm (baseline/_ref not in the tree)"
+    return {"value": round(B / best, 3), "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"1 MC sample x {B} fields of the cfg-3 model ({best:.2f} s, {what}, torch CPU, {threads} threads)"}
 
 
 def run_reference(args):
@@ -236,18 +293,156 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ref_cuda(device):
+    """The UNMODIFIED reference classes run eagerly on this B200 (cuFFT / cuBLAS, TF32 off = torch default): the real bar to beat
+    (BASELINE.md section 4.2).  cfg 3: fields/s of the MC loop; cfg 1: ms of one fwd+bwd."""
+    ref = import_reference()
+    if ref is None:
+        return {"unavailable": "baseline/_ref is not in the tree"}
+    out = {"allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32)}
+    try:
+        torch.manual_seed(0)
+        model = ref.ProbabilisticNeuralOperator(CFG["in_dim"], CFG["C"], CFG["layers"], CFG["modes"]).to(device)
+        x = torch.randn(CFG["B"], CFG["in_dim"], CFG["H"], CFG["W"], device=device)
+        S = 4
+        ms = event_time(lambda: model.predict_with_uncertainty(x, num_samples=S), 3, 1)
+        out["cfg3"] = {"value": round(S * CFG["B"] / ms * 1e3, 1), "unit": UNIT, "ms_per_mc_sample": round(ms / S, 2),
+                       "what": f"reference predict_with_uncertainty(x[64,3,64,64], num_samples={S}) eager on cuda"}
+        del model, x
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        model = ref.ProbabilisticNeuralOperator(3, 32, 4, 12).to(device).train()
+        x, y = torch.randn(8, 3, 64, 64, device=device), torch.randn(8, 1, 64, 64, device=device)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            loss = torch.mean((model(x, sample=True) - y) ** 2) + 1e-4 * model.kl_divergence()
+            loss.backward()
+        out["cfg1"] = {"ms_per_step": round(event_time(step, 10, 3), 3), "what": "reference fwd+bwd (MSE + 1e-4 KL), batch 8, eager on cuda"}
+        del model
+        torch.manual_seed(0)
+        fno = ref.FourierNeuralOperator(3, 128, 4, 32).to(device).eval()
+        x4 = torch.randn(64, 3, 128, 128, device=device)
+        with torch.no_grad():
+            ms = event_time(lambda: fno(x4), 5, 2)
+        out["cfg4"] = {"value": round(64 / ms * 1e3, 1), "unit": UNIT, "ms_per_batch": round(ms, 3),
+                       "what": "reference FourierNeuralOperator(3,128,4,32).eval() batch 64 at 128x128, eager on cuda"}
+        del fno, x4
+        torch.cuda.empty_cache()
+    except Exception as e:                                       # noqa: BLE001
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the other BASELINE configs (step / batch time; parity for these shapes is tests/, this is the measurement)
+# ----------------------------------------------------------------------------------------------------------------------
+def other_configs(device, engine):
+    import pno_physics_bench_b200 as pno
+    from pno_physics_bench_b200 import _lib
+    from pno_physics_bench_b200.training import ELBOLoss, PNOTrainer
+    out = {}
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:                                   # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    def cfg1():
+        torch.manual_seed(0)
+        model = pno.ProbabilisticNeuralOperator(3, 32, 4, 12).to(device).train()          # engine "auto": hid 32 is below the MMA tile
+        x, y = torch.randn(8, 3, 64, 64, device=device), torch.randn(8, 1, 64, 64, device=device)
+
+        def step(xx, yy):
+            loss = torch.mean((model(xx, sample=True) - yy) ** 2) + 1e-4 * model.kl_divergence()
+            loss.backward()
+            return loss
+
+        def eager():
+            model.zero_grad(set_to_none=True)
+            with pno.noise_scope(1, 0):
+                step(x, y)
+        c0 = _lib.stage_counts()
+        ms_eager = event_time(eager, 10, 3)
+        calls = _lib.tensor_core_calls(c0)
+        from pno_physics_bench_b200.graphs import TrainStepGraph
+        g = TrainStepGraph(model, None, x, y, step)
+        k = [0]
+
+        def graphed():
+            k[0] += 1
+            g.run(x, y, 1, k[0])
+        ms_graph = event_time(graphed, 20, 3)
+        return {"what": "PNO 64x64 in3 hid32 L4 modes12 batch 8: fwd+bwd, sample=True, MSE + 1e-4 KL", "engine": "auto",
+                "ms_per_step": round(ms_graph, 3), "ms_per_step_eager": round(ms_eager, 3), "mode": "CUDA graph of fwd + loss + bwd",
+                "tensor_core_stages": [s for s, (a, b) in calls.items() if b > 0]}
+
+    def cfg2():
+        torch.manual_seed(0)
+        model = pno.ProbabilisticNeuralOperator(3, 256, 4, 20, engine=engine)
+        trainer = PNOTrainer(model, ELBOLoss(kl_weight=1e-4), device=str(device), seed=1)
+        x, y = torch.randn(32, 3, 64, 64, device=device), torch.randn(32, 1, 64, 64, device=device)
+        ms = event_time(lambda: trainer.train_step(x, y), 4, 2)
+        return {"what": "PNOTrainer step (sampled fwd, ELBO, bwd, clip 1.0, AdamW) 64x64 hid256 L4 modes20 batch 32", "engine": engine,
+                "ms_per_step": round(ms, 3), "fields_per_s": round(32 / ms * 1e3, 1)}
+
+    def cfg4():
+        torch.manual_seed(0)
+        fno = pno.FourierNeuralOperator(3, 128, 4, 32, engine=engine).to(device).eval()
+        x = torch.randn(64, 3, 128, 128, device=device)
+        c0 = _lib.stage_counts()
+        with torch.no_grad():
+            ms = event_time(lambda: fno(x), 5, 2)
+        calls = _lib.tensor_core_calls(c0)
+        return {"what": "FourierNeuralOperator(3,128,4,32).eval() batch 64 at 128x128 (sample=False path)", "engine": engine,
+                "ms_per_batch": round(ms, 3), "fields_per_s": round(64 / ms * 1e3, 1),
+                "cuda_core_stages": [s for s, (a, b) in calls.items() if a > 0 and s not in ("local_fwd",)]}
+
+    def cfg5():
+        torch.manual_seed(0)
+        with torch.device(device):                 # 14.5 GB of parameters: initialise on the GPU
+            model = pno.ProbabilisticNeuralOperator(3, 256, 4, 48, engine=engine).train()
+        x, y = torch.randn(2, 3, 256, 256, device=device), torch.randn(2, 1, 256, 256, device=device)
+        c0 = _lib.stage_counts()
+        with torch.no_grad():
+            ms_fwd = event_time(lambda: model(x, sample=True), 3, 1)
+        calls = _lib.tensor_core_calls(c0)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            loss = torch.mean((model(x, sample=True) - y) ** 2) + 1e-4 * model.kl_divergence()
+            loss.backward()
+        ms_step = event_time(step, 2, 1)
+        return {"what": "PNO 256x256 hid256 L4 modes48, batch 2 (the per-GPU share of global batch 16 on 8 GPUs)", "engine": engine,
+                "ms_sampled_forward": round(ms_fwd, 2), "ms_fwd_bwd": round(ms_step, 2),
+                "cuda_core_stages": [s for s, (a, b) in calls.items() if a > 0 and s not in ("local_fwd",)]}
+
+    guarded("cfg1", cfg1)
+    guarded("cfg2", cfg2)
+    guarded("cfg4", cfg4)
+    guarded("cfg5", cfg5)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("PNO_BENCH_ENGINE", "tf32"), choices=["fp32", "tf32x3", "tf32"],
-                    help="tf32 = the reduced-precision (bf16-compute class, rel-L2 <= 2e-2) mode of BASELINE.json; tf32x3 = the fp32-parity mode")
-    ap.add_argument("--no-strict", action="store_true", help="skip the secondary fp32-parity (tf32x3) measurement")
+    ap.add_argument("--engine", default=os.environ.get("PNO_BENCH_ENGINE", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
+                    help="tf32x3 = the fp32-parity engine (headline); tf32 = the reduced-precision (rel-L2 <= 2e-2) mode of BASELINE.json")
     ap.add_argument("--mc-samples", type=int, default=int(os.environ.get("PNO_BENCH_MC_SAMPLES", "20")),
-                    help="MC samples per GPU per step")
+                    help="MC samples per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--mc-samples-total", type=int, default=100, help="total MC samples per step with --scaling strong (config 3: 100)")
+    ap.add_argument("--workload", default="mc_cfg3", choices=["mc_cfg3", "train_cfg2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (other configs, reference on cuda, tf32)")
+    ap.add_argument("--eager", action="store_true", help="run the MC loop eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -272,25 +467,8 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    from pno_physics_bench_b200 import _lib
+    from pno_physics_bench_b200 import _lib, graphs
     lib = _lib.load()
-    model = build_model(args.engine, device)
-    B, S = CFG["B"], args.mc_samples
-    torch.manual_seed(1)
-    x_host = torch.randn(B, CFG["in_dim"], CFG["H"], CFG["W"]).pin_memory()
-    x_dev = x_host.to(device)
-    mean_host = torch.empty(B, 1, CFG["H"], CFG["W"]).pin_memory()
-    std_host = torch.empty_like(mean_host)
-    total_samples = S * world
-
-    def step_resident(i):
-        return model.predict_with_uncertainty(x_dev, num_samples=total_samples, seed=1000 + i)
-
-    def step_e2e(i):
-        xd = x_host.to(device, non_blocking=True)
-        mean, std = model.predict_with_uncertainty(xd, num_samples=total_samples, seed=2000 + i)
-        mean_host.copy_(mean, non_blocking=True)
-        std_host.copy_(std, non_blocking=True)
 
     def timed(fn, steps):
         if world > 1:
@@ -309,62 +487,165 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # per-kernel roofline first: each kernel timed alone (L2 flushed), before the long timed region heats the part into its power cap
-    roof = None
-    if rank == 0:
-        roof = layer_roofline(args.engine, device)
-    if world > 1:
-        dist.barrier()
+    if args.workload == "train_cfg2":
+        return run_train(args, device, rank, world, local, timed)
+
+    model = build_model(args.engine, device)
+    B = CFG["B"]
+    strong = args.scaling == "strong"
+    total_samples = args.mc_samples_total if strong else args.mc_samples * world
+    torch.manual_seed(1)
+    x_host = torch.randn(B, CFG["in_dim"], CFG["H"], CFG["W"]).pin_memory()
+    x_dev = x_host.to(device)
+    mean_host = torch.empty(B, 1, CFG["H"], CFG["W"]).pin_memory()
+    std_host = torch.empty_like(mean_host)
+    use_graph = not args.eager
+
+    def mc_steps(mdl, S):
+        def resident(i):
+            return mdl.predict_with_uncertainty(x_dev, num_samples=S, seed=1000 + i, use_graph=use_graph)
+
+        def e2e(i):
+            xd = x_host.to(device, non_blocking=True)
+            mean, std = mdl.predict_with_uncertainty(xd, num_samples=S, seed=2000 + i, use_graph=use_graph)
+            mean_host.copy_(mean, non_blocking=True)
+            std_host.copy_(std, non_blocking=True)
+        return resident, e2e
+
+    def launches_now():
+        return lib.pno_launch_count() + graphs.replayed_launches()
+
+    step_resident, step_e2e = mc_steps(model, total_samples)
+    roof = strong_line = reduced = None
     with ClockSampler(local) as clocks:        # nvidia-smi needs ~1 s to start: launched before the warm-up, rows filtered by time
         for i in range(args.warmup):
             step_resident(i)
             step_e2e(i)
-        launches0 = lib.pno_launch_count()
-        clocks.mark_start()
+        launches0 = launches_now()
+        clocks.mark("start")
         ms_total = timed(step_resident, args.steps)
-        launches = lib.pno_launch_count() - launches0
+        launches = launches_now() - launches0
         ms_e2e = timed(step_e2e, args.steps)
-        clocks.mark_end()
+        clocks.mark("end")
+        # per-kernel roofline right after the timed region: the part is at its loop clocks (power-capped), not cold
+        if rank == 0:
+            roof = layer_roofline(args.engine, device)
+        clocks.mark("kernels_end")
+        if world > 1:
+            dist.barrier()
+        fields = B * total_samples
+        # config 3 as written (strong scaling: S = 100 in total) next to the weak-scaling headline, on every N
+        if not strong and not args.no_extras:
+            sr, se = mc_steps(model, args.mc_samples_total)
+            for i in range(2):
+                sr(i)
+            ms_s = timed(sr, args.steps)
+            ms_se = timed(se, args.steps)
+            strong_line = {"scaling": "strong", "mc_samples_total": args.mc_samples_total,
+                           "samples_on_busiest_rank": -(-args.mc_samples_total // world),
+                           "value": round(B * args.mc_samples_total / (ms_s / args.steps * 1e-3), 2), "unit": UNIT,
+                           "ms_per_step": round(ms_s / args.steps, 3),
+                           "e2e_value": round(B * args.mc_samples_total / (ms_se / args.steps * 1e-3), 2)}
+        # the reduced-precision engine with the same steps / warm-up
+        if not args.no_extras and args.engine != "tf32":
+            model.set_engine("tf32")
+            rr, re_ = mc_steps(model, total_samples)
+            for i in range(args.warmup):
+                rr(i)
+                re_(i)
+            clocks.mark("tf32_start")
+            ms_r = timed(rr, args.steps)
+            ms_re = timed(re_, args.steps)
+            clocks.mark("tf32_end")
+            reduced = {"engine": "tf32", "dtype": "tf32 (single pass; rel-L2 <= 2e-2 tested on mean, std, loss and gradients)",
+                       "value": round(fields / (ms_r / args.steps * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms_r / args.steps, 3),
+                       "e2e_value": round(fields / (ms_re / args.steps * 1e-3), 2), "steps": args.steps, "warmup": args.warmup}
+            if rank == 0:
+                reduced["roofline"] = layer_roofline("tf32", device)
+            clocks.mark("tf32_kernels_end")
+            reduced["clocks"] = clocks.summary("tf32_start", "tf32_end")
+            model.set_engine(args.engine)
+            if world > 1:
+                dist.barrier()
     ms_step = ms_total / args.steps
-    fields = B * total_samples
     value = fields / (ms_step * 1e-3)
     e2e_value = fields / (ms_e2e / args.steps * 1e-3)
-    # secondary measurement in the fp32-parity mode (error-compensated 3xTF32): one warm-up + one timed step
-    strict = None
-    if not args.no_strict and args.engine != "tf32x3":
-        model.set_engine("tf32x3")
-        step_resident(0)
-        ms_strict = timed(step_resident, 1)
-        model.set_engine(args.engine)
-        strict = {"engine": "tf32x3", "value": round(fields / (ms_strict * 1e-3), 2), "unit": UNIT,
-                  "ms_per_step": round(ms_strict, 3), "parity": "rel-L2 <= 1e-5 vs the fp32 reference (tests/test_gpu_tc.py)"}
-    base = None
-    if rank == 0:
-        if strict is not None:
-            ks = block_kernel_times("tf32x3", device, iters=3)
-            strict["block_kernels_us"] = {n: v["us"] for n, v in ks.items()}
-        if not args.no_cpu_baseline and world == 1:
-            base = cpu_baseline()
+    base = others = refgpu = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del model
+        graphs._MC_GRAPHS.clear()
+        torch.cuda.empty_cache()
+        others = other_configs(device, args.engine)
+        refgpu = ref_cuda(device)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = cpu_baseline()
     if world > 1:
         dist.barrier()
     if rank == 0:
         # every MC sample streams all parameters once (2.5 GB) and the working set per layer (> 1 GB) exceeds the 126 MB L2
+        S_per = f"{args.mc_samples_total} MC samples in total (strong scaling)" if strong else f"{args.mc_samples} MC samples per GPU per step"
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-equivalent)", "tf32": "tf32"}[args.engine],
+                "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (error-compensated 3xTF32 = fp32 parity, rel-L2 <= 1e-5)",
+                                               "tf32": "tf32"}[args.engine],
                 "data": "synthetic",
-                "config": {"workload": f"cfg3: predict_with_uncertainty 64x64 in3 hid256 L4 modes20, batch {B} x {S} MC "
-                                       f"samples per GPU per step", "engine": args.engine,
+                "config": {"workload": f"cfg3: predict_with_uncertainty 64x64 in3 hid256 L4 modes20, batch {B} x {S_per}",
+                           "engine": args.engine, "mc_loop": "eager launches" if args.eager else "CUDA graph of one sampled forward, replayed per sample",
                            "l2": "inputs larger than L2 (2.5 GB of parameters + >1 GB of activations streamed per sample)",
-                           "precision_mode": {"tf32": "north_star's reduced-precision (bf16-compute class) mode: tf32 operands, fp32 "
-                                                      "accumulate, rel-L2 <= 2e-2 tested; fp32-parity numbers under `strict`",
-                                              "tf32x3": "fp32-parity mode (3xTF32, rel-L2 <= 1e-5)",
-                                              "fp32": "fp32 CUDA-core engine"}[args.engine],
                            "parallelism": f"mc-sample sharding x{world}, 1 all-reduce of 2x[B,1,H,W] fp64 per step"},
-                "clocks": clocks.summary(), "gpu_launches": int(launches),
+                "clocks": clocks.summary("start", "end"), "gpu_launches": int(launches),
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": mean_host.numel() * 8},
-                "roofline": roof, "cpu_baseline": base, "strict": strict}
+                "roofline": roof, "clocks_kernels": clocks.summary("end", "kernels_end"), "cpu_baseline": base,
+                "reduced_precision": reduced, "strong_scaling": strong_line, "other_configs": others, "ref_cuda": refgpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args, device, rank, world, local, timed):
+    """--workload train_cfg2: one data-parallel PNOTrainer step (BASELINE config 2) per GPU-batch of 32 as the timed step."""
+    import torch.distributed as dist
+    import pno_physics_bench_b200 as pno
+    from pno_physics_bench_b200 import _lib
+    from pno_physics_bench_b200.training import ELBOLoss, PNOTrainer
+    lib = _lib.load()
+    torch.manual_seed(0)
+    model = pno.ProbabilisticNeuralOperator(3, 256, 4, 20, engine=args.engine)
+    trainer = PNOTrainer(model, ELBOLoss(kl_weight=1e-4), device=str(device), seed=1)
+    Bl = 32
+    torch.manual_seed(1 + rank)
+    x_host, y_host = torch.randn(Bl, 3, 64, 64).pin_memory(), torch.randn(Bl, 1, 64, 64).pin_memory()
+    x, y = x_host.to(device), y_host.to(device)
+    loss_host = torch.empty(()).pin_memory()
+
+    def resident(i):
+        trainer.train_step(x, y, batch_offset=rank * Bl)
+
+    def e2e(i):
+        losses = trainer.train_step(x_host, y_host, batch_offset=rank * Bl)
+        loss_host.copy_(losses["total"].detach().float(), non_blocking=True)
+
+    with ClockSampler(local) as clocks:
+        for i in range(args.warmup):
+            resident(i)
+        l0 = lib.pno_launch_count()
+        clocks.mark("start")
+        ms = timed(resident, args.steps) / args.steps
+        launches = lib.pno_launch_count() - l0
+        ms_e = timed(e2e, args.steps) / args.steps
+        clocks.mark("end")
+    if rank == 0:
+        line = {"metric": "PNOTrainer fields/sec at 64^2 hid256 modes20 (one ELBO step: fwd, bwd, clip, AdamW)", "value": round(world * Bl / ms * 1e3, 2),
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.engine, "data": "synthetic",
+                "config": {"workload": f"cfg2: PNOTrainer.train_step 64x64 in3 hid256 L4 modes20, batch {Bl} per GPU (global {Bl * world})",
+                           "engine": args.engine, "parallelism": f"data parallel x{world}: per-parameter NCCL all-reduce (AVG) of the 2.5 GB of "
+                                                                  "gradients, launched from autograd hooks while backward continues",
+                           "l2": "inputs larger than L2 (10 GB of parameters / gradients / AdamW state per step)"},
+                "clocks": clocks.summary("start", "end"), "gpu_launches": int(launches),
+                "e2e": {"value": round(world * Bl / ms_e * 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": (x_host.numel() + y_host.numel()) * 4,
+                        "d2h_bytes_per_step": 4}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -245,6 +245,17 @@ int pno_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                    float eps, float weight_decay, uint32_t step, const double* grad_sumsq, float max_norm,
                    int write_clipped_grad, int kl_kind, const float* kl_gscale, void* stream);
 
+/* Multi-tensor forms of the two calls above: ONE launch (per 40 tensors) over HOST arrays of `count` device pointers / sizes /
+ * kl_kinds (kl_kinds may be NULL = all 0; params may be NULL in the norm call when every kind is 0).  All tensors of one call share
+ * the hyper-parameters and the step count (one torch param_group whose states are in step).  Same arithmetic per element as the
+ * per-tensor calls; the norm accumulates in a different order (fp64), so results agree to rounding. */
+int pno_sumsq_accumulate_multi(int count, float* const* grads, const uint64_t* ns, float* const* params, const int* kl_kinds,
+                               const float* kl_gscale, double* acc, void* stream);
+int pno_adamw_step_multi(int count, float* const* params, float* const* grads, float* const* exp_avgs, float* const* exp_avg_sqs,
+                         const uint64_t* ns, const int* kl_kinds, float lr, float beta1, float beta2, float eps, float weight_decay,
+                         uint32_t step, const double* grad_sumsq, float max_norm, int write_clipped_grad, const float* kl_gscale,
+                         void* stream);
+
 /* Diagnostics: device buffer (>= 148*16 int64) into which the tensor-core kernels dump per-CTA barrier-wait cycle counters
  * (NULL switches it off, the default).  Used by tools/phase_times.py to find the stage a pipeline is waiting on. */
 int pno_debug_set_buffer(void* device_ptr);

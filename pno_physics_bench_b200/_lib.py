@@ -71,6 +71,8 @@ SIGNATURES = {
     "pno_loss_data_bwd": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "pno_sumsq_accumulate": (_int, [_vp, _u64, _vp, _vp, _int, _vp, _vp]),
     "pno_adamw_step": (_int, [_vp, _vp, _vp, _vp, _u64, _f32, _f32, _f32, _f32, _f32, _u32, _vp, _f32, _int, _int, _vp, _vp]),
+    "pno_sumsq_accumulate_multi": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pno_adamw_step_multi": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _u32, _vp, _f32, _int, _vp, _vp]),
     "pno_debug_set_buffer": (_int, [_vp]),
     "pno_selftest_umma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

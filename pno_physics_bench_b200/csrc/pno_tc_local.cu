@@ -310,21 +310,23 @@ __global__ void k_split_weights(const float* __restrict__ wm, const float* __res
 }
 
 // Library-owned scratch for the split weights: one grow-only buffer per (device, stream) so that calls on different streams
-// never share it (calls on one stream are ordered).  A handful of entries at most; never freed before process exit.
+// never share it (calls on one stream are ordered).  A buffer that is outgrown is NOT freed: a captured CUDA graph may still
+// hold its address (16 bytes per weight, i.e. at most a few MB per stream over the life of the process).
 struct SplitScratch { int dev; cudaStream_t st; float* buf; size_t floats; };
-static SplitScratch g_split[16];
+static SplitScratch g_split[512];
 static int g_nsplit = 0;
 static float* split_scratch(int dev, cudaStream_t st, size_t floats) {
     for (int i = 0; i < g_nsplit; ++i)
         if (g_split[i].dev == dev && g_split[i].st == st) {
             if (g_split[i].floats < floats) {
-                cudaFree(g_split[i].buf);
-                if (cudaMalloc(&g_split[i].buf, floats * 4) != cudaSuccess) { g_split[i].floats = 0; return nullptr; }
+                float* bigger = nullptr;
+                if (cudaMalloc(&bigger, floats * 4) != cudaSuccess) return nullptr;
+                g_split[i].buf = bigger;          // the old buffer stays allocated (see above)
                 g_split[i].floats = floats;
             }
             return g_split[i].buf;
         }
-    if (g_nsplit == 16) return nullptr;
+    if (g_nsplit == 512) return nullptr;
     SplitScratch& e = g_split[g_nsplit];
     e.dev = dev; e.st = st; e.floats = floats;
     if (cudaMalloc(&e.buf, floats * 4) != cudaSuccess) return nullptr;

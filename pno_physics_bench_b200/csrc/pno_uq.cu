@@ -262,7 +262,160 @@ __global__ void __launch_bounds__(kThreads) k_adamw(float* __restrict__ p, float
     }
 }
 
+// ---- multi-tensor forms: ONE launch over a table of tensors (the per-tensor forms cost 2 launches x ~40 tensors per step) ----
+constexpr int kMtMax = 40;                 // tensors per launch (table travels as a kernel parameter: 40 x 48 B + header < 4 KB)
+constexpr int kMtChunk = kThreads * 4 * 8; // floats per block
+struct MtTensor {
+    float *p, *g, *m, *v;
+    unsigned long long n;
+    int kl_kind;
+    unsigned first_block;
+};
+struct MtTable {
+    MtTensor t[kMtMax];
+    int count;
+};
+
+__device__ __forceinline__ int mt_find(const MtTable& tab, unsigned block) {
+    int k = 0;
+    while (k + 1 < tab.count && tab.t[k + 1].first_block <= block) ++k;
+    return k;
+}
+
+__global__ void __launch_bounds__(kThreads) k_sumsq_multi(const __grid_constant__ MtTable tab, double* __restrict__ acc,
+                                                         const float* __restrict__ kl_gscale) {
+    __shared__ double s_red[kThreads / 32];
+    const int k = mt_find(tab, blockIdx.x);
+    const MtTensor& t = tab.t[k];
+    const float gs = t.kl_kind ? *kl_gscale : 0.f;
+    const unsigned long long lo = (unsigned long long)(blockIdx.x - t.first_block) * kMtChunk;
+    const unsigned long long hi = lo + kMtChunk < t.n ? lo + kMtChunk : t.n;
+    double s = 0.0;
+    const unsigned long long v_hi = lo + ((hi - lo) & ~3ull);
+    for (unsigned long long i = lo + 4ull * threadIdx.x; i < v_hi; i += 4ull * kThreads) {
+        float4 v = *reinterpret_cast<const float4*>(t.g + i);
+        if (t.kl_kind) {
+            const float4 q = *reinterpret_cast<const float4*>(t.p + i);
+            v.x += kl_extra(q.x, t.kl_kind, gs); v.y += kl_extra(q.y, t.kl_kind, gs);
+            v.z += kl_extra(q.z, t.kl_kind, gs); v.w += kl_extra(q.w, t.kl_kind, gs);
+        }
+        s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    for (unsigned long long i = v_hi + threadIdx.x; i < hi; i += kThreads) {
+        const float v = t.g[i] + (t.kl_kind ? kl_extra(t.p[i], t.kl_kind, gs) : 0.f);
+        s += (double)v * v;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double w = threadIdx.x < kThreads / 32 ? s_red[threadIdx.x] : 0.0;
+        w = warp_sum(w);
+        if (threadIdx.x == 0 && w != 0.0) atomicAdd(acc, w);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_adamw_multi(const __grid_constant__ MtTable tab, AdamArgs a,
+                                                         const double* __restrict__ gsumsq, int write_grad,
+                                                         const float* __restrict__ kl_gscale) {
+    const int k = mt_find(tab, blockIdx.x);
+    const MtTensor& t = tab.t[k];
+    a.kl_kind = t.kl_kind;
+    a.kl_gs = t.kl_kind ? *kl_gscale : 0.f;
+    float clip = 1.f;
+    if (gsumsq && a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / ((float)sqrt(*gsumsq) + 1e-6f));
+    const unsigned long long lo = (unsigned long long)(blockIdx.x - t.first_block) * kMtChunk;
+    const unsigned long long hi = lo + kMtChunk < t.n ? lo + kMtChunk : t.n;
+    const unsigned long long v_hi = lo + ((hi - lo) & ~3ull);
+#pragma unroll 2
+    for (unsigned long long i = lo + 4ull * threadIdx.x; i < v_hi; i += 4ull * kThreads) {
+        float4 pp = *reinterpret_cast<float4*>(t.p + i), gg = *reinterpret_cast<float4*>(t.g + i),
+               mm = *reinterpret_cast<float4*>(t.m + i), vv = *reinterpret_cast<float4*>(t.v + i);
+        gg.x = adam_one(pp.x, gg.x, mm.x, vv.x, a, clip);
+        gg.y = adam_one(pp.y, gg.y, mm.y, vv.y, a, clip);
+        gg.z = adam_one(pp.z, gg.z, mm.z, vv.z, a, clip);
+        gg.w = adam_one(pp.w, gg.w, mm.w, vv.w, a, clip);
+        *reinterpret_cast<float4*>(t.p + i) = pp;
+        *reinterpret_cast<float4*>(t.m + i) = mm;
+        *reinterpret_cast<float4*>(t.v + i) = vv;
+        if (write_grad) *reinterpret_cast<float4*>(t.g + i) = gg;
+    }
+    for (unsigned long long i = v_hi + threadIdx.x; i < hi; i += kThreads) {
+        float pp = t.p[i], mm = t.m[i], vv = t.v[i];
+        const float gg = adam_one(pp, t.g[i], mm, vv, a, clip);
+        t.p[i] = pp; t.m[i] = mm; t.v[i] = vv;
+        if (write_grad) t.g[i] = gg;
+    }
+}
+
+// fills `tab` from host arrays [first, first + count); returns the number of blocks
+static unsigned mt_fill(MtTable& tab, int first, int count, float* const* params, float* const* grads, float* const* ms,
+                        float* const* vs, const uint64_t* ns, const int* kl_kinds) {
+    unsigned blocks = 0;
+    tab.count = count;
+    for (int k = 0; k < count; ++k) {
+        MtTensor& t = tab.t[k];
+        t.p = params ? params[first + k] : nullptr;
+        t.g = grads[first + k];
+        t.m = ms ? ms[first + k] : nullptr;
+        t.v = vs ? vs[first + k] : nullptr;
+        t.n = ns[first + k];
+        t.kl_kind = kl_kinds ? kl_kinds[first + k] : 0;
+        t.first_block = blocks;
+        blocks += (unsigned)((t.n + kMtChunk - 1) / kMtChunk);
+    }
+    return blocks;
+}
+
 }  // namespace
+
+extern "C" int pno_sumsq_accumulate_multi(int count, float* const* grads, const uint64_t* ns, float* const* params,
+                                          const int* kl_kinds, const float* kl_gscale, double* acc, void* stream) {
+    if (count <= 0) return PNO_OK;
+    if (!grads || !ns || !acc) PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate_multi: null pointer");
+    for (int k = 0; k < count; ++k) {
+        const int kind = kl_kinds ? kl_kinds[k] : 0;
+        if (ns[k] == 0 || !grads[k] || (reinterpret_cast<uintptr_t>(grads[k]) & 15) || kind < 0 || kind > 2 ||
+            (kind && (!params || !params[k] || !kl_gscale || (reinterpret_cast<uintptr_t>(params[k]) & 15))))
+            PNO_FAIL(PNO_E_INVALID, "pno_sumsq_accumulate_multi: tensor %d: empty, null or misaligned, or bad kl_kind", k);
+    }
+    for (int first = 0; first < count; first += kMtMax) {
+        MtTable tab;
+        const int c = count - first < kMtMax ? count - first : kMtMax;
+        const unsigned blocks = mt_fill(tab, first, c, params, grads, nullptr, nullptr, ns, kl_kinds);
+        k_sumsq_multi<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(tab, acc, kl_gscale);
+        PNO_LAUNCH_CHECK();
+    }
+    return PNO_OK;
+}
+
+extern "C" int pno_adamw_step_multi(int count, float* const* params, float* const* grads, float* const* exp_avgs,
+                                    float* const* exp_avg_sqs, const uint64_t* ns, const int* kl_kinds, float lr, float beta1,
+                                    float beta2, float eps, float weight_decay, uint32_t step, const double* grad_sumsq,
+                                    float max_norm, int write_clipped_grad, const float* kl_gscale, void* stream) {
+    if (count <= 0) return PNO_OK;
+    if (!params || !grads || !exp_avgs || !exp_avg_sqs || !ns || step == 0) PNO_FAIL(PNO_E_INVALID, "pno_adamw_step_multi: bad arguments");
+    for (int k = 0; k < count; ++k) {
+        const int kind = kl_kinds ? kl_kinds[k] : 0;
+        if (ns[k] == 0 || !params[k] || !grads[k] || !exp_avgs[k] || !exp_avg_sqs[k] || kind < 0 || kind > 2 || (kind && !kl_gscale) ||
+            ((reinterpret_cast<uintptr_t>(params[k]) | reinterpret_cast<uintptr_t>(grads[k]) | reinterpret_cast<uintptr_t>(exp_avgs[k]) |
+              reinterpret_cast<uintptr_t>(exp_avg_sqs[k])) & 15))
+            PNO_FAIL(PNO_E_INVALID, "pno_adamw_step_multi: tensor %d: empty, null or misaligned, or bad kl_kind", k);
+    }
+    AdamArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+    a.kl_kind = 0; a.kl_gs = 0.f;
+    a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    for (int first = 0; first < count; first += kMtMax) {
+        MtTable tab;
+        const int c = count - first < kMtMax ? count - first : kMtMax;
+        const unsigned blocks = mt_fill(tab, first, c, params, grads, exp_avgs, exp_avg_sqs, ns, kl_kinds);
+        k_adamw_multi<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(tab, a, grad_sumsq, write_clipped_grad, kl_gscale);
+        PNO_LAUNCH_CHECK();
+    }
+    return PNO_OK;
+}
 
 extern "C" int pno_sumsq_accumulate(const float* g, uint64_t n, double* acc, const float* param, int kl_kind, const float* kl_gscale,
                                     void* stream) {

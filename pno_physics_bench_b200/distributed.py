@@ -63,42 +63,86 @@ def allreduce_moments(s1, s2, group=None):
     s2.copy_(buf[1])
 
 
-def allreduce_gradients(params, group=None, bucket_bytes=256 << 20):
-    """Average .grad over ranks with large flat buckets (few launches; NVSwitch bandwidth is not per-link bound).
+def _grad_storage(p):
+    """The gradient of p as a flat real view of its storage (spectral gradients are permuted views of kernel-native storage;
+    complex ones travel as (re, im) pairs), or None when the gradient is not dense."""
+    g = p.grad
+    g = torch.view_as_real(g) if g.is_complex() else g
+    return F_.storage_order(g)
 
-    Complex gradients travel as their real views.  Parameters without a gradient contribute zeros so that all ranks
-    issue identical collectives."""
+
+def _avg_inplace(t, group, async_op=False):
+    """Average t over the group in place.  NCCL averages inside the collective (ncclAvg); gloo sums and the division follows."""
+    if dist.get_backend(group) == "nccl":
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op), None
+    work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return work, dist.get_world_size(group)
+
+
+class GradientSynchronizer:
+    """Data-parallel gradient averaging overlapped with backward (the reference's side module relies on DDP's bucket overlap,
+    distributed_training.py:96-101).
+
+    Every parameter gets a post-accumulate-grad hook.  A gradient of at least `large_bytes` (the spectral weights: 210-420 MB
+    each at cfg 2) is all-reduced IN ITS OWN STORAGE the moment autograd has produced it -- asynchronously on NCCL's stream, while
+    backward continues on the compute stream -- with no flattening copy.  The small ones (1x1 conv weights and biases) are
+    gathered into one flat bucket at `finish()`.  All ranks run the same autograd graph, so the collectives are issued in the
+    same order everywhere.  Parameters that received no gradient take no part (a single-GPU run would skip them, too)."""
+
+    def __init__(self, params, group=None, large_bytes=4 << 20):
+        self.group, self.large_bytes = group, large_bytes
+        self.params = [p for p in params if p.requires_grad]
+        self.pending, self.small = [], []
+        self.enabled = True
+        self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def _on_grad(self, p):
+        if not self.enabled or not _active(self.group) or p.grad is None:
+            return
+        flat = _grad_storage(p)
+        if flat is not None and flat.numel() * flat.element_size() >= self.large_bytes:
+            work, div = _avg_inplace(flat, self.group, async_op=True)
+            self.pending.append((work, flat, div))
+        else:
+            self.small.append(p)
+
+    def finish(self):
+        """Reduce the small gradients, then make the compute stream wait for every outstanding collective."""
+        if self.small:
+            views = []
+            for p in self.small:
+                g = torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad
+                views.append(g)
+            flat = torch.cat([g.reshape(-1) for g in views])
+            work, div = _avg_inplace(flat, self.group, async_op=False)
+            if div:
+                flat.div_(div)
+            off = 0
+            for g in views:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+            self.small = []
+        for work, flat, div in self.pending:
+            work.wait()
+            if div:
+                flat.div_(div)
+        self.pending = []
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
+def allreduce_gradients(params, group=None, large_bytes=4 << 20):
+    """Average .grad over ranks after backward has finished (the un-overlapped form of GradientSynchronizer, for callers that own
+    their backward pass): large gradients in their own storage, small ones through one flat bucket.  Parameters without a
+    gradient are skipped."""
     if not _active(group):
         return
-    ws = dist.get_world_size(group)
-    bucket, size = [], 0
-
-    def flush():
-        nonlocal bucket, size
-        if not bucket:
-            return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(ws)
-        off = 0
-        for g in bucket:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
-            off += n
-        bucket, size = [], 0
-
+    sync = GradientSynchronizer([], group, large_bytes)
     for p in params:
-        if not p.requires_grad:
-            continue
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-        g = torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad
-        if not g.is_contiguous():
-            # kernel-native spectral grads are permuted views of contiguous storage: reduce the storage order
-            g = g.permute(*sorted(range(g.dim()), key=lambda d: -g.stride(d)))
-        nbytes = g.numel() * g.element_size()
-        if size + nbytes > bucket_bytes:
-            flush()
-        bucket.append(g)
-        size += nbytes
-    flush()
+        if p.requires_grad and p.grad is not None:
+            sync._on_grad(p)
+    sync.finish()

@@ -67,6 +67,17 @@ def alloc_spectral(ci, co, m1, m2, dtype, device=None):
     return torch.empty(m1, m2, ci, co, dtype=dtype, device=device).permute(2, 3, 0, 1)
 
 
+def storage_order(t):
+    """Flat view of a dense (non-overlapping, gap-free) real tensor in memory order, or None (complex: pass view_as_real)."""
+    dims = sorted((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1)
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return None
+        expect *= sz
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+
+
 def _check_x(x, ci):
     _lib.require_cuda(x, "input")
     if x.dtype != torch.float32:

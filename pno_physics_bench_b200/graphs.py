@@ -14,6 +14,14 @@ from . import _lib
 from . import functional as F_
 
 
+_replayed = [0]          # kernels launched through graph replays (each replay re-runs the launches recorded at capture time)
+
+
+def replayed_launches():
+    """Kernels of this library launched by graph replays so far (pno_launch_count only sees host-side launches)."""
+    return _replayed[0]
+
+
 class NoiseKey:
     """The device-resident (seed lo, seed hi, sample_idx, unused) words the graph's kernels read."""
 
@@ -62,8 +70,10 @@ class MCForwardGraph:
             # argument error is raised here, outside the capture
             self._body(model)
             self.stream.synchronize()
+            n0 = _lib.load().pno_launch_count()
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self._body(model)
+            self.launches = _lib.load().pno_launch_count() - n0          # library kernels recorded in the graph
         torch.cuda.current_stream(dev).wait_stream(self.stream)
 
     def _body(self, model):
@@ -82,6 +92,7 @@ class MCForwardGraph:
         self.key.set(seed, first_sample)
         for _ in range(count):
             self.graph.replay()
+        _replayed[0] += count * self.launches
         return self.moments[0], self.moments[1]
 
 
@@ -131,8 +142,10 @@ class TrainStepGraph:
             self.stream.synchronize()
             for p in params:
                 p.grad = None
+            n0 = _lib.load().pno_launch_count()
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.out = step_fn(self.x, self.y)
+            self.launches = _lib.load().pno_launch_count() - n0
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         self.grads = [p.grad for p in params]                             # static gradient buffers owned by the graph's pool
         self.params = params
@@ -148,6 +161,7 @@ class TrainStepGraph:
         self.y.copy_(y, non_blocking=True)
         self.key.set(seed, step)
         self.graph.replay()
+        _replayed[0] += self.launches
         for p, g in zip(self.params, self.grads):
             p.grad = g
         return self.out

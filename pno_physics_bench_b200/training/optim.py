@@ -2,9 +2,10 @@
 
 `FusedAdamW` has torch.optim.AdamW's update rule (decoupled weight decay, bias correction, `sqrt(v_hat) + eps`) and state
 (`step`, `exp_avg`, `exp_avg_sq`), and folds `torch.nn.utils.clip_grad_norm_` (reference training/trainer.py:283-288) into
-the same pass: one reduction launch per tensor for the global gradient norm, one update launch per tensor that reads the norm
-from device memory -- no host sync, two passes over the 10 GB of parameter / gradient / moment state of the cfg-2 model instead
-of torch's clip (norm + scale) and multi-pass foreach update.  Complex parameters are updated through their real view in
+the same pass: ONE multi-tensor launch for the global gradient norm and ONE multi-tensor update launch that reads the norm from
+device memory (`pno_sumsq_accumulate_multi`, `pno_adamw_step_multi`: a table of tensor pointers travels as a kernel parameter) --
+no host sync, two launches and two passes over the 10 GB of parameter / gradient / moment state of the cfg-2 model instead of
+torch's clip (norm + scale) and multi-pass foreach update.  Complex parameters are updated through their real view in
 storage order (the spectral weights are permuted views of kernel-native storage)."""
 from typing import Optional
 
@@ -13,15 +14,7 @@ import torch
 from .. import _lib
 
 
-def _storage_order(t: torch.Tensor) -> Optional[torch.Tensor]:
-    """Flat view of a dense (non-overlapping, gap-free) real tensor in memory order, or None."""
-    dims = sorted((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1)
-    expect = 1
-    for st, sz in dims:
-        if st != expect:
-            return None
-        expect *= sz
-    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+from ..functional import storage_order as _storage_order  # noqa: E402
 
 
 def _real(t):
@@ -58,7 +51,6 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
-        stream = _lib.stream_ptr()
         work = []
         for group in self.param_groups:
             for p in group["params"]:
@@ -92,23 +84,46 @@ class FusedAdamW(torch.optim.Optimizer):
                              _storage_order(_real(state["exp_avg_sq"])), kind))
         if not work:
             return loss
+        import ctypes
+        dev = work[0][2].device
+
+        def ptrs(ts):
+            return (ctypes.c_void_p * len(ts))(*[_lib.ptr(t) for t in ts])
+
+        n = len(work)
+        ns = (ctypes.c_uint64 * n)(*[w[2].numel() for w in work])
+        kinds = (ctypes.c_int * n)(*[w[6] for w in work])
+        p_arr, g_arr = ptrs([w[2] for w in work]), ptrs([w[3] for w in work])
+        kl_ptr = _lib.ptr(self._kl_gscale) if self._kl_gscale is not None else None
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
-        if clip:
-            dev = work[0][2].device
-            if self._gsq is None or self._gsq.device != dev:
-                self._gsq = torch.zeros(1, dtype=torch.float64, device=dev)
-            self._gsq.zero_()
-            for _, _, pf, gf, _, _, kind in work:
-                _lib.check(lib.pno_sumsq_accumulate(_lib.ptr(gf), gf.numel(), _lib.ptr(self._gsq), _lib.ptr(pf) if kind else None, kind,
-                                                    _lib.ptr(self._kl_gscale) if kind else None, stream), "pno_sumsq_accumulate")
-        for group, state, pf, gf, mf, vf, kind in work:
-            state["step"] += 1
-            b1, b2 = group["betas"]
-            _lib.check(lib.pno_adamw_step(_lib.ptr(pf), _lib.ptr(gf), _lib.ptr(mf), _lib.ptr(vf), pf.numel(), group["lr"], b1, b2,
-                                          group["eps"], group["weight_decay"], int(state["step"]),
-                                          _lib.ptr(self._gsq) if clip else None, float(self.max_grad_norm) if clip else 0.0,
-                                          int(self.write_clipped_grads), kind, _lib.ptr(self._kl_gscale) if kind else None, stream),
-                       "pno_adamw_step")
+        with _lib.on_device(work[0][2]):
+            stream = _lib.stream_ptr(dev)
+            if clip:
+                if self._gsq is None or self._gsq.device != dev:
+                    self._gsq = torch.zeros(1, dtype=torch.float64, device=dev)
+                self._gsq.zero_()
+                # one launch: global gradient norm over every tensor (KL gradient of the spectral weights added on the fly)
+                _lib.check(lib.pno_sumsq_accumulate_multi(n, g_arr, ns, p_arr, kinds, kl_ptr, _lib.ptr(self._gsq), stream),
+                           "pno_sumsq_accumulate_multi")
+            # one launch per run of tensors that share hyper-parameters and step count (normally: one launch)
+            start = 0
+            while start < n:
+                group, state = work[start][0], work[start][1]
+                step_now = int(state["step"]) + 1
+                end = start
+                while end < n and work[end][0] is group and int(work[end][1]["step"]) + 1 == step_now:
+                    end += 1
+                for w in work[start:end]:
+                    w[1]["step"] += 1
+                b1, b2 = group["betas"]
+                c = end - start
+                sub = lambda arr, typ: (typ * c)(*arr[start:end])      # noqa: E731
+                _lib.check(lib.pno_adamw_step_multi(
+                    c, sub(p_arr, ctypes.c_void_p), sub(g_arr, ctypes.c_void_p), ptrs([w[4] for w in work[start:end]]),
+                    ptrs([w[5] for w in work[start:end]]), sub(ns, ctypes.c_uint64), sub(kinds, ctypes.c_int), group["lr"], b1, b2,
+                    group["eps"], group["weight_decay"], step_now, _lib.ptr(self._gsq) if clip else None,
+                    float(self.max_grad_norm) if clip else 0.0, int(self.write_clipped_grads), kl_ptr, stream), "pno_adamw_step_multi")
+                start = end
         self._kl, self._kl_gscale = {}, None          # one step only: the scale belongs to this step's loss
         return loss
 

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as F_
-from ..distributed import allreduce_gradients, shared_seed, world
+from ..distributed import GradientSynchronizer, shared_seed, world
 from .losses import ELBOLoss
 from .optim import FusedAdamW
 
@@ -45,6 +45,9 @@ class PNOTrainer:
         self.best_val_loss = float("inf")
         self.training_history = {"train_loss": [], "val_loss": [], "learning_rate": []}
         self.seed = shared_seed(seed, self.device, group)
+        _, ws = world(group)
+        # data parallel: gradient all-reduces are launched from autograd hooks while backward is still running
+        self.grad_sync = GradientSynchronizer(self.model.parameters(), group) if ws > 1 else None
 
     # ------------------------------------------------------------------------------------------------------------------
     def train_step(self, inputs, targets, batch_offset: int = 0) -> Dict[str, torch.Tensor]:
@@ -68,7 +71,8 @@ class PNOTrainer:
                     self.optimizer.set_analytic_kl(self.model.kl_params(), kl_leaf.grad)     # added inside the optimiser kernels
                 else:
                     F_.kl_grad_accumulate_(self.model.kl_params(), kl_leaf.grad)
-        allreduce_gradients(self.model.parameters(), self.group)
+        if self.grad_sync is not None:
+            self.grad_sync.finish()
         fused_clip = isinstance(self.optimizer, FusedAdamW) and self.optimizer.max_grad_norm == self.gradient_clipping
         if self.gradient_clipping and not fused_clip:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.gradient_clipping)

@@ -59,11 +59,23 @@ def _worker(rank, world, port, out):
         w.grad = F_.alloc_spectral(2, 3, 4, 5, torch.complex64).copy_(w.grad)      # strided like the kernels' outputs
         lv.grad = F_.alloc_spectral(2, 3, 4, 5, torch.float32).copy_(full[1][rank])
         cw.grad = full[2][rank].clone()
-        D.allreduce_gradients([w, lv, cw, nograd], bucket_bytes=256)                # tiny buckets: several flushes
+        D.allreduce_gradients([w, lv, cw, nograd], large_bytes=256)     # w, lv: reduced in their own storage; cw: the small bucket
         res["gw"] = float((torch.view_as_real(w.grad) - full[0].mean(0)).abs().max())
         res["glv"] = float((lv.grad - full[1].mean(0)).abs().max())
         res["gcw"] = float((cw.grad - full[2].mean(0)).abs().max())
-        res["gnone"] = float(nograd.grad.abs().max())
+        res["gnone"] = nograd.grad is None            # a parameter without a gradient stays without one (like a single-GPU run)
+        # --- the same through autograd hooks (the trainer's path): collectives are launched while backward is running
+        a = torch.nn.Parameter(torch.zeros(300))      # "large" (>= 256 bytes): async all-reduce in place from its hook
+        b = torch.nn.Parameter(torch.zeros(5))        # small: flat bucket at finish()
+        unused = torch.nn.Parameter(torch.zeros(3))
+        sync = D.GradientSynchronizer([a, b, unused], large_bytes=256)
+        xa = torch.arange(300, dtype=torch.float32) * (rank + 1)
+        ((a * xa).sum() + (b * (rank + 2.0)).sum()).backward()
+        sync.finish()
+        res["hook_a"] = float((a.grad - torch.arange(300, dtype=torch.float32) * 1.5).abs().max())
+        res["hook_b"] = float((b.grad - 2.5).abs().max())
+        res["hook_unused"] = unused.grad is None
+        sync.remove()
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -80,4 +92,5 @@ def test_world_size_2_gloo():
     assert r0["shard"] == (0, 4) and r1["shard"] == (4, 3)
     for r in (r0, r1):
         assert r["mean_err"] < 1e-12 and r["std_err"] < 1e-12
-        assert r["gw"] < 1e-6 and r["glv"] < 1e-6 and r["gcw"] < 1e-6 and r["gnone"] == 0.0
+        assert r["gw"] < 1e-6 and r["glv"] < 1e-6 and r["gcw"] < 1e-6 and r["gnone"] is True
+        assert r["hook_a"] < 1e-6 and r["hook_b"] < 1e-6 and r["hook_unused"] is True

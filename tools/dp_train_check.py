@@ -37,14 +37,12 @@ tr_dp = PNOTrainer(m_dp, ELBOLoss(kl_weight=1e-4), device=str(dev), seed=7)
 per = B // world
 loss_dp = tr_dp.train_step(x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per], batch_offset=rank * per)
 
-# reference: the whole batch on every GPU with the gradient all-reduce switched off (all ranks take part in the seed broadcast)
-import pno_physics_bench_b200.training.trainer as T  # noqa: E402
+# reference: the whole batch on every GPU with the gradient synchronisation switched off
 m_1 = make()
 tr_1 = PNOTrainer(m_1, ELBOLoss(kl_weight=1e-4), device=str(dev), seed=7)
-saved = T.allreduce_gradients
-T.allreduce_gradients = lambda *a, **k: None
+if tr_1.grad_sync is not None:
+    tr_1.grad_sync.enabled = False
 loss_1 = tr_1.train_step(x, y, batch_offset=0)
-T.allreduce_gradients = saved
 worst = 0.0
 for (k, a), (_, b_) in zip(m_dp.state_dict().items(), m_1.state_dict().items()):
     a, b_ = (torch.view_as_real(t) if t.is_complex() else t for t in (a, b_))
@@ -52,6 +50,7 @@ for (k, a), (_, b_) in zip(m_dp.state_dict().items(), m_1.state_dict().items()):
     worst = max(worst, d)
 if rank == 0:
     print(f"world {world}: max relative parameter difference after one step (sharded vs whole batch) = {worst:.3e}")
+    print("DP_CHECK_OK" if worst < 1e-5 else "DP_CHECK_FAILED")
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
