@@ -36,6 +36,7 @@
  *   PNO_MIX_RAW=0        single pass: register-prefetched mu / log_var instead of the TMA-staged tiles
  *   PNO_FWD_STAGES=n, PNO_FWD_KPS=1|2                                ring depth / stage size of the forward-transform kernel
  *   PNO_MIX_STAGES=2..4                                              ring depth of the channel-mix kernel
+ *   PNO_DFT_TWOPASS=1    use the two-pass transforms (pno_tc_dft2.cu) wherever they tile the shape, not only where the fused kernels do not
  *   PNO_DEBUG_MMA=1      (PNO_TRACE builds) serialise the inverse kernel's MMA batches to time them
  * A library built with `make EXTRA=-DPNO_TRACE` records per-role event timelines of CTA 0 into the pno_debug_set_buffer() buffer
  * (tools/trace_*.py); production builds compile all of that away.
@@ -79,7 +80,9 @@ enum {
 /* stages whose engine is dispatched (index into pno_stage_counts) */
 enum {
     PNO_STAGE_DFT_FWD = 0, PNO_STAGE_DFT_INV = 1, PNO_STAGE_MIX_FWD = 2, PNO_STAGE_MIX_BWD_DX = 3, PNO_STAGE_MIX_BWD_DW = 4,
-    PNO_STAGE_LOCAL_FWD = 5, PNO_STAGE_LOCAL_BWD = 6, PNO_N_STAGES = 7
+    PNO_STAGE_LOCAL_FWD = 5, PNO_STAGE_LOCAL_BWD = 6,
+    PNO_STAGE_LOCAL_THIN = 7,   /* lift- / projection-shaped 1x1 convs, forward or backward: streaming CUDA-core kernels by design */
+    PNO_N_STAGES = 8
 };
 
 typedef struct pno_plan pno_plan_t;

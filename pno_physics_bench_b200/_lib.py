@@ -23,7 +23,7 @@ ENGINE_ALLOW_FALLBACK = 0x100
 ENGINES = {"fp32": ENGINE_FP32, "tf32x3": ENGINE_TC_TF32X3, "tf32": ENGINE_TC_TF32,
            "auto": ENGINE_TC_TF32X3 | ENGINE_ALLOW_FALLBACK,
            "tf32x3+fallback": ENGINE_TC_TF32X3 | ENGINE_ALLOW_FALLBACK, "tf32+fallback": ENGINE_TC_TF32 | ENGINE_ALLOW_FALLBACK}
-STAGES = ("dft_fwd", "dft_inv", "mix_fwd", "mix_bwd_dx", "mix_bwd_dw", "local_fwd", "local_bwd")
+STAGES = ("dft_fwd", "dft_inv", "mix_fwd", "mix_bwd_dx", "mix_bwd_dw", "local_fwd", "local_bwd", "local_thin")
 
 _c_float_p = ctypes.c_void_p      # device pointers travel as integers
 _u64, _u32, _int, _vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p

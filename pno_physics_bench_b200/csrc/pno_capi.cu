@@ -34,6 +34,32 @@ extern "C" int pno_stage_counts(uint64_t* out) {
 
 thread_local int g_pno_dry_run = 0;
 
+struct ScratchEntry { int dev, slot; cudaStream_t st; float* buf; size_t bytes; };
+static ScratchEntry g_scratch[1024];
+static int g_nscratch = 0;
+float* pno_scratch(int slot, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < g_nscratch; ++i) {
+        ScratchEntry& e = g_scratch[i];
+        if (e.dev == dev && e.st == st && e.slot == slot) {
+            if (e.bytes < bytes) {
+                float* bigger = nullptr;
+                if (cudaMalloc(&bigger, bytes) != cudaSuccess) return nullptr;
+                e.buf = bigger;          // the outgrown buffer stays allocated (see pno_common.cuh)
+                e.bytes = bytes;
+            }
+            return e.buf;
+        }
+    }
+    if (g_nscratch == 1024) return nullptr;
+    ScratchEntry& e = g_scratch[g_nscratch];
+    e.dev = dev; e.slot = slot; e.st = st; e.bytes = bytes;
+    if (cudaMalloc(&e.buf, bytes) != cudaSuccess) return nullptr;
+    ++g_nscratch;
+    return e.buf;
+}
+
 // Host-only (no CUDA call): would `engine` run `stage` on its tensor-core kernel at this shape?  The tilings' own validation code
 // answers (dry run), so this can never disagree with what a launch would do.
 extern "C" int pno_engine_supports(int stage, int engine, int H, int W, int m1, int m2, int B, int Ci, int Co) {
@@ -133,6 +159,7 @@ extern "C" int pno_plan_create(int H, int W, int m1, int m2, pno_plan_t** out) {
     p->H = H; p->W = W; p->m1 = m1; p->m2 = m2; p->M = 2 * m1 * m2;
     p->tc_tables = nullptr;
     p->tc_tables_inv = nullptr;
+    p->tc_tables2 = nullptr;
     PNO_CUDA(cudaGetDevice(&p->device));
     std::vector<float2> th(H), tw(W);
     const double two_pi = 6.283185307179586476925286766559;
@@ -165,6 +192,7 @@ extern "C" int pno_plan_destroy(pno_plan_t* p) {
     if (!p) return PNO_OK;
     tc_plan_release(p);
     tc_plan_release_inv(p);
+    tc_plan_release2(p);
     cudaFree(p->tabH);
     cudaFree(p->tabW);
     cudaFree(p->kx);
@@ -324,7 +352,7 @@ extern "C" int pno_local_bwd(int engine, const float* x, const float* g, const f
     const bool thin = HW % 4 == 0 && ((Ci <= 4 && dx == nullptr) || Co <= 4);
     if (thin) {
         const int rc = tc_local_bwd(PNO_ENGINE_TC_TF32X3, x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, workspace, as_stream(stream));
-        if (rc == PNO_OK) { ++g_stage_counts[PNO_STAGE_LOCAL_BWD][0]; return rc; }
+        if (rc == PNO_OK) { ++g_stage_counts[PNO_STAGE_LOCAL_THIN][0]; return rc; }
         if (rc != PNO_E_UNSUPPORTED) return rc;       // (misaligned thin layers take the general kernels below)
         return simt_local_bwd(x, g, dout_dlv, B, Ci, Co, HW, Wm, Wl, dx, dw, db, as_stream(stream));
     }
@@ -344,7 +372,7 @@ extern "C" int pno_local_fwd(int engine, const float* x, int B, int Ci, int Co, 
     // GEMM in them to put on the tensor cores
     if (Ci <= 8 || Co <= 4) {
         const int rc = simt_local_fwd(x, B, Ci, Co, HW, Wm, bm, Wl, bl, key, batch_offset, out, dout_dlv, as_stream(stream));
-        if (rc == PNO_OK) ++g_stage_counts[PNO_STAGE_LOCAL_FWD][0];
+        if (rc == PNO_OK) ++g_stage_counts[PNO_STAGE_LOCAL_THIN][0];
         return rc;
     }
     return dispatch(engine, PNO_STAGE_LOCAL_FWD, "pno_local_fwd",

@@ -48,9 +48,15 @@ struct pno_plan {
     // dense twiddle matrices for the tensor-core engines (allocated lazily by the engines that use them)
     void* tc_tables;
     void* tc_tables_inv;
+    void* tc_tables2;   // tables of the two-pass transforms (pno_tc_dft2.cu)
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Library-owned scratch: one grow-only buffer per (device, stream, slot), so that calls on different streams never share one
+// (calls on one stream are ordered).  A buffer that is outgrown is NOT freed: a captured CUDA graph may still hold its address.
+// Slots: 0 = tf32 hi / lo parts of 1x1 weights / twiddle tables, 1 and 2 = intermediates of the two-pass transforms.
+float* pno_scratch(int slot, size_t bytes, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // single-instruction approximations (flush-to-zero forms: no denormal fix-up code around the MUFU)

@@ -4,6 +4,19 @@
 
 void tc_plan_release(pno_plan* p);
 void tc_plan_release_inv(pno_plan* p);
+void tc_plan_release2(pno_plan* p);
+// building blocks of the two-pass transforms (pno_tc_gemm.cu, pno_tc_local.cu) and the transforms themselves (pno_tc_dft2.cu)
+int tc_rowgemm(int engine, const float* A, long long rows, int K, int N, const float* t_hi, const float* t_lo, int epi, int act,
+               const float* addend, float* out, float* pre_act, cudaStream_t st);
+int tc_local_combine(int engine, const float* x, int B, int Ci, int Co, int TN, const float* Wc, const float* Ws, float sign, float* out,
+                     cudaStream_t st);
+int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
+                     cudaStream_t st);
+int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
+                     const float* addend, int act, float* y, float* pre_act, cudaStream_t st);
+int tc_dft2_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi, cudaStream_t st);
+int tc_dft2_inv(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint, const float* addend,
+                int act, float* y, float* pre_act, cudaStream_t st);
 int tc_tables_get(const pno_plan* p, void** tables);
 int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
                cudaStream_t st);

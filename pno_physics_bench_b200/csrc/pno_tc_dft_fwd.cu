@@ -474,8 +474,8 @@ void tc_plan_release(pno_plan* p) {
     p->tc_tables = nullptr;
 }
 
-int tc_dft_fwd(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
-               cudaStream_t st) {
+int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C, int grad_scale, float* xr, float* xi,
+                     cudaStream_t st) {
     const int H = p->H, W = p->W, m1 = p->m1, m2 = p->m2;
     if (!(H == 32 || H == 64 || H == 128) || W % 32 || W > 256 || m2 % 4 || 2 * m1 > 128)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd tiles H in {32,64,128}, W%%32 == 0, W <= 256, m2%%4 == 0, 2*m1 <= 128");

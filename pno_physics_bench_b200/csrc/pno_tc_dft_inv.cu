@@ -680,8 +680,8 @@ void tc_plan_release_inv(pno_plan* p) {
     p->tc_tables_inv = nullptr;
 }
 
-int tc_dft_inv(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
-               const float* addend, int act, float* y, float* pre_act, cudaStream_t st) {
+int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float* yi, int B, int C, int adjoint,
+                     const float* addend, int act, float* y, float* pre_act, cudaStream_t st) {
     const int H = p->H, W = p->W, m1 = p->m1, m2 = p->m2;
     if (!(H == 32 || H == 64 || H == 128) || W % 32 || W > 256 || W < 32 || m1 % 4 || m2 % 4 || m2 > 64)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv tiles H in {32,64,128}, W%%32 == 0, W <= 256, m1%%4 == 0, m2%%4 == 0");

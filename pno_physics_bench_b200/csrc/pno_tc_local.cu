@@ -41,6 +41,7 @@ struct LocalArgs {
     float *out, *dlv;
     PhiloxKey key;
     uint64_t batch_offset;
+    float sign;             // EPI == 1: sign of the cross terms of the complex combine
     int n_tiles, p_tiles, o_tiles;
     long long* dbg;   // optional event trace (PNO_TRACE builds)
 };
@@ -54,7 +55,7 @@ struct Cfg {
     static constexpr int kStageBytes = kOperandBytes * (NSPLIT == 3 ? 2 : 1);    // + lo copies
     static constexpr int kStages = (224 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (3xTF32)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-    static constexpr int kAcc = TN == 128 ? 2 : 1;                               // accumulator buffers in tensor memory
+    static constexpr int kAcc = 4 * TN <= 512 ? 2 : 1;                           // accumulator buffers in tensor memory
     static_assert(kStages >= 2, "stage does not fit");
 };
 
@@ -67,7 +68,11 @@ __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-neares
     return r;
 }
 
-template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW>
+// EPI == 1 (NOISY = true: two weight matrices): the H-axis pass of the two-pass pruned transforms (pno_tc_dft2.cu).  The "weights"
+// are the cos / sin twiddle tables (A_m = C, A_l = S), the "pixels" of an image are its TN = 2 * m2p spectrum columns (re | im), and
+// the epilogue combines the two accumulators into the complex product instead of drawing noise:
+//   out[:, c] = Dm[:, c] + sign * Dl[:, c + TN/2]  (real part),   out[:, c + TN/2] = Dm[:, c + TN/2] - sign * Dl[:, c]  (imaginary part)
+template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW, int EPI = 0>
 __global__ void __launch_bounds__(threads_for(NSPLIT, EW), 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
            const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmWmLo,
@@ -250,6 +255,30 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             if (warp == kEpi0) TRACE(2, 1);
             tc_fence_after_sync();
             const uint32_t t_m = tmem_addr(tmem, q * 32, acc * (2 * TN)), t_l = t_m + TN;
+            if (EPI == 1) {
+                constexpr int H2 = TN / 2;
+                static_assert(EPI == 0 || H2 % 16 == 0, "complex combine needs 16-column halves");
+#pragma unroll 1
+                for (int c = kq * 16; c < H2; c += EWQ * 16) {
+                    float mr[16], mi[16], lr[16], li[16];
+                    tmem_ld16(t_m + c, mr);
+                    tmem_ld16(t_m + H2 + c, mi);
+                    tmem_ld16(t_l + c, lr);
+                    tmem_ld16(t_l + H2 + c, li);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float re = fmaf(a.sign, li[j], mr[j]), im = fmaf(-a.sign, lr[j], mi[j]);
+                        mr[j] = re;
+                        mi[j] = im;
+                    }
+                    lane_store16(a.out + wrow + c, mr);
+                    lane_store16(a.out + wrow + H2 + c, mi);
+                }
+                tc_fence_before_sync();
+                mbar_arrive(&bar_tempty[acc]);
+                continue;
+            }
             int p0 = kq - base;
             if (p0 < 0) p0 += EWQ;
 #pragma unroll 1
@@ -309,41 +338,18 @@ __global__ void k_split_weights(const float* __restrict__ wm, const float* __res
     out[3 * n + i] = b_ - bh;
 }
 
-// Library-owned scratch for the split weights: one grow-only buffer per (device, stream) so that calls on different streams
-// never share it (calls on one stream are ordered).  A buffer that is outgrown is NOT freed: a captured CUDA graph may still
-// hold its address (16 bytes per weight, i.e. at most a few MB per stream over the life of the process).
-struct SplitScratch { int dev; cudaStream_t st; float* buf; size_t floats; };
-static SplitScratch g_split[512];
-static int g_nsplit = 0;
-static float* split_scratch(int dev, cudaStream_t st, size_t floats) {
-    for (int i = 0; i < g_nsplit; ++i)
-        if (g_split[i].dev == dev && g_split[i].st == st) {
-            if (g_split[i].floats < floats) {
-                float* bigger = nullptr;
-                if (cudaMalloc(&bigger, floats * 4) != cudaSuccess) return nullptr;
-                g_split[i].buf = bigger;          // the old buffer stays allocated (see above)
-                g_split[i].floats = floats;
-            }
-            return g_split[i].buf;
-        }
-    if (g_nsplit == 512) return nullptr;
-    SplitScratch& e = g_split[g_nsplit];
-    e.dev = dev; e.st = st; e.floats = floats;
-    if (cudaMalloc(&e.buf, floats * 4) != cudaSuccess) return nullptr;
-    ++g_nsplit;
-    return e.buf;
-}
+static float* split_scratch(int /*dev*/, cudaStream_t st, size_t floats) { return pno_scratch(0, floats * 4, st); }
 
-template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16>
+template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16, int EPI = 0>
 int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
            const CUtensorMap& tmWlLo, cudaStream_t st) {
     using C = Cfg<NSPLIT, TN, EW>;
-    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN, EW>, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl,
+    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI>, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl,
                         tmWmLo, tmWlLo));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
@@ -373,7 +379,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;
     a.dbg = g_pno_debug_buffer;
     a.prefetch = getenv("PNO_LOCAL_PREFETCH") ? atoi(getenv("PNO_LOCAL_PREFETCH")) : 1;
-    a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset;
+    a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset; a.sign = 0.f;
     // pixel-tile width (see the header comment): 128 unless PNO_LOCAL_TN=256 asks for the wide tile
     const char* e_tn = getenv("PNO_LOCAL_TN");
     const int TN = (e_tn && atoi(e_tn) == 256 && engine != PNO_ENGINE_TC_TF32X3 && HW % 256 == 0) ? 256 : 128;
@@ -416,4 +422,59 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
     if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
     return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+}
+
+// H-axis pass of the two-pass transforms: out[b][o][c] for c in [0, TN): complex combine (see k_tc_local, EPI == 1) of
+//   Dm = Wc . x[b]  and  Dl = Ws . x[b],   x [B][Ci][TN], Wc / Ws [Co][Ci] (cos / sin tables), out [B][Co][TN].
+// Ci % 32 == 0, Co % 128 == 0, TN in {64, 96, 128}.  3xTF32: the tables are split per call like the 1x1 weights.
+int tc_local_combine(int engine, const float* x, int B, int Ci, int Co, int TN, const float* Wc, const float* Ws, float sign, float* out,
+                     cudaStream_t st) {
+    if (Ci % TK || Co % TM || !(TN == 64 || TN == 96 || TN == 128))
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_combine tiles Ci%%32 == 0, Co%%128 == 0, TN in {64, 96, 128} (got %d, %d, %d)", Ci, Co, TN);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wc) | reinterpret_cast<uintptr_t>(Ws) | reinterpret_cast<uintptr_t>(out)) & 31)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_combine needs 32-byte aligned tensors");
+    if (g_pno_dry_run) return PNO_OK;
+    LocalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Ci = Ci; a.Co = Co; a.HW = TN;
+    a.noisy = 1; a.want_dlv = 0;
+    a.dbg = g_pno_debug_buffer;
+    a.prefetch = 0;
+    a.out = out; a.sign = sign;
+    a.o_tiles = Co / TM; a.p_tiles = 1; a.n_tiles = B * a.o_tiles;
+    CUtensorMap tmX, tmWm, tmWl, tmWmLo, tmWlLo;
+    int rc;
+    {   // x as (c % 32, row = b*Ci + i, c / 32)
+        const uint64_t dims[3] = {32, (uint64_t)B * Ci, (uint64_t)TN / 32};
+        const uint64_t str[2] = {(uint64_t)TN * 4, 128};
+        const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
+        if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
+        const uint64_t str[1] = {(uint64_t)Ci * 4};
+        const uint32_t box[2] = {TK, TM};
+        const float *wm_hi = Wc, *wl_hi = Ws, *wm_lo = Wc, *wl_lo = Ws;
+        if (engine == PNO_ENGINE_TC_TF32X3) {
+            int dev = 0;
+            PNO_CUDA(cudaGetDevice(&dev));
+            const size_t n = (size_t)Co * Ci;
+            float* sc = split_scratch(dev, st, 4 * n);
+            if (!sc) PNO_FAIL(PNO_E_CUDA, "tc_local_combine: cannot allocate the split-table scratch (%zu bytes)", 16 * n);
+            k_split_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wc, Ws, (int)n, sc);
+            PNO_LAUNCH_CHECK();
+            wm_hi = sc; wl_hi = sc + n; wm_lo = sc + 2 * n; wl_lo = sc + 3 * n;
+        }
+        if ((rc = pno_encode_tmap(&tmWm, wm_hi, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWl, wl_hi, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWmLo, wm_lo, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmWlLo, wl_lo, 2, dims, str, box, 1))) return rc;
+    }
+    const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
+#define PNO_COMBINE(TN_) (x3 ? launch<3, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) \
+                             : launch<1, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st))
+    if (TN == 64) return PNO_COMBINE(64);
+    if (TN == 96) return PNO_COMBINE(96);
+    return PNO_COMBINE(128);
+#undef PNO_COMBINE
 }

@@ -178,10 +178,9 @@ BASELINE_SHAPES = {          # (H, W, m1, m2, B per GPU, Ci, Co)
     "cfg4": (128, 128, 32, 32, 64, 128, 128),
     "cfg5": (256, 256, 48, 48, 2, 256, 256),
 }
-# stages of BASELINE configs 4 / 5 that still run on CUDA cores (transforms of 256-row images; the fp32-parity transforms at
-# 128x128 with 32 modes)
-KNOWN_GAPS = {("cfg4", "tf32x3", "dft_fwd"), ("cfg4", "tf32x3", "dft_inv"), ("cfg5", "tf32x3", "dft_fwd"),
-              ("cfg5", "tf32x3", "dft_inv"), ("cfg5", "tf32", "dft_fwd"), ("cfg5", "tf32", "dft_inv")}
+# stages of BASELINE configs 4 / 5 that still run on CUDA cores: none (the transforms of 256-row images and the fp32-parity
+# transforms at 128x128 / 32 modes are the two-pass tensor-core form, csrc/pno_tc_dft2.cu)
+KNOWN_GAPS = set()
 FWD_STAGES = ("dft_fwd", "mix_fwd", "dft_inv", "local_fwd")
 BWD_STAGES = ("mix_bwd_dx", "mix_bwd_dw", "local_bwd")
 

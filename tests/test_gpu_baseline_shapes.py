@@ -48,10 +48,14 @@ def assert_tensor_cores(counts, stages):
 
 
 def trained_like_(layer, gen, ci):
+    """"trained-like" parameters that exercise the mean path at full precision AND keep a 4-block
+    model well conditioned (unit gain per block): mu ~ CN(0, 1/Ci), log_var ~ U(-10, -6).  (The default initialisation is
+    useless for parity: sigma/|mu| ~ 1e4, the output is pure noise and activations grow to ~1e2, where fp32 itself -- the
+    reference's arithmetic -- is only good to ~1e-4; `conditioning` below measures exactly that on the case used.)"""
     with torch.no_grad():
         for w, lv in ((layer.weights1, layer.weights1_log_var), (layer.weights2, layer.weights2_log_var)):
-            w.copy_(torch.complex(torch.randn(w.shape, generator=gen), torch.randn(w.shape, generator=gen)) / ci ** 0.5)
-            lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 6)
+            w.copy_(torch.complex(torch.randn(w.shape, generator=gen), torch.randn(w.shape, generator=gen)) / (2 * ci) ** 0.5)
+            lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 10)
 
 
 def trained_like_model(hid, layers, modes, gen):
@@ -148,28 +152,38 @@ def cfg3_mc_case():
             table = noise_table(seed, s, B, hid, L, m, hw)
             ys.append(orc.pno_forward(p, x, orc.InjectedNoise(table), True, True, "gelu"))
             del table
+    # conditioning of the case: the reference algorithm in fp64 vs itself in fp32 on sample 0 (how far two correct fp32
+    # implementations may legitimately differ here)
+    with torch.no_grad():
+        table = noise_table(seed, 0, B, hid, L, m, hw)
+        t64 = {k: (tuple(t.double() for t in v) if isinstance(v, tuple) else v.double()) for k, v in table.items()}
+        p64 = {k: (v.to(torch.complex128) if v.is_complex() else v.double()) for k, v in p.items()}
+        y64 = orc.pno_forward(p64, x.double(), orc.InjectedNoise(t64), True, True, "gelu")
+        cond = rel_l2(ys[0], y64)
+        del table, t64, p64
+    print(f"\n[cfg3_mc] conditioning: oracle fp32 vs oracle fp64 on sample 0: rel-L2 {cond:.2e}; mean |y| {float(ys[0].abs().mean()):.3f}")
     ys = torch.stack(ys)
-    return model, x, seed, S, ys.mean(0), ys.std(0)
+    return model, x, seed, S, ys.mean(0), ys.std(0), cond
 
 
 @pytest.mark.parametrize("engine", ["tf32x3", "tf32"])
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_cfg3_mc_mean_and_std_against_oracle(cfg3_mc_case, engine, use_graph):
-    model, x, seed, S, mean_ref, std_ref = cfg3_mc_case
+    model, x, seed, S, mean_ref, std_ref, cond = cfg3_mc_case
     model = model.to(DEV)
     model.set_engine(engine)                                   # strict: any stage outside the tensor-core tilings would raise
     c0 = _lib.stage_counts()
     mean, std = model.predict_with_uncertainty(x.to(DEV), num_samples=S, seed=seed, use_graph=use_graph)
     torch.cuda.synchronize()
     counts = _lib.tensor_core_calls(c0)
-    errs = {"mean": rel_l2(mean, mean_ref), "std": rel_l2(std, std_ref)}
+    errs = {"mean": rel_l2(mean, mean_ref), "std": rel_l2(std, std_ref), "oracle_fp32_vs_fp64": cond}
     report(f"cfg3_mc_S{S}" + ("_graph" if use_graph else ""), engine, errs, counts)
     assert_tensor_cores(counts, ["dft_fwd", "mix_fwd", "dft_inv", "local_fwd"])
     assert errs["mean"] < TOL[engine] and errs["std"] < TOL[engine]
 
 
 def test_graph_replay_is_bit_identical_to_the_eager_loop(cfg3_mc_case):
-    model, x, seed, _, _, _ = cfg3_mc_case
+    model, x, seed = cfg3_mc_case[:3]
     model = model.to(DEV)
     model.set_engine("tf32x3")
     xd = x[:8].to(DEV).contiguous()
@@ -298,13 +312,15 @@ def test_cfg1_step_runs_without_library_gemms():
     counts = _lib.tensor_core_calls(c0)
     assert counts["local_bwd"] == (1, 0)
     got = [t.grad.clone() for t in (x, wm, bm, wl, bl)]
-    # torch autograd of the same function with the same noise
-    eps = F_.materialize_activation_noise(3, 1, 2, out.shape)
-    xs = [t.detach().clone().requires_grad_(True) for t in (x, wm, bm, wl, bl)]
-    mean = torch.nn.functional.conv2d(xs[0], xs[1], xs[2])
-    lv = torch.clamp(torch.nn.functional.conv2d(xs[0], xs[3], xs[4]), -10, 10)
-    ref = mean + eps * torch.exp(0.5 * lv).clamp(min=1e-6)
-    ref.backward(up)
+    # torch autograd of the same function with the same noise, in fp64 (cuDNN fp32 convolutions may run in TF32)
+    eps = F_.materialize_activation_noise(3, 1, 2, out.shape).double()
+    xs = [t.detach().double().requires_grad_(True) for t in (x, wm, bm, wl, bl)]
+
+    def conv(inp, w, b):
+        return torch.einsum("oi,bihw->bohw", w.reshape(w.shape[0], w.shape[1]), inp) + b.view(1, -1, 1, 1)
+    lv = torch.clamp(conv(xs[0], xs[3], xs[4]), -10, 10)
+    ref = conv(xs[0], xs[1], xs[2]) + eps * torch.exp(0.5 * lv).clamp(min=1e-6)
+    ref.backward(up.double())
     assert rel_l2(out, ref) < 1e-5
     for a_, b_ in zip(got, xs):
         assert rel_l2(a_, b_.grad) < 2e-5

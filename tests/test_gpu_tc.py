@@ -25,15 +25,19 @@ def eng(stage, engine, h, w, m1, m2, b, ci, co):
 
 
 def torch_local_reference(x, wm, bm, wl, bl, seed, sidx, site, up, batch_offset=0):
-    """out and gradients of the local branch by torch autograd with the kernels' own noise (independent of every kernel here)."""
+    """out and gradients of the local branch by torch autograd in FLOAT64 with the kernels' own noise (independent of every
+    kernel here; fp64 because cuDNN / cuBLAS fp32 convolutions may run in TF32)."""
     from pno_physics_bench_b200 import functional as F_
-    xs = [None if t is None else t.detach().clone().requires_grad_(True) for t in (x, wm, bm, wl, bl)]
-    out = torch.nn.functional.conv2d(xs[0], xs[1], xs[2])
+    xs = [None if t is None else t.detach().double().requires_grad_(True) for t in (x, wm, bm, wl, bl)]
+
+    def conv(inp, w, b):
+        return torch.einsum("oi,bihw->bohw", w.reshape(w.shape[0], w.shape[1]), inp) + b.view(1, -1, 1, 1)
+    out = conv(xs[0], xs[1], xs[2])
     if wl is not None:
-        eps = F_.materialize_activation_noise(seed, sidx, site, out.shape, batch_offset)
-        lv = torch.clamp(torch.nn.functional.conv2d(xs[0], xs[3], xs[4]), -10, 10)
+        eps = F_.materialize_activation_noise(seed, sidx, site, out.shape, batch_offset).double()
+        lv = torch.clamp(conv(xs[0], xs[3], xs[4]), -10, 10)
         out = out + eps * torch.exp(0.5 * lv).clamp(min=1e-6)
-    out.backward(up)
+    out.backward(up.double())
     return out.detach(), [None if t is None else t.grad for t in xs]
 
 
@@ -482,3 +486,97 @@ def test_local_branch_wide_tile_variant(monkeypatch):
                                  bl.data_ptr(), 5, 1, 2, 0, ref.data_ptr(), 0, _lib.stream_ptr()))
     assert rel_l2(outs[0], ref) < 5e-3 and rel_l2(outs[1], ref) < 5e-3
     assert rel_l2(outs[1], outs[0]) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# two-pass tensor-core transforms (grids beyond the fused kernels: 256-row images; fp32-parity engine at 128x128 / 32 modes)
+# ----------------------------------------------------------------------------------------------------------------------
+def _fft_reference(x, m1, m2):
+    b, c, h, w = x.shape
+    xf = torch.fft.rfft2(x.double())
+    want = torch.cat([xf[:, :, :m1, :m2], xf[:, :, h - m1:, :m2]], dim=2)          # [b,c,2m1,m2]
+    return want.permute(2, 3, 0, 1).reshape(2 * m1 * m2, b, c)
+
+
+def _ifft_reference(yr, yi, h, w, m1, m2):
+    m, b, c = yr.shape
+    yh = torch.complex(yr.double(), yi.double()).reshape(2 * m1, m2, b, c).permute(2, 3, 0, 1)
+    full = torch.zeros(b, c, h, w // 2 + 1, dtype=torch.complex128, device=yr.device)
+    full[:, :, :m1, :m2] = yh[:, :, :m1]
+    full[:, :, h - m1:, :m2] = yh[:, :, m1:]
+    return torch.fft.irfft2(full, s=(h, w))
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("shape,forced", [((2, 16, 256, 256, 48, 48), False), ((1, 8, 256, 128, 20, 33), False),
+                                          ((3, 8, 128, 128, 32, 32), True), ((2, 4, 128, 64, 17, 20), True),
+                                          ((1, 5, 128, 96, 64, 24), True)])
+def test_two_pass_transforms_against_fft(engine, tol, shape, forced, monkeypatch):
+    """Forward and inverse two-pass transforms (k_tc_rowgemm + k_tc_local<EPI=1> + the spectrum transpositions) against torch.fft in
+    fp64; `forced` shapes are also tiled by the fused kernels and take the two-pass path through PNO_DFT_TWOPASS=1."""
+    b, c, h, w, m1, m2 = shape
+    if forced:
+        monkeypatch.setenv("PNO_DFT_TWOPASS", "1")
+    assert _lib.engine_supports("dft_fwd", engine, h, w, m1, m2, b, c, c) and _lib.engine_supports("dft_inv", engine, h, w, m1, m2, b, c, c)
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(b, c, h, w, generator=gen).to(DEV)
+    want = _fft_reference(x, m1, m2)
+    for gs in (0, 1):
+        tr, ti = _dft_fwd(x, m1, m2, engine, gs)
+        if gs == 0:
+            assert rel_l2(torch.complex(tr.double(), ti.double()), want) < max(tol, 5e-7)
+        else:       # adjoint scaling = alive * c_ky / (HW): compare with the CUDA-core engine
+            rr, ri = _dft_fwd(x, m1, m2, "fp32", gs)
+            assert rel_l2(tr, rr) < max(tol, 2e-6) and rel_l2(ti, ri) < max(tol, 2e-6)
+    m = 2 * m1 * m2
+    yr = torch.randn(m, b, c, generator=gen).to(DEV)
+    yi = torch.randn(m, b, c, generator=gen).to(DEV)
+    add = torch.randn(b, c, h, w, generator=gen).to(DEV)
+    if 2 * m1 <= h:                                     # no overlapping rows: irfft2 of the scattered spectrum is the reference
+        out, _ = _dft_inv(yr, yi, h, w, m1, m2, engine, 0, None, 0)
+        # irfft2 ignores the imaginary part of the self-conjugate columns exactly as the kernels do
+        assert rel_l2(out, _ifft_reference(yr, yi, h, w, m1, m2)) < max(tol, 5e-7)
+    for adjoint, addend, act in ((1, None, 0), (0, add, 1), (0, add, 2)):
+        ref, ref_pre = _dft_inv(yr, yi, h, w, m1, m2, "fp32", adjoint, addend, act, True)
+        out, pre = _dft_inv(yr, yi, h, w, m1, m2, engine, adjoint, addend, act, True)
+        assert rel_l2(out, ref) < max(tol, 2e-6) and rel_l2(pre, ref_pre) < max(tol, 2e-6), (adjoint, act, rel_l2(out, ref))
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 2e-2)])
+def test_cfg5_shaped_layer_against_oracle(engine, tol):
+    """A sampled spectral layer at the BASELINE config-5 grid (256 x 256, 48 modes; 128 channels, batch 2) against the oracle:
+    forward and every gradient, all stages on the tensor cores (strict engine)."""
+    import pno_physics_bench_b200 as pno
+    from pno_physics_bench_b200 import functional as F_
+    from oracle import pno_oracle as orc
+    B, C, H, m = 2, 128, 256, 48
+    gen = torch.Generator().manual_seed(55)
+    torch.manual_seed(55)
+    layer = pno.SpectralConv2d_Probabilistic(C, C, m, m, engine=engine)
+    with torch.no_grad():
+        for w_, lv in ((layer.weights1, layer.weights1_log_var), (layer.weights2, layer.weights2_log_var)):
+            w_.copy_(torch.complex(torch.randn(w_.shape, generator=gen), torch.randn(w_.shape, generator=gen)) / (2 * C) ** 0.5)
+            lv.copy_(torch.rand(lv.shape, generator=gen) * 4 - 10)
+    layer.noise_site = 7
+    x = torch.randn(B, C, H, H, generator=gen)
+    up = torch.randn(B, C, H, H, generator=gen)
+    p = {k: v.detach().clone().contiguous().requires_grad_(True) for k, v in layer.state_dict().items()}
+    layer = layer.to(DEV).train()
+    xg = x.to(DEV).requires_grad_(True)
+    c0 = _lib.stage_counts()
+    with pno.noise_scope(17, 2):
+        y = layer(xg, sample=True)
+    y.backward(up.to(DEV))
+    counts = _lib.tensor_core_calls(c0)
+    for st in ("dft_fwd", "mix_fwd", "dft_inv", "mix_bwd_dx", "mix_bwd_dw"):
+        assert counts[st][0] == 0 and counts[st][1] > 0, (st, counts[st])
+    re, im = F_.materialize_spectral_noise(17, 2, 7, C, C, m, m)
+    xo = x.clone().requires_grad_(True)
+    yo = orc.spectral_layer(xo, p, "", orc.InjectedNoise({7: (re.cpu(), im.cpu())}), site=7)
+    yo.backward(up)
+    errs = {"y": rel_l2(y, yo), "dx": rel_l2(xg.grad, xo.grad)}
+    for k, v in layer.named_parameters():
+        errs["d" + k] = rel_l2(v.grad, p[k].grad)
+    print(f"\n[cfg5_layer | {engine}] " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < (tol if engine == "tf32" else 2 * tol), (k, v)
