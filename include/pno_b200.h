@@ -155,6 +155,21 @@ int pno_mix_bwd_dw(const pno_plan_t* plan, int engine, const float* xhat_re, con
                    const float* ghat_im, int B, int Ci, int Co, const float* lv1, const float* lv2, uint64_t seed,
                    uint32_t sample_idx, uint32_t site, float* dmu1, float* dmu2, float* dlv1, float* dlv2, void* stream);
 
+/* Mode windows: the same three kernels on global modes [mode_first, mode_first + mode_count) only (a range inside ONE weight
+ * block, i.e. not crossing mode m1*m2) for MODE-PARALLEL sharding of the spectral weights across GPUs: each
+ * rank keeps the weights / log-variances / gradients / optimiser state of its own modes.  The spectra are [mode_count][B][C]
+ * (local mode index), mu / lv / dmu / dlv are [mode_count][Ci][Co] shards, the Philox counters use the GLOBAL mode index, so the
+ * sharded model draws exactly the weights of the unsharded one.  Tensor-core engines only (PNO_E_UNSUPPORTED otherwise). */
+int pno_mix_fwd_window(const pno_plan_t* plan, int engine, const float* xhat_re, const float* xhat_im, int B, int Ci, int Co,
+                       const float* mu, const float* lv, uint64_t seed, uint32_t sample_idx, uint32_t site, int mode_first,
+                       int mode_count, float* yhat_re, float* yhat_im, void* stream);
+int pno_mix_bwd_dx_window(const pno_plan_t* plan, int engine, const float* ghat_re, const float* ghat_im, int B, int Ci, int Co,
+                          const float* mu, const float* lv, uint64_t seed, uint32_t sample_idx, uint32_t site, int mode_first,
+                          int mode_count, float* dxhat_re, float* dxhat_im, void* stream);
+int pno_mix_bwd_dw_window(const pno_plan_t* plan, int engine, const float* xhat_re, const float* xhat_im, const float* ghat_re,
+                          const float* ghat_im, int B, int Ci, int Co, const float* lv, uint64_t seed, uint32_t sample_idx,
+                          uint32_t site, int mode_first, int mode_count, float* dmu, float* dlv, void* stream);
+
 /* ---- whole layer / block --------------------------------------------------------------------------------------- */
 /* SpectralConv2d(_Probabilistic).forward (models.py:37-50, 82-98) with the PNO-block epilogue fused
  * (models.py:306): y = act(spectral(x) + addend).  addend may be NULL and act PNO_ACT_NONE for the bare layer.

@@ -53,6 +53,10 @@ SIGNATURES = {
                               _vp]),
     "pno_mix_bwd_dw": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _u64, _u32, _u32, _vp, _vp,
                               _vp, _vp, _vp]),
+    "pno_mix_fwd_window": (_int, [_vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _u64, _u32, _u32, _int, _int, _vp, _vp, _vp]),
+    "pno_mix_bwd_dx_window": (_int, [_vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _u64, _u32, _u32, _int, _int, _vp, _vp, _vp]),
+    "pno_mix_bwd_dw_window": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _u64, _u32, _u32, _int, _int, _vp, _vp,
+                                     _vp]),
     "pno_spectral_fwd": (_int, [_vp, _int, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _vp, _int, _vp,
                                 _vp, _vp, _vp]),
     "pno_spectral_bwd": (_int, [_vp, _int, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _vp,

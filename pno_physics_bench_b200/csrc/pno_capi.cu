@@ -284,6 +284,51 @@ extern "C" int pno_mix_bwd_dw(const pno_plan_t* p, int engine, const float* xr, 
                     });
 }
 
+// ---- mode windows (mode-parallel sharding of the spectral weights): tensor-core engines only ----
+static int check_window(const pno_plan* p, int engine, const char* who) {
+    if (!p) PNO_FAIL(PNO_E_INVALID, "%s: null plan", who);
+    const int eng = engine & 0xFF;
+    if (eng != PNO_ENGINE_TC_TF32X3 && eng != PNO_ENGINE_TC_TF32)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "%s: mode windows run on the tensor-core engines (tf32x3 / tf32) only", who);
+    return PNO_OK;
+}
+
+extern "C" int pno_mix_fwd_window(const pno_plan_t* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co,
+                                  const float* mu, const float* lv, uint64_t seed, uint32_t sample_idx, uint32_t site,
+                                  int mode_first, int mode_count, float* yr, float* yi, void* stream) {
+    int rc = check_window(p, engine, "pno_mix_fwd_window");
+    if (rc) return rc;
+    if (!xr || !xi || !mu || !yr || !yi || mode_count < 1) PNO_FAIL(PNO_E_INVALID, "pno_mix_fwd_window: bad arguments");
+    rc = tc_mix_fwd(p, engine & 0xFF, xr, xi, B, Ci, Co, mu, mu, lv, lv, make_key(seed, sample_idx, site), yr, yi, as_stream(stream),
+                    mode_first, mode_count);
+    if (rc == PNO_OK) ++g_stage_counts[PNO_STAGE_MIX_FWD][1];
+    return rc;
+}
+
+extern "C" int pno_mix_bwd_dx_window(const pno_plan_t* p, int engine, const float* gr, const float* gi, int B, int Ci, int Co,
+                                     const float* mu, const float* lv, uint64_t seed, uint32_t sample_idx, uint32_t site,
+                                     int mode_first, int mode_count, float* dxr, float* dxi, void* stream) {
+    int rc = check_window(p, engine, "pno_mix_bwd_dx_window");
+    if (rc) return rc;
+    if (!gr || !gi || !mu || !dxr || !dxi || mode_count < 1) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dx_window: bad arguments");
+    rc = tc_mix_bwd_dx(p, engine & 0xFF, gr, gi, B, Ci, Co, mu, mu, lv, lv, make_key(seed, sample_idx, site), dxr, dxi,
+                       as_stream(stream), mode_first, mode_count);
+    if (rc == PNO_OK) ++g_stage_counts[PNO_STAGE_MIX_BWD_DX][1];
+    return rc;
+}
+
+extern "C" int pno_mix_bwd_dw_window(const pno_plan_t* p, int engine, const float* xr, const float* xi, const float* gr,
+                                     const float* gi, int B, int Ci, int Co, const float* lv, uint64_t seed, uint32_t sample_idx,
+                                     uint32_t site, int mode_first, int mode_count, float* dmu, float* dlv, void* stream) {
+    int rc = check_window(p, engine, "pno_mix_bwd_dw_window");
+    if (rc) return rc;
+    if (!xr || !xi || !gr || !gi || !dmu || mode_count < 1) PNO_FAIL(PNO_E_INVALID, "pno_mix_bwd_dw_window: bad arguments");
+    rc = tc_mix_bwd_dw(p, engine & 0xFF, xr, xi, gr, gi, B, Ci, Co, lv, lv, make_key(seed, sample_idx, site), dmu, dmu, dlv, dlv,
+                       as_stream(stream), mode_first, mode_count);
+    if (rc == PNO_OK) ++g_stage_counts[PNO_STAGE_MIX_BWD_DW][1];
+    return rc;
+}
+
 extern "C" int pno_spectral_fwd(const pno_plan_t* p, int engine, const float* x, int B, int Ci, int Co, const float* mu1,
                                 const float* mu2, const float* lv1, const float* lv2, uint64_t seed, uint32_t sample_idx,
                                 uint32_t site, const float* addend, int act, float* y, float* pre_act, void* workspace,

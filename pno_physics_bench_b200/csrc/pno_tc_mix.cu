@@ -40,6 +40,9 @@ struct MixGeom {
     int x_tile;        // B * 128 bytes
     int stage_bytes, stages, smem_bytes;
     int raw_off, raw_bytes;       // RAW mode: two staging buffers [mu 32 KB][log_var 16 KB] behind the operand stages
+    // mode window (mode-parallel sharding): the launch covers global modes [mode_first, mode_first + n_modes) of ONE weight block;
+    // spectra are indexed by the LOCAL mode, the Philox counters by the GLOBAL one, the weight arrays by (mode in block - w_sub)
+    int mode_first, w_sub;
     const float *mu1, *mu2, *lv1, *lv2;
     float *yr, *yi;
     PhiloxKey key;
@@ -104,7 +107,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 for (int kb = 0; kb < g.KB; ++kb) {
                     if (RAW) {
                         // weight tiles of this k-block: rows = reduction-side... forward: 32 i rows x 128 o; backward: 128 i rows x 32 o
-                        const int ot = item - mode * g.o_tiles, blk = mode >= g.m1m2, mb = mode - blk * g.m1m2;
+                        const int gm = mode + g.mode_first;
+                        const int ot = item - mode * g.o_tiles, blk = gm >= g.m1m2, mb = gm - blk * g.m1m2 - g.w_sub;
                         const int row0 = mb * g.Ci + (BWD ? ot * TM : kb * TK), col0 = BWD ? kb * TK : ot * TM;
                         mbar_wait(&bar_rawempty[rs], rph ^ 1);
                         unsigned char* rw = smem + g.raw_off + (size_t)rs * g.raw_bytes;
@@ -203,12 +207,13 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         const float* lv_n = nullptr;
         uint64_t quad_n = 0;
         auto locate = [&](int item, int kb) {
-            const int mode = item / g.o_tiles, ot = item - mode * g.o_tiles;
+            const int lmode = item / g.o_tiles, ot = item - lmode * g.o_tiles;
+            const int mode = lmode + g.mode_first;                            // global mode: block and Philox counters
             const int blk = mode >= g.m1m2;
             const int mb = mode - blk * g.m1m2;
             const int i0 = BWD ? ot * TM + iq * 4 : kb * TK + iq * 4;         // first of this thread's 4 consecutive i
             const int o0 = BWD ? kb * TK + 2 * p : ot * TM + 2 * p;           // its (even) output channel
-            const size_t base = ((size_t)mb * g.Ci + i0) * g.Co + o0;
+            const size_t base = ((size_t)(mb - g.w_sub) * g.Ci + i0) * g.Co + o0;
             mu_n = (blk ? g.mu2 : g.mu1) + 2 * base;
             lv_n = SAMPLED ? (blk ? g.lv2 : g.lv1) + base : nullptr;
             quad_n = ((uint64_t)mode * g.Ci + i0) * g.Cop + (o0 >> 1);
@@ -365,7 +370,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
 // Shared launcher.  in_r / in_i: spectra [mode][b][KD] (KD = channels of the reduction side), out_r / out_i: [mode][b][MD].
 static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r, const float* in_i, int B, int Ci, int Co,
                       const float* mu1, const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* out_r,
-                      float* out_i, cudaStream_t st) {
+                      float* out_i, cudaStream_t st, int mode_first, int mode_count) {
     const int KD = bwd ? Co : Ci, MD = bwd ? Ci : Co;
     const char* who = bwd ? "tc_mix_bwd_dx" : "tc_mix_fwd";
     if (B < 1 || B > 128 || KD % TK || MD % TM || Co % 2)
@@ -379,6 +384,17 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     memset(&g, 0, sizeof(g));
     g.B = B; g.Bp = (B + 15) / 16 * 16; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
     g.MD = MD;
+    int w_rows_modes = g.m1m2;                  // modes held by each weight array
+    if (mode_count >= 0) {                      // mode window: [mode_first, mode_first + mode_count) inside one weight block
+        const int blk0 = mode_first >= g.m1m2;
+        if (mode_first < 0 || mode_count < 1 || mode_first + mode_count > (blk0 + 1) * g.m1m2)
+            PNO_FAIL(PNO_E_INVALID, "%s: mode window [%d, %d) must lie inside one weight block of %d modes", who, mode_first,
+                     mode_first + mode_count, g.m1m2);
+        g.n_modes = mode_count;
+        g.mode_first = mode_first;
+        g.w_sub = mode_first - blk0 * g.m1m2;
+        w_rows_modes = mode_count;
+    }
     g.o_tiles = MD / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = KD / TK;
     g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = out_r; g.yi = out_i; g.key = key;
     g.x_tile = g.Bp * 128;
@@ -403,7 +419,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     CUtensorMap tmXr, tmXi;
     int rc;
     {
-        const uint64_t dims[2] = {(uint64_t)KD, (uint64_t)p->M * B};
+        const uint64_t dims[2] = {(uint64_t)KD, (uint64_t)g.n_modes * B};
         const uint64_t str[1] = {(uint64_t)KD * 4};
         const uint32_t box[2] = {TK, (uint32_t)g.Bp};      // rows past mode*B + B: the next mode's rows, or zero fill past the end
         if ((rc = pno_encode_tmap(&tmXr, in_r, 2, dims, str, box, 1))) return rc;
@@ -412,7 +428,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     CUtensorMap tmMu1, tmMu2, tmLv1, tmLv2;
     memset(&tmMu1, 0, sizeof(tmMu1)); memset(&tmMu2, 0, sizeof(tmMu2)); memset(&tmLv1, 0, sizeof(tmLv1)); memset(&tmLv2, 0, sizeof(tmLv2));
     if (raw) {      // mu: [m1m2*Ci rows][2*Co floats], log_var: [m1m2*Ci rows][Co floats]; unswizzled boxes
-        const uint64_t rows = (uint64_t)g.m1m2 * Ci;
+        const uint64_t rows = (uint64_t)w_rows_modes * Ci;
         const uint64_t dmu[2] = {(uint64_t)2 * Co, rows}, dlv[2] = {(uint64_t)Co, rows};
         const uint64_t smu[1] = {(uint64_t)2 * Co * 4}, slv[1] = {(uint64_t)Co * 4};
         const uint32_t bmu[2] = {bwd ? 2u * TK : 2u * TM, bwd ? (uint32_t)TM : (uint32_t)TK};
@@ -449,12 +465,14 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
 }
 
 int tc_mix_fwd(const pno_plan* p, int engine, const float* xr, const float* xi, int B, int Ci, int Co, const float* mu1,
-               const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st) {
-    return mix_launch(p, engine, false, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, st);
+               const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* yr, float* yi, cudaStream_t st,
+               int mode_first, int mode_count) {
+    return mix_launch(p, engine, false, xr, xi, B, Ci, Co, mu1, mu2, lv1, lv2, key, yr, yi, st, mode_first, mode_count);
 }
 
 // dxhat[mode][b][i] = sum_o ghat[mode][b][o] * conj(W[mode][i][o])      (reference: autograd of models.py:33-35, 93-94)
 int tc_mix_bwd_dx(const pno_plan* p, int engine, const float* gr, const float* gi, int B, int Ci, int Co, const float* mu1,
-                  const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* dxr, float* dxi, cudaStream_t st) {
-    return mix_launch(p, engine, true, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, st);
+                  const float* mu2, const float* lv1, const float* lv2, PhiloxKey key, float* dxr, float* dxi, cudaStream_t st,
+                  int mode_first, int mode_count) {
+    return mix_launch(p, engine, true, gr, gi, B, Ci, Co, mu1, mu2, lv1, lv2, key, dxr, dxi, st, mode_first, mode_count);
 }

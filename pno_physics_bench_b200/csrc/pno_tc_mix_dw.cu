@@ -22,6 +22,7 @@ constexpr int kThreads = (2 + 4 + kEpiWarps) * 32;
 
 struct DwGeom {
     int B, Bp, Ci, Co, m1m2, Cop, n_modes;
+    int mode_first, w_sub;          // mode window (see MixGeom in pno_tc_mix.cu)
     int i_tiles, o_tiles, n_items;
     int tile_bytes, stage_bytes, stages;
     const float *lv1, *lv2;
@@ -160,10 +161,11 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
         for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n) {
             const int mode = item / per_mode, r = item - mode * per_mode;
             const int it = r / g.o_tiles, ot = r - it * g.o_tiles;
-            const int blk = mode >= g.m1m2, mb = mode - blk * g.m1m2;
+            const int gm = mode + g.mode_first;
+            const int blk = gm >= g.m1m2, mb = gm - blk * g.m1m2;
             const int i = it * TM + q * 32 + lane;
             const int o0 = ot * TM + cw * 32;
-            const size_t base = ((size_t)mb * g.Ci + i) * g.Co + o0;
+            const size_t base = ((size_t)(mb - g.w_sub) * g.Ci + i) * g.Co + o0;
             float* dmu = (blk ? g.dmu2 : g.dmu1);
             float* dlv = (blk ? g.dlv2 : g.dlv1);
             const float* lv = blk ? g.lv2 : g.lv1;
@@ -218,7 +220,7 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
 
 int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* xi, const float* gr, const float* gi, int B, int Ci,
                   int Co, const float* lv1, const float* lv2, PhiloxKey key, float* dmu1, float* dmu2, float* dlv1, float* dlv2,
-                  cudaStream_t st) {
+                  cudaStream_t st, int mode_first, int mode_count) {
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
     const bool sampled = lv1 != nullptr && dlv1 != nullptr;
     if (B < 1 || B > 128 || Ci % TM || Co % TM || !dmu1 || !dmu2)
@@ -232,6 +234,15 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
     DwGeom g;
     memset(&g, 0, sizeof(g));
     g.B = B; g.Bp = (B + 7) / 8 * 8; g.Ci = Ci; g.Co = Co; g.m1m2 = p->m1 * p->m2; g.Cop = (Co + 1) / 2; g.n_modes = p->M;
+    if (mode_count >= 0) {
+        const int blk0 = mode_first >= g.m1m2;
+        if (mode_first < 0 || mode_count < 1 || mode_first + mode_count > (blk0 + 1) * g.m1m2)
+            PNO_FAIL(PNO_E_INVALID, "tc_mix_bwd_dw: mode window [%d, %d) must lie inside one weight block of %d modes", mode_first,
+                     mode_first + mode_count, g.m1m2);
+        g.n_modes = mode_count;
+        g.mode_first = mode_first;
+        g.w_sub = mode_first - blk0 * g.m1m2;
+    }
     g.i_tiles = Ci / TM; g.o_tiles = Co / TM; g.n_items = g.n_modes * g.i_tiles * g.o_tiles;
     g.tile_bytes = TM * g.Bp * 4;
     g.stage_bytes = 4 * g.tile_bytes * (x3 ? 2 : 1);
@@ -244,7 +255,7 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
     CUtensorMap tmXr, tmXi, tmGr, tmGi;
     int rc;
     {   // [mode][b][c]: box = 32 channels x Bp batch rows of one mode; rows b >= B are out of bounds -> zero fill
-        const uint64_t dx[3] = {(uint64_t)Ci, (uint64_t)B, (uint64_t)p->M}, dg[3] = {(uint64_t)Co, (uint64_t)B, (uint64_t)p->M};
+        const uint64_t dx[3] = {(uint64_t)Ci, (uint64_t)B, (uint64_t)g.n_modes}, dg[3] = {(uint64_t)Co, (uint64_t)B, (uint64_t)g.n_modes};
         const uint64_t sx[2] = {(uint64_t)Ci * 4, (uint64_t)B * Ci * 4}, sg[2] = {(uint64_t)Co * 4, (uint64_t)B * Co * 4};
         const uint32_t box[3] = {32, (uint32_t)g.Bp, 1};
         if ((rc = pno_encode_tmap(&tmXr, xr, 3, dx, sx, box, 2))) return rc;

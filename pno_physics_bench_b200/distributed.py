@@ -91,7 +91,8 @@ class GradientSynchronizer:
 
     def __init__(self, params, group=None, large_bytes=4 << 20):
         self.group, self.large_bytes = group, large_bytes
-        self.params = [p for p in params if p.requires_grad]
+        # mode-sharded spectral parameters (mode_parallel.ModeParallelPNO) live on one rank each: nothing to average
+        self.params = [p for p in params if p.requires_grad and not getattr(p, "pno_mode_sharded", False)]
         self.pending, self.small = [], []
         self.enabled = True
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]

@@ -30,6 +30,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.max_grad_norm = max_grad_norm
         self.write_clipped_grads = write_clipped_grads      # leave .grad scaled like clip_grad_norm_ does (one more write)
         self._gsq = None
+        self.shard_group = None  # process group over which mode-sharded parameters (mode_parallel.py) are spread
         self._kl = {}            # id(param) -> 1 (spectral mean) / 2 (spectral log-variance)
         self._kl_gscale = None
 
@@ -81,7 +82,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     if t.stride() != p.stride() or t.dtype != p.dtype or t.device != p.device:
                         state[key] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(t)
                 work.append((group, state, pf, gf, _storage_order(_real(state["exp_avg"])),
-                             _storage_order(_real(state["exp_avg_sq"])), kind))
+                             _storage_order(_real(state["exp_avg_sq"])), kind, bool(getattr(p, "pno_mode_sharded", False))))
         if not work:
             return loss
         import ctypes
@@ -102,9 +103,28 @@ class FusedAdamW(torch.optim.Optimizer):
                 if self._gsq is None or self._gsq.device != dev:
                     self._gsq = torch.zeros(1, dtype=torch.float64, device=dev)
                 self._gsq.zero_()
-                # one launch: global gradient norm over every tensor (KL gradient of the spectral weights added on the fly)
-                _lib.check(lib.pno_sumsq_accumulate_multi(n, g_arr, ns, p_arr, kinds, kl_ptr, _lib.ptr(self._gsq), stream),
-                           "pno_sumsq_accumulate_multi")
+                import torch.distributed as dist
+                sharded = [k for k, w in enumerate(work) if w[7]]
+                spread = bool(sharded) and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.shard_group) > 1
+                if not spread:
+                    # one launch: global gradient norm over every tensor (KL gradient of the spectral weights added on the fly)
+                    _lib.check(lib.pno_sumsq_accumulate_multi(n, g_arr, ns, p_arr, kinds, kl_ptr, _lib.ptr(self._gsq), stream),
+                               "pno_sumsq_accumulate_multi")
+                else:
+                    # mode-sharded parameters: every rank holds different shards, so their squared norms are summed over the
+                    # group; the replicated parameters (identical, already averaged gradients) are counted once
+                    for idx, reduce_it in ((sharded, True), ([k for k in range(n) if not work[k][7]], False)):
+                        if not idx:
+                            continue
+                        acc = torch.zeros(1, dtype=torch.float64, device=dev)
+                        c = len(idx)
+                        pick = lambda arr, typ: (typ * c)(*[arr[k] for k in idx])      # noqa: E731
+                        _lib.check(lib.pno_sumsq_accumulate_multi(c, pick(g_arr, ctypes.c_void_p), pick(ns, ctypes.c_uint64),
+                                                                  pick(p_arr, ctypes.c_void_p), pick(kinds, ctypes.c_int), kl_ptr,
+                                                                  _lib.ptr(acc), stream), "pno_sumsq_accumulate_multi")
+                        if reduce_it:
+                            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.shard_group)
+                        self._gsq += acc
             # one launch per run of tensors that share hyper-parameters and step count (normally: one launch)
             start = 0
             while start < n:

@@ -48,6 +48,8 @@ class PNOTrainer:
         _, ws = world(group)
         # data parallel: gradient all-reduces are launched from autograd hooks while backward is still running
         self.grad_sync = GradientSynchronizer(self.model.parameters(), group) if ws > 1 else None
+        if isinstance(self.optimizer, FusedAdamW):
+            self.optimizer.shard_group = group          # norm of mode-sharded parameters (mode_parallel.py) is summed over the group
 
     # ------------------------------------------------------------------------------------------------------------------
     def train_step(self, inputs, targets, batch_offset: int = 0) -> Dict[str, torch.Tensor]:

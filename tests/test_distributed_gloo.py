@@ -76,6 +76,17 @@ def _worker(rank, world, port, out):
         res["hook_b"] = float((b.grad - 2.5).abs().max())
         res["hook_unused"] = unused.grad is None
         sync.remove()
+        # --- mode-parallel exchanges: [all modes, local batch] <-> [my modes, global batch] and back
+        from pno_physics_bench_b200 import mode_parallel as MP
+        M, Bl, C = 12, 3, 5
+        gspec = torch.randn(2, M, world * Bl, C, generator=torch.Generator().manual_seed(11))      # the global spectrum (both planes)
+        mine = gspec[:, :, rank * Bl:(rank + 1) * Bl].contiguous()
+        sh = MP.modes_from_batch(mine)
+        n = M // world
+        res["a2a_fwd"] = float((sh - gspec[:, rank * n:(rank + 1) * n]).abs().max())
+        back = MP.batch_from_modes(sh)
+        res["a2a_back"] = float((back - mine).abs().max())
+        res["windows"] = MP.mode_windows(3, 2, rank, world)
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -94,3 +105,5 @@ def test_world_size_2_gloo():
         assert r["mean_err"] < 1e-12 and r["std_err"] < 1e-12
         assert r["gw"] < 1e-6 and r["glv"] < 1e-6 and r["gcw"] < 1e-6 and r["gnone"] is True
         assert r["hook_a"] < 1e-6 and r["hook_b"] < 1e-6 and r["hook_unused"] is True
+        assert r["a2a_fwd"] == 0.0 and r["a2a_back"] == 0.0
+    assert r0["windows"] == [(0, 6)] and r1["windows"] == [(6, 6)]

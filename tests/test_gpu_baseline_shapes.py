@@ -198,6 +198,20 @@ def test_graph_replay_is_bit_identical_to_the_eager_loop(cfg3_mc_case):
 # ----------------------------------------------------------------------------------------------------------------------
 # (c) cfg-2 trainer step
 # ----------------------------------------------------------------------------------------------------------------------
+def _oracle_cfg2_data_grads(p, x, tgt, table, kl_weight, dtype):
+    """loss dict and data-term gradients of the cfg-2 step on the oracle in `dtype` (KL detached: the fused optimiser path adds
+    the analytic KL gradient itself, so `.grad` of the product holds the data term)."""
+    cd = torch.complex128 if dtype == torch.float64 else torch.complex64
+    q = {k: (v.detach().to(cd) if v.is_complex() else v.detach().to(dtype)).requires_grad_(True) for k, v in p.items()}
+    tab = {k: (tuple(t.to(dtype) for t in v) if isinstance(v, tuple) else v.to(dtype)) for k, v in table.items()}
+    h = orc.pno_forward(q, x.to(dtype), orc.InjectedNoise(tab), True, True, "gelu", features_only=True)
+    mean = orc.conv1x1(h, q["project_mean.weight"], q["project_mean.bias"])
+    lv = torch.clamp(orc.conv1x1(h, q["project_log_var.weight"], q["project_log_var.bias"]), -10, 10)
+    ref = orc.elbo_loss((mean, lv), tgt.to(dtype), kl=orc.pno_kl(q).detach(), kl_weight=kl_weight)
+    ref["total"].backward()
+    return {k: v.detach() for k, v in ref.items()}, {k: v.grad for k, v in q.items()}
+
+
 @pytest.fixture(scope="module")
 def cfg2_step_case():
     B, hid, L, m, hw = 32, 256, 4, 20, 64
@@ -206,38 +220,33 @@ def cfg2_step_case():
     x = torch.randn(B, 3, hw, hw, generator=gen)
     tgt = torch.randn(B, 1, hw, hw, generator=gen)
     seed, kl_weight = 77, 1e-4
-    p = {k: v.detach().clone().contiguous().requires_grad_(True) for k, v in model.state_dict().items()}
+    p = {k: v.detach().clone().contiguous() for k, v in model.state_dict().items()}
     torch.set_num_threads(os.cpu_count() or 8)
     table = noise_table(seed, 0, B, hid, L, m, hw)
-    h = orc.pno_forward(p, x, orc.InjectedNoise(table), True, True, "gelu", features_only=True)
-    mean = orc.conv1x1(h, p["project_mean.weight"], p["project_mean.bias"])
-    lv = torch.clamp(orc.conv1x1(h, p["project_log_var.weight"], p["project_log_var.bias"]), -10, 10)
-    kl = orc.pno_kl(p)
-    ref = orc.elbo_loss((mean, lv), tgt, kl=kl.detach(), kl_weight=kl_weight)      # KL detached: .grad = data-term gradient,
-    ref["total"].backward()                                                        # which is what the fused optimiser path keeps
-    del table, h
-    data_grads = {k: (None if v.grad is None else v.grad.clone()) for k, v in p.items()}
+    losses, data_grads = _oracle_cfg2_data_grads(p, x, tgt, table, kl_weight, torch.float32)
+    # the same step in fp64: the yardstick for "how far may two correct fp32 implementations be apart" on these gradients
+    _, grads64 = _oracle_cfg2_data_grads(p, x, tgt, table, kl_weight, torch.float64)
+    del table
     # full gradient = data term + kl_weight * dKL (analytic, models.py:100-104), then clip(1.0) + AdamW(1e-3, wd 1e-4)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
     with torch.no_grad():
-        for k, v in p.items():
-            if v.grad is None:
-                v.grad = torch.zeros_like(v)
+        for k, v in q.items():
+            v.grad = torch.zeros_like(v) if data_grads[k] is None else data_grads[k].clone()
             if k.endswith("_log_var") and "fourier" in k:
                 v.grad += kl_weight * (-0.5 * (1 - torch.exp(v)))
             elif "fourier" in k:
                 v.grad += kl_weight * v
-    opt = torch.optim.AdamW(p.values(), lr=1e-3, weight_decay=1e-4)
-    torch.nn.utils.clip_grad_norm_(p.values(), 1.0)
+    opt = torch.optim.AdamW(q.values(), lr=1e-3, weight_decay=1e-4)
+    torch.nn.utils.clip_grad_norm_(q.values(), 1.0)
     opt.step()
-    losses = {k: v.detach().clone() for k, v in ref.items()}
-    return model, x, tgt, seed, kl_weight, losses, data_grads, {k: v.detach() for k, v in p.items()}
+    return model, x, tgt, seed, kl_weight, losses, data_grads, grads64, {k: v.detach() for k, v in q.items()}
 
 
 @pytest.mark.parametrize("engine", ["tf32x3", "tf32"])
 def test_cfg2_trainer_step_against_oracle(cfg2_step_case, engine):
     import copy
     from pno_physics_bench_b200.training import PNOTrainer
-    model0, x, tgt, seed, kl_weight, losses_ref, grads_ref, params_ref = cfg2_step_case
+    model0, x, tgt, seed, kl_weight, losses_ref, grads_ref, grads64, params_ref = cfg2_step_case
     model = copy.deepcopy(model0)
     model.set_engine(engine)                                   # strict
     trainer = PNOTrainer(model, device=DEV, seed=seed, kl_weight=kl_weight)
@@ -246,20 +255,29 @@ def test_cfg2_trainer_step_against_oracle(cfg2_step_case, engine):
     torch.cuda.synchronize()
     counts = _lib.tensor_core_calls(c0)
     errs = {"total": rel_l2(losses["total"], losses_ref["total"]), "kl": rel_l2(losses["kl"], losses_ref["kl"])}
-    gerrs = {}
+    gerrs, g_ours64, g_ref64 = {}, {}, {}
     for k, v in model.named_parameters():
         g = grads_ref[k]
         if g is not None and float(g.abs().max()) > 0:
-            gerrs["d" + k] = rel_l2(v.grad, g)
+            gerrs["d" + k] = rel_l2(v.grad, g)                  # ours vs the reference algorithm in fp32
+            g_ours64["d" + k] = rel_l2(v.grad, grads64[k])      # ours vs the same algorithm in fp64
+            g_ref64["d" + k] = rel_l2(g, grads64[k])            # the fp32 reference vs fp64: the conditioning of this gradient
     perrs = {"p:" + k: rel_l2(v, params_ref[k]) for k, v in model.state_dict().items()}
     worst_g = max(gerrs, key=gerrs.get)
     worst_p = max(perrs, key=perrs.get)
-    report("cfg2_train_step", engine, dict(errs, **{"worst grad " + worst_g: gerrs[worst_g], "worst param " + worst_p: perrs[worst_p]},
-                                         **gerrs), counts)
+    report("cfg2_train_step", engine,
+           dict(errs, **{"worst grad vs oracle fp32 (" + worst_g + ")": gerrs[worst_g], "worst grad vs oracle fp64": max(g_ours64.values()),
+                         "worst oracle fp32 vs fp64": max(g_ref64.values()), "worst param " + worst_p: perrs[worst_p]}, **gerrs), counts)
     assert_tensor_cores(counts, ["dft_fwd", "mix_fwd", "dft_inv", "local_fwd", "mix_bwd_dx", "mix_bwd_dw", "local_bwd"])
     assert errs["total"] < TOL[engine] and errs["kl"] < 1e-6
     for k, v in gerrs.items():
-        assert v < GTOL[engine], (k, v)
+        if engine == "tf32":
+            assert v < GTOL[engine], (k, v)
+        else:
+            # fp32 parity: within 1e-5 of the fp32 reference, or -- where the gradient itself is conditioned worse than that in
+            # fp32 (backward through 4 blocks, reductions over 131 072 pixels x 32 fields) -- as close to the fp64 value as the
+            # fp32 reference is, up to a factor 2
+            assert v < 1e-5 or g_ours64[k] < 2 * g_ref64[k] + 1e-6, (k, v, g_ours64[k], g_ref64[k])
     for k, v in perrs.items():
         assert v < (1e-4 if engine == "tf32x3" else 2e-2), (k, v)
 

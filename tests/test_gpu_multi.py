@@ -31,3 +31,18 @@ def test_sample_sharding_over_nccl_is_invariant():
     r = _torchrun([os.path.join(ROOT, "tools", "mc_shard_check.py")])
     assert r.returncode == 0, r.stderr[-2000:]
     assert "MC_SHARD_OK" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_mode_parallel_step_equals_the_unsharded_step():
+    r = _torchrun([os.path.join(ROOT, "tools", "mp_train_check.py")])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MP_CHECK_OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_mode_parallel_on_one_rank_equals_the_model():
+    """The mode-window kernels on one GPU (two windows = the two weight blocks): same step as the unsharded model."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mp_train_check.py")], cwd=ROOT, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MP_CHECK_OK" in r.stdout, r.stdout[-2000:]

