@@ -419,8 +419,7 @@ def other_configs(device, engine):
                 "ms_sampled_forward": round(ms_fwd, 2), "ms_fwd_bwd": round(ms_step, 2),
                 "cuda_core_stages": [s for s, (a, b) in calls.items() if a > 0 and s not in ("local_fwd",)]}
 
-    guarded("cfg1", cfg1)
-    guarded("cfg2", cfg2)
+    guarded("cfg1", cfg1)          # (cfg 2 = the `train_cfg2` legs of the main line)
     guarded("cfg4", cfg4)
     guarded("cfg5", cfg5)
     return out
@@ -440,6 +439,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--mc-samples-total", type=int, default=100, help="total MC samples per step with --scaling strong (config 3: 100)")
     ap.add_argument("--workload", default="mc_cfg3", choices=["mc_cfg3", "train_cfg2"])
+    ap.add_argument("--parallel", default="dp", choices=["dp", "mp"], help="train_cfg2: data parallel or mode parallel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (other configs, reference on cuda, tf32)")
     ap.add_argument("--eager", action="store_true", help="run the MC loop eagerly instead of replaying the captured CUDA graph")
@@ -570,11 +570,21 @@ def main():
     ms_step = ms_total / args.steps
     value = fields / (ms_step * 1e-3)
     e2e_value = fields / (ms_e2e / args.steps * 1e-3)
-    base = others = refgpu = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    base = others = refgpu = train = None
+    if not args.no_extras:
         del model
         graphs._MC_GRAPHS.clear()
         torch.cuda.empty_cache()
+        # BASELINE config 2 on the same N GPUs: data-parallel and mode-parallel trainer steps (weak scaling, batch 32 per GPU)
+        train = {}
+        for par in ("dp", "mp"):
+            try:
+                train[par] = train_leg(args.engine, par, device, rank, world, timed, args.steps, 2)
+            except Exception as e:                                   # noqa: BLE001
+                train[par] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise
+    if rank == 0 and world == 1 and not args.no_extras:
         others = other_configs(device, args.engine)
         refgpu = ref_cuda(device)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -597,21 +607,25 @@ def main():
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": mean_host.numel() * 8},
                 "roofline": roof, "clocks_kernels": clocks.summary("end", "kernels_end"), "cpu_baseline": base,
-                "reduced_precision": reduced, "strong_scaling": strong_line, "other_configs": others, "ref_cuda": refgpu}
+                "reduced_precision": reduced, "strong_scaling": strong_line, "train_cfg2": train, "other_configs": others, "ref_cuda": refgpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_train(args, device, rank, world, local, timed):
-    """--workload train_cfg2: one data-parallel PNOTrainer step (BASELINE config 2) per GPU-batch of 32 as the timed step."""
-    import torch.distributed as dist
+def train_leg(engine, parallel, device, rank, world, timed, steps, warmup):
+    """One PNOTrainer step of BASELINE config 2 (batch 32 per GPU) as the timed step.  parallel = "dp": data parallel (replicated
+    weights, per-parameter gradient all-reduce overlapped with backward); "mp": mode parallel (spectral weights sharded by modes,
+    spectrum all-to-alls; mode_parallel.py)."""
     import pno_physics_bench_b200 as pno
     from pno_physics_bench_b200 import _lib
     from pno_physics_bench_b200.training import ELBOLoss, PNOTrainer
     lib = _lib.load()
     torch.manual_seed(0)
-    model = pno.ProbabilisticNeuralOperator(3, 256, 4, 20, engine=args.engine)
+    model = pno.ProbabilisticNeuralOperator(3, 256, 4, 20, engine=engine)
+    if parallel == "mp":
+        from pno_physics_bench_b200.mode_parallel import ModeParallelPNO
+        model = ModeParallelPNO(model, engine=engine)
     trainer = PNOTrainer(model, ELBOLoss(kl_weight=1e-4), device=str(device), seed=1)
     Bl = 32
     torch.manual_seed(1 + rank)
@@ -626,26 +640,43 @@ def run_train(args, device, rank, world, local, timed):
         losses = trainer.train_step(x_host, y_host, batch_offset=rank * Bl)
         loss_host.copy_(losses["total"].detach().float(), non_blocking=True)
 
+    for i in range(warmup):
+        resident(i)
+    l0 = lib.pno_launch_count()
+    ms = timed(resident, steps) / steps
+    launches = lib.pno_launch_count() - l0
+    ms_e = timed(e2e, steps) / steps
+    mem = torch.cuda.max_memory_allocated(device) / 2 ** 30
+    if trainer.grad_sync is not None:
+        trainer.grad_sync.remove()
+    del trainer, model
+    torch.cuda.empty_cache()
+    return {"parallel": parallel, "engine": engine, "value": round(world * Bl / ms * 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 3),
+            "e2e_value": round(world * Bl / ms_e * 1e3, 2), "batch_per_gpu": Bl, "gpu_launches": int(launches),
+            "peak_mem_gib": round(mem, 2), "h2d_bytes_per_step": (x_host.numel() + y_host.numel()) * 4, "d2h_bytes_per_step": 4}
+
+
+def run_train(args, device, rank, world, local, timed):
+    """--workload train_cfg2 [--parallel dp|mp]: the data- or mode-parallel trainer step as the headline of the line."""
+    import torch.distributed as dist
     with ClockSampler(local) as clocks:
-        for i in range(args.warmup):
-            resident(i)
-        l0 = lib.pno_launch_count()
         clocks.mark("start")
-        ms = timed(resident, args.steps) / args.steps
-        launches = lib.pno_launch_count() - l0
-        ms_e = timed(e2e, args.steps) / args.steps
+        leg = train_leg(args.engine, args.parallel, device, rank, world, timed, args.steps, args.warmup)
         clocks.mark("end")
     if rank == 0:
-        line = {"metric": "PNOTrainer fields/sec at 64^2 hid256 modes20 (one ELBO step: fwd, bwd, clip, AdamW)", "value": round(world * Bl / ms * 1e3, 2),
-                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.engine, "data": "synthetic",
-                "config": {"workload": f"cfg2: PNOTrainer.train_step 64x64 in3 hid256 L4 modes20, batch {Bl} per GPU (global {Bl * world})",
-                           "engine": args.engine, "parallelism": f"data parallel x{world}: per-parameter NCCL all-reduce (AVG) of the 2.5 GB of "
-                                                                  "gradients, launched from autograd hooks while backward continues",
+        how = ("data parallel: per-parameter NCCL all-reduce (AVG) of the 2.5 GB of gradients, launched from autograd hooks while backward "
+               "continues" if args.parallel == "dp" else
+               "mode parallel: spectral weights / gradients / AdamW state sharded by modes, two all-to-alls of the truncated spectrum per "
+               "layer and direction")
+        line = {"metric": "PNOTrainer fields/sec at 64^2 hid256 modes20 (one ELBO step: fwd, bwd, clip, AdamW)", "value": leg["value"],
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.engine, "data": "synthetic",
+                "config": {"workload": f"cfg2: PNOTrainer.train_step 64x64 in3 hid256 L4 modes20, batch 32 per GPU (global {32 * world})",
+                           "engine": args.engine, "parallelism": f"x{world}, {how}",
                            "l2": "inputs larger than L2 (10 GB of parameters / gradients / AdamW state per step)"},
-                "clocks": clocks.summary("start", "end"), "gpu_launches": int(launches),
-                "e2e": {"value": round(world * Bl / ms_e * 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": (x_host.numel() + y_host.numel()) * 4,
-                        "d2h_bytes_per_step": 4}}
+                "clocks": clocks.summary("start", "end"), "gpu_launches": leg["gpu_launches"], "peak_mem_gib": leg["peak_mem_gib"],
+                "e2e": {"value": leg["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": leg["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": leg["d2h_bytes_per_step"]}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
