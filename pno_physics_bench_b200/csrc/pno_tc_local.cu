@@ -174,6 +174,10 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 TRACE(0, 1);
                 tc_fence_after_sync();
                 const uint32_t d_m = tmem + acc * (2 * TN), d_l = d_m + TN;
+                // 3xTF32 without a second conv: the lo x hi / hi x lo corrections accumulate in the otherwise unused second
+                // accumulator and are added in the epilogue (round-to-nearest): the tensor core's fp32 accumulator truncates on
+                // every MMA, so the error grows with the number of MMAs chained into one accumulator (K/8 instead of 3 K/8 here)
+                const uint32_t d_c = NOISY ? d_m : d_l;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
                     TRACE(0, 2);
@@ -189,8 +193,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                         const uint32_t ao = ks * 2, bo = ks * 64;    // 32 B / 1024 B per K step
                         mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
                         if (NSPLIT == 3) {
-                            mma_tf32(d_m, am + lo + ao, ahi, xb + bo, bhi, idesc, 1u, el);
-                            mma_tf32(d_m, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u, el);
+                            mma_tf32(d_c, am + lo + ao, ahi, xb + bo, bhi, idesc, NOISY ? 1u : acc_flag, el);
+                            mma_tf32(d_c, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u, el);
                         }
                         if (NOISY) {
                             mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
@@ -303,6 +307,11 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                         v[j] = fmaf(z[j], s, v[j] + bias_m);
                         if (DLV) l[j] = ((lv >= -10.f) && (lv <= 10.f) && (s_raw >= 1e-6f)) ? 0.5f * z[j] * s : 0.f;
                     }
+                } else if (NSPLIT == 3) {
+                    tmem_ld16(t_l + c, l);                 // the separately accumulated 3xTF32 corrections
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = (v[j] + l[j]) + bias_m;
                 } else {
                     tmem_ld_wait();
 #pragma unroll

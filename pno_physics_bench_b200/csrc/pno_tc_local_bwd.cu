@@ -369,6 +369,10 @@ int tc_local_bwd(int engine, const float* x, const float* g, const float* dout_d
         PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         a.kb_total = (int)((long long)B * HW / TK);
         a.k_splits = sms / a.m_tiles;
+        // 3xTF32: eight times as many (shorter) pixel slices.  The tensor core's fp32 accumulator truncates on every MMA, so the
+        // error of the accumulated sum grows with the number of MMAs chained into it (1 329 per slice of the cfg-2 reduction over
+        // 131 072 pixels otherwise); the slices are combined by fp32 atomics (round to nearest).
+        if (x3) a.k_splits *= 8;
         if (a.k_splits > a.kb_total) a.k_splits = a.kb_total;
         if (a.k_splits < 1) a.k_splits = 1;
         a.b_bytes = Ci * TK * 4;

@@ -43,6 +43,11 @@ struct MixGeom {
     // mode window (mode-parallel sharding): the launch covers global modes [mode_first, mode_first + n_modes) of ONE weight block;
     // spectra are indexed by the LOCAL mode, the Philox counters by the GLOBAL one, the weight arrays by (mode in block - w_sub)
     int mode_first, w_sub;
+    // 3xTF32: the correction terms (lo x hi, hi x lo) accumulate in their OWN tensor-memory columns and are added to the main term
+    // in the epilogue with a round-to-nearest fp32 add.  The tensor core's fp32 accumulator truncates on every MMA, so the error of
+    // an output grows with the number of MMAs chained into it: 64 instead of 192 for a 256-channel complex product this way
+    // (measured at the cfg-3 layer: rel-L2 5.6e-6 -> see DESIGN.md).  Needs 4 * Bp <= 256 columns per buffer, i.e. batch <= 64.
+    int split_acc;
     const float *mu1, *mu2, *lv1, *lv2;
     float *yr, *yi;
     PhiloxKey key;
@@ -95,7 +100,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
     const uint32_t tmem = tmem_slot;
     pdl_launch_dependents();
     pdl_wait();                                     // the spectrum written by the forward transform is complete from here on
-    const int acc_cols = 2 * g.Bp;                  // Dre | Dim (columns >= B are padding: rows of the next mode / zero fill)
+    // Dre | Dim (columns >= B are padding: rows of the next mode / zero fill) [| Dre corrections | Dim corrections]
+    const int acc_cols = (g.split_acc ? 4 : 2) * g.Bp;
     const int x_off = NW * W_TILE;                  // byte offset of the xhat tiles inside a stage
 
     if (warp == 0) {
@@ -143,6 +149,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 mbar_wait(&bar_tempty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_re = tmem + acc * acc_cols, d_im = d_re + g.Bp;
+                // correction accumulators (3xTF32 with split_acc), else the main ones
+                const uint32_t c_re = g.split_acc ? d_re + 2 * g.Bp : d_re, c_im = g.split_acc ? d_im + 2 * g.Bp : d_im;
                 for (int kb = 0; kb < g.KB; ++kb) {
                     mbar_wait(&bar_ready[stage], phase);
                     if (NSPLIT != 3) mbar_wait(&bar_raw[stage], phase);   // xhat tiles landed (3xTF32: the generators already waited)
@@ -174,16 +182,17 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                             mma_tf32(d_im, a_im2 + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
                         }
                         if (NSPLIT == 3) {
+                            const uint32_t cfirst = g.split_acc ? first : 1u;      // first MMA into the correction accumulator
                             if (do_re) {
-                                mma_tf32(d_re, wre_l + o, dhi, xre + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_re, wim_l + o, dhi, xim + o, dhi, id_re2, 1u, el);
-                                mma_tf32(d_re, wim + o, dhi, xim_l + o, dhi, id_re2, 1u, el);
+                                mma_tf32(c_re, wre_l + o, dhi, xre + o, dhi, idesc, cfirst, el);
+                                mma_tf32(c_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
+                                mma_tf32(c_re, wim_l + o, dhi, xim + o, dhi, id_re2, 1u, el);
+                                mma_tf32(c_re, wim + o, dhi, xim_l + o, dhi, id_re2, 1u, el);
                             } else {
-                                mma_tf32(d_im, a_im1l + o, dhi, b_im1 + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_im, a_im1 + o, dhi, b_im1l + o, dhi, idesc, 1u, el);
-                                mma_tf32(d_im, a_im2l + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
-                                mma_tf32(d_im, a_im2 + o, dhi, b_im2l + o, dhi, id_im2, 1u, el);
+                                mma_tf32(c_im, a_im1l + o, dhi, b_im1 + o, dhi, idesc, cfirst, el);
+                                mma_tf32(c_im, a_im1 + o, dhi, b_im1l + o, dhi, idesc, 1u, el);
+                                mma_tf32(c_im, a_im2l + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
+                                mma_tf32(c_im, a_im2 + o, dhi, b_im2l + o, dhi, id_im2, 1u, el);
                             }
                         }
                     }
@@ -347,7 +356,16 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 float vr[16], vi[16];
                 tmem_ld16(ta + b0, vr);
                 tmem_ld16(ta + g.Bp + b0, vi);
-                tmem_ld_wait();
+                if (NSPLIT == 3 && g.split_acc) {
+                    float cr[16], ci[16];
+                    tmem_ld16(ta + 2 * g.Bp + b0, cr);
+                    tmem_ld16(ta + 3 * g.Bp + b0, ci);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { vr[j] += cr[j]; vi[j] += ci[j]; }
+                } else {
+                    tmem_ld_wait();
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (b0 + j < g.B) {             // warp-uniform: skips the padding columns when B is not a multiple of 16
@@ -398,6 +416,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     g.o_tiles = MD / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = KD / TK;
     g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = out_r; g.yi = out_i; g.key = key;
     g.x_tile = g.Bp * 128;
+    g.split_acc = engine == PNO_ENGINE_TC_TF32X3 && 2 * 4 * g.Bp <= 512 && !(getenv("PNO_MIX_SPLITACC") && atoi(getenv("PNO_MIX_SPLITACC")) == 0);
     g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
     g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
     g.stages = getenv("PNO_MIX_STAGES") ? atoi(getenv("PNO_MIX_STAGES")) : 4;   // diagnostics override

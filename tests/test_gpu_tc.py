@@ -527,7 +527,8 @@ def test_two_pass_transforms_against_fft(engine, tol, shape, forced, monkeypatch
             assert rel_l2(torch.complex(tr.double(), ti.double()), want) < max(tol, 5e-6 if h > 128 else 5e-7)
         else:       # adjoint scaling = alive * c_ky / (HW): compare with the CUDA-core engine
             rr, ri = _dft_fwd(x, m1, m2, "fp32", gs)
-            assert rel_l2(tr, rr) < max(tol, 2e-6) and rel_l2(ti, ri) < max(tol, 2e-6)
+            lim = max(tol, 5e-6 if h > 128 else 2e-6)
+            assert rel_l2(tr, rr) < lim and rel_l2(ti, ri) < lim
     m = 2 * m1 * m2
     yr = torch.randn(m, b, c, generator=gen).to(DEV)
     yi = torch.randn(m, b, c, generator=gen).to(DEV)
@@ -539,7 +540,8 @@ def test_two_pass_transforms_against_fft(engine, tol, shape, forced, monkeypatch
     for adjoint, addend, act in ((1, None, 0), (0, add, 1), (0, add, 2)):
         ref, ref_pre = _dft_inv(yr, yi, h, w, m1, m2, "fp32", adjoint, addend, act, True)
         out, pre = _dft_inv(yr, yi, h, w, m1, m2, engine, adjoint, addend, act, True)
-        assert rel_l2(out, ref) < max(tol, 2e-6) and rel_l2(pre, ref_pre) < max(tol, 2e-6), (adjoint, act, rel_l2(out, ref))
+        lim = max(tol, 5e-6 if h > 128 else 2e-6)
+        assert rel_l2(out, ref) < lim and rel_l2(pre, ref_pre) < lim, (adjoint, act, rel_l2(out, ref))
 
 
 @pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 2e-2)])
