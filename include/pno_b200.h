@@ -286,6 +286,11 @@ int pno_debug_set_buffer(void* device_ptr);
  * (K-major A: A itself; MN-major A: A^T [K][128]; K-major B: B^T [N][K]; MN-major B: B itself). */
 int pno_selftest_umma(int flags, int N, int K, const float* A, const float* B, const float* A_tma_src,
                       const float* B_tma_src, float* D, void* stream);
+/* The fp32-parity product of the tensor-core engines on RAW fp32 operands: one kind::tf32 MMA on the fp32 tiles plus two
+ * kind::f16 MMAs on bf16 copies (bf16(A) x bf16(A-lo part of B), bf16(lo part of A) x bf16(B)) into one accumulator.
+ * flags: bit0 B MN-major, bit1 the bf16 tiles of A staged by TMA (scratch: 512*K bytes), bit2 main term only (what the
+ * tensor core does with the 13 low mantissa bits of a raw fp32 operand).  K%32 == 0, K <= 128, N%16 == 0 (N%64 MN-major). */
+int pno_selftest_umma_mixed(int flags, int N, int K, const float* A, const float* B, float* D, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

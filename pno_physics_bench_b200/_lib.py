@@ -79,6 +79,7 @@ SIGNATURES = {
     "pno_adamw_step_multi": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _u32, _vp, _f32, _int, _vp, _vp]),
     "pno_debug_set_buffer": (_int, [_vp]),
     "pno_selftest_umma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pno_selftest_umma_mixed": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -221,6 +221,21 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         : "memory");
 }
 
+// The same for 16-bit operands (kind::f16; the instruction descriptor says bf16): K = 16 per instruction, half the shared-memory
+// bytes and twice the multiply rate of kind::tf32.  Used for the cross terms of the fp32-parity engine (see pno_x3b below).
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate, uint32_t elected = 1u) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -273,6 +288,45 @@ __host__ __device__ __forceinline__ uint32_t kslab_sw32_off(int r, int k, int R)
     return (uint32_t)(s * R * 32 + r * 32 + ((((kk >> 2) ^ ((r >> 2) & 1)) << 4) | ((kk & 3) << 2)));
 }
 
+
+// ---- 16-bit operand tiles (bf16 cross terms of the fp32-parity engine) -------------------------------------------------------
+// K-major, one k-block of 32 elements per 64-byte row, SWIZZLE_64B (16-byte chunk index XOR bits 1-2 of the row): tile
+// [R rows][64 B], R a multiple of 8, tile base 512-byte aligned.  Descriptor: SBO = 512 (8 rows), layout SWIZZLE_64B; one K = 16
+// instruction spans 32 bytes of the row.  TMA writes it with CU_TENSOR_MAP_SWIZZLE_64B and a {32 elements, R rows} bf16 box.
+__host__ __device__ __forceinline__ uint32_t kmajor16_sw64_off(int r, int k) {
+    return (uint32_t)(r * 64 + ((((k >> 3) ^ ((r >> 1) & 3)) << 4) | ((k & 7) << 1)));
+}
+// MN-major, 64 elements of N per 128-byte line, SWIZZLE_128B (16-byte chunk XOR (K row & 7)): block nb of 64 N is a dense
+// [Kt rows x 128 B] region.  Descriptor: LBO = Kt * 128 (next block of 64 N), SBO = 1024 (next 8 K rows); one K = 16 instruction
+// spans 2048 bytes.
+__host__ __device__ __forceinline__ uint32_t mnmajor16_sw128_off(int k, int n, int Kt) {
+    const int nb = n >> 6, nn = n & 63;
+    return (uint32_t)(nb * Kt * 128 + k * 128 + ((((nn >> 3) ^ (k & 7)) << 4) | ((nn & 7) << 1)));
+}
+
+// The fp32-parity product on the tensor cores ("x3b"): with  h(v) = v truncated to tf32 (what kind::tf32 reads of a raw fp32
+// operand) and  l(v) = v - h(v)  (exact, <= 13 significant bits),
+//     a * b  =  h(a) h(b)  +  [ h(a) l(b) + l(a) h(b) ]  +  l(a) l(b)
+// the first term is ONE kind::tf32 MMA on the raw fp32 tiles (no hi copy needed), the bracket is TWO kind::f16 MMAs on bf16 copies
+// (bf16(a) x bf16(l(b)) and bf16(l(a)) x bf16(b): the 8-bit mantissas cost 2^-9 relative on terms that are 2^-11 of the product,
+// i.e. ~1e-6), the last term (2^-22) is dropped.  Against three kind::tf32 MMAs on hi / lo fp32 copies this is 2/3 of the tensor
+// time and 2/3 of the operand bytes read from shared memory, for the same fp32-grade result.
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// bf16 pair (lo half = a, hi half = b), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// four consecutive fp32 -> 8 bytes of bf16(v) and 8 bytes of bf16(v - trunc_tf32(v))
+__device__ __forceinline__ void x3b_split4(const float4 v, uint2& full, uint2& low) {
+    full = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    low = make_uint2(pack_bf16(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y)), pack_bf16(v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w)));
+}
+__device__ __forceinline__ void sts64u(uint32_t a, const uint2 v) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void sts128u(uint32_t a, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
 // pdl_wait(): everything the preceding kernel of the stream wrote is complete and visible after this returns (a no-op when the
@@ -381,3 +435,6 @@ static inline cudaError_t pno_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 int pno_encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle /* 0 none, 1 = 128B (16-byte atoms), 2 = 128B with 32-byte atoms */);
+// the same with swizzle 3 = 64B and an element type switch (bf16 = 1: 2-byte elements; dims / boxes count elements)
+int pno_encode_tmap_ex(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int swizzle, int bf16);

@@ -3,8 +3,10 @@
 // (reference models.py:298-303 + 264-275) as ONE persistent, warp-specialised kernel:
 //   warp 0      TMA producer: x tile [32 i][128 p] (MN-major B operand, straight from the NCHW tensor) and the Wm / Wl tiles
 //               [128 o][32 i] (K-major A operands) into a multi-stage shared-memory ring
-//   warps 2-5   (3xTF32 only) split every staged tile into tf32 hi (in place) + lo (second buffer)
-//   warp 1      one thread issues tcgen05.mma kind::tf32 into two TMEM accumulators (mean, log-var), double buffered
+//   warps 2-5   (fp32-parity engine only) write the bf16 copies bf16(x), bf16(x - trunc_tf32(x)) of every staged x tile
+//   warp 1      one thread issues tcgen05.mma into two TMEM accumulators (mean, log-var), double buffered.  Single pass: kind::tf32.
+//               fp32-parity engine ("x3b", pno_sm100.cuh): per product ONE kind::tf32 MMA on the raw fp32 tiles plus TWO kind::f16
+//               MMAs on bf16 copies (the hi x lo cross terms) -- 2/3 of the tensor time and operand reads of three tf32 MMAs
 //   then EW epilogue warps (8 by default = 2 per scheduler): tcgen05.ld -> bias, clamp/exp, Philox noise, (d out / d lv for
 //               backward) -> each lane stores its own output row straight from registers with 256-bit stores
 // A tile is (batch item b, 128 output channels, TN pixels); tiles are statically strided over the persistent grid with the
@@ -51,22 +53,17 @@ struct LocalArgs {
 template <int NSPLIT, int TN, int EW>
 struct Cfg {
     static constexpr int kXBytes = TK * TN * 4;                                  // X tile [TN/32 p-blocks][32 rows][128 B]
-    static constexpr int kOperandBytes = 2 * TILE_BYTES + kXBytes;               // Am, Al, X
-    static constexpr int kStageBytes = kOperandBytes * (NSPLIT == 3 ? 2 : 1);    // + lo copies
-    static constexpr int kStages = (224 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (3xTF32)
+    static constexpr int kOperandBytes = 2 * TILE_BYTES + kXBytes;               // Am, Al, X (fp32)
+    // fp32-parity engine: bf16 copies behind the fp32 operands: [Am][Al][Am lo][Al lo] (K-major, 64-byte rows, 8 KB each), then
+    // [X][X lo] (MN-major, blocks of 64 pixels x 32 rows x 128 B)
+    static constexpr int kW16 = TM * TK * 2;
+    static constexpr int kX16 = ((TN + 63) / 64) * TK * 128;
+    static constexpr int kStageBytes = kOperandBytes + (NSPLIT == 3 ? 4 * kW16 + 2 * kX16 : 0);
+    static constexpr int kStages = (224 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (fp32 parity)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
     static constexpr int kAcc = 4 * TN <= 512 ? 2 : 1;                           // accumulator buffers in tensor memory
     static_assert(kStages >= 2, "stage does not fit");
 };
-
-__device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-nearest on the 13 dropped mantissa bits
-    float4 r;
-    r.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-    r.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-    r.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-    r.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-    return r;
-}
 
 // EPI == 1 (NOISY = true: two weight matrices): the H-axis pass of the two-pass pruned transforms (pno_tc_dft2.cu).  The "weights"
 // are the cos / sin twiddle tables (A_m = C, A_l = S), the "pixels" of an image are its TN = 2 * m2p spectrum columns (re | im), and
@@ -75,8 +72,7 @@ __device__ __forceinline__ float4 tf32_hi(const float4 v) {   // round-to-neares
 template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW, int EPI = 0>
 __global__ void __launch_bounds__(threads_for(NSPLIT, EW), 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
-           const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmWmLo,
-           const __grid_constant__ CUtensorMap tmWlLo) {
+           const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmW16) {
     using C = Cfg<NSPLIT, TN, EW>;
     constexpr int kEpi0 = epi0(NSPLIT);
     extern __shared__ unsigned char smem_raw[];
@@ -104,8 +100,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmWm);
         tma_prefetch_desc(&tmWl);
-        tma_prefetch_desc(&tmWmLo);
-        tma_prefetch_desc(&tmWlLo);
+        tma_prefetch_desc(&tmW16);
     }
     for (int it = threadIdx.x; it < kTileTab; it += blockDim.x) {
         const int tile = blockIdx.x + it * gridDim.x;
@@ -145,14 +140,19 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     TRACE(3, 1);
                     unsigned char* st = stage_ptr(stage);
-                    // 3xTF32: the weights arrive pre-split (tmWm / tmWl = hi parts, tmWmLo / tmWlLo = lo parts, k_split_weights);
-                    // only the x tile is split on the fly
-                    mbar_arrive_expect_tx(&bar_raw[stage], (NSPLIT == 3 ? 2 : 1) * (NOISY ? 2 : 1) * TILE_BYTES + C::kXBytes);
+                    // fp32-parity engine: the bf16 copies of the weights arrive pre-computed (k_split_weights: one bf16 array of
+                    // rows [Wm][Wl][Wm lo][Wl lo], Co rows each); only the x tile is converted on the fly
+                    mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 2 : 1) * (TILE_BYTES + (NSPLIT == 3 ? 2 * C::kW16 : 0)) + C::kXBytes);
                     tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
                     if (NOISY) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
                     if (NSPLIT == 3) {
-                        tma_load_2d(st + C::kOperandBytes, &tmWmLo, &bar_raw[stage], kb * TK, ot * TM);
-                        if (NOISY) tma_load_2d(st + C::kOperandBytes + TILE_BYTES, &tmWlLo, &bar_raw[stage], kb * TK, ot * TM);
+                        unsigned char* w16 = st + C::kOperandBytes;
+                        tma_load_2d(w16, &tmW16, &bar_raw[stage], kb * TK, ot * TM);
+                        tma_load_2d(w16 + 2 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 2 * a.Co + ot * TM);
+                        if (NOISY) {
+                            tma_load_2d(w16 + C::kW16, &tmW16, &bar_raw[stage], kb * TK, a.Co + ot * TM);
+                            tma_load_2d(w16 + 3 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 3 * a.Co + ot * TM);
+                        }
                     }
                     // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, TN/32} lands as [TN/32 p-blocks][32 rows][128 B]
                     tma_load_3d(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32));
@@ -165,8 +165,11 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
             const uint32_t idesc = make_idesc(FMT_TF32, TM, TN, MAJOR_K, MAJOR_MN);
+            const uint32_t idesc16 = make_idesc(FMT_BF16, TM, TN, MAJOR_K, MAJOR_MN);
             const uint32_t ahi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
             const uint32_t bhi = sdesc_base(0, TK * 128, 512, SWIZZLE_128B_BASE32B).hi;
+            const uint32_t ahi16 = sdesc_base(0, 16, 512, SWIZZLE_64B).hi;               // bf16 K-major, 64-byte rows
+            const uint32_t bhi16 = sdesc_base(0, TK * 128, 1024, SWIZZLE_128B).hi;       // bf16 MN-major, blocks of 64 pixels
             int stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
                 const int acc = it % C::kAcc;
@@ -174,33 +177,42 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 TRACE(0, 1);
                 tc_fence_after_sync();
                 const uint32_t d_m = tmem + acc * (2 * TN), d_l = d_m + TN;
-                // 3xTF32 without a second conv: the lo x hi / hi x lo corrections accumulate in the otherwise unused second
-                // accumulator and are added in the epilogue (round-to-nearest): the tensor core's fp32 accumulator truncates on
-                // every MMA, so the error grows with the number of MMAs chained into one accumulator (K/8 instead of 3 K/8 here)
+                // fp32-parity engine without a second conv: the cross terms accumulate in the otherwise unused second accumulator
+                // and are added in the epilogue (round-to-nearest): the tensor core's fp32 accumulator truncates on every MMA, so
+                // the error grows with the number of MMAs chained into one accumulator
                 const uint32_t d_c = NOISY ? d_m : d_l;
                 for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
+                    mbar_wait(&bar_raw[stage], phase);
                     TRACE(0, 2);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(stage_ptr(stage));
                     const uint32_t am = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;                       // A tiles: K-major SW128
                     const uint32_t al = am + (TILE_BYTES >> 4);
                     const uint32_t xb = sdesc_base(s0 + 2 * TILE_BYTES, TK * 128, 512, SWIZZLE_128B_BASE32B).lo;   // B: MN-major
-                    const uint32_t lo = C::kOperandBytes >> 4;       // distance from a hi tile to its lo copy
 #pragma unroll
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
                         const uint32_t ao = ks * 2, bo = ks * 64;    // 32 B / 1024 B per K step
                         mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
-                        if (NSPLIT == 3) {
-                            mma_tf32(d_c, am + lo + ao, ahi, xb + bo, bhi, idesc, NOISY ? 1u : acc_flag, el);
-                            mma_tf32(d_c, am + ao, ahi, xb + lo + bo, bhi, idesc, 1u, el);
-                        }
-                        if (NOISY) {
-                            mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
-                            if (NSPLIT == 3) {
-                                mma_tf32(d_l, al + lo + ao, ahi, xb + bo, bhi, idesc, 1u, el);
-                                mma_tf32(d_l, al + ao, ahi, xb + lo + bo, bhi, idesc, 1u, el);
+                        if (NOISY) mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
+                    }
+                    if (NSPLIT == 3) {
+                        // cross terms on the bf16 copies (K = 16 per instruction): bf16(W) x bf16(lo x) + bf16(lo W) x bf16(x)
+                        mbar_wait(&bar_split[stage], phase);
+                        tc_fence_after_sync();
+                        const uint32_t w16 = sdesc_base(s0 + C::kOperandBytes, 16, 512, SWIZZLE_64B).lo;   // [Wm][Wl][Wm lo][Wl lo]
+                        const uint32_t x16 = sdesc_base(s0 + C::kOperandBytes + 4 * C::kW16, TK * 128, 1024, SWIZZLE_128B).lo;
+                        const uint32_t x16l = x16 + (C::kX16 >> 4);
+                        constexpr uint32_t W1 = C::kW16 >> 4;
+#pragma unroll
+                        for (int kh = 0; kh < TK / 16; ++kh) {
+                            const uint32_t cflag = (NOISY || kb || kh) ? 1u : 0u;
+                            const uint32_t ao = kh * 2, bo = kh * 128;   // 32 B / 2048 B per K = 16 step
+                            mma_bf16(d_c, w16 + ao, ahi16, x16l + bo, bhi16, idesc16, cflag, el);
+                            mma_bf16(d_c, w16 + 2 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
+                            if (NOISY) {
+                                mma_bf16(d_l, w16 + W1 + ao, ahi16, x16l + bo, bhi16, idesc16, 1u, el);
+                                mma_bf16(d_l, w16 + 3 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
                             }
                         }
                     }
@@ -212,21 +224,27 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             }
         }
     } else if (warp < kEpi0) {
-        // ================================ hi/lo splitter (3xTF32) ================================
+        // ================================ bf16 copies of the x tile (fp32-parity engine) ================================
         if (NSPLIT == 3) {
             const int t = threadIdx.x - 64;   // 0..127
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_raw[stage], phase);
-                    const uint32_t hi = smem_u32(stage_ptr(stage)), lo = hi + C::kOperandBytes;
-                    constexpr int kVec = TILE_BYTES / 16;
+                    const uint32_t xf = smem_u32(stage_ptr(stage)) + 2 * TILE_BYTES;            // fp32 [TN/32][32 rows][128 B]
+                    const uint32_t xh = smem_u32(stage_ptr(stage)) + C::kOperandBytes + 4 * C::kW16, xl = xh + C::kX16;
 #pragma unroll 4
-                    for (int i = 2 * kVec + t; i < C::kOperandBytes / 16; i += 128) {       // the x tile (weights are pre-split)
-                        const float4 v = lds128(hi + 16 * i);
-                        const float4 h = tf32_hi(v);
-                        sts128(hi + 16 * i, h);
-                        sts128(lo + 16 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+                    for (int c = t; c < C::kXBytes / 16; c += 128) {
+                        // 16-byte chunk c of the fp32 tile: pixel block pb (32 pixels), row r (input channel), chunk j; the fp32 layout
+                        // swizzles 32-byte chunks with (r & 3), the bf16 layout 16-byte chunks (8 pixels) with (r & 7)
+                        const int pb = c >> 8, r = (c >> 3) & 31, j = c & 7;
+                        const int p = pb * 32 + ((((j >> 1) ^ (r & 3)) << 3) | ((j & 1) << 2));   // first of 4 consecutive pixels
+                        const float4 v = lds128(xf + 16 * c);
+                        uint2 full, low;
+                        x3b_split4(v, full, low);
+                        const uint32_t off = (uint32_t)((p >> 6) * (TK * 128) + r * 128 + (((((p & 63) >> 3) ^ (r & 7)) << 4) | ((p & 4) << 1)));
+                        sts64u(xh + off, full);
+                        sts64u(xl + off, low);
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar_split[stage]);
@@ -334,24 +352,46 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// hi / lo tf32 parts of the two 1x1 weight matrices for the 3xTF32 engine: out = [Wm hi][Wl hi][Wm lo][Wl lo], each n floats
-__global__ void k_split_weights(const float* __restrict__ wm, const float* __restrict__ wl, int n, float* __restrict__ out) {
+// bf16 copies of the two 1x1 weight matrices for the fp32-parity engine: out = rows [Wm][Wl][Wm lo][Wl lo], n bf16 each, where
+// lo = w - trunc_tf32(w) is what the kind::tf32 main term (run on the raw fp32 weights) leaves out
+__global__ void k_split_weights(const float* __restrict__ wm, const float* __restrict__ wl, int n, uint16_t* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float a_ = wm[i], b_ = wl ? wl[i] : 0.f;
-    const float ah = __uint_as_float((__float_as_uint(a_) + 0x1000u) & 0xFFFFE000u);
-    const float bh = __uint_as_float((__float_as_uint(b_) + 0x1000u) & 0xFFFFE000u);
-    out[i] = ah;
-    out[n + i] = bh;
-    out[2 * n + i] = a_ - ah;
-    out[3 * n + i] = b_ - bh;
+    const uint32_t f = pack_bf16(a_, b_), l = pack_bf16(a_ - tf32_trunc(a_), b_ - tf32_trunc(b_));
+    out[i] = (uint16_t)(f & 0xFFFF);
+    out[n + i] = (uint16_t)(f >> 16);
+    out[2 * n + i] = (uint16_t)(l & 0xFFFF);
+    out[3 * n + i] = (uint16_t)(l >> 16);
 }
 
-static float* split_scratch(int /*dev*/, cudaStream_t st, size_t floats) { return pno_scratch(0, floats * 4, st); }
+// Tensor maps of the two [Co][Ci] weight matrices: fp32 K-major boxes for the kind::tf32 term and -- fp32-parity engine -- one bf16
+// array of rows [Wm][Wl][Wm lo][Wl lo] (written here, once per call: tiny next to the activations) for the kind::f16 cross terms.
+static int weight_maps(int engine, const float* Wm, const float* Wl, int Ci, int Co, cudaStream_t st, CUtensorMap* tmWm,
+                       CUtensorMap* tmWl, CUtensorMap* tmW16, const char* who) {
+    int rc;
+    const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
+    const uint64_t str[1] = {(uint64_t)Ci * 4};
+    const uint32_t box[2] = {TK, TM};
+    if ((rc = pno_encode_tmap(tmWm, Wm, 2, dims, str, box, 1))) return rc;
+    if ((rc = pno_encode_tmap(tmWl, Wl ? Wl : Wm, 2, dims, str, box, 1))) return rc;
+    *tmW16 = *tmWm;                                   // unused by the single-pass engine
+    if (engine == PNO_ENGINE_TC_TF32X3) {
+        const size_t n = (size_t)Co * Ci;
+        uint16_t* sc = reinterpret_cast<uint16_t*>(pno_scratch(0, 4 * n * 2, st));
+        if (!sc) PNO_FAIL(PNO_E_CUDA, "%s: cannot allocate the bf16 weight scratch (%zu bytes)", who, 8 * n);
+        k_split_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wm, Wl, (int)n, sc);
+        PNO_LAUNCH_CHECK();
+        const uint64_t d16[2] = {(uint64_t)Ci, (uint64_t)4 * Co};
+        const uint64_t s16[1] = {(uint64_t)Ci * 2};
+        if ((rc = pno_encode_tmap_ex(tmW16, sc, 2, d16, s16, box, 3, 1))) return rc;
+    }
+    return PNO_OK;
+}
 
 template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16, int EPI = 0>
-int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
-           const CUtensorMap& tmWlLo, cudaStream_t st) {
+int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmW16,
+           cudaStream_t st) {
     using C = Cfg<NSPLIT, TN, EW>;
     PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     int dev = 0, sms = 148;
@@ -359,17 +399,17 @@ int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, 
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
     PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI>, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl,
-                        tmWmLo, tmWlLo));
+                        tmW16));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
 template <int NSPLIT, int TN, int EW>
-int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmWmLo,
-              const CUtensorMap& tmWlLo, cudaStream_t st) {
-    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    return launch<NSPLIT, true, false, TN, EW>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmW16,
+              cudaStream_t st) {
+    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW>(a, tmX, tmWm, tmWl, tmW16, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW>(a, tmX, tmWm, tmWl, tmW16, st);
+    return launch<NSPLIT, true, false, TN, EW>(a, tmX, tmWm, tmWl, tmW16, st);
 }
 
 }  // namespace
@@ -401,36 +441,17 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
-    CUtensorMap tmWmLo, tmWlLo;
-    {
-        const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
-        const uint64_t str[1] = {(uint64_t)Ci * 4};
-        const uint32_t box[2] = {TK, TM};
-        const float *wm_hi = Wm, *wl_hi = Wl ? Wl : Wm, *wm_lo = Wm, *wl_lo = Wm;
-        if (engine == PNO_ENGINE_TC_TF32X3) {          // split the weights once per call (tiny) instead of once per pixel tile
-            int dev = 0;
-            PNO_CUDA(cudaGetDevice(&dev));
-            const size_t n = (size_t)Co * Ci;
-            float* sc = split_scratch(dev, st, 4 * n);
-            if (!sc) PNO_FAIL(PNO_E_CUDA, "tc_local_fwd: cannot allocate the split-weight scratch (%zu bytes)", 16 * n);
-            k_split_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wm, Wl, (int)n, sc);
-            PNO_LAUNCH_CHECK();
-            wm_hi = sc; wl_hi = sc + n; wm_lo = sc + 2 * n; wl_lo = sc + 3 * n;
-        }
-        if ((rc = pno_encode_tmap(&tmWm, wm_hi, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWl, wl_hi, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWmLo, wm_lo, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWlLo, wl_lo, 2, dims, str, box, 1))) return rc;
-    }
+    CUtensorMap tmW16;
+    if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd"))) return rc;
     // Epilogue warps: measured on B200 at the headline shape (single pass): 4 warps 177 us, 8 warps 163, 16 warps 177, 24 warps
     // 196 -- two per scheduler keep up with the tensor pipe, more only take issue slots and power from it.  PNO_LOCAL_EW=16
     // selects the wide epilogue (tuning).
     const char* e_ew = getenv("PNO_LOCAL_EW");
     const bool wide = e_ew && atoi(e_ew) == 16;
     if (engine == PNO_ENGINE_TC_TF32X3)
-        return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
-    return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st);
+        return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmW16, st);
+    if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmW16, st);
+    return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmW16, st);
 }
 
 // H-axis pass of the two-pass transforms: out[b][o][c] for c in [0, TN): complex combine (see k_tc_local, EPI == 1) of
@@ -451,7 +472,7 @@ int tc_local_combine(int engine, const float* x, int B, int Ci, int Co, int TN, 
     a.prefetch = 0;
     a.out = out; a.sign = sign;
     a.o_tiles = Co / TM; a.p_tiles = 1; a.n_tiles = B * a.o_tiles;
-    CUtensorMap tmX, tmWm, tmWl, tmWmLo, tmWlLo;
+    CUtensorMap tmX, tmWm, tmWl, tmW16;
     int rc;
     {   // x as (c % 32, row = b*Ci + i, c / 32)
         const uint64_t dims[3] = {32, (uint64_t)B * Ci, (uint64_t)TN / 32};
@@ -459,29 +480,10 @@ int tc_local_combine(int engine, const float* x, int B, int Ci, int Co, int TN, 
         const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
-    {
-        const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
-        const uint64_t str[1] = {(uint64_t)Ci * 4};
-        const uint32_t box[2] = {TK, TM};
-        const float *wm_hi = Wc, *wl_hi = Ws, *wm_lo = Wc, *wl_lo = Ws;
-        if (engine == PNO_ENGINE_TC_TF32X3) {
-            int dev = 0;
-            PNO_CUDA(cudaGetDevice(&dev));
-            const size_t n = (size_t)Co * Ci;
-            float* sc = split_scratch(dev, st, 4 * n);
-            if (!sc) PNO_FAIL(PNO_E_CUDA, "tc_local_combine: cannot allocate the split-table scratch (%zu bytes)", 16 * n);
-            k_split_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wc, Ws, (int)n, sc);
-            PNO_LAUNCH_CHECK();
-            wm_hi = sc; wl_hi = sc + n; wm_lo = sc + 2 * n; wl_lo = sc + 3 * n;
-        }
-        if ((rc = pno_encode_tmap(&tmWm, wm_hi, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWl, wl_hi, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWmLo, wm_lo, 2, dims, str, box, 1))) return rc;
-        if ((rc = pno_encode_tmap(&tmWlLo, wl_lo, 2, dims, str, box, 1))) return rc;
-    }
+    if ((rc = weight_maps(engine, Wc, Ws, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_combine"))) return rc;
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
-#define PNO_COMBINE(TN_) (x3 ? launch<3, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st) \
-                             : launch<1, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmWmLo, tmWlLo, st))
+#define PNO_COMBINE(TN_) (x3 ? launch<3, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmW16, st) \
+                             : launch<1, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmW16, st))
     if (TN == 64) return PNO_COMBINE(64);
     if (TN == 96) return PNO_COMBINE(96);
     return PNO_COMBINE(128);

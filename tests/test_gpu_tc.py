@@ -64,6 +64,42 @@ def test_umma_selftest(flags, n, k):
     assert rel_l2(d, want) < 1e-6, f"flags={flags:06b}"
 
 
+@pytest.mark.parametrize("flags,n,k", [(0, 64, 64), (1, 64, 64), (2, 64, 32), (3, 128, 128), (1, 128, 32), (0, 16, 96), (2, 48, 64),
+                                       (3, 192, 64)])
+def test_umma_selftest_mixed_fp32_parity_product(flags, n, k):
+    """kind::tf32 on the RAW fp32 tiles + two kind::f16 (bf16) cross-term MMAs reproduce the fp32 product to ~1e-6
+    (pno_sm100.cuh, "x3b"); operands are full-precision normals (NOT pre-truncated to tf32)."""
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(flags * 77 + n + k)
+    a = torch.randn(128, k, generator=gen).to(DEV)
+    b = torch.randn(k, n, generator=gen).to(DEV)
+    d = torch.full((128, n), float("nan"), device=DEV)
+    scratch = torch.empty(512 * k, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.pno_selftest_umma_mixed(flags, n, k, a.data_ptr(), b.data_ptr(), d.data_ptr(), scratch.data_ptr(),
+                                           _lib.stream_ptr()), "selftest mixed")
+    torch.cuda.synchronize()
+    err = rel_l2(d, a.double() @ b.double())
+    print(f"\n[x3b selftest flags={flags:03b} N={n} K={k}] rel-L2 vs fp64 product: {err:.2e}")
+    assert err < 2e-6
+
+
+def test_tf32_mma_truncates_raw_fp32_operands():
+    """The main term of the x3b product relies on kind::tf32 IGNORING the 13 low mantissa bits of a raw fp32 operand
+    (truncation, not rounding): lo = v - trunc(v) is then exactly what the main term missed."""
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(9)
+    a = torch.randn(128, 64, generator=gen).to(DEV)
+    b = torch.randn(64, 64, generator=gen).to(DEV)
+    outs = []
+    for aa, bb in ((a, b), (tf32_trunc(a.cpu()).to(DEV), tf32_trunc(b.cpu()).to(DEV))):
+        d = torch.full((128, 64), float("nan"), device=DEV)
+        _lib.check(lib.pno_selftest_umma_mixed(4, 64, 64, aa.data_ptr(), bb.data_ptr(), d.data_ptr(), None, _lib.stream_ptr()),
+                   "selftest mixed")
+        torch.cuda.synchronize()
+        outs.append(d)
+    assert torch.equal(outs[0], outs[1])
+
+
 def _local_case(b, ci, co, h, w, noisy, engine, gen):
     from pno_physics_bench_b200 import functional as F_
     x = torch.randn(b, ci, h, w, generator=gen).to(DEV).requires_grad_(True)
