@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpno_b200.so")
+LIB_PATH = os.environ.get("PNO_LIB_PATH") or os.path.join(_HERE, "libpno_b200.so")      # PNO_LIB_PATH: diagnostics builds
 
 PNO_OK, PNO_E_INVALID, PNO_E_MODES, PNO_E_CUDA, PNO_E_ARCH, PNO_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2

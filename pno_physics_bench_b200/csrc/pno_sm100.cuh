@@ -118,6 +118,32 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// ---- thread-block clusters: multicast TMA loads and cluster-wide barrier arrivals -----------------------------------------------
+// A multicast load writes the box at the SAME shared-memory offset in every CTA of `mask` and signals complete_tx on the mbarrier
+// at the same offset in each of them: CTAs that consume the same operand tile (e.g. one weight tile, different pixel tiles) each
+// fetch 1/n of it and receive all of it -- one L2 read instead of n.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive (when complete) on the mbarrier at this offset in EVERY CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask, uint32_t elected = 1u) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"(mask), "r"(elected)
+        : "memory");
+}
+
 // ---- TMEM --------------------------------------------------------------------------------------------------------------
 // one full warp; ncols a power of two in [32, 512]; the base address is written to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -428,6 +454,25 @@ static inline cudaError_t pno_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// the same with a thread-block cluster of `cl` CTAs along x (grid.x must be a multiple of cl)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pno_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cl,
+                                             Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -28,9 +28,13 @@ using namespace sm100;
 namespace {
 
 constexpr int kTileTab = 128;
-// CTA: warp 0 TMA, warp 1 MMA issuer, (3xTF32 only) warps 2-5 x-tile splitter, then EW epilogue warps
-constexpr int epi0(int nsplit) { return nsplit == 3 ? 6 : 2; }
-constexpr int threads_for(int nsplit, int ew) { return (epi0(nsplit) + ew) * 32; }
+// CTA: EW epilogue warps first (warp & 3 = the TMEM lane quarter a warp may read), then (fp32-parity engine only) 4 warps that convert
+// the x tile, then the TMA producer and LAST the MMA issuer: the warp scheduler favours the highest warp id among the eligible warps
+// of a sub-partition, and the issuer shares its sub-partition with ALU-bound epilogue warps -- as warp 1 it waited behind them for
+// every instruction of its issue loop and a k-block took 1.4 k cycles while an epilogue ran against 0.8 k when none did
+// (tools/trace_local.py).
+constexpr int aux_warps(int nsplit) { return nsplit == 3 ? 7 : 3; }      // (4 converters +) producer + two issuers
+constexpr int threads_for(int nsplit, int ew) { return (aux_warps(nsplit) + ew) * 32; }
 constexpr int TM = 128;          // output channels per tile (UMMA M)
 constexpr int TK = 32;           // input channels per stage (one 128-byte swizzle row)
 constexpr int TILE_BYTES = TM * TK * 4;   // 16 KB, same for A [128][32] and B [32][128]
@@ -39,6 +43,7 @@ struct LocalArgs {
     int B, Ci, Co, HW;
     int noisy, want_dlv;
     int prefetch;           // L2 prefetch of the next tile's x boxes
+    int ablate;             // measurement only (PNO_LOCAL_ABLATE, wrong results): 1 = weight tiles fetched for the first k-block of a tile only
     const float *bm, *bl;
     float *out, *dlv;
     PhiloxKey key;
@@ -69,12 +74,21 @@ struct Cfg {
 // are the cos / sin twiddle tables (A_m = C, A_l = S), the "pixels" of an image are its TN = 2 * m2p spectrum columns (re | im), and
 // the epilogue combines the two accumulators into the complex product instead of drawing noise:
 //   out[:, c] = Dm[:, c] + sign * Dl[:, c + TN/2]  (real part),   out[:, c + TN/2] = Dm[:, c + TN/2] - sign * Dl[:, c]  (imaginary part)
-template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW, int EPI = 0>
+// CL > 1: thread-block clusters of CL CTAs work on CL consecutive pixel tiles of the SAME output-channel tile in lock step; each
+// CTA fetches 1/CL of every weight tile and multicasts it to the whole cluster.  The weight tiles are re-streamed from L2 for every
+// pixel tile (2 x 16 KB of fp32 + 4 x 8 KB of bf16 per 16 KB of x): without sharing, the kernel moves 9-11 TB/s out of L2 -- its
+// measured bound at the headline shape, not the tensor pipe or shared memory.
+template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW, int EPI = 0, int CL = 1>
 __global__ void __launch_bounds__(threads_for(NSPLIT, EW), 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
            const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmW16) {
     using C = Cfg<NSPLIT, TN, EW>;
-    constexpr int kEpi0 = epi0(NSPLIT);
+    // two MMA issuers on different sub-partitions, one per accumulator (mean conv / log-var conv): an issuer needs ~53 of the 64
+    // cycles an N = 128 MMA takes just to issue it, so ONE issuer feeding both accumulators has no slack at all when the ALU-bound
+    // epilogue warps of its sub-partition compete for issue / MIO slots (measured: skipping the epilogue math on the issuer's
+    // sub-partition alone gave 167 -> 140 us, on any other sub-partition nothing)
+    constexpr int kWarps = aux_warps(NSPLIT) + EW, kIssuer = kWarps - 2, kIssuer2 = kWarps - 1, kProducer = kWarps - 3;
+    constexpr int NI = NOISY ? 2 : 1;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bar_raw[C::kStages], bar_split[C::kStages], bar_empty[C::kStages];
@@ -90,10 +104,10 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&bar_raw[s], 1);
             mbar_init(&bar_split[s], 128);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], CL * NI);         // one commit from every MMA issuer of every CTA of the cluster
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bar_tfull[s], 1);
+            mbar_init(&bar_tfull[s], NI);
             mbar_init(&bar_tempty[s], EW * 32);
         }
         fence_mbar_init();
@@ -102,15 +116,21 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         tma_prefetch_desc(&tmWl);
         tma_prefetch_desc(&tmW16);
     }
-    for (int it = threadIdx.x; it < kTileTab; it += blockDim.x) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        s_tile[it][0] = tile % a.o_tiles;
-        s_tile[it][1] = (tile / a.o_tiles) % a.p_tiles;
-        s_tile[it][2] = tile / (a.o_tiles * a.p_tiles);
-    }
-    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    // work items: "super tiles" su = (output-channel tile, group of CL consecutive pixel tiles), output-channel tile fastest; the CTA
+    // of cluster rank r takes pixel tile CL * group + r
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int su0 = blockIdx.x / CL, su_step = gridDim.x / CL, n_super = a.n_tiles / CL;
+    auto decode = [&](int su, int& ot, int& pt, int& b) {
+        ot = su % a.o_tiles;
+        const int ptile = (su / a.o_tiles) * CL + crank;
+        pt = ptile % a.p_tiles;
+        b = ptile / a.p_tiles;
+    };
+    for (int it = threadIdx.x; it < kTileTab; it += blockDim.x) decode(su0 + it * su_step, s_tile[it][0], s_tile[it][1], s_tile[it][2]);
+    if (warp == kIssuer) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                 // every CTA's barriers are initialised before any remote arrival / multicast write
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
     pdl_launch_dependents();
@@ -118,22 +138,25 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
 
     auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
 
-    if (warp == 0) {
+    if (warp == kProducer) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0, phase = 0, itp = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++itp) {
+            constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+            constexpr int kRows = TM / CL;               // weight-tile rows fetched (and multicast) by this CTA
+            for (int tile = su0; tile < n_super; tile += su_step, ++itp) {
                 int ot, pt, b;
                 if (itp < kTileTab) { ot = s_tile[itp][0]; pt = s_tile[itp][1]; b = s_tile[itp][2]; }
-                else { ot = tile % a.o_tiles; pt = (tile / a.o_tiles) % a.p_tiles; b = tile / (a.o_tiles * a.p_tiles); }
+                else decode(tile, ot, pt, b);
                 // x tiles of this CTA's NEXT tile are pulled into L2 one tile ahead: the stage fills then see L2 latency instead
                 // of HBM latency (the ring holds only kStages stages, too few bytes in flight to cover ~1.5 us of HBM latency)
                 int npt = 0, nb = 0;
-                const int ntile = tile + gridDim.x;
-                const bool pf = a.prefetch && ntile < a.n_tiles;
+                const int ntile = tile + su_step;
+                const bool pf = a.prefetch && ntile < n_super;
                 if (pf) {
+                    int not_;
                     if (itp + 1 < kTileTab) { npt = s_tile[itp + 1][1]; nb = s_tile[itp + 1][2]; }
-                    else { npt = (ntile / a.o_tiles) % a.p_tiles; nb = ntile / (a.o_tiles * a.p_tiles); }
+                    else decode(ntile, not_, npt, nb);
                 }
                 for (int kb = 0; kb < KB; ++kb) {
                     if (pf) tma_prefetch_l2_3d(&tmX, 0, nb * a.Ci + kb * TK, npt * (TN / 32));
@@ -142,16 +165,37 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     unsigned char* st = stage_ptr(stage);
                     // fp32-parity engine: the bf16 copies of the weights arrive pre-computed (k_split_weights: one bf16 array of
                     // rows [Wm][Wl][Wm lo][Wl lo], Co rows each); only the x tile is converted on the fly
-                    mbar_arrive_expect_tx(&bar_raw[stage], (NOISY ? 2 : 1) * (TILE_BYTES + (NSPLIT == 3 ? 2 * C::kW16 : 0)) + C::kXBytes);
-                    tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
-                    if (NOISY) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
-                    if (NSPLIT == 3) {
-                        unsigned char* w16 = st + C::kOperandBytes;
-                        tma_load_2d(w16, &tmW16, &bar_raw[stage], kb * TK, ot * TM);
-                        tma_load_2d(w16 + 2 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 2 * a.Co + ot * TM);
-                        if (NOISY) {
-                            tma_load_2d(w16 + C::kW16, &tmW16, &bar_raw[stage], kb * TK, a.Co + ot * TM);
-                            tma_load_2d(w16 + 3 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 3 * a.Co + ot * TM);
+                    const bool skip_w = a.ablate == 1 && kb > 0;
+                    mbar_arrive_expect_tx(&bar_raw[stage], (skip_w ? 0 : (NOISY ? 2 : 1) * (TILE_BYTES + (NSPLIT == 3 ? 2 * C::kW16 : 0))) + C::kXBytes);
+                    if (skip_w) {
+                    } else if (CL == 1) {
+                        tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
+                        if (NOISY) tma_load_2d(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
+                        if (NSPLIT == 3) {
+                            unsigned char* w16 = st + C::kOperandBytes;
+                            tma_load_2d(w16, &tmW16, &bar_raw[stage], kb * TK, ot * TM);
+                            tma_load_2d(w16 + 2 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 2 * a.Co + ot * TM);
+                            if (NOISY) {
+                                tma_load_2d(w16 + C::kW16, &tmW16, &bar_raw[stage], kb * TK, a.Co + ot * TM);
+                                tma_load_2d(w16 + 3 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 3 * a.Co + ot * TM);
+                            }
+                        }
+                    } else {
+                        // this CTA's slice (rows [crank * kRows, +kRows) of every weight tile) goes to every CTA of the cluster; the
+                        // other slices arrive from the peers and complete on this CTA's barrier as well (the tensor maps have
+                        // kRows-row boxes)
+                        const int r0 = ot * TM + crank * kRows;
+                        unsigned char* wf = st + crank * (TILE_BYTES / CL);
+                        tma_load_2d_mc(wf, &tmWm, &bar_raw[stage], kb * TK, r0, kMask);
+                        if (NOISY) tma_load_2d_mc(wf + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, r0, kMask);
+                        if (NSPLIT == 3) {
+                            unsigned char* w16 = st + C::kOperandBytes + crank * (C::kW16 / CL);
+                            tma_load_2d_mc(w16, &tmW16, &bar_raw[stage], kb * TK, r0, kMask);
+                            tma_load_2d_mc(w16 + 2 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 2 * a.Co + r0, kMask);
+                            if (NOISY) {
+                                tma_load_2d_mc(w16 + C::kW16, &tmW16, &bar_raw[stage], kb * TK, a.Co + r0, kMask);
+                                tma_load_2d_mc(w16 + 3 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 3 * a.Co + r0, kMask);
+                            }
                         }
                     }
                     // x viewed as (p%32, row = b*Ci + i, p/32): box {32, 32, TN/32} lands as [TN/32 p-blocks][32 rows][128 B]
@@ -160,8 +204,9 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
+    } else if (warp == kIssuer || (NOISY && warp == kIssuer2)) {
+        // ================================ MMA issuers ================================
+        const bool second = NOISY && warp == kIssuer2;      // this warp issues the log-var conv
         {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
             const uint32_t idesc = make_idesc(FMT_TF32, TM, TN, MAJOR_K, MAJOR_MN);
@@ -171,12 +216,12 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             const uint32_t ahi16 = sdesc_base(0, 16, 512, SWIZZLE_64B).hi;               // bf16 K-major, 64-byte rows
             const uint32_t bhi16 = sdesc_base(0, TK * 128, 1024, SWIZZLE_128B).hi;       // bf16 MN-major, blocks of 64 pixels
             int stage = 0, phase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = su0; tile < n_super; tile += su_step, ++it) {
                 const int acc = it % C::kAcc;
                 mbar_wait(&bar_tempty[acc], ((it / C::kAcc) & 1) ^ 1);
                 TRACE(0, 1);
                 tc_fence_after_sync();
-                const uint32_t d_m = tmem + acc * (2 * TN), d_l = d_m + TN;
+                const uint32_t d_m = tmem + acc * (2 * TN) + (second ? TN : 0), d_l = tmem + acc * (2 * TN) + TN;
                 // fp32-parity engine without a second conv: the cross terms accumulate in the otherwise unused second accumulator
                 // and are added in the epilogue (round-to-nearest): the tensor core's fp32 accumulator truncates on every MMA, so
                 // the error grows with the number of MMAs chained into one accumulator
@@ -186,21 +231,19 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     TRACE(0, 2);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(stage_ptr(stage));
-                    const uint32_t am = sdesc_base(s0, 16, 1024, SWIZZLE_128B).lo;                       // A tiles: K-major SW128
-                    const uint32_t al = am + (TILE_BYTES >> 4);
+                    const uint32_t am = sdesc_base(s0 + (second ? TILE_BYTES : 0), 16, 1024, SWIZZLE_128B).lo;   // A tile: K-major SW128
                     const uint32_t xb = sdesc_base(s0 + 2 * TILE_BYTES, TK * 128, 512, SWIZZLE_128B_BASE32B).lo;   // B: MN-major
 #pragma unroll
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
                         const uint32_t ao = ks * 2, bo = ks * 64;    // 32 B / 1024 B per K step
                         mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
-                        if (NOISY) mma_tf32(d_l, al + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
                     }
                     if (NSPLIT == 3) {
                         // cross terms on the bf16 copies (K = 16 per instruction): bf16(W) x bf16(lo x) + bf16(lo W) x bf16(x)
                         mbar_wait(&bar_split[stage], phase);
                         tc_fence_after_sync();
-                        const uint32_t w16 = sdesc_base(s0 + C::kOperandBytes, 16, 512, SWIZZLE_64B).lo;   // [Wm][Wl][Wm lo][Wl lo]
+                        const uint32_t w16 = sdesc_base(s0 + C::kOperandBytes + (second ? C::kW16 : 0), 16, 512, SWIZZLE_64B).lo;   // [Wm][Wl][Wm lo][Wl lo]
                         const uint32_t x16 = sdesc_base(s0 + C::kOperandBytes + 4 * C::kW16, TK * 128, 1024, SWIZZLE_128B).lo;
                         const uint32_t x16l = x16 + (C::kX16 >> 4);
                         constexpr uint32_t W1 = C::kW16 >> 4;
@@ -210,25 +253,23 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                             const uint32_t ao = kh * 2, bo = kh * 128;   // 32 B / 2048 B per K = 16 step
                             mma_bf16(d_c, w16 + ao, ahi16, x16l + bo, bhi16, idesc16, cflag, el);
                             mma_bf16(d_c, w16 + 2 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
-                            if (NOISY) {
-                                mma_bf16(d_l, w16 + W1 + ao, ahi16, x16l + bo, bhi16, idesc16, 1u, el);
-                                mma_bf16(d_l, w16 + 3 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
-                            }
                         }
                     }
-                    mma_commit(&bar_empty[stage], el);       // frees the stage when these MMAs have read it
+                    // frees the stage when these MMAs have read it -- in every CTA of the cluster: a peer's next multicast writes here
+                    if (CL > 1) mma_commit_mc(&bar_empty[stage], (uint16_t)((1u << CL) - 1), el);
+                    else mma_commit(&bar_empty[stage], el);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 mma_commit(&bar_tfull[acc], el);
                 TRACE(0, 3);
             }
         }
-    } else if (warp < kEpi0) {
+    } else if (warp >= EW) {
         // ================================ bf16 copies of the x tile (fp32-parity engine) ================================
-        if (NSPLIT == 3) {
-            const int t = threadIdx.x - 64;   // 0..127
+        if (NSPLIT == 3 && warp < EW + 4) {
+            const int t = threadIdx.x - EW * 32;   // 0..127
             int stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int tile = su0; tile < n_super; tile += su_step) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_raw[stage], phase);
                     const uint32_t xf = smem_u32(stage_ptr(stage)) + 2 * TILE_BYTES;            // fp32 [TN/32][32 rows][128 B]
@@ -257,15 +298,15 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         // A tile is NP passes of 16 pixel columns per lane quarter; the EW / 4 warps of a quarter take the passes of the tile
         // stream round-robin (pass s = it * NP + p goes to warp s % (EW/4)), so any warp count divides the work evenly
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int kq = (warp - kEpi0) >> 2;     // index of this warp among the warps of its quarter
+        const int kq = warp >> 2;               // index of this warp among the warps of its quarter
         const PhiloxKey key = resolve_key(a.key);
         constexpr int EWQ = EW / 4, NP = TN / 16;
         static_assert(EW % 4 == 0 && NP >= EWQ, "every epilogue warp needs a pass in every tile");
         int it = 0, base = 0;                   // base = (it * NP) % EWQ
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = su0; tile < n_super; tile += su_step, ++it) {
             int ot, pt, b;
             if (it < kTileTab) { ot = s_tile[it][0]; pt = s_tile[it][1]; b = s_tile[it][2]; }
-            else { ot = tile % a.o_tiles; pt = (tile / a.o_tiles) % a.p_tiles; b = tile / (a.o_tiles * a.p_tiles); }
+            else decode(tile, ot, pt, b);
             const int acc = it % C::kAcc;
             const int o = ot * TM + q * 32 + lane;
             const float bias_m = a.bm ? a.bm[o] : 0.f;
@@ -274,7 +315,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             const size_t wrow = ((size_t)b * a.Co + o) * a.HW + (size_t)pt * TN;      // this lane's row
             const uint64_t e_row = ((a.batch_offset + b) * (uint64_t)a.Co + o) * (uint64_t)a.HW + (uint64_t)pt * TN;
             mbar_wait(&bar_tfull[acc], (it / C::kAcc) & 1);
-            if (warp == kEpi0) TRACE(2, 1);
+            if (warp == 0) TRACE(2, 1);
             tc_fence_after_sync();
             const uint32_t t_m = tmem_addr(tmem, q * 32, acc * (2 * TN)), t_l = t_m + TN;
             if (EPI == 1) {
@@ -303,11 +344,20 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             }
             int p0 = kq - base;
             if (p0 < 0) p0 += EWQ;
+            // measurement only (wrong results): 2 = the epilogue does nothing, 3 = TMEM loads only, 4 = loads + stores (no noise / math),
+            // 5 = everything but the stores
+            if (a.ablate == 2) p0 = TN;
 #pragma unroll 1
             for (int c = p0 * 16; c < TN; c += EWQ * 16) {
                 float v[16], l[16];
                 tmem_ld16(t_m + c, v);
                 if (NOISY) tmem_ld16(t_l + c, l);
+                if (a.ablate == 3 || a.ablate == 4 || (a.ablate == 6 && q == (kIssuer & 3)) || (a.ablate == 7 && q == ((kIssuer + 1) & 3))) {
+                    tmem_ld_wait();
+                    if (a.ablate == 4) lane_store16(a.out + wrow + c, v);
+                    else if (v[0] == 1.2345e-30f && l[3] == 7.7e-20f) a.out[0] = v[1];
+                    continue;
+                }
                 if (NOISY) {
                     // the noise does not depend on the accumulators: it is generated while the TMEM loads are in flight
                     float z[16];
@@ -337,6 +387,10 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 }
                 // each lane owns one output row: 64 contiguous bytes per pass, stored from registers as two 256-bit stores
                 // (whole sectors; measured faster than a shared-memory transpose, which competes with the MMA operand reads)
+                if (a.ablate == 5) {
+                    if (v[0] == 1.2345e-30f && v[7] == 7.7e-20f) a.out[0] = v[1];
+                    continue;
+                }
                 lane_store16(a.out + wrow + c, v);
                 if (NOISY && DLV) lane_store16(a.dlv + wrow + c, l);
             }
@@ -344,12 +398,13 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             if (base >= EWQ) base -= EWQ;
             tc_fence_before_sync();
             mbar_arrive(&bar_tempty[acc]);
-            if (warp == kEpi0) TRACE(2, 2);
+            if (warp == 0) TRACE(2, 2);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (CL > 1) cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it / arrive on its barriers
+    if (warp == kIssuer) tmem_dealloc(tmem, 512);
 }
 
 // bf16 copies of the two 1x1 weight matrices for the fp32-parity engine: out = rows [Wm][Wl][Wm lo][Wl lo], n bf16 each, where
@@ -368,11 +423,11 @@ __global__ void k_split_weights(const float* __restrict__ wm, const float* __res
 // Tensor maps of the two [Co][Ci] weight matrices: fp32 K-major boxes for the kind::tf32 term and -- fp32-parity engine -- one bf16
 // array of rows [Wm][Wl][Wm lo][Wl lo] (written here, once per call: tiny next to the activations) for the kind::f16 cross terms.
 static int weight_maps(int engine, const float* Wm, const float* Wl, int Ci, int Co, cudaStream_t st, CUtensorMap* tmWm,
-                       CUtensorMap* tmWl, CUtensorMap* tmW16, const char* who) {
+                       CUtensorMap* tmWl, CUtensorMap* tmW16, const char* who, int cl = 1) {
     int rc;
     const uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)Co};
     const uint64_t str[1] = {(uint64_t)Ci * 4};
-    const uint32_t box[2] = {TK, TM};
+    const uint32_t box[2] = {TK, (uint32_t)(TM / cl)};      // clusters: every CTA fetches (and multicasts) TM / cl rows of a tile
     if ((rc = pno_encode_tmap(tmWm, Wm, 2, dims, str, box, 1))) return rc;
     if ((rc = pno_encode_tmap(tmWl, Wl ? Wl : Wm, 2, dims, str, box, 1))) return rc;
     *tmW16 = *tmWm;                                   // unused by the single-pass engine
@@ -389,27 +444,29 @@ static int weight_maps(int engine, const float* Wm, const float* Wl, int Ci, int
     return PNO_OK;
 }
 
-template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16, int EPI = 0>
+template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16, int EPI = 0, int CL = 1>
 int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmW16,
            cudaStream_t st) {
     using C = Cfg<NSPLIT, TN, EW>;
-    PNO_CUDA(cudaFuncSetAttribute(k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    auto kern = k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI, CL>;
+    PNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    PNO_CUDA(pno_launch(k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI>, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl,
-                        tmW16));
+    const int n_super = a.n_tiles / CL, groups = sms / CL;
+    const int grid = (n_super < groups ? n_super : groups) * CL;
+    if (CL > 1) PNO_CUDA(pno_launch_cluster(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, CL, a, tmX, tmWm, tmWl, tmW16));
+    else PNO_CUDA(pno_launch(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl, tmW16));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
-template <int NSPLIT, int TN, int EW>
+template <int NSPLIT, int TN, int EW, int CL = 1>
 int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmW16,
               cudaStream_t st) {
-    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW>(a, tmX, tmWm, tmWl, tmW16, st);
-    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW>(a, tmX, tmWm, tmWl, tmW16, st);
-    return launch<NSPLIT, true, false, TN, EW>(a, tmX, tmWm, tmWl, tmW16, st);
+    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, st);
+    return launch<NSPLIT, true, false, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, st);
 }
 
 }  // namespace
@@ -428,6 +485,7 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     a.noisy = Wl != nullptr; a.want_dlv = dout_dlv != nullptr;
     a.dbg = g_pno_debug_buffer;
     a.prefetch = getenv("PNO_LOCAL_PREFETCH") ? atoi(getenv("PNO_LOCAL_PREFETCH")) : 1;
+    a.ablate = getenv("PNO_LOCAL_ABLATE") ? atoi(getenv("PNO_LOCAL_ABLATE")) : 0;
     a.bm = bm; a.bl = bl; a.out = out; a.dlv = dout_dlv; a.key = key; a.batch_offset = batch_offset; a.sign = 0.f;
     // pixel-tile width (see the header comment): 128 unless PNO_LOCAL_TN=256 asks for the wide tile
     const char* e_tn = getenv("PNO_LOCAL_TN");
@@ -441,13 +499,19 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
+    // clusters of 2 CTAs share every weight tile through TMA multicast (see k_tc_local); PNO_LOCAL_CL=1 switches them off (tuning)
+    const char* e_cl = getenv("PNO_LOCAL_CL");
+    const int cl = (TN == 128 && (B * a.p_tiles) % 2 == 0 && !(e_cl && atoi(e_cl) == 1)) ? 2 : 1;
     CUtensorMap tmW16;
-    if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd"))) return rc;
+    if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd", cl))) return rc;
     // Epilogue warps: measured on B200 at the headline shape (single pass): 4 warps 177 us, 8 warps 163, 16 warps 177, 24 warps
     // 196 -- two per scheduler keep up with the tensor pipe, more only take issue slots and power from it.  PNO_LOCAL_EW=16
     // selects the wide epilogue (tuning).
     const char* e_ew = getenv("PNO_LOCAL_EW");
     const bool wide = e_ew && atoi(e_ew) == 16;
+    if (cl == 2)
+        return engine == PNO_ENGINE_TC_TF32X3 ? launch_ns<3, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, st)
+                                              : launch_ns<1, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, st);
     if (engine == PNO_ENGINE_TC_TF32X3)
         return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmW16, st);
     if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmW16, st);
@@ -470,6 +534,7 @@ int tc_local_combine(int engine, const float* x, int B, int Ci, int Co, int TN, 
     a.noisy = 1; a.want_dlv = 0;
     a.dbg = g_pno_debug_buffer;
     a.prefetch = 0;
+    a.ablate = 0;
     a.out = out; a.sign = sign;
     a.o_tiles = Co / TM; a.p_tiles = 1; a.n_tiles = B * a.o_tiles;
     CUtensorMap tmX, tmWm, tmWl, tmW16;
