@@ -14,6 +14,9 @@
 // boxes of its next tile into L2 one tile ahead.
 // TN = 128 by default (double-buffered accumulators).  TN = 256 (PNO_LOCAL_TN=256, single-pass mode only) halves the weight-tile
 // fill per output at the price of single-buffered accumulators (mean | log-var = 512 TMEM columns); measured slower.
+// Tried and dropped (round 2): the transposed product D[pixel][channel of both convs] (one N = 256 MMA per K step, x tile read
+// once, whole-line stores): the MMA side is no faster (90 vs 92 us with the epilogue switched off -- at the HBM floor either way)
+// and the epilogue needs per-channel biases, 16 scalar stores and a 4x4 shuffle transpose of every Philox quad: 181 vs 149 us.
 // What bounds it (measured on B200, headline shape, ablations of the epilogue): without noise generation the kernel still takes
 // 136 of its 164 us -- the MMA side is shared-memory-bandwidth bound (a 128x128x8 SS MMA reads 8 KB per 64 tensor cycles = the
 // full 128 B/clk, and the TMA stage fills write another 48 KB per 64 KB of operand reads); TMEM loads and the global stores cost

@@ -29,7 +29,7 @@ constexpr int kThreads = 64 + kGen + 128 + 32;   // + a second MMA issuer warp (
 // some schedulers) allow 80 per thread, and only <= 20 warps would allow 96 -- the generators (24 registers of prefetched
 // mu / log_var) sit right at the cap: small additions to their loop spill and cost 20-50% (measured: an L2 prefetch added to
 // the loop took the kernel from 206 to 245 us, 3xTF32 from 245 to 326-358 us).
-constexpr int threads_for(int nsplit) { return nsplit == 3 ? kThreads : kThreads - 32; }
+constexpr int threads_for(int /*nsplit*/) { return kThreads; }
 constexpr int TM = 128;          // output channels per item
 constexpr int TK = 32;           // input channels per stage
 constexpr int W_TILE = TM * TK * 4;      // 16 KB
@@ -48,6 +48,7 @@ struct MixGeom {
     // an output grows with the number of MMAs chained into it: 64 instead of 192 for a 256-channel complex product this way
     // (measured at the cfg-3 layer: rel-L2 5.6e-6 -> see DESIGN.md).  Needs 4 * Bp <= 256 columns per buffer, i.e. batch <= 64.
     int split_acc;
+    int iss2;          // two MMA issuer warps (one per accumulator: Dre / Dim) on different sub-partitions
     const float *mu1, *mu2, *lv1, *lv2;
     float *yr, *yi;
     PhiloxKey key;
@@ -81,10 +82,10 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
             mbar_init(&bar_raw[s], 1);
             mbar_init(&bar_ready[s], kGen);
             mbar_init(&bar_free[s], 1);
-            mbar_init(&bar_empty[s], NSPLIT == 3 ? 2 : 1);      // one commit per issuer warp
+            mbar_init(&bar_empty[s], g.iss2 ? 2 : 1);           // one commit per issuer warp
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bar_tfull[s], NSPLIT == 3 ? 2 : 1);
+            mbar_init(&bar_tfull[s], g.iss2 ? 2 : 1);
             mbar_init(&bar_tempty[s], 128);
             mbar_init(&bar_rawfull[s], 1);
             mbar_init(&bar_rawempty[s], kGen);
@@ -137,8 +138,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
         // ================================ MMA issuer(s) ================================
         // single pass: warp 1 issues everything.  3xTF32: 48 MMAs per k-block at >= ~53 issue cycles each outrun the generators, so
         // warp 1 issues the Dre accumulator and the extra warp the Dim accumulator.
-        const bool do_re = NSPLIT != 3 || warp == 1, do_im = NSPLIT != 3 || warp != 1;
-        if (NSPLIT == 3 || warp == 1) {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+        const bool do_re = !g.iss2 || warp == 1, do_im = !g.iss2 || warp != 1;
+        if (g.iss2 || warp == 1) {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
             const uint32_t idesc = make_idesc(FMT_TF32, TM, g.Bp, MAJOR_K, MAJOR_K);
             const uint32_t idesc_n = make_idesc(FMT_TF32, TM, g.Bp, MAJOR_K, MAJOR_K, 1, 0);
@@ -188,7 +189,8 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                                 mma_tf32(c_re, wre + o, dhi, xre_l + o, dhi, idesc, 1u, el);
                                 mma_tf32(c_re, wim_l + o, dhi, xim + o, dhi, id_re2, 1u, el);
                                 mma_tf32(c_re, wim + o, dhi, xim_l + o, dhi, id_re2, 1u, el);
-                            } else {
+                            }
+                            if (do_im) {
                                 mma_tf32(c_im, a_im1l + o, dhi, b_im1 + o, dhi, idesc, cfirst, el);
                                 mma_tf32(c_im, a_im1 + o, dhi, b_im1l + o, dhi, idesc, 1u, el);
                                 mma_tf32(c_im, a_im2l + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
@@ -416,6 +418,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     g.o_tiles = MD / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = KD / TK;
     g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = out_r; g.yi = out_i; g.key = key;
     g.x_tile = g.Bp * 128;
+    g.iss2 = x3 || !(getenv("PNO_MIX_ISS2") && atoi(getenv("PNO_MIX_ISS2")) == 0);
     g.split_acc = engine == PNO_ENGINE_TC_TF32X3 && 2 * 4 * g.Bp <= 512 && !(getenv("PNO_MIX_SPLITACC") && atoi(getenv("PNO_MIX_SPLITACC")) == 0);
     g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
     g.stage_bytes = (g.stage_bytes + 1023) / 1024 * 1024;
