@@ -163,19 +163,26 @@ def block_kernel_times(engine, device, iters=5):
     spec = 4.0 * M * B * C * 2           # one truncated spectrum (re + im planes)
     nbytes = {"local": 2 * act + 8.0 * C * C, "dft_fwd": act + spec, "mix": 2 * spec + 12.0 * C * C * M,
               "dft_inv": spec + 2 * act}
+    # algorithmic flops: two 1x1 convs; W-axis + H-axis contractions of the pruned transforms; complex channel mix
+    dft = 4.0 * B * C * H * W * m + 8.0 * B * C * H * 2 * m * m
+    flops = {"local": 2 * 2.0 * B * H * W * C * C, "dft_fwd": dft, "mix": 8.0 * B * C * C * M, "dft_inv": dft}
+    # tensor-core passes per product in units of one kind::tf32 MMA: single pass 1; fp32-parity engine 3 (hi*hi + lo*hi + hi*lo in
+    # tf32), except the local branch, which runs its two cross terms as kind::f16 MMAs on bf16 copies at twice the rate (1 + 2/2)
+    passes = {n: (1.0 if engine != "tf32x3" else (2.0 if n == "local" else 3.0)) for n in flops}
     out = {}
     for name, fn in calls.items():
         us = event_time(fn, iters, 2, flush) * 1e3
-        out[name] = {"us": round(us, 1), "bytes": nbytes[name], "gbs": round(nbytes[name] / us / 1e3, 1)}
+        out[name] = {"us": round(us, 1), "bytes": nbytes[name], "gbs": round(nbytes[name] / us / 1e3, 1), "flops": flops[name],
+                     "tf32_passes": passes[name]}
     return out
 
 
-def ncu_traffic(kernel):
-    """dram bytes (read + write) per launch of `kernel` from the committed `ncu --set full` summary, or None."""
+def ncu_traffic(kernel, engine="tf32x3"):
+    """dram bytes (read + write) per launch of `kernel` from the committed `ncu --set full` summaries, or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(kernel)
+            return json.load(f).get(engine, {}).get(kernel)
     return None
 
 
@@ -189,17 +196,30 @@ def layer_roofline(engine, device):
     """Roofline of the dominant kernel of the block (the slowest of the four) + the whole spectral layer / block."""
     k = block_kernel_times(engine, device)
     hbm, tc, src = measured_peaks()
+    tf32_peak = tc / 2.0          # TF/s: kind::tf32 runs at half the measured dense bf16 rate (no separate tf32 measurement exists)
+    for v in k.values():          # the roof that binds each kernel: HBM time of its algorithmic bytes vs tensor time of its MMA passes
+        t_hbm = v["bytes"] / hbm / 1e3
+        t_tc = v["flops"] * v["tf32_passes"] / tf32_peak / 1e6
+        v["bound"] = "tensor" if t_tc > t_hbm else "hbm"
+        v["roof_us"] = round(max(t_hbm, t_tc), 1)
+        v["frac"] = round(max(t_hbm, t_tc) / v["us"], 4)
+        v["tflops_tf32_equiv"] = round(v["flops"] * v["tf32_passes"] / v["us"] / 1e6, 1)
     top = max(k, key=lambda n: k[n]["us"])
     B, C, H, W, m = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["modes"]
     layer_bytes = 4.0 * B * C * H * W * 2 + 12.0 * C * C * 2 * m * m        # SURVEY.md 8(d): x in + y out + mu + log_var
     layer_us = k["dft_fwd"]["us"] + k["mix"]["us"] + k["dft_inv"]["us"]
     block_us = layer_us + k["local"]["us"]
-    return {"bound": "hbm", "achieved": k[top]["gbs"], "peak": hbm, "unit": "GB/s", "frac": round(k[top]["gbs"] / hbm, 4),
-            "traffic": ncu_traffic(top), "peak_source": src, "kernel": KERNEL_NAMES[top], "kernel_us": k[top]["us"],
-            "algorithmic_bytes": k[top]["bytes"], "engine": engine,
+    t = k[top]
+    tensor = t["bound"] == "tensor"
+    return {"bound": t["bound"], "achieved": t["tflops_tf32_equiv"] if tensor else t["gbs"], "peak": round(tf32_peak, 1) if tensor else hbm,
+            "unit": "TFLOP/s" if tensor else "GB/s", "frac": t["frac"],
+            "traffic": ncu_traffic(top, engine), "peak_source": src + ("; tf32 peak = measured bf16 / 2; flops in tf32-MMA equivalents "
+                                                                "(1 tf32 + 2 bf16 passes = 2 per product)" if tensor else ""),
+            "kernel": KERNEL_NAMES[top], "kernel_us": t["us"],
+            "algorithmic_bytes": t["bytes"], "algorithmic_flops": t["flops"], "engine": engine,
             "timed": "each kernel alone, L2 flushed before every launch, right AFTER the timed region (loop clocks: `clocks_kernels`)",
-            "kernels": {n: {"us": v["us"], "gbs": v["gbs"], "frac": round(v["gbs"] / hbm, 4), "traffic": ncu_traffic(n)}
-                        for n, v in k.items()},
+            "kernels": {n: {"us": v["us"], "gbs": v["gbs"], "bound": v["bound"], "roof_us": v["roof_us"], "frac": v["frac"],
+                            "frac_of_hbm": round(v["gbs"] / hbm, 4), "traffic": ncu_traffic(n, engine)} for n, v in k.items()},
             "layer": {"us": round(layer_us, 1), "algorithmic_bytes": layer_bytes,
                       "frac_of_hbm_roofline": round(layer_bytes / layer_us / 1e3 / hbm, 4)},
             "block_us": round(block_us, 1)}

@@ -502,9 +502,12 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
-    // clusters of 2 CTAs share every weight tile through TMA multicast (see k_tc_local); PNO_LOCAL_CL=1 switches them off (tuning)
+    // clusters of 2 CTAs share every weight tile through TMA multicast (see k_tc_local).  Measured at the headline shape: fp32-parity
+    // engine (80 KB of weight tiles per k-block) 296 vs 308 us, single pass (32 KB) 150.5 vs 149.3 us -> on for the former only;
+    // PNO_LOCAL_CL=1 / 2 forces the choice (tuning)
     const char* e_cl = getenv("PNO_LOCAL_CL");
-    const int cl = (TN == 128 && (B * a.p_tiles) % 2 == 0 && !(e_cl && atoi(e_cl) == 1)) ? 2 : 1;
+    const int want_cl = e_cl ? atoi(e_cl) : (engine == PNO_ENGINE_TC_TF32X3 ? 2 : 1);
+    const int cl = (TN == 128 && (B * a.p_tiles) % 2 == 0 && want_cl == 2) ? 2 : 1;
     CUtensorMap tmW16;
     if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd", cl))) return rc;
     // Epilogue warps: measured on B200 at the headline shape (single pass): 4 warps 177 us, 8 warps 163, 16 warps 177, 24 warps
