@@ -48,6 +48,8 @@ struct MixGeom {
     // an output grows with the number of MMAs chained into it: 64 instead of 192 for a 256-channel complex product this way
     // (measured at the cfg-3 layer: rel-L2 5.6e-6 -> see DESIGN.md).  Needs 4 * Bp <= 256 columns per buffer, i.e. batch <= 64.
     int split_acc;
+    int ablate;        // measurement only (PNO_MIX_ABLATE, wrong results): 1 = no correction MMAs, 2 = no MMAs at all.  Round 2, headline
+                       // shape: fp32-parity engine 301 -> 267 / 282 us, single pass 179 -> 178 / 166 us: the generators bound the kernel
     int iss2;          // two MMA issuer warps (one per accumulator: Dre / Dim) on different sub-partitions
     const float *mu1, *mu2, *lv1, *lv2;
     float *yr, *yi;
@@ -174,6 +176,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                         const uint32_t b_im1 = BWD ? xim : xre, b_im2 = BWD ? xre : xim;        // and their B operands
                         const uint32_t b_im1l = BWD ? xim_l : xre_l, b_im2l = BWD ? xre_l : xim_l;
                         const uint32_t id_im2 = BWD ? idesc_n : idesc;          // sign of the second Dim term
+                        if (g.ablate == 2) continue;
                         if (do_re) {
                             mma_tf32(d_re, wre + o, dhi, xre + o, dhi, idesc, first, el);
                             mma_tf32(d_re, wim + o, dhi, xim + o, dhi, id_re2, 1u, el);
@@ -182,7 +185,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                             mma_tf32(d_im, a_im1 + o, dhi, b_im1 + o, dhi, idesc, first, el);
                             mma_tf32(d_im, a_im2 + o, dhi, b_im2 + o, dhi, id_im2, 1u, el);
                         }
-                        if (NSPLIT == 3) {
+                        if (NSPLIT == 3 && g.ablate != 1) {
                             const uint32_t cfirst = g.split_acc ? first : 1u;      // first MMA into the correction accumulator
                             if (do_re) {
                                 mma_tf32(c_re, wre_l + o, dhi, xre + o, dhi, idesc, cfirst, el);
@@ -418,6 +421,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     g.o_tiles = MD / TM; g.n_items = g.n_modes * g.o_tiles; g.KB = KD / TK;
     g.mu1 = mu1; g.mu2 = mu2; g.lv1 = lv1; g.lv2 = lv2; g.yr = out_r; g.yi = out_i; g.key = key;
     g.x_tile = g.Bp * 128;
+    g.ablate = getenv("PNO_MIX_ABLATE") ? atoi(getenv("PNO_MIX_ABLATE")) : 0;
     g.iss2 = x3 || !(getenv("PNO_MIX_ISS2") && atoi(getenv("PNO_MIX_ISS2")) == 0);
     g.split_acc = engine == PNO_ENGINE_TC_TF32X3 && 2 * 4 * g.Bp <= 512 && !(getenv("PNO_MIX_SPLITACC") && atoi(getenv("PNO_MIX_SPLITACC")) == 0);
     g.stage_bytes = (x3 ? 4 : 2) * (W_TILE + g.x_tile);
