@@ -136,6 +136,16 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
 }
 // all previously issued MMAs of this thread arrive (when complete) on the mbarrier at this offset in EVERY CTA of `mask`
 __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask, uint32_t elected = 1u) {
+#ifdef PNO_ELECT_ASM
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+    (void)elected;
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
         "setp.ne.b32 q, %2, 0;\n\t"
@@ -221,6 +231,19 @@ __device__ __forceinline__ SDesc sdesc_base(uint32_t smem_addr, uint32_t lbo_byt
 // registers and paying an R2UR round trip per operand, which is what bounds the issue rate of small (N <= 64) MMAs.
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                          uint32_t idesc, uint32_t accumulate, uint32_t elected = 1u) {
+#ifdef PNO_ELECT_ASM
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+    (void)elected;
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
         "mov.b64 da, {%1, %2};\n\t"
@@ -237,6 +260,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_
 // MMAs of one thread execute in issue order, so an MMA may consume the accumulator of the one issued before it.
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                             uint32_t accumulate, uint32_t elected = 1u) {
+#ifdef PNO_ELECT_ASM
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+    (void)elected;
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
         "mov.b64 db, {%2, %3};\n\t"
@@ -251,6 +286,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // bytes and twice the multiply rate of kind::tf32.  Used for the cross terms of the fp32-parity engine (see pno_x3b below).
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                          uint32_t idesc, uint32_t accumulate, uint32_t elected = 1u) {
+#ifdef PNO_ELECT_ASM
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+    (void)elected;
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
         "mov.b64 da, {%1, %2};\n\t"
@@ -282,7 +330,20 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uin
         : "memory");
 }
 // all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
+// (issued by ONE thread inside a divergent branch: the self-tests)
+__device__ __forceinline__ void mma_commit_1t(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar, uint32_t elected = 1u) {
+#ifdef PNO_ELECT_ASM
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+    (void)elected;
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
         "setp.ne.b32 q, %1, 0;\n\t"

@@ -43,6 +43,7 @@ struct FwdGeom {
     int grad_scale;
     int KPS;        // x k-blocks per ring stage (a whole tile when W <= 64: one barrier round trip per tile instead of per k-block)
     int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
+    int swap13;               // physical warps 1 and 3 swap roles (see the kernel)
     // shared-memory byte offsets (from the 1024-aligned base)
     int off_tab, off_tw, off_ring, off_b2, stage_bytes, x_bytes, tw_one, tab_one, b2_one, b2_bytes, smem_bytes;
     long long* dbg;   // optional event trace (PNO_TRACE builds)
@@ -92,7 +93,12 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         bar_d2_empty[2];
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Role index of this warp.  Physical warps 1 and 3 swap roles: the stage-1 MMA issuer (role 1) then runs on sub-partition 3 and
+    // the stage-2 issuer of the 3xTF32 form (role 22) on sub-partition 2 -- the two sub-partitions whose epilogue warps hold TMEM
+    // lane quarters beyond the 2*m1 retained rows and idle.  An issuer that shares its sub-partition with busy transposer AND
+    // epilogue warps paid 140 (stage 1) / 80 (stage 2) cycles per MMA instead of ~53 (tools/trace_fwd.py, round 2).
+    const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = g.swap13 ? (pwarp == 1 ? 3 : pwarp == 3 ? 1 : pwarp) : pwarp;
     PNO_TRACE_DECL();
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -275,7 +281,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     } else if (warp < 6) {
         // ================================ hi/lo splitter of the x tile (3xTF32) ================================
         if (NSPLIT == 3) {
-            const int t = threadIdx.x - 64;
+            const int t = warp * 32 + lane - 64;
             int stage = 0, phase = 0;
             for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
                 for (int tt = 0; tt < g.TPS * (g.KB1 / g.KPS); ++tt) {
@@ -536,6 +542,7 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     g = bg;
     if (!fits) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: tables and operands do not fit in shared / tensor memory");
     g.n_super = B * C / (g.TPS * g.IPT);
+    g.swap13 = !(getenv("PNO_FWD_SWAP13") && atoi(getenv("PNO_FWD_SWAP13")) == 0);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
     g.dbg = g_pno_debug_buffer;
     if ((reinterpret_cast<uintptr_t>(x) & 15)) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd needs a 16-byte aligned input");

@@ -16,6 +16,10 @@
 // tiles are [128 i][32 o] (o is contiguous in the parameter arrays, so no transposition) and the MMA sign pattern conjugates W.
 #include <stdlib.h>
 
+// tcgen05.mma / commit predicated by an elect.sync INSIDE the asm statement instead of by a lane == 0 flag: ptxas then knows the
+// instruction has one executing lane and drops its per-instruction ELECT loop.  Measured over all kernels (round 2): neutral except
+// here -- fp32-parity mix 301 -> 284 us (48 MMAs per k-block) -- and the forward transform, which loses 5 us; so only this file.
+#define PNO_ELECT_ASM 1
 #include "pno_sm100.cuh"
 #include "pno_tc.cuh"
 

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const SelfTestArgs a, con
             else         bd = make_sdesc(b0 + ks * 1024, (uint32_t)K * 128, 512, SWIZZLE_128B_BASE32B);
             mma_tf32_ss(tmem, ad, bd, idesc, ks > 0);
         }
-        mma_commit(&bar_mma);
+        mma_commit_1t(&bar_mma);
     }
     mbar_wait(&bar_mma, 0);
     tc_fence_after_sync();
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(128) k_umma_selftest_mixed(const MixedArgs a, 
                 }
             }
         }
-        mma_commit(&bar_mma);
+        mma_commit_1t(&bar_mma);
     }
     mbar_wait(&bar_mma, 0);
     tc_fence_after_sync();
