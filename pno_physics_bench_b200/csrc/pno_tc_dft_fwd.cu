@@ -44,6 +44,9 @@ struct FwdGeom {
     int KPS;        // x k-blocks per ring stage (a whole tile when W <= 64: one barrier round trip per tile instead of per k-block)
     int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
     int swap13;               // physical warps 1 and 3 swap roles (see the kernel)
+    int stack;                // stage 2 with the stacked table T = [S; C; -S] (see issue_stage2): half the MMAs, one accumulator
+    int pf;                   // L2 prefetch distance of the x tiles, in 128-row tiles (0 = off)
+    int tw_rows;              // rows of one TwT k-block in shared memory (N1p, or 2*m2 rounded to 8 when the padding rows are not stored)
     // shared-memory byte offsets (from the 1024-aligned base)
     int off_tab, off_tw, off_ring, off_b2, stage_bytes, x_bytes, tw_one, tab_one, b2_one, b2_bytes, smem_bytes;
     long long* dbg;   // optional event trace (PNO_TRACE builds)
@@ -54,6 +57,7 @@ struct FwdGeom {
 struct TcTables {
     float *twT_hi, *twT_lo;   // [N1p][W]
     float *c_hi, *c_lo, *s_hi, *s_lo;   // [R2][H]
+    float *t_hi, *t_lo;                 // [3*R2][H]: S, C, -S stacked (rows [0, 2 R2) = [S; C], rows [R2, 3 R2) = [C; -S])
     // inverse-transform tables (pno_tc_dft_inv.cu)
     float *inv_a_hi, *inv_a_lo, *inv_w_hi, *inv_w_lo;
     int N1p, R2;
@@ -131,16 +135,21 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     // tables: (C hi, [C lo], S hi, [S lo]), each KB2 k-blocks of [R2 x 128 B]; TwT (hi, [lo]) each KB1 k-blocks of [N1p x 128 B]
     unsigned char* tab = smem + g.off_tab;
     unsigned char* twt = smem + g.off_tw;
-    const int tab_kb = g.R2 * 128;
-    const int tw_kb = g.N1p * 128;
+    const int tab_kb = (g.stack ? 3 : 1) * g.R2 * 128;
+    const int tw_kb = g.tw_rows * 128;
     // B2 operands: (Rre hi, [Rre lo], Rim hi, [Rim lo]), each KB2 k-blocks of [N2p x 128 B]; rows = (tile in batch, image, ky)
     const int b2_kb = g.N2p * 128;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bar_tab, 2 * NT * g.tab_one + NT * g.tw_one);
+            mbar_arrive_expect_tx(&bar_tab, (g.stack ? 1 : 2) * NT * g.tab_one + NT * g.tw_one);
             for (int kb = 0; kb < g.KB2; ++kb) {
+                if (g.stack) {          // tmCHi / tmCLo carry the stacked table (hi / lo)
+                    tma_load_2d(tab + kb * tab_kb, &tmCHi, &bar_tab, kb * 32, 0);
+                    if (NSPLIT == 3) tma_load_2d(tab + g.tab_one + kb * tab_kb, &tmCLo, &bar_tab, kb * 32, 0);
+                    continue;
+                }
                 tma_load_2d(tab + 0 * g.tab_one + kb * tab_kb, &tmCHi, &bar_tab, kb * 32, 0);
                 tma_load_2d(tab + NT * g.tab_one + kb * tab_kb, &tmSHi, &bar_tab, kb * 32, 0);
                 if (NSPLIT == 3) {
@@ -153,9 +162,19 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (NSPLIT == 3) tma_load_2d(twt + g.tw_one + kb * tw_kb, &tmTwLo, &bar_tab, kb * 32, 0);
             }
             int stage = 0, phase = 0;
+            // this CTA's tiles are TPS consecutive 128-row tiles per super tile, super tiles gridDim.x apart: pull the tile that is
+            // g.pf tiles ahead into L2 so that the ring (2-3 stages: tables and B2 operands take most of the shared memory) is filled
+            // at L2 latency
+            const int total_rows = g.n_super * g.TPS * 128;
             for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
                 for (int t = 0; t < g.TPS; ++t) {
                     const int row0 = (sup * g.TPS + t) * 128;          // row of the [B*C*H][W] view
+                    if (g.pf) {
+                        const int ta = t + g.pf;                       // tile index ahead, in this CTA's sequence
+                        const int prow = ((sup + (ta / g.TPS) * (int)gridDim.x) * g.TPS + ta % g.TPS) * 128;
+                        if (prow < total_rows)
+                            for (int kb = 0; kb < g.KB1; ++kb) tma_prefetch_l2_2d(&tmX, kb * 32, prow);
+                    }
                     for (int kb = 0; kb < g.KB1; kb += g.KPS) {
                         mbar_wait(&bar_empty[stage], phase ^ 1);
                         TRACE(3, 1);
@@ -234,6 +253,20 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         const uint32_t first = (kb | ks) ? 1u : 0u;
                         const uint32_t c = tb + ((kb * tab_kb) >> 4) + ks * 2, r = bbase + ((kb * b2_kb) >> 4) + ks * 2;
                         const uint32_t sn = c + NT * t1, ri = r + NT * bo1;
+                        if (g.stack) {
+                            // one accumulator, rows [0, R2) = Xre = C Rre + S Rim, rows [R2, 2 R2) = Xim = -S Rre + C Rim:
+                            // A = [C; -S] (table rows R2 ..) with Rre, A = [S; C] (table rows 0 ..) with Rim
+                            const uint32_t a_cs = c + ((g.R2 * 128) >> 4), a_sc = c;
+                            mma_tf32(d_re, a_cs, khi, r, khi, idesc2, first, el);
+                            mma_tf32(d_re, a_sc, khi, ri, khi, idesc2, 1u, el);
+                            if (NSPLIT == 3) {
+                                mma_tf32(d_re, a_cs + t1, khi, r, khi, idesc2, 1u, el);
+                                mma_tf32(d_re, a_cs, khi, r + bo1, khi, idesc2, 1u, el);
+                                mma_tf32(d_re, a_sc + t1, khi, ri, khi, idesc2, 1u, el);
+                                mma_tf32(d_re, a_sc, khi, ri + bo1, khi, idesc2, 1u, el);
+                            }
+                            continue;
+                        }
                         // Xre += C Rre + S Rim ; Xim += C Rim - S Rre
                         mma_tf32(d_re, c, khi, r, khi, idesc2, first, el);
                         mma_tf32(d_re, sn, khi, ri, khi, idesc2, 1u, el);
@@ -363,11 +396,16 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         // lanes kx2 < 2*m1 of a D2 buffer hold Xre / Xim of one batch = GB = TPB*IPT images (consecutive channels);
         // warp = (lane quarter, re / im plane).  The batches of a super tile are adjacent pieces of the same 32-byte runs.
         const int q = warp & 3, part = (warp - 14) >> 2;
-        const int row = q * 32 + lane;
+        const int lrow = q * 32 + lane;                  // TMEM lane
         const int GB = g.TPB * g.IPT;
-        const bool warp_active = q * 32 < 2 * g.m1;      // warp-uniform: tcgen05.ld is warp-collective
-        const bool active = row < 2 * g.m1;
-        float* dst_plane = part ? xi : xr;
+        // separate accumulators: lanes [0, 2 m1) of buffer `part` (re / im).  Stacked: ONE accumulator, lanes [0, R2) = re and
+        // [R2, 2 R2) = im rows; the two warps of a quarter take alternate groups of four ky
+        const int half = g.stack ? lrow / g.R2 : part;
+        const int row = g.stack ? lrow - half * g.R2 : lrow;        // kx2
+        const bool warp_active = q * 32 < (g.stack ? 2 * g.R2 : 2 * g.m1);      // warp-uniform: tcgen05.ld is warp-collective
+        const bool active = row < 2 * g.m1 && half < 2;
+        float* dst_plane = half ? xi : xr;
+        const int ky_first = g.stack ? part * 4 : 0, ky_step = g.stack ? 8 : 4;
         const int bps = g.TPS / g.TPB;                   // batches per super tile
         int slot = 0, sph = 0;
         for (int sup = blockIdx.x; sup < g.n_super; sup += gridDim.x) {
@@ -379,8 +417,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 tc_fence_after_sync();
                 if (warp_active) {
                     const int b = sb, c0 = sc0 + k * GB;         // a super tile never straddles a batch item (C % (bps*GB) == 0)
-                    const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + part * g.N2p);
-                    for (int ky0 = 0; ky0 < g.m2; ky0 += 4) {
+                    const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + (g.stack ? 0 : part * g.N2p));
+                    for (int ky0 = ky_first; ky0 < g.m2; ky0 += ky_step) {
                         float vals[8][4];
 #pragma unroll
                         for (int gi = 0; gi < 8; ++gi) {
@@ -461,9 +499,17 @@ int tc_tables_get(const pno_plan* cp, void** out) {
             s_hi[(size_t)r * H + h] = sh; s_lo[(size_t)r * H + h] = tf32_round_host(s - (double)sh);
         }
     }
+    // stacked form [S; C; -S] (hi / lo parts negate exactly)
+    const size_t n1 = (size_t)t->R2 * H;
+    std::vector<float> st_hi(3 * n1), st_lo(3 * n1);
+    for (size_t i = 0; i < n1; ++i) {
+        st_hi[i] = s_hi[i]; st_hi[n1 + i] = c_hi[i]; st_hi[2 * n1 + i] = -s_hi[i];
+        st_lo[i] = s_lo[i]; st_lo[n1 + i] = c_lo[i]; st_lo[2 * n1 + i] = -s_lo[i];
+    }
     int rc;
     if ((rc = upload(&t->twT_hi, tw_hi)) || (rc = upload(&t->twT_lo, tw_lo)) || (rc = upload(&t->c_hi, c_hi)) ||
-        (rc = upload(&t->c_lo, c_lo)) || (rc = upload(&t->s_hi, s_hi)) || (rc = upload(&t->s_lo, s_lo)))
+        (rc = upload(&t->c_lo, c_lo)) || (rc = upload(&t->s_hi, s_hi)) || (rc = upload(&t->s_lo, s_lo)) ||
+        (rc = upload(&t->t_hi, st_hi)) || (rc = upload(&t->t_lo, st_lo)))
         return rc;
     p->tc_tables = t;
     *out = t;
@@ -473,7 +519,8 @@ int tc_tables_get(const pno_plan* cp, void** out) {
 void tc_plan_release(pno_plan* p) {
     if (!p->tc_tables) return;
     TcTables* t = static_cast<TcTables*>(p->tc_tables);
-    float* ptrs[] = {t->twT_hi, t->twT_lo, t->c_hi, t->c_lo, t->s_hi, t->s_lo, t->inv_a_hi, t->inv_a_lo, t->inv_w_hi, t->inv_w_lo};
+    float* ptrs[] = {t->twT_hi, t->twT_lo, t->c_hi, t->c_lo, t->s_hi, t->s_lo, t->t_hi, t->t_lo, t->inv_a_hi, t->inv_a_lo, t->inv_w_hi,
+                     t->inv_w_lo};
     for (float* q : ptrs)
         if (q) cudaFree(q);
     delete t;
@@ -499,21 +546,32 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     g.x_bytes = 128 * 128;                        // [128 rows][32 floats]
     g.KPS = 1;
     g.stage_bytes = NT * g.x_bytes;
-    g.tab_one = g.KB2 * g.R2 * 128;
-    g.tw_one = g.KB1 * g.N1p * 128;
+    // stacked stage-2 tables (see the kernel): on for the fp32-parity engine, where stage 2 is 96 MMAs per batch on one issuer and
+    // serialises with the transposer (one B2 operand buffer); PNO_FWD_STACK=0 / 1 forces the choice (tuning)
+    // (measured at the headline shape: fp32-parity 202 -> 192 us, single pass 121 -> 137 us).  If the larger tables do not fit, the
+    // un-stacked form is tried next.
+    int want_stack = getenv("PNO_FWD_STACK") ? atoi(getenv("PNO_FWD_STACK")) : (x3 ? 1 : 0);
+    if (2 * g.R2 > 128 || 3 * g.R2 > 256) want_stack = 0;      // accumulator lanes; TMA box rows
+    bool fits = false;
+    int best = -1;
+    FwdGeom bg = g;
+  for (int stack_try = want_stack; stack_try >= 0 && !fits; --stack_try) {
+    g.stack = stack_try;
+    g.tab_one = g.KB2 * (g.stack ? 3 : 1) * g.R2 * 128;
+    // the padding rows [2 m2, N1p) of a TwT k-block are not stored when the stacked tables need the room: the MMA reads the rows
+    // that follow instead, and the accumulator columns they feed are never read
+    g.tw_rows = g.stack ? pad_to(2 * m2, 8) : g.N1p;
+    g.tw_one = g.KB1 * g.tw_rows * 128;
     g.off_tab = 0;
-    g.off_tw = pad_to(2 * NT * g.tab_one, 1024);
+    g.off_tw = pad_to((g.stack ? 1 : 2) * NT * g.tab_one, 1024);
     g.off_b2 = g.off_tw + pad_to(NT * g.tw_one, 1024);
     // M = 128 operand reads run past the R2 rows of the last table k-block: the regions that follow (TwT, B2, ring) are at
     // least 16 KB, so those reads stay inside the allocation (the rows they produce are never read back).
     // super tile = up to 8 consecutive channels (32-byte runs in the [mode][b][c] output); stage-2 batch = as many of its
     // tiles as TMEM (512 columns), the MMA (N <= 256) and shared memory (>= 3 ring stages) allow
     const int budget = 226 * 1024 - 1024;
-    bool fits = false;
     int want = 8 / g.IPT;
     if (want < 1) want = 1;
-    int best = -1;
-    FwdGeom bg = g;
     for (int ns = want; ns >= 1; ns >>= 1) {
         if (C % (ns * g.IPT)) continue;
         for (int tpb = ns; tpb >= 1; tpb >>= 1) {
@@ -539,9 +597,13 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
             }
         }
     }
+  }
     g = bg;
     if (!fits) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_fwd: tables and operands do not fit in shared / tensor memory");
     g.n_super = B * C / (g.TPS * g.IPT);
+    // measured at the headline shape: fp32-parity engine (2 ring stages) 191 -> 185 us with a distance of 1, single pass (3 stages)
+    // 128 -> 131 / 136 us with 1 / 4: on for the former only
+    g.pf = getenv("PNO_FWD_PF") ? atoi(getenv("PNO_FWD_PF")) : (x3 ? 1 : 0);
     g.swap13 = !(getenv("PNO_FWD_SWAP13") && atoi(getenv("PNO_FWD_SWAP13")) == 0);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
     g.dbg = g_pno_debug_buffer;
@@ -562,7 +624,7 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     {
         const uint64_t dims[2] = {(uint64_t)W, (uint64_t)g.N1p};
         const uint64_t str[1] = {(uint64_t)W * 4};
-        const uint32_t box[2] = {32, (uint32_t)g.N1p};
+        const uint32_t box[2] = {32, (uint32_t)g.tw_rows};
         if ((rc = pno_encode_tmap(&tmTwHi, t->twT_hi, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmTwLo, t->twT_lo, 2, dims, str, box, 1))) return rc;
     }
@@ -574,6 +636,13 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
         if ((rc = pno_encode_tmap(&tmCLo, t->c_lo, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmSHi, t->s_hi, 2, dims, str, box, 1))) return rc;
         if ((rc = pno_encode_tmap(&tmSLo, t->s_lo, 2, dims, str, box, 1))) return rc;
+    }
+    if (g.stack) {
+        const uint64_t dims[2] = {(uint64_t)H, (uint64_t)3 * g.R2};
+        const uint64_t str[1] = {(uint64_t)H * 4};
+        const uint32_t box[2] = {32, (uint32_t)(3 * g.R2)};
+        if ((rc = pno_encode_tmap(&tmCHi, t->t_hi, 2, dims, str, box, 1))) return rc;
+        if ((rc = pno_encode_tmap(&tmCLo, t->t_lo, 2, dims, str, box, 1))) return rc;
     }
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
