@@ -1,8 +1,9 @@
 // Weight gradient of the spectral channel mix on the tensor cores (autograd of reference models.py:33-35, 63-80, 93-94):
 //   dmu[mode][i][o] = sum_b conj(xhat[mode][b][i]) ghat[mode][b][o]
 //   dlv[mode][i][o] = 0.5 exp(lv/2) (eps_re Re(dmu) + eps_im Im(dmu))        (eps re-drawn from the forward's Philox counters)
-// Work item = (mode, 128 input channels i, 128 output channels o).  The reduction runs over the batch (K = B, a few K steps), so
-// the kernel is all epilogue: both operands are MN-major tiles straight from the [mode][b][c] spectra by TMA (3-D maps: rows
+// Work item = (mode, 128 input channels i, 128 output channels o).  The reduction runs over the batch (K = B): a few K steps, fed
+// through the stage ring in chunks of KC batch rows (one chunk for the training batches of BASELINE config 2; several for the global
+// batches of mode-parallel training, any B), so the kernel is all epilogue: both operands are MN-major tiles straight from the [mode][b][c] spectra by TMA (3-D maps: rows
 // b >= B are zero-filled), the issuer needs 4 real MMAs per K step (a negated-A instruction descriptor gives the minus sign),
 // accumulators (Re | Im, 2 x 128 columns) are double buffered in tensor memory, and 16 epilogue warps re-draw the noise, load
 // log_var and write dmu (interleaved complex) and dlv as whole 32-byte sectors per lane.
@@ -24,6 +25,7 @@ struct DwGeom {
     int B, Bp, Ci, Co, m1m2, Cop, n_modes;
     int mode_first, w_sub;          // mode window (see MixGeom in pno_tc_mix.cu)
     int i_tiles, o_tiles, n_items;
+    int KC, n_kc;                   // batch rows per ring stage (multiple of 8), chunks per work item
     int tile_bytes, stage_bytes, stages;
     const float *lv1, *lv2;
     float *dmu1, *dmu2, *dlv1, *dlv2;
@@ -71,7 +73,7 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const int T = g.tile_bytes;                      // one operand tile: [4 blocks of 32 channels][Bp rows][128 B]
+    const int T = g.tile_bytes;                      // one operand tile: [4 blocks of 32 channels][KC batch rows][128 B]
     const int per_mode = g.i_tiles * g.o_tiles;
 
     if (warp == 0) {
@@ -80,36 +82,40 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int mode = item / per_mode, r = item - mode * per_mode;
                 const int it = r / g.o_tiles, ot = r - it * g.o_tiles;
-                mbar_wait(&bar_empty[stage], phase ^ 1);
-                unsigned char* st = smem + (size_t)stage * g.stage_bytes;
-                mbar_arrive_expect_tx(&bar_full[stage], 4 * T);
-                for (int cb = 0; cb < 4; ++cb) {
-                    tma_load_3d(st + 0 * T + cb * g.Bp * 128, &tmXr, &bar_full[stage], it * TM + cb * 32, 0, mode);
-                    tma_load_3d(st + 1 * T + cb * g.Bp * 128, &tmXi, &bar_full[stage], it * TM + cb * 32, 0, mode);
-                    tma_load_3d(st + 2 * T + cb * g.Bp * 128, &tmGr, &bar_full[stage], ot * TM + cb * 32, 0, mode);
-                    tma_load_3d(st + 3 * T + cb * g.Bp * 128, &tmGi, &bar_full[stage], ot * TM + cb * 32, 0, mode);
+                for (int kc = 0; kc < g.n_kc; ++kc) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    unsigned char* st = smem + (size_t)stage * g.stage_bytes;
+                    mbar_arrive_expect_tx(&bar_full[stage], 4 * T);
+                    const int b0 = kc * g.KC;                      // rows b >= B of the box are out of bounds: zero fill
+                    for (int cb = 0; cb < 4; ++cb) {
+                        tma_load_3d(st + 0 * T + cb * g.KC * 128, &tmXr, &bar_full[stage], it * TM + cb * 32, b0, mode);
+                        tma_load_3d(st + 1 * T + cb * g.KC * 128, &tmXi, &bar_full[stage], it * TM + cb * 32, b0, mode);
+                        tma_load_3d(st + 2 * T + cb * g.KC * 128, &tmGr, &bar_full[stage], ot * TM + cb * 32, b0, mode);
+                        tma_load_3d(st + 3 * T + cb * g.KC * 128, &tmGi, &bar_full[stage], ot * TM + cb * 32, b0, mode);
+                    }
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         const uint32_t el = lane == 0;
         const uint32_t id = make_idesc(FMT_TF32, TM, TM, MAJOR_MN, MAJOR_MN);
         const uint32_t idn = make_idesc(FMT_TF32, TM, TM, MAJOR_MN, MAJOR_MN, 1, 0);        // -A
-        const uint32_t dhi = sdesc_base(0, (uint32_t)g.Bp * 128, 512, SWIZZLE_128B_BASE32B).hi;
+        const uint32_t dhi = sdesc_base(0, (uint32_t)g.KC * 128, 512, SWIZZLE_128B_BASE32B).hi;
         const uint32_t t16 = T >> 4, lo = (4 * T) >> 4;
         int stage = 0, phase = 0, n = 0;
         for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n) {
             const int acc = n & 1;
             mbar_wait(&bar_tempty[acc], ((n >> 1) & 1) ^ 1);
+            const uint32_t d_re = tmem + acc * 256, d_im = d_re + 128;
+          for (int kc = 0; kc < g.n_kc; ++kc) {
             mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_full[stage], phase);
             tc_fence_after_sync();
-            const uint32_t d_re = tmem + acc * 256, d_im = d_re + 128;
-            const uint32_t xr = sdesc_base(smem_u32(smem + (size_t)stage * g.stage_bytes), (uint32_t)g.Bp * 128, 512, SWIZZLE_128B_BASE32B).lo;
+            const uint32_t xr = sdesc_base(smem_u32(smem + (size_t)stage * g.stage_bytes), (uint32_t)g.KC * 128, 512, SWIZZLE_128B_BASE32B).lo;
             const uint32_t xi = xr + t16, gr = xr + 2 * t16, gi = xr + 3 * t16;
-            for (int ks = 0; ks < g.Bp / 8; ++ks) {
+            for (int ks = 0; ks < g.KC / 8; ++ks) {
                 const uint32_t o = ks * 64;                 // 8 K rows x 128 B
-                const uint32_t first = ks ? 1u : 0u;
+                const uint32_t first = (kc | ks) ? 1u : 0u;
                 // Re += Xre^T Gre + Xim^T Gim ; Im += Xre^T Gim - Xim^T Gre
                 mma_tf32(d_re, xr + o, dhi, gr + o, dhi, id, first, el);
                 mma_tf32(d_re, xi + o, dhi, gi + o, dhi, id, 1u, el);
@@ -127,14 +133,16 @@ k_tc_mix_dw(const DwGeom g, const __grid_constant__ CUtensorMap tmXr, const __gr
                 }
             }
             mma_commit(&bar_empty[stage], el);
-            mma_commit(&bar_tfull[acc], el);
             if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          }
+            mma_commit(&bar_tfull[acc], el);
         }
     } else if (warp < 6) {
         if (NSPLIT == 3) {
             const int t = threadIdx.x - 64;
             int stage = 0, phase = 0;
-            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x)
+            for (int kc = 0; kc < g.n_kc; ++kc) {
                 mbar_wait(&bar_full[stage], phase);
                 const uint32_t hi = smem_u32(smem + (size_t)stage * g.stage_bytes), lw = hi + 4 * T;
 #pragma unroll 4
@@ -223,8 +231,8 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
                   cudaStream_t st, int mode_first, int mode_count) {
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
     const bool sampled = lv1 != nullptr && dlv1 != nullptr;
-    if (B < 1 || B > 128 || Ci % TM || Co % TM || !dmu1 || !dmu2)
-        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_bwd_dw tiles 1 <= B <= 128, Ci%%128 == 0, Co%%128 == 0 and writes both dmu blocks (got %d, %d, %d)",
+    if (B < 1 || Ci % TM || Co % TM || !dmu1 || !dmu2)
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_bwd_dw tiles B >= 1, Ci%%128 == 0, Co%%128 == 0 and writes both dmu blocks (got %d, %d, %d)",
                  B, Ci, Co);
     if ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(xi) | reinterpret_cast<uintptr_t>(gr) |
          reinterpret_cast<uintptr_t>(gi) | reinterpret_cast<uintptr_t>(lv1) | reinterpret_cast<uintptr_t>(lv2) |
@@ -244,11 +252,16 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
         g.w_sub = mode_first - blk0 * g.m1m2;
     }
     g.i_tiles = Ci / TM; g.o_tiles = Co / TM; g.n_items = g.n_modes * g.i_tiles * g.o_tiles;
-    g.tile_bytes = TM * g.Bp * 4;
+    // batch rows per ring stage: the whole batch while one stage holds it (B <= 32 with hi / lo copies, <= 48 single pass: the
+    // training batches), else chunks small enough for a three-stage ring
+    const int kc_one = x3 ? 32 : 48, kc_many = x3 ? 16 : 32;
+    g.KC = g.Bp <= kc_one ? g.Bp : kc_many;
+    g.n_kc = (g.Bp + g.KC - 1) / g.KC;
+    g.tile_bytes = TM * g.KC * 4;
     g.stage_bytes = 4 * g.tile_bytes * (x3 ? 2 : 1);
     g.stages = (200 * 1024) / g.stage_bytes;
     if (g.stages > 3) g.stages = 3;
-    if (g.stages < 1) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_bwd_dw: batch %d needs %d bytes of shared memory per stage", B, g.stage_bytes);
+    if (g.stages < 1) PNO_FAIL(PNO_E_UNSUPPORTED, "tc_mix_bwd_dw: %d bytes of shared memory per stage", g.stage_bytes);
     if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     g.lv1 = lv1; g.lv2 = lv2; g.dmu1 = dmu1; g.dmu2 = dmu2; g.dlv1 = dlv1; g.dlv2 = dlv2; g.key = key;
     const int smem = g.stages * g.stage_bytes + 1024;
@@ -257,7 +270,7 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
     {   // [mode][b][c]: box = 32 channels x Bp batch rows of one mode; rows b >= B are out of bounds -> zero fill
         const uint64_t dx[3] = {(uint64_t)Ci, (uint64_t)B, (uint64_t)g.n_modes}, dg[3] = {(uint64_t)Co, (uint64_t)B, (uint64_t)g.n_modes};
         const uint64_t sx[2] = {(uint64_t)Ci * 4, (uint64_t)B * Ci * 4}, sg[2] = {(uint64_t)Co * 4, (uint64_t)B * Co * 4};
-        const uint32_t box[3] = {32, (uint32_t)g.Bp, 1};
+        const uint32_t box[3] = {32, (uint32_t)g.KC, 1};
         if ((rc = pno_encode_tmap(&tmXr, xr, 3, dx, sx, box, 2))) return rc;
         if ((rc = pno_encode_tmap(&tmXi, xi, 3, dx, sx, box, 2))) return rc;
         if ((rc = pno_encode_tmap(&tmGr, gr, 3, dg, sg, box, 2))) return rc;

@@ -69,6 +69,27 @@ def batch_from_modes(spec, group=None):
     return recv.permute(1, 0, 2, 3, 4).reshape(P, ws * n, B, C)
 
 
+MIX_MAX_BATCH = 128          # batch rows one launch of the forward / input-gradient channel-mix kernels takes (their MMA N)
+
+
+def _mix_window_batched(fn, name, plan, engine, src, bg, ci, co, mu_ptr, lv_ptr, key, first, count, dst, st):
+    """One mode window of pno_mix_fwd_window / pno_mix_bwd_dx_window over a global batch of any size: src / dst are the
+    [2, count, bg, C] slices of this window.  Up to MIX_MAX_BATCH rows go through in place; a larger global batch (8 ranks x 32) is
+    cut into batch chunks, each staged through a dense copy (the kernels take dense [mode][b][c] spectra)."""
+    seed, sample_idx, site = key
+    if bg <= MIX_MAX_BATCH:
+        _lib.check(fn(plan, engine, src[0].data_ptr(), src[1].data_ptr(), bg, ci, co, mu_ptr, lv_ptr, seed, sample_idx, site, first,
+                      count, dst[0].data_ptr(), dst[1].data_ptr(), st), name)
+        return
+    for b0 in range(0, bg, MIX_MAX_BATCH):
+        b1 = min(bg, b0 + MIX_MAX_BATCH)
+        part = src[:, :, b0:b1].contiguous()
+        out = torch.empty(2, count, b1 - b0, dst.shape[3], dtype=torch.float32, device=src.device)
+        _lib.check(fn(plan, engine, part[0].data_ptr(), part[1].data_ptr(), b1 - b0, ci, co, mu_ptr, lv_ptr, seed, sample_idx, site, first,
+                      count, out[0].data_ptr(), out[1].data_ptr(), st), name)
+        dst[:, :, b0:b1].copy_(out)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # the sharded spectral layer
 # ----------------------------------------------------------------------------------------------------------------------
@@ -98,11 +119,9 @@ class _ModeParallelSpectralFn(torch.autograd.Function):
             mu_r = torch.view_as_real(mu.detach())
             off = 0
             for first, count in windows:
-                _lib.check(lib.pno_mix_fwd_window(plan, engine, xs[0, off:off + count].data_ptr(), xs[1, off:off + count].data_ptr(),
-                                                  bg, ci, co, mu_r[off:off + count].data_ptr(),
-                                                  lv[off:off + count].data_ptr() if sampled else None, seed, sample_idx, site,
-                                                  first, count, ys[0, off:off + count].data_ptr(), ys[1, off:off + count].data_ptr(),
-                                                  st), "pno_mix_fwd_window")
+                _mix_window_batched(lib.pno_mix_fwd_window, "pno_mix_fwd_window", plan, engine, xs[:, off:off + count], bg, ci, co,
+                                    mu_r[off:off + count].data_ptr(), lv[off:off + count].data_ptr() if sampled else None,
+                                    (seed, sample_idx, site), first, count, ys[:, off:off + count], st)
                 off += count
             yh = batch_from_modes(ys, group)                                        # [2, M, B_loc, Co]
             y = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
@@ -152,10 +171,9 @@ class _ModeParallelSpectralFn(torch.autograd.Function):
                                                          sample_idx, site, first, count, dmu[sl].data_ptr(),
                                                          dlv[sl].data_ptr() if need_lv else None, st), "pno_mix_bwd_dw_window")
                 if dxs is not None:
-                    _lib.check(lib.pno_mix_bwd_dx_window(plan, engine, gs[0, sl].data_ptr(), gs[1, sl].data_ptr(), bg, ci, co,
-                                                         mu_r[sl].data_ptr(), lv[sl].data_ptr() if sampled else None, seed, sample_idx,
-                                                         site, first, count, dxs[0, sl].data_ptr(), dxs[1, sl].data_ptr(), st),
-                               "pno_mix_bwd_dx_window")
+                    _mix_window_batched(lib.pno_mix_bwd_dx_window, "pno_mix_bwd_dx_window", plan, engine, gs[:, sl], bg, ci, co,
+                                        mu_r[sl].data_ptr(), lv[sl].data_ptr() if sampled else None, (seed, sample_idx, site), first,
+                                        count, dxs[:, sl], st)
                 off += count
             dx = None
             if dxs is not None:

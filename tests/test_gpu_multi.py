@@ -46,3 +46,13 @@ def test_mode_parallel_on_one_rank_equals_the_model():
                        timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "MP_CHECK_OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_mode_parallel_batch_chunks_on_one_rank():
+    """A global batch larger than one channel-mix launch takes (8 ranks x 32 fields = 256 rows) is cut into batch chunks, and the
+    weight-gradient kernel walks the batch in K chunks: same step as the unsharded model (batch 40, 16 rows per launch)."""
+    env = dict(os.environ, PNO_MP_BATCH="40", PNO_MP_MAX_BATCH="16")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mp_train_check.py")], cwd=ROOT, capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MP_CHECK_OK" in r.stdout, r.stdout[-2000:]

@@ -396,7 +396,8 @@ def _mix_bwd_dw(xr, xi, gr, gi, layer, sampled, engine):
 
 @pytest.mark.parametrize("engine,tol", [("tf32x3", 5e-6), ("tf32", 2e-3)])
 @pytest.mark.parametrize("sampled", [False, True])
-@pytest.mark.parametrize("shape", [(32, 256, 256, 6, 5), (5, 128, 256, 3, 4), (64, 128, 128, 2, 2), (12, 256, 128, 4, 4)])
+@pytest.mark.parametrize("shape", [(32, 256, 256, 6, 5), (5, 128, 256, 3, 4), (64, 128, 128, 2, 2), (12, 256, 128, 4, 4),
+                                   (72, 128, 128, 2, 3), (200, 128, 128, 1, 2)])      # the last two: several K chunks of the batch
 def test_mix_backward_dw_tensor_core_vs_cuda_core(engine, tol, sampled, shape):
     """Weight gradient of the channel mix (dmu and, with the noise re-drawn, dlv): tensor-core kernel vs the fp32 CUDA-core
     kernel, which the layer-level tests pin to the oracle's autograd.  Ragged batches exercise the TMA zero fill."""

@@ -35,8 +35,13 @@ def make():
     return m
 
 
+# PNO_MP_BATCH: batch per rank (default 4); PNO_MP_MAX_BATCH: batch rows per channel-mix launch (default 128) -- small values
+# exercise the batch chunking of the global batch (8 ranks x 32 fields) and the K chunks of the weight-gradient kernel
+import pno_physics_bench_b200.mode_parallel as mp_mod  # noqa: E402
+if os.environ.get("PNO_MP_MAX_BATCH"):
+    mp_mod.MIX_MAX_BATCH = int(os.environ["PNO_MP_MAX_BATCH"])
 g = torch.Generator().manual_seed(1)
-B = 4 * world
+B = int(os.environ.get("PNO_MP_BATCH", "4")) * world
 x, y = torch.randn(B, 3, 32, 32, generator=g), torch.randn(B, 1, 32, 32, generator=g)
 
 # sharded step: modes and batch split over the ranks
