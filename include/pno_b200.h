@@ -93,6 +93,10 @@ const char* pno_last_error(void);
 int pno_check_device(void);
 /* number of CUDA kernels this library has launched in this process (monotonic; bench.py reports deltas) */
 uint64_t pno_launch_count(void);
+/* The persistent tensor-core kernels size their grids to (SM count - n): n SMs stay free for a kernel of another stream, e.g. the
+ * NCCL all-reduce of data-parallel training launched while backward is still running (reference: DDP bucket overlap,
+ * distributed_training.py:96-101).  Process-wide, 0 by default; takes effect at the next launch (captured graphs keep theirs). */
+int pno_set_sm_reserve(int n);
 /* out[2*stage + 0] / out[2*stage + 1] = successful calls of `stage` that ran on CUDA cores / on the tensor cores since the process
  * started (monotonic; PNO_N_STAGES pairs).  Tests assert on deltas that the tensor-core kernel really ran. */
 int pno_stage_counts(uint64_t* out);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "pno_last_error": (ctypes.c_char_p, []),
     "pno_check_device": (_int, []),
     "pno_launch_count": (_u64, []),
+    "pno_set_sm_reserve": (_int, [_int]),
     "pno_stage_counts": (_int, [_vp]),
     "pno_engine_supports": (_int, [_int] * 9),
     "pno_set_dynamic_noise": (_int, [_vp]),

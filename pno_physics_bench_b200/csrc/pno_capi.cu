@@ -17,6 +17,7 @@ void pno_set_error(const char* fmt, ...) {
 }
 
 unsigned long long g_pno_launches = 0;
+int g_pno_sm_reserve = 0;
 long long* g_pno_debug_buffer = nullptr;
 thread_local const uint32_t* g_pno_dyn_key = nullptr;
 
@@ -136,6 +137,11 @@ extern "C" int pno_debug_set_buffer(void* device_ptr) {
 
 extern "C" int pno_version(void) { return PNO_VERSION; }
 extern "C" uint64_t pno_launch_count(void) { return g_pno_launches; }
+extern "C" int pno_set_sm_reserve(int n) {
+    if (n < 0 || n > 64) PNO_FAIL(PNO_E_INVALID, "pno_set_sm_reserve: 0 <= n <= 64 (got %d)", n);
+    g_pno_sm_reserve = n;
+    return PNO_OK;
+}
 extern "C" const char* pno_last_error(void) { return g_err; }
 
 extern "C" int pno_check_device(void) {

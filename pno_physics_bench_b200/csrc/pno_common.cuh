@@ -27,6 +27,11 @@ void pno_set_error(const char* fmt, ...);
 
 extern long long* g_pno_debug_buffer;        // device buffer for kernel phase counters (NULL = off)
 extern unsigned long long g_pno_launches;   // kernels launched by this library (pno_launch_count)
+// SMs the persistent kernels leave free (pno_set_sm_reserve): a concurrent NCCL kernel needs somewhere to run -- every kernel here
+// owns a whole SM (shared memory, TMEM), so with grids of all 148 SMs a gradient all-reduce launched during backward only runs in
+// the gaps between our kernels
+extern int g_pno_sm_reserve;
+static inline int pno_usable_sms(int sms) { return sms - g_pno_sm_reserve < 1 ? 1 : sms - g_pno_sm_reserve; }
 #define PNO_LAUNCH_CHECK()            \
     do {                              \
         ++g_pno_launches;             \

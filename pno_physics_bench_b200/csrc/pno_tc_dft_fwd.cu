@@ -647,6 +647,7 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = pno_usable_sms(sms);
     const int grid = g.n_super < sms ? g.n_super : sms;
     if (x3) {
         PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

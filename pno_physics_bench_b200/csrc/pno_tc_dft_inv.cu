@@ -818,6 +818,7 @@ int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = pno_usable_sms(sms);
     const int grid = g.n_groups < sms ? g.n_groups : sms;
 #define PNO_LAUNCH_INV(NS, GG, AC, TSM)                                                                                         \
     do {                                                                                                                        \

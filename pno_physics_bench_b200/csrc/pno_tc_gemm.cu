@@ -239,6 +239,7 @@ int tc_rowgemm(int engine, const float* A, long long rows, int K, int N, const f
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = pno_usable_sms(sms);
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (x3) {
         PNO_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

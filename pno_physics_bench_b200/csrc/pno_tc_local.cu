@@ -456,6 +456,7 @@ int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, 
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = pno_usable_sms(sms);
     const int n_super = a.n_tiles / CL, groups = sms / CL;
     const int grid = (n_super < groups ? n_super : groups) * CL;
     if (CL > 1) PNO_CUDA(pno_launch_cluster(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, CL, a, tmX, tmWm, tmWl, tmW16));

@@ -471,6 +471,7 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = pno_usable_sms(sms);
     const int grid = g.n_items < sms ? g.n_items : sms;
 #define PNO_LAUNCH_MIX(NS, SM, BW, RW)                                                                                          \
     do {                                                                                                                       \

@@ -279,6 +279,7 @@ int tc_mix_bwd_dw(const pno_plan* p, int engine, const float* xr, const float* x
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = pno_usable_sms(sms);
     const int grid = g.n_items < sms ? g.n_items : sms;
 #define PNO_LAUNCH_DW(NS, SM)                                                                                      \
     do {                                                                                                           \

@@ -97,6 +97,13 @@ class GradientSynchronizer:
         self.enabled = True
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
 
+    def has_large(self):
+        """True when some parameter's gradient is all-reduced on its own, concurrently with backward (data parallelism over
+        replicated spectral weights; with mode-sharded weights only the small 1x1-conv gradients are left)."""
+        if not (self.enabled and _active(self.group)):
+            return False
+        return any(p.numel() * p.element_size() >= self.large_bytes for p in self.params)
+
     def _on_grad(self, p):
         if not self.enabled or not _active(self.group) or p.grad is None:
             return

@@ -3,7 +3,9 @@
 loss -> backward -> clip_grad_norm_ -> optimizer.step).  Additions: `train_step` is public, the step's Philox seed is
 shared across data-parallel ranks, gradients are averaged with bucketed NCCL all-reduces, and per-step `.item()` host
 syncs are deferred to the end of the epoch."""
+import contextlib
 import logging
+import os
 import time
 from pathlib import Path
 from typing import Dict, List, Optional
@@ -11,6 +13,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from .. import _lib
 from .. import functional as F_
 from ..distributed import GradientSynchronizer, shared_seed, world
 from .losses import ELBOLoss
@@ -67,7 +70,8 @@ class PNOTrainer:
                 kl_leaf = outputs[2].detach().requires_grad_(True)
                 outputs = (outputs[0], outputs[1], kl_leaf)
             losses = self.loss_fn(outputs, targets, self.model)
-            losses["total"].backward()
+            with self._sm_reserve_for_allreduce():
+                losses["total"].backward()
             if kl_leaf is not None and kl_leaf.grad is not None:
                 if isinstance(self.optimizer, FusedAdamW):      # identical on every rank: added after the gradient all-reduce
                     self.optimizer.set_analytic_kl(self.model.kl_params(), kl_leaf.grad)     # added inside the optimiser kernels
@@ -81,6 +85,22 @@ class PNOTrainer:
         self.optimizer.step()
         self.global_step += 1
         return losses
+
+    @contextlib.contextmanager
+    def _sm_reserve_for_allreduce(self):
+        """Data parallel: the gradient all-reduces are launched from autograd hooks while backward is still running, but every
+        kernel of this library is persistent and owns all 148 SMs, so the NCCL kernels would only run in the gaps.  During backward
+        the library leaves `PNO_DP_SM_RESERVE` SMs (default 8) to them (`pno_set_sm_reserve`)."""
+        n = int(os.environ.get("PNO_DP_SM_RESERVE", "8")) if (self.grad_sync is not None and self.grad_sync.has_large()) else 0
+        if n <= 0:
+            yield
+            return
+        lib = _lib.load()
+        _lib.check(lib.pno_set_sm_reserve(n), "pno_set_sm_reserve")
+        try:
+            yield
+        finally:
+            _lib.check(lib.pno_set_sm_reserve(0), "pno_set_sm_reserve")
 
     def _train_epoch(self, loader) -> Dict[str, float]:
         sums, count = {}, 0
