@@ -46,6 +46,7 @@ struct LocalArgs {
     int B, Ci, Co, HW;
     int noisy, want_dlv;
     int prefetch;           // L2 prefetch of the next tile's x boxes
+    int tma_out;            // the epilogue stages each pass ([32 rows][16 px]) in shared memory and a TMA store writes it (see below)
     int ablate;             // measurement only (PNO_LOCAL_ABLATE, wrong results): 1 = weight tiles fetched for the first k-block of a tile only
     const float *bm, *bl;
     float *out, *dlv;
@@ -68,7 +69,10 @@ struct Cfg {
     static constexpr int kX16 = ((TN + 63) / 64) * TK * 128;
     static constexpr int kStageBytes = kOperandBytes + (NSPLIT == 3 ? 4 * kW16 + 2 * kX16 : 0);
     static constexpr int kStages = (224 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (fp32 parity)
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    // output staging of the epilogue warps (tma_out): two [32 rows][64 B] buffers per warp behind the operand ring
+    static constexpr int kOutStage = 32 * 64;
+    static constexpr int kOutBytes = EW == 8 ? EW * 2 * kOutStage : 0;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024;
     static constexpr int kAcc = 4 * TN <= 512 ? 2 : 1;                           // accumulator buffers in tensor memory
     static_assert(kStages >= 2, "stage does not fit");
 };
@@ -84,7 +88,8 @@ struct Cfg {
 template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW, int EPI = 0, int CL = 1>
 __global__ void __launch_bounds__(threads_for(NSPLIT, EW), 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
-           const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmW16) {
+           const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmW16,
+           const __grid_constant__ CUtensorMap tmOut) {
     using C = Cfg<NSPLIT, TN, EW>;
     // two MMA issuers on different sub-partitions, one per accumulator (mean conv / log-var conv): an issuer needs ~53 of the 64
     // cycles an N = 128 MMA takes just to issue it, so ONE issuer feeding both accumulators has no slack at all when the ALU-bound
@@ -306,6 +311,12 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         constexpr int EWQ = EW / 4, NP = TN / 16;
         static_assert(EW % 4 == 0 && NP >= EWQ, "every epilogue warp needs a pass in every tile");
         int it = 0, base = 0;                   // base = (it * NP) % EWQ
+        // tma_out: a lane's 64-byte piece of its output row goes to a swizzled [32 rows][64 B] staging buffer (two per warp) and one
+        // TMA store per pass writes the 32 x 16 block: the scattered row stores (32 lines per store instruction) cost L1 / LSU
+        // wavefronts that the MMA's operand reads lack (52 of 312 us in the fp32-parity kernel, 17 of 168 single pass)
+        const uint32_t ostage = smem_u32(smem + (size_t)C::kStages * C::kStageBytes) + warp * 2 * C::kOutStage;
+        const uint32_t orow = ostage + lane * 64, osw = (lane >> 1) & 3;
+        int obuf = 0;
         for (int tile = su0; tile < n_super; tile += su_step, ++it) {
             int ot, pt, b;
             if (it < kTileTab) { ot = s_tile[it][0]; pt = s_tile[it][1]; b = s_tile[it][2]; }
@@ -394,7 +405,25 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     if (v[0] == 1.2345e-30f && v[7] == 7.7e-20f) a.out[0] = v[1];
                     continue;
                 }
-                lane_store16(a.out + wrow + c, v);
+                if (C::kOutBytes && a.tma_out) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the store that read this buffer two passes ago
+                    __syncwarp();
+                    const uint32_t dst = orow + obuf * C::kOutStage;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        sts128(dst + ((k ^ osw) << 4), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, reinterpret_cast<const void*>(smem + (size_t)C::kStages * C::kStageBytes +
+                                                                            (size_t)(warp * 2 + obuf) * C::kOutStage),
+                                     pt * TN + c, b * a.Co + ot * TM + q * 32);
+                        bulk_commit_group();
+                    }
+                    obuf ^= 1;
+                } else {
+                    lane_store16(a.out + wrow + c, v);
+                }
                 if (NOISY && DLV) lane_store16(a.dlv + wrow + c, l);
             }
             base += NP % EWQ;
@@ -404,6 +433,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             if (warp == 0) TRACE(2, 2);
         }
     }
+    if (C::kOutBytes && a.tma_out && warp < EW && lane == 0) bulk_wait0();      // this lane's output stores are complete
     tc_fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it / arrive on its barriers
@@ -449,7 +479,7 @@ static int weight_maps(int engine, const float* Wm, const float* Wl, int Ci, int
 
 template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW = 16, int EPI = 0, int CL = 1>
 int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmW16,
-           cudaStream_t st) {
+           const CUtensorMap& tmOut, cudaStream_t st) {
     using C = Cfg<NSPLIT, TN, EW>;
     auto kern = k_tc_local<NSPLIT, NOISY, DLV, TN, EW, EPI, CL>;
     PNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -459,18 +489,18 @@ int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, 
     sms = pno_usable_sms(sms);
     const int n_super = a.n_tiles / CL, groups = sms / CL;
     const int grid = (n_super < groups ? n_super : groups) * CL;
-    if (CL > 1) PNO_CUDA(pno_launch_cluster(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, CL, a, tmX, tmWm, tmWl, tmW16));
-    else PNO_CUDA(pno_launch(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl, tmW16));
+    if (CL > 1) PNO_CUDA(pno_launch_cluster(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, CL, a, tmX, tmWm, tmWl, tmW16, tmOut));
+    else PNO_CUDA(pno_launch(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl, tmW16, tmOut));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
 }
 
 template <int NSPLIT, int TN, int EW, int CL = 1>
 int launch_ns(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, const CUtensorMap& tmWl, const CUtensorMap& tmW16,
-              cudaStream_t st) {
-    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, st);
-    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, st);
-    return launch<NSPLIT, true, false, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, st);
+              const CUtensorMap& tmOut, cudaStream_t st) {
+    if (!a.noisy) return launch<NSPLIT, false, false, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
+    if (a.want_dlv) return launch<NSPLIT, true, true, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
+    return launch<NSPLIT, true, false, TN, EW, 0, CL>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
 }
 
 }  // namespace
@@ -511,18 +541,29 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     const int cl = (TN == 128 && (B * a.p_tiles) % 2 == 0 && want_cl == 2) ? 2 : 1;
     CUtensorMap tmW16;
     if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd", cl))) return rc;
+    // output through TMA stores of [32 rows][16 px] blocks (see the epilogue).  Measured at the headline shape: fp32-parity engine
+    // 294 -> 280 us, single pass 153 -> 160 us (its MMA side is not shared-memory bound and the staging costs more than the row
+    // stores): on for the former only; PNO_LOCAL_TMAOUT=0 / 1 forces the choice (tuning)
+    CUtensorMap tmOut = tmWm;
+    a.tma_out = getenv("PNO_LOCAL_TMAOUT") ? atoi(getenv("PNO_LOCAL_TMAOUT")) != 0 : engine == PNO_ENGINE_TC_TF32X3;
+    if (a.tma_out) {
+        const uint64_t dims[2] = {(uint64_t)HW, (uint64_t)B * Co};
+        const uint64_t str[1] = {(uint64_t)HW * 4};
+        const uint32_t box[2] = {16, 32};
+        if ((rc = pno_encode_tmap_ex(&tmOut, out, 2, dims, str, box, 3, 0))) return rc;
+    }
     // Epilogue warps: measured on B200 at the headline shape (single pass): 4 warps 177 us, 8 warps 163, 16 warps 177, 24 warps
     // 196 -- two per scheduler keep up with the tensor pipe, more only take issue slots and power from it.  PNO_LOCAL_EW=16
     // selects the wide epilogue (tuning).
     const char* e_ew = getenv("PNO_LOCAL_EW");
     const bool wide = e_ew && atoi(e_ew) == 16;
     if (cl == 2)
-        return engine == PNO_ENGINE_TC_TF32X3 ? launch_ns<3, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, st)
-                                              : launch_ns<1, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, st);
+        return engine == PNO_ENGINE_TC_TF32X3 ? launch_ns<3, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, tmOut, st)
+                                              : launch_ns<1, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
     if (engine == PNO_ENGINE_TC_TF32X3)
-        return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmW16, st);
-    if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmW16, st);
-    return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmW16, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmW16, st);
+        return wide ? launch_ns<3, 128, 16>(a, tmX, tmWm, tmWl, tmW16, tmOut, st) : launch_ns<3, 128, 8>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
+    if (TN == 256) return wide ? launch_ns<1, 256, 16>(a, tmX, tmWm, tmWl, tmW16, tmOut, st) : launch_ns<1, 256, 8>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
+    return wide ? launch_ns<1, 128, 16>(a, tmX, tmWm, tmWl, tmW16, tmOut, st) : launch_ns<1, 128, 8>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
 }
 
 // H-axis pass of the two-pass transforms: out[b][o][c] for c in [0, TN): complex combine (see k_tc_local, EPI == 1) of
@@ -553,9 +594,11 @@ int tc_local_combine(int engine, const float* x, int B, int Ci, int Co, int TN, 
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
     if ((rc = weight_maps(engine, Wc, Ws, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_combine"))) return rc;
+    const CUtensorMap tmOut = tmWm;              // unused: the combine epilogue stores from registers
+    a.tma_out = 0;
     const bool x3 = engine == PNO_ENGINE_TC_TF32X3;
-#define PNO_COMBINE(TN_) (x3 ? launch<3, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmW16, st) \
-                             : launch<1, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmW16, st))
+#define PNO_COMBINE(TN_) (x3 ? launch<3, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmW16, tmOut, st) \
+                             : launch<1, true, false, TN_, 8, 1>(a, tmX, tmWm, tmWl, tmW16, tmOut, st))
     if (TN == 64) return PNO_COMBINE(64);
     if (TN == 96) return PNO_COMBINE(96);
     return PNO_COMBINE(128);

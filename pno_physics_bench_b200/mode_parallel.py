@@ -69,20 +69,32 @@ def batch_from_modes(spec, group=None):
     return recv.permute(1, 0, 2, 3, 4).reshape(P, ws * n, B, C)
 
 
-MIX_MAX_BATCH = 128          # batch rows one launch of the forward / input-gradient channel-mix kernels takes (their MMA N)
+MIX_MAX_BATCH = 128          # batch rows one launch of the forward / input-gradient channel-mix kernels takes at most (their MMA N)
 
 
-def _mix_window_batched(fn, name, plan, engine, src, bg, ci, co, mu_ptr, lv_ptr, key, first, count, dst, st):
+def _mix_chunk_rows(stage, engine, plan_shape, bg, ci, co):
+    """Largest batch chunk <= min(bg, MIX_MAX_BATCH) the channel-mix kernel `stage` tiles for this engine (the fp32-parity engine
+    keeps hi / lo copies of its operand tiles: 64 rows; single pass: 128)."""
+    h, w, m1, m2 = plan_shape
+    for rows in (128, 96, 64, 32, 16, 8):
+        if rows <= MIX_MAX_BATCH and rows < bg and _lib.engine_supports(stage, engine & 0xFF, h, w, m1, m2, rows, ci, co):
+            return rows
+    return min(bg, MIX_MAX_BATCH)
+
+
+def _mix_window_batched(fn, name, plan, engine, src, bg, ci, co, mu_ptr, lv_ptr, key, first, count, dst, st, plan_shape):
     """One mode window of pno_mix_fwd_window / pno_mix_bwd_dx_window over a global batch of any size: src / dst are the
     [2, count, bg, C] slices of this window.  Up to MIX_MAX_BATCH rows go through in place; a larger global batch (8 ranks x 32) is
     cut into batch chunks, each staged through a dense copy (the kernels take dense [mode][b][c] spectra)."""
     seed, sample_idx, site = key
-    if bg <= MIX_MAX_BATCH:
+    stage = "mix_fwd" if name == "pno_mix_fwd_window" else "mix_bwd_dx"
+    if bg <= MIX_MAX_BATCH and _lib.engine_supports(stage, engine & 0xFF, *plan_shape, bg, ci, co):
         _lib.check(fn(plan, engine, src[0].data_ptr(), src[1].data_ptr(), bg, ci, co, mu_ptr, lv_ptr, seed, sample_idx, site, first,
                       count, dst[0].data_ptr(), dst[1].data_ptr(), st), name)
         return
-    for b0 in range(0, bg, MIX_MAX_BATCH):
-        b1 = min(bg, b0 + MIX_MAX_BATCH)
+    rows = _mix_chunk_rows(stage, engine, plan_shape, bg, ci, co)
+    for b0 in range(0, bg, rows):
+        b1 = min(bg, b0 + rows)
         part = src[:, :, b0:b1].contiguous()
         out = torch.empty(2, count, b1 - b0, dst.shape[3], dtype=torch.float32, device=src.device)
         _lib.check(fn(plan, engine, part[0].data_ptr(), part[1].data_ptr(), b1 - b0, ci, co, mu_ptr, lv_ptr, seed, sample_idx, site, first,
@@ -121,7 +133,7 @@ class _ModeParallelSpectralFn(torch.autograd.Function):
             for first, count in windows:
                 _mix_window_batched(lib.pno_mix_fwd_window, "pno_mix_fwd_window", plan, engine, xs[:, off:off + count], bg, ci, co,
                                     mu_r[off:off + count].data_ptr(), lv[off:off + count].data_ptr() if sampled else None,
-                                    (seed, sample_idx, site), first, count, ys[:, off:off + count], st)
+                                    (seed, sample_idx, site), first, count, ys[:, off:off + count], st, (h, w, m1, m2))
                 off += count
             yh = batch_from_modes(ys, group)                                        # [2, M, B_loc, Co]
             y = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
@@ -173,7 +185,7 @@ class _ModeParallelSpectralFn(torch.autograd.Function):
                 if dxs is not None:
                     _mix_window_batched(lib.pno_mix_bwd_dx_window, "pno_mix_bwd_dx_window", plan, engine, gs[:, sl], bg, ci, co,
                                         mu_r[sl].data_ptr(), lv[sl].data_ptr() if sampled else None, (seed, sample_idx, site), first,
-                                        count, dxs[:, sl], st)
+                                        count, dxs[:, sl], st, (h, w, m1, m2))
                 off += count
             dx = None
             if dxs is not None:
