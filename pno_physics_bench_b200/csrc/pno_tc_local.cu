@@ -68,10 +68,11 @@ struct Cfg {
     static constexpr int kW16 = TM * TK * 2;
     static constexpr int kX16 = ((TN + 63) / 64) * TK * 128;
     static constexpr int kStageBytes = kOperandBytes + (NSPLIT == 3 ? 4 * kW16 + 2 * kX16 : 0);
-    static constexpr int kStages = (224 * 1024) / kStageBytes;                   // 4 / 3 (TN 256) / 2 (fp32 parity)
+
     // output staging of the epilogue warps (tma_out): two [32 rows][64 B] buffers per warp behind the operand ring
     static constexpr int kOutStage = 32 * 64;
     static constexpr int kOutBytes = EW == 8 ? EW * 2 * kOutStage : 0;
+    static constexpr int kStages = (224 * 1024 - kOutBytes) / kStageBytes;       // 4 / 3 (TN 256) / 2 (fp32 parity)
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024;
     static constexpr int kAcc = 4 * TN <= 512 ? 2 : 1;                           // accumulator buffers in tensor memory
     static_assert(kStages >= 2, "stage does not fit");
