@@ -52,8 +52,10 @@ struct MixGeom {
     // an output grows with the number of MMAs chained into it: 64 instead of 192 for a 256-channel complex product this way
     // (measured at the cfg-3 layer: rel-L2 5.6e-6 -> see DESIGN.md).  Needs 4 * Bp <= 256 columns per buffer, i.e. batch <= 64.
     int split_acc;
-    int ablate;        // measurement only (PNO_MIX_ABLATE, wrong results): 1 = no correction MMAs, 2 = no MMAs at all.  Round 2, headline
+    int ablate;        // measurement only (PNO_MIX_ABLATE, wrong results): 1 = no correction MMAs, 2 = no MMAs at all, 3 = no noise,
+                       // 4 = no hi / lo pass over the xhat tiles, 5 = no lo stores of the weight tiles.  Round 2, headline
                        // shape: fp32-parity engine 301 -> 267 / 282 us, single pass 179 -> 178 / 166 us: the generators bound the kernel
+    int pf_w;          // register-prefetch mode: the producer pulls the mu / log_var tiles of the k-block pf_w ahead into L2 (0 = off)
     int iss2;          // two MMA issuer warps (one per accumulator: Dre / Dim) on different sub-partitions
     const float *mu1, *mu2, *lv1, *lv2;
     float *yr, *yi;
@@ -129,6 +131,19 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                         tma_load_2d(rw, blk ? &tmMu2 : &tmMu1, &bar_rawfull[rs], 2 * col0, row0);
                         if (SAMPLED) tma_load_2d(rw + 2 * W_TILE, blk ? &tmLv2 : &tmLv1, &bar_rawfull[rs], col0, row0);
                         if (++rs == 2) { rs = 0; rph ^= 1; }
+                    }
+                    if (!RAW && g.pf_w) {
+                        // the generators fetch their weights with plain loads one k-block ahead (registers); pulling the tiles of a
+                        // later k-block into L2 from here turns that load's HBM latency into L2 latency
+                        int pkb = kb + g.pf_w, pitem = item;
+                        while (pkb >= g.KB) { pkb -= g.KB; pitem += gridDim.x; }
+                        if (pitem < g.n_items) {
+                            const int pmode = pitem / g.o_tiles, pot = pitem - pmode * g.o_tiles, gm = pmode + g.mode_first;
+                            const int blk = gm >= g.m1m2, mb = gm - blk * g.m1m2 - g.w_sub;
+                            const int row0 = mb * g.Ci + (BWD ? pot * TM : pkb * TK), col0 = BWD ? pkb * TK : pot * TM;
+                            tma_prefetch_l2_2d(blk ? &tmMu2 : &tmMu1, 2 * col0, row0);
+                            if (SAMPLED) tma_prefetch_l2_2d(blk ? &tmLv2 : &tmLv1, col0, row0);
+                        }
                     }
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     mbar_arrive(&bar_free[stage]);                 // the generators may fill the W tiles while the xhat tiles are in flight
@@ -284,7 +299,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                     const float2 l2 = RAW ? (SAMPLED ? lds64(raw_lv + j * (BWD ? 128 : 512)) : make_float2(0.f, 0.f)) : bl[j];
                     if (!RAW && more) fetch(j);                  // refill the slot just consumed: next k-block's loads in flight
                     wr[0][j] = m4.x; wi[0][j] = m4.y; wr[1][j] = m4.z; wi[1][j] = m4.w;
-                    if (SAMPLED) {
+                    if (SAMPLED && g.ablate != 3) {
                         const float4 z = philox_quad_normals(key, quad + (uint64_t)j * g.Cop);
                         const float s0 = fast_ex2(0.72134752044448170f * l2.x), s1 = fast_ex2(0.72134752044448170f * l2.y);   // exp(lv/2)
                         wr[0][j] = fmaf(s0, z.x, wr[0][j]); wi[0][j] = fmaf(s0, z.y, wi[0][j]);
@@ -320,8 +335,10 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                         const float4 hr = tf32_rn4(vr), hi = tf32_rn4(vi);
                         sts128(st + off, hr);
                         sts128(st + W_TILE + off, hi);
-                        sts128(st + 2 * W_TILE + off, sub4(vr, hr));
-                        sts128(st + 3 * W_TILE + off, sub4(vi, hi));
+                        if (g.ablate != 5) {
+                            sts128(st + 2 * W_TILE + off, sub4(vr, hr));
+                            sts128(st + 3 * W_TILE + off, sub4(vi, hi));
+                        }
                     } else {
                         sts128(st + off, vr);
                         sts128(st + W_TILE + off, vi);
@@ -332,7 +349,7 @@ k_tc_mix_fwd(const MixGeom g, const __grid_constant__ CUtensorMap tmXr, const __
                 if (NSPLIT == 3) {
                     mbar_wait(&bar_raw[stage], phase);          // xhat tiles landed
                     const uint32_t xh = st + x_off, xl = st + x_off + 2 * g.x_tile;
-                    for (int i = t; i < 2 * g.x_tile / 16; i += kGen) {
+                    for (int i = t; i < 2 * g.x_tile / 16 && g.ablate != 4; i += kGen) {
                         const float4 v = lds128(xh + 16 * i);
                         const float4 h = tf32_rn4(v);
                         sts128(xh + 16 * i, h);
@@ -437,6 +454,9 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     // RAW mode (see the kernel): single pass with sampled weights; two operand stages + two 48 KB mu / log_var staging buffers
     const bool sampled = lv1 != nullptr;
     const char* e_raw = getenv("PNO_MIX_RAW");          // tuning override: 0 = register-prefetched weights
+    // (fp32-parity engine: hi / lo copies make a stage 96 KB, so the staging buffers would only fit next to ONE operand stage;
+    //  measured 359 vs 287 us -- generation of k-block n+1 then waits for the MMAs of k-block n -- so it keeps the register prefetch
+    //  plus the producer's L2 prefetch, pf_w)
     const bool raw = !x3 && sampled && !(e_raw && atoi(e_raw) == 0) && 2 * g.stage_bytes + 2 * 3 * W_TILE + 1024 <= 225 * 1024;
     if (raw) {
         g.stages = 2;
@@ -457,7 +477,8 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
     }
     CUtensorMap tmMu1, tmMu2, tmLv1, tmLv2;
     memset(&tmMu1, 0, sizeof(tmMu1)); memset(&tmMu2, 0, sizeof(tmMu2)); memset(&tmLv1, 0, sizeof(tmLv1)); memset(&tmLv2, 0, sizeof(tmLv2));
-    if (raw) {      // mu: [m1m2*Ci rows][2*Co floats], log_var: [m1m2*Ci rows][Co floats]; unswizzled boxes
+    g.pf_w = raw ? 0 : (getenv("PNO_MIX_PFW") ? atoi(getenv("PNO_MIX_PFW")) : 1);      // fp32-parity, headline shape: 286 -> 275 us
+    if (raw || g.pf_w) {      // mu: [m1m2*Ci rows][2*Co floats], log_var: [m1m2*Ci rows][Co floats]; unswizzled boxes
         const uint64_t rows = (uint64_t)w_rows_modes * Ci;
         const uint64_t dmu[2] = {(uint64_t)2 * Co, rows}, dlv[2] = {(uint64_t)Co, rows};
         const uint64_t smu[1] = {(uint64_t)2 * Co * 4}, slv[1] = {(uint64_t)Co * 4};
@@ -465,8 +486,10 @@ static int mix_launch(const pno_plan* p, int engine, bool bwd, const float* in_r
         const uint32_t blv[2] = {bwd ? (uint32_t)TK : (uint32_t)TM, bwd ? (uint32_t)TM : (uint32_t)TK};
         if ((rc = pno_encode_tmap(&tmMu1, mu1, 2, dmu, smu, bmu, 0))) return rc;
         if ((rc = pno_encode_tmap(&tmMu2, mu2, 2, dmu, smu, bmu, 0))) return rc;
-        if ((rc = pno_encode_tmap(&tmLv1, lv1, 2, dlv, slv, blv, 0))) return rc;
-        if ((rc = pno_encode_tmap(&tmLv2, lv2, 2, dlv, slv, blv, 0))) return rc;
+        if (sampled) {
+            if ((rc = pno_encode_tmap(&tmLv1, lv1, 2, dlv, slv, blv, 0))) return rc;
+            if ((rc = pno_encode_tmap(&tmLv2, lv2, 2, dlv, slv, blv, 0))) return rc;
+        }
     }
     int dev = 0, sms = 148;
     PNO_CUDA(cudaGetDevice(&dev));
