@@ -185,6 +185,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Up to 32 consecutive columns (n a multiple of 4) with the widest loads that cover them: x16 / x8 / x4.  Several narrow loads of
+// one warp do not overlap the way independent global loads do: five x4 loads took ~1.45 k cycles in the inverse transform's
+// transposer (tools/trace_inv.py), one x16 + one x4 a third of that.  v[c] = columns 4c .. 4c+3; no wait inside.
+__device__ __forceinline__ void tmem_ld_cols(uint32_t ta, int n, uint32_t (&r)[8][4]) {
+#define PNO_LD4(c0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"                                   \
+                                 : "=r"(r[c0][0]), "=r"(r[c0][1]), "=r"(r[c0][2]), "=r"(r[c0][3]) : "r"(ta + 4 * (c0)))
+#define PNO_LD8(c0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                   \
+                                 : "=r"(r[c0][0]), "=r"(r[c0][1]), "=r"(r[c0][2]), "=r"(r[c0][3]), "=r"(r[c0 + 1][0]),               \
+                                   "=r"(r[c0 + 1][1]), "=r"(r[c0 + 1][2]), "=r"(r[c0 + 1][3]) : "r"(ta + 4 * (c0)))
+#define PNO_LD16(c0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "  \
+                                  "%13, %14, %15}, [%16];"                                                                           \
+                                  : "=r"(r[c0][0]), "=r"(r[c0][1]), "=r"(r[c0][2]), "=r"(r[c0][3]), "=r"(r[c0 + 1][0]),              \
+                                    "=r"(r[c0 + 1][1]), "=r"(r[c0 + 1][2]), "=r"(r[c0 + 1][3]), "=r"(r[c0 + 2][0]),                  \
+                                    "=r"(r[c0 + 2][1]), "=r"(r[c0 + 2][2]), "=r"(r[c0 + 2][3]), "=r"(r[c0 + 3][0]),                  \
+                                    "=r"(r[c0 + 3][1]), "=r"(r[c0 + 3][2]), "=r"(r[c0 + 3][3]) : "r"(ta + 4 * (c0)))
+    if (n >= 16) {
+        PNO_LD16(0);
+        if (n >= 32) PNO_LD16(4);
+        else {
+            if (n >= 24) { PNO_LD8(4); if (n >= 28) PNO_LD4(6); }
+            else if (n >= 20) PNO_LD4(4);
+        }
+    } else {
+        if (n >= 8) { PNO_LD8(0); if (n >= 12) PNO_LD4(2); }
+        else PNO_LD4(0);
+    }
+#undef PNO_LD4
+#undef PNO_LD8
+#undef PNO_LD16
+}
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) {
     return base + ((uint32_t)lane << 16) + (uint32_t)col;
 }

@@ -355,12 +355,15 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p + im * g.m2);
                 const uint32_t dst0 = smem_u32(smem + g.off_b2) + bb * g.b2_bytes + im * NT * g.b2_one + col_off;
                 const int r0 = (tb_ * g.IPT + img_l) * g.m2;
-                for (int c0 = 0; c0 < g.m2; c0 += 32) {          // up to 8 x4 loads in flight, one wait
+                for (int c0 = 0; c0 < g.m2; c0 += 32) {          // up to 32 columns with the widest loads (x16 / x8 / x4), one wait
+                    uint32_t rv[8][4];
+                    tmem_ld_cols(t1 + c0, g.m2 - c0, rv);
+                    tmem_ld_wait();
                     float v[8][4];
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        if (c0 + 4 * u < g.m2) tmem_ld4(t1 + c0 + 4 * u, v[u]);
-                    tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[u][j] = __uint_as_float(rv[u][j]);
                     if (warp == 8) TRACE(1, 3);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -405,6 +408,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         const bool warp_active = q * 32 < (g.stack ? 2 * g.R2 : 2 * g.m1);      // warp-uniform: tcgen05.ld is warp-collective
         const bool active = row < 2 * g.m1 && half < 2;
         float* dst_plane = half ? xi : xr;
+        // (x8 loads of 8 ky per image were tried here: 64 values in flight spill at the 80-register cap of this 22-23 warp CTA:
+        //  128 -> 193 us)
         const int ky_first = g.stack ? part * 4 : 0, ky_step = g.stack ? 8 : 4;
         const int bps = g.TPS / g.TPB;                   // batches per super tile
         int slot = 0, sph = 0;

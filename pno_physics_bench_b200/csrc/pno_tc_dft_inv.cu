@@ -418,36 +418,8 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                     const uint32_t rbase = zrow * 32, rsw = (zrow >> 2) & 1;
                     for (int part = part_lo; part < part_hi; ++part)
                     for (int kyb = 0; kyb < g.m2; kyb += 32) {          // up to 8 x4 loads in flight, one wait
-                        // the widest loads that cover the (multiple of 4) columns left: x16 / x8 / x4.  Five x4 loads of one warp took
-                        // ~1.45 k cycles here (tools/trace_inv.py) -- they do not overlap the way independent LDGs do
                         uint32_t r[8][4];
-                        const uint32_t ta = tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + kyb);
-                        const int nleft = g.m2 - kyb;
-#define PNO_LD4(c0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"                                   \
-                                 : "=r"(r[c0][0]), "=r"(r[c0][1]), "=r"(r[c0][2]), "=r"(r[c0][3]) : "r"(ta + 4 * (c0)))
-#define PNO_LD8(c0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                   \
-                                 : "=r"(r[c0][0]), "=r"(r[c0][1]), "=r"(r[c0][2]), "=r"(r[c0][3]), "=r"(r[c0 + 1][0]),               \
-                                   "=r"(r[c0 + 1][1]), "=r"(r[c0 + 1][2]), "=r"(r[c0 + 1][3]) : "r"(ta + 4 * (c0)))
-#define PNO_LD16(c0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "  \
-                                  "%13, %14, %15}, [%16];"                                                                           \
-                                  : "=r"(r[c0][0]), "=r"(r[c0][1]), "=r"(r[c0][2]), "=r"(r[c0][3]), "=r"(r[c0 + 1][0]),              \
-                                    "=r"(r[c0 + 1][1]), "=r"(r[c0 + 1][2]), "=r"(r[c0 + 1][3]), "=r"(r[c0 + 2][0]),                  \
-                                    "=r"(r[c0 + 2][1]), "=r"(r[c0 + 2][2]), "=r"(r[c0 + 2][3]), "=r"(r[c0 + 3][0]),                  \
-                                    "=r"(r[c0 + 3][1]), "=r"(r[c0 + 3][2]), "=r"(r[c0 + 3][3]) : "r"(ta + 4 * (c0)))
-                        if (nleft >= 16) {
-                            PNO_LD16(0);
-                            if (nleft >= 32) PNO_LD16(4);
-                            else {
-                                if (nleft >= 24) { PNO_LD8(4); if (nleft >= 28) PNO_LD4(6); }
-                                else if (nleft >= 20) PNO_LD4(4);
-                            }
-                        } else {
-                            if (nleft >= 8) { PNO_LD8(0); if (nleft >= 12) PNO_LD4(2); }
-                            else PNO_LD4(0);
-                        }
-#undef PNO_LD4
-#undef PNO_LD8
-#undef PNO_LD16
+                        tmem_ld_cols(tmem_addr(tmem, q * 32, part * g.N1 + img * g.m2 + kyb), g.m2 - kyb, r);   // x16 / x8 / x4
                         tmem_ld_wait();
                         if (warp == 8) TRACE(1, 5);
                         if (row < g.H) {
