@@ -45,6 +45,7 @@ struct FwdGeom {
     int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
     int swap13;               // physical warps 1 and 3 swap roles (see the kernel)
     int stack;                // stage 2 with the stacked table T = [S; C; -S] (see issue_stage2): half the MMAs, one accumulator
+    int ablate;               // measurement only (PNO_FWD_ABLATE, wrong results): 1 = no correction MMAs in stage 1, 2 = none in stage 2
     int pf;                   // L2 prefetch distance of the x tiles, in 128-row tiles (0 = off)
     int tw_rows;              // rows of one TwT k-block in shared memory (N1p, or 2*m2 rounded to 8 when the padding rows are not stored)
     // shared-memory byte offsets (from the 1024-aligned base)
@@ -223,7 +224,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                             const uint32_t accf = (kb | ks) ? 1u : 0u;
                             const uint32_t o = ks * 2;
                             mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf, el);
-                            if (NSPLIT == 3) {
+                            if (NSPLIT == 3 && g.ablate != 1) {
                                 mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u, el);
                                 mma_tf32(d1, x_hi + o, khi, tw_lo + o, khi, idesc1, 1u, el);
                             }
@@ -259,7 +260,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                             const uint32_t a_cs = c + ((g.R2 * 128) >> 4), a_sc = c;
                             mma_tf32(d_re, a_cs, khi, r, khi, idesc2, first, el);
                             mma_tf32(d_re, a_sc, khi, ri, khi, idesc2, 1u, el);
-                            if (NSPLIT == 3) {
+                            if (NSPLIT == 3 && g.ablate != 2) {
                                 mma_tf32(d_re, a_cs + t1, khi, r, khi, idesc2, 1u, el);
                                 mma_tf32(d_re, a_cs, khi, r + bo1, khi, idesc2, 1u, el);
                                 mma_tf32(d_re, a_sc + t1, khi, ri, khi, idesc2, 1u, el);
@@ -608,6 +609,7 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     g.n_super = B * C / (g.TPS * g.IPT);
     // measured at the headline shape: fp32-parity engine (2 ring stages) 191 -> 185 us with a distance of 1, single pass (3 stages)
     // 128 -> 131 / 136 us with 1 / 4: on for the former only
+    g.ablate = getenv("PNO_FWD_ABLATE") ? atoi(getenv("PNO_FWD_ABLATE")) : 0;
     g.pf = getenv("PNO_FWD_PF") ? atoi(getenv("PNO_FWD_PF")) : (x3 ? 1 : 0);
     g.swap13 = !(getenv("PNO_FWD_SWAP13") && atoi(getenv("PNO_FWD_SWAP13")) == 0);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
