@@ -154,6 +154,72 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask, uint
         : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one MMA over the two SMs of a cluster of 2 -------------------------------------------------------
+// The pair's MMA has M = 256: each CTA supplies its own 128 rows of A and HALF of the N columns of B from its own shared memory (same
+// offsets in both CTAs) and keeps its 128 accumulator rows in its own tensor memory.  Only the leader (cluster rank 0) issues it;
+// everything the issuer waits for is signalled on the LEADER's mbarriers: a shared-window address with bit 24 cleared names the
+// barrier at the same offset in the even CTA of the pair (cute::Sm100MmaPeerBitMask).
+__device__ __forceinline__ uint32_t leader_bar(const uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
+__device__ __forceinline__ void mbar_arrive_leader(const uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_bar(bar)) : "memory");
+}
+// TMA loads into this CTA's shared memory whose bytes complete on the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, const uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"((uint64_t)m), "r"(leader_bar(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, const uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"((uint64_t)m), "r"(leader_bar(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t ncols) {      // the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+// all previously issued pair MMAs of this thread arrive (when complete) on the barrier at this offset in both CTAs
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(smem_u32(bar)),
+        "r"(elected)
+        : "memory");
+}
+
 // ---- TMEM --------------------------------------------------------------------------------------------------------------
 // one full warp; ncols a power of two in [32, 512]; the base address is written to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {

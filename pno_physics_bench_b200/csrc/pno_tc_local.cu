@@ -86,6 +86,11 @@ struct Cfg {
 // CTA fetches 1/CL of every weight tile and multicasts it to the whole cluster.  The weight tiles are re-streamed from L2 for every
 // pixel tile (2 x 16 KB of fp32 + 4 x 8 KB of bf16 per 16 KB of x): without sharing, the kernel moves 9-11 TB/s out of L2 -- its
 // measured bound at the headline shape, not the tensor pipe or shared memory.
+// CL == 3 ("pair"): a cluster of two CTAs runs ONE MMA over both SMs (tcgen05 cta_group::2, M = 256): both CTAs work on the same
+// pixel tile, the CTA of rank r on output-channel tile 2 j + r.  Each CTA loads its own weight tiles (its 128 rows of A) but only
+// HALF of the x tile (64 of the 128 columns of B) and converts only that half, so per k-block the MMA reads 6 KB instead of 8 KB of
+// operands per instruction and the x fill / conversion halve -- the shared-memory traffic that bounds the fp32-parity kernel drops
+// from 240 to 184 KB per k-block.  The leader (rank 0) issues; all issuer-side barriers live in the leader.
 template <int NSPLIT, bool NOISY, bool DLV, int TN, int EW, int EPI = 0, int CL = 1>
 __global__ void __launch_bounds__(threads_for(NSPLIT, EW), 1)
 k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWm,
@@ -98,6 +103,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     // sub-partition alone gave 167 -> 140 us, on any other sub-partition nothing)
     constexpr int kWarps = aux_warps(NSPLIT) + EW, kIssuer = kWarps - 2, kIssuer2 = kWarps - 1, kProducer = kWarps - 3;
     constexpr int NI = NOISY ? 2 : 1;
+    constexpr bool PAIR = CL == 3;                  // 2-CTA MMA
+    constexpr int CS = PAIR ? 2 : CL;               // cluster size
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bar_raw[C::kStages], bar_split[C::kStages], bar_empty[C::kStages];
@@ -112,12 +119,12 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&bar_raw[s], 1);
-            mbar_init(&bar_split[s], 128);
-            mbar_init(&bar_empty[s], CL * NI);         // one commit from every MMA issuer of every CTA of the cluster
+            mbar_init(&bar_split[s], PAIR ? 8 : 128);          // pair: one (remote) arrival per converter warp of both CTAs, on the leader's
+            mbar_init(&bar_empty[s], PAIR ? NI : CL * NI);     // one commit from every MMA issuer of the cluster that reads this CTA's stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_tfull[s], NI);
-            mbar_init(&bar_tempty[s], EW * 32);
+            mbar_init(&bar_tempty[s], PAIR ? 2 * EW : EW * 32);       // pair: one arrival per epilogue warp of both CTAs, on the leader's
         }
         fence_mbar_init();
         tma_prefetch_desc(&tmX);
@@ -127,19 +134,24 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     }
     // work items: "super tiles" su = (output-channel tile, group of CL consecutive pixel tiles), output-channel tile fastest; the CTA
     // of cluster rank r takes pixel tile CL * group + r
-    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-    const int su0 = blockIdx.x / CL, su_step = gridDim.x / CL, n_super = a.n_tiles / CL;
+    const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int su0 = blockIdx.x / CS, su_step = gridDim.x / CS, n_super = a.n_tiles / CS;
     auto decode = [&](int su, int& ot, int& pt, int& b) {
-        ot = su % a.o_tiles;
-        const int ptile = (su / a.o_tiles) * CL + crank;
+        // pair: (pair of output-channel tiles, pixel tile); multicast cluster: (output-channel tile, CL consecutive pixel tiles)
+        const int ots = PAIR ? a.o_tiles / 2 : a.o_tiles;
+        ot = PAIR ? (su % ots) * 2 + crank : su % ots;
+        const int ptile = PAIR ? su / ots : (su / ots) * CS + crank;
         pt = ptile % a.p_tiles;
         b = ptile / a.p_tiles;
     };
     for (int it = threadIdx.x; it < kTileTab; it += blockDim.x) decode(su0 + it * su_step, s_tile[it][0], s_tile[it][1], s_tile[it][2]);
-    if (warp == kIssuer) tmem_alloc(&tmem_slot, 512);
+    if (warp == kIssuer) {
+        if (PAIR) tmem_alloc_pair(&tmem_slot, 512);
+        else tmem_alloc(&tmem_slot, 512);
+    }
     tc_fence_before_sync();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();                 // every CTA's barriers are initialised before any remote arrival / multicast write
+    if (CS > 1) cluster_sync_all();                 // every CTA's barriers are initialised before any remote arrival / multicast write
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
     pdl_launch_dependents();
@@ -151,8 +163,9 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0, phase = 0, itp = 0;
-            constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
-            constexpr int kRows = TM / CL;               // weight-tile rows fetched (and multicast) by this CTA
+            constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
+            constexpr int kRows = PAIR ? TM : TM / CS;   // weight-tile rows fetched (and, multicast cluster, sent to the peers) by this CTA
+            constexpr int kWBytes = (NOISY ? 2 : 1) * (TILE_BYTES + (NSPLIT == 3 ? 2 * C::kW16 : 0));
             for (int tile = su0; tile < n_super; tile += su_step, ++itp) {
                 int ot, pt, b;
                 if (itp < kTileTab) { ot = s_tile[itp][0]; pt = s_tile[itp][1]; b = s_tile[itp][2]; }
@@ -168,14 +181,37 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     else decode(ntile, not_, npt, nb);
                 }
                 for (int kb = 0; kb < KB; ++kb) {
-                    if (pf) tma_prefetch_l2_3d(&tmX, 0, nb * a.Ci + kb * TK, npt * (TN / 32));
+                    if (pf) tma_prefetch_l2_3d(&tmX, 0, nb * a.Ci + kb * TK, npt * (TN / 32) + (PAIR ? crank * (TN / 64) : 0));
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     TRACE(3, 1);
                     unsigned char* st = stage_ptr(stage);
                     // fp32-parity engine: the bf16 copies of the weights arrive pre-computed (k_split_weights: one bf16 array of
                     // rows [Wm][Wl][Wm lo][Wl lo], Co rows each); only the x tile is converted on the fly
-                    const bool skip_w = a.ablate == 1 && kb > 0;
-                    mbar_arrive_expect_tx(&bar_raw[stage], (skip_w ? 0 : (NOISY ? 2 : 1) * (TILE_BYTES + (NSPLIT == 3 ? 2 * C::kW16 : 0))) + C::kXBytes);
+                    const bool skip_w = !PAIR && a.ablate == 1 && kb > 0;
+                    if (PAIR) {
+                        // the weight tiles of BOTH CTAs complete on the leader's barrier (its issuer reads both CTAs' stages).  The x
+                        // half: fp32-parity -> this CTA's own barrier (its converter warps wait for it and then arrive on the
+                        // leader's bar_split); single pass -> the leader's barrier as well.  tmX has a half-tile box here.
+                        if (NSPLIT == 3) mbar_arrive_expect_tx(&bar_raw[stage], (crank == 0 ? 2 * kWBytes : 0) + C::kXBytes / 2);
+                        else if (crank == 0) mbar_arrive_expect_tx(&bar_raw[stage], 2 * (kWBytes + C::kXBytes / 2));
+                        tma_load_2d_pair(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
+                        if (NOISY) tma_load_2d_pair(st + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, ot * TM);
+                        if (NSPLIT == 3) {
+                            unsigned char* w16 = st + C::kOperandBytes;
+                            tma_load_2d_pair(w16, &tmW16, &bar_raw[stage], kb * TK, ot * TM);
+                            tma_load_2d_pair(w16 + 2 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 2 * a.Co + ot * TM);
+                            if (NOISY) {
+                                tma_load_2d_pair(w16 + C::kW16, &tmW16, &bar_raw[stage], kb * TK, a.Co + ot * TM);
+                                tma_load_2d_pair(w16 + 3 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 3 * a.Co + ot * TM);
+                            }
+                            tma_load_3d(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32) + crank * (TN / 64));
+                        } else {
+                            tma_load_3d_pair(st + 2 * TILE_BYTES, &tmX, &bar_raw[stage], 0, b * a.Ci + kb * TK, pt * (TN / 32) + crank * (TN / 64));
+                        }
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(&bar_raw[stage], (skip_w ? 0 : kWBytes) + C::kXBytes);
                     if (skip_w) {
                     } else if (CL == 1) {
                         tma_load_2d(st, &tmWm, &bar_raw[stage], kb * TK, ot * TM);
@@ -194,11 +230,11 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                         // other slices arrive from the peers and complete on this CTA's barrier as well (the tensor maps have
                         // kRows-row boxes)
                         const int r0 = ot * TM + crank * kRows;
-                        unsigned char* wf = st + crank * (TILE_BYTES / CL);
+                        unsigned char* wf = st + crank * (TILE_BYTES / CS);
                         tma_load_2d_mc(wf, &tmWm, &bar_raw[stage], kb * TK, r0, kMask);
                         if (NOISY) tma_load_2d_mc(wf + TILE_BYTES, &tmWl, &bar_raw[stage], kb * TK, r0, kMask);
                         if (NSPLIT == 3) {
-                            unsigned char* w16 = st + C::kOperandBytes + crank * (C::kW16 / CL);
+                            unsigned char* w16 = st + C::kOperandBytes + crank * (C::kW16 / CS);
                             tma_load_2d_mc(w16, &tmW16, &bar_raw[stage], kb * TK, r0, kMask);
                             tma_load_2d_mc(w16 + 2 * C::kW16, &tmW16, &bar_raw[stage], kb * TK, 2 * a.Co + r0, kMask);
                             if (NOISY) {
@@ -216,10 +252,11 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
     } else if (warp == kIssuer || (NOISY && warp == kIssuer2)) {
         // ================================ MMA issuers ================================
         const bool second = NOISY && warp == kIssuer2;      // this warp issues the log-var conv
-        {   // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
+        if (!PAIR || crank == 0) {   // pair: the leader issues for both CTAs
+            // all 32 lanes run the loop (uniform registers); `el` predicates the tcgen05 instructions
             const uint32_t el = lane == 0;
-            const uint32_t idesc = make_idesc(FMT_TF32, TM, TN, MAJOR_K, MAJOR_MN);
-            const uint32_t idesc16 = make_idesc(FMT_BF16, TM, TN, MAJOR_K, MAJOR_MN);
+            const uint32_t idesc = make_idesc(FMT_TF32, PAIR ? 2 * TM : TM, TN, MAJOR_K, MAJOR_MN);
+            const uint32_t idesc16 = make_idesc(FMT_BF16, PAIR ? 2 * TM : TM, TN, MAJOR_K, MAJOR_MN);
             const uint32_t ahi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;
             const uint32_t bhi = sdesc_base(0, TK * 128, 512, SWIZZLE_128B_BASE32B).hi;
             const uint32_t ahi16 = sdesc_base(0, 16, 512, SWIZZLE_64B).hi;               // bf16 K-major, 64-byte rows
@@ -237,6 +274,9 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                 const uint32_t d_c = NOISY ? d_m : d_l;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_raw[stage], phase);
+                    // pair, fp32-parity: the peer's x half completes on the PEER's barrier (its converter warps wait there); what tells
+                    // this issuer that it has landed is their arrival on bar_split -- before the first MMA, not only before the bf16 ones
+                    if (PAIR && NSPLIT == 3) mbar_wait(&bar_split[stage], phase);
                     TRACE(0, 2);
                     tc_fence_after_sync();
                     const uint32_t s0 = smem_u32(stage_ptr(stage));
@@ -246,7 +286,8 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     for (int ks = 0; ks < TK / 8; ++ks) {
                         const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
                         const uint32_t ao = ks * 2, bo = ks * 64;    // 32 B / 1024 B per K step
-                        mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
+                        if (PAIR) mma_tf32_pair(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
+                        else mma_tf32(d_m, am + ao, ahi, xb + bo, bhi, idesc, acc_flag, el);
                     }
                     if (NSPLIT == 3) {
                         // cross terms on the bf16 copies (K = 16 per instruction): bf16(W) x bf16(lo x) + bf16(lo W) x bf16(x)
@@ -260,16 +301,23 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                         for (int kh = 0; kh < TK / 16; ++kh) {
                             const uint32_t cflag = (NOISY || kb || kh) ? 1u : 0u;
                             const uint32_t ao = kh * 2, bo = kh * 128;   // 32 B / 2048 B per K = 16 step
-                            mma_bf16(d_c, w16 + ao, ahi16, x16l + bo, bhi16, idesc16, cflag, el);
-                            mma_bf16(d_c, w16 + 2 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
+                            if (PAIR) {
+                                mma_bf16_pair(d_c, w16 + ao, ahi16, x16l + bo, bhi16, idesc16, cflag, el);
+                                mma_bf16_pair(d_c, w16 + 2 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
+                            } else {
+                                mma_bf16(d_c, w16 + ao, ahi16, x16l + bo, bhi16, idesc16, cflag, el);
+                                mma_bf16(d_c, w16 + 2 * W1 + ao, ahi16, x16 + bo, bhi16, idesc16, 1u, el);
+                            }
                         }
                     }
                     // frees the stage when these MMAs have read it -- in every CTA of the cluster: a peer's next multicast writes here
-                    if (CL > 1) mma_commit_mc(&bar_empty[stage], (uint16_t)((1u << CL) - 1), el);
+                    if (PAIR) mma_commit_pair(&bar_empty[stage], el);
+                    else if (CL > 1) mma_commit_mc(&bar_empty[stage], (uint16_t)((1u << CL) - 1), el);
                     else mma_commit(&bar_empty[stage], el);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&bar_tfull[acc], el);
+                if (PAIR) mma_commit_pair(&bar_tfull[acc], el);
+                else mma_commit(&bar_tfull[acc], el);
                 TRACE(0, 3);
             }
         }
@@ -284,7 +332,7 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                     const uint32_t xf = smem_u32(stage_ptr(stage)) + 2 * TILE_BYTES;            // fp32 [TN/32][32 rows][128 B]
                     const uint32_t xh = smem_u32(stage_ptr(stage)) + C::kOperandBytes + 4 * C::kW16, xl = xh + C::kX16;
 #pragma unroll 4
-                    for (int c = t; c < C::kXBytes / 16; c += 128) {
+                    for (int c = t; c < C::kXBytes / (PAIR ? 32 : 16); c += 128) {      // pair: this CTA's half of the tile
                         // 16-byte chunk c of the fp32 tile: pixel block pb (32 pixels), row r (input channel), chunk j; the fp32 layout
                         // swizzles 32-byte chunks with (r & 3), the bf16 layout 16-byte chunks (8 pixels) with (r & 7)
                         const int pb = c >> 8, r = (c >> 3) & 31, j = c & 7;
@@ -297,7 +345,12 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
                         sts64u(xl + off, low);
                     }
                     fence_proxy_async_smem();
-                    mbar_arrive(&bar_split[stage]);
+                    if (PAIR) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&bar_split[stage]);
+                    } else {
+                        mbar_arrive(&bar_split[stage]);
+                    }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -430,15 +483,23 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
             base += NP % EWQ;
             if (base >= EWQ) base -= EWQ;
             tc_fence_before_sync();
-            mbar_arrive(&bar_tempty[acc]);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&bar_tempty[acc]);
+            } else {
+                mbar_arrive(&bar_tempty[acc]);
+            }
             if (warp == 0) TRACE(2, 2);
         }
     }
     if (C::kOutBytes && a.tma_out && warp < EW && lane == 0) bulk_wait0();      // this lane's output stores are complete
     tc_fence_before_sync();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it / arrive on its barriers
-    if (warp == kIssuer) tmem_dealloc(tmem, 512);
+    if (CS > 1) cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it / arrive on its barriers
+    if (warp == kIssuer) {
+        if (PAIR) tmem_dealloc_pair(tmem, 512);
+        else tmem_dealloc(tmem, 512);
+    }
 }
 
 // bf16 copies of the two 1x1 weight matrices for the fp32-parity engine: out = rows [Wm][Wl][Wm lo][Wl lo], n bf16 each, where
@@ -488,9 +549,10 @@ int launch(const LocalArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmWm, 
     PNO_CUDA(cudaGetDevice(&dev));
     PNO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     sms = pno_usable_sms(sms);
-    const int n_super = a.n_tiles / CL, groups = sms / CL;
-    const int grid = (n_super < groups ? n_super : groups) * CL;
-    if (CL > 1) PNO_CUDA(pno_launch_cluster(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, CL, a, tmX, tmWm, tmWl, tmW16, tmOut));
+    constexpr int CS = CL == 3 ? 2 : CL;            // cluster size (CL == 3: a pair running 2-CTA MMAs)
+    const int n_super = a.n_tiles / CS, groups = sms / CS;
+    const int grid = (n_super < groups ? n_super : groups) * CS;
+    if (CS > 1) PNO_CUDA(pno_launch_cluster(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, CS, a, tmX, tmWm, tmWl, tmW16, tmOut));
     else PNO_CUDA(pno_launch(kern, grid, threads_for(NSPLIT, EW), C::kSmemBytes, st, a, tmX, tmWm, tmWl, tmW16, tmOut));
     PNO_LAUNCH_CHECK();
     return PNO_OK;
@@ -534,14 +596,21 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
         const uint32_t box[3] = {32, TK, (uint32_t)TN / 32};
         if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
     }
+    const CUtensorMap tmXfull = tmX;
     // clusters of 2 CTAs share every weight tile through TMA multicast (see k_tc_local).  Measured at the headline shape: fp32-parity
     // engine (80 KB of weight tiles per k-block) 296 vs 308 us, single pass (32 KB) 150.5 vs 149.3 us -> on for the former only;
     // PNO_LOCAL_CL=1 / 2 forces the choice (tuning)
     const char* e_cl = getenv("PNO_LOCAL_CL");
     const int want_cl = e_cl ? atoi(e_cl) : (engine == PNO_ENGINE_TC_TF32X3 ? 2 : 1);
-    const int cl = (TN == 128 && (B * a.p_tiles) % 2 == 0 && want_cl == 2) ? 2 : 1;
+    // 3 = CTA pairs running 2-CTA MMAs (k_tc_local): needs an even number of output-channel tiles.  Opt-in only: measured at the
+    // headline shape 171 vs 156 us (single pass) and 367 vs 282 us (fp32 parity) -- the operand traffic per SM drops as planned, but
+    // every k-block now waits for a cross-CTA round trip (peer's TMA / converter warps -> leader's barrier -> MMA -> multicast
+    // commit -> peer's producer) that the 2-4 stage ring does not cover, and the fp32-parity form can no longer start its tf32 MMAs
+    // before the conversion of the x tile has finished
+    const int cl = (want_cl == 3 && TN == 128 && a.o_tiles % 2 == 0) ? 3
+                   : (TN == 128 && (B * a.p_tiles) % 2 == 0 && want_cl == 2) ? 2 : 1;
     CUtensorMap tmW16;
-    if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd", cl))) return rc;
+    if ((rc = weight_maps(engine, Wm, Wl, Ci, Co, st, &tmWm, &tmWl, &tmW16, "tc_local_fwd", cl == 2 ? 2 : 1))) return rc;
     // output through TMA stores of [32 rows][16 px] blocks (see the epilogue).  Measured at the headline shape: fp32-parity engine
     // 294 -> 280 us, single pass 153 -> 160 us (its MMA side is not shared-memory bound and the staging costs more than the row
     // stores): on for the former only; PNO_LOCAL_TMAOUT=0 / 1 forces the choice (tuning)
@@ -558,6 +627,15 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     // selects the wide epilogue (tuning).
     const char* e_ew = getenv("PNO_LOCAL_EW");
     const bool wide = e_ew && atoi(e_ew) == 16;
+    if (cl == 3) {       // each CTA of a pair loads half of the x tile: half-tile box
+        const uint64_t dims[3] = {32, (uint64_t)B * Ci, (uint64_t)HW / 32};
+        const uint64_t str[2] = {(uint64_t)HW * 4, 128};
+        const uint32_t box[3] = {32, TK, (uint32_t)TN / 64};
+        if ((rc = pno_encode_tmap(&tmX, x, 3, dims, str, box, 2))) return rc;
+        return engine == PNO_ENGINE_TC_TF32X3 ? launch_ns<3, 128, 8, 3>(a, tmX, tmWm, tmWl, tmW16, tmOut, st)
+                                              : launch_ns<1, 128, 8, 3>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);
+    }
+    (void)tmXfull;
     if (cl == 2)
         return engine == PNO_ENGINE_TC_TF32X3 ? launch_ns<3, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, tmOut, st)
                                               : launch_ns<1, 128, 8, 2>(a, tmX, tmWm, tmWl, tmW16, tmOut, st);

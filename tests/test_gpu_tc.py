@@ -129,6 +129,19 @@ def test_local_branch_tensor_core_vs_cuda_core(engine, tol, noisy, shape):
         assert rel_l2(a_, b_) < (10 * tol if engine == "tf32x3" else 0.2)
 
 
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
+def test_local_branch_cluster_modes(monkeypatch, engine, tol, mode):
+    """The three launch forms of the local-branch kernel agree with the CUDA-core engine: single CTAs (1), 2-CTA clusters that
+    multicast the weight tiles (2), CTA pairs running 2-CTA MMAs (tcgen05 cta_group::2, M = 256; 3).  PNO_LOCAL_CL selects the
+    form; several tiles per CTA (persistent loop), both 1x1 convs with noise."""
+    shape = (3, 256, 256, 64, 64)
+    ref_out, _ = _local_case(*shape, True, "fp32", torch.Generator().manual_seed(77))
+    monkeypatch.setenv("PNO_LOCAL_CL", mode)
+    out, _ = _local_case(*shape, True, engine, torch.Generator().manual_seed(77))
+    assert rel_l2(out, ref_out) < tol
+
+
 def test_full_size_inverse_every_tile_is_right(monkeypatch):
     """Single pass, full cfg-3 shape, repeated launches: stage 2 reads Z from tensor memory behind stage 1 with no barrier in
     between (in-order MMA pipe) and y leaves by TMA store from the staged addend buffers.  A protocol race would corrupt
