@@ -458,7 +458,7 @@ def main():
                     help="MC samples per GPU per step (weak scaling)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--mc-samples-total", type=int, default=100, help="total MC samples per step with --scaling strong (config 3: 100)")
-    ap.add_argument("--workload", default="mc_cfg3", choices=["mc_cfg3", "train_cfg2"])
+    ap.add_argument("--workload", default="mc_cfg3", choices=["mc_cfg3", "train_cfg2", "train_cfg5"])
     ap.add_argument("--parallel", default="dp", choices=["dp", "mp"], help="train_cfg2: data parallel or mode parallel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (other configs, reference on cuda, tf32)")
@@ -507,7 +507,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    if args.workload == "train_cfg2":
+    if args.workload in ("train_cfg2", "train_cfg5"):
         return run_train(args, device, rank, world, local, timed)
 
     model = build_model(args.engine, device)
@@ -644,23 +644,31 @@ def main():
         dist.destroy_process_group()
 
 
-def train_leg(engine, parallel, device, rank, world, timed, steps, warmup):
-    """One PNOTrainer step of BASELINE config 2 (batch 32 per GPU) as the timed step.  parallel = "dp": data parallel (replicated
-    weights, per-parameter gradient all-reduce overlapped with backward); "mp": mode parallel (spectral weights sharded by modes,
-    spectrum all-to-alls; mode_parallel.py)."""
+TRAIN_CFGS = {   # BASELINE.json configs 2 and 5: (hidden, layers, modes, grid, batch per GPU)
+    "train_cfg2": (256, 4, 20, 64, 32),
+    "train_cfg5": (256, 4, 48, 256, 2),
+}
+
+
+def train_leg(engine, parallel, device, rank, world, timed, steps, warmup, cfg="train_cfg2"):
+    """One PNOTrainer step of BASELINE config 2 (batch 32 per GPU) or 5 (256x256, 48 modes, batch 2 per GPU = 16 on 8 GPUs) as the
+    timed step.  parallel = "dp": data parallel (replicated weights, per-parameter gradient all-reduce overlapped with backward);
+    "mp": mode parallel (spectral weights sharded by modes, spectrum all-to-alls; mode_parallel.py)."""
     import pno_physics_bench_b200 as pno
     from pno_physics_bench_b200 import _lib
     from pno_physics_bench_b200.training import ELBOLoss, PNOTrainer
     lib = _lib.load()
+    hid, layers, modes, hw, Bl = TRAIN_CFGS[cfg]
     torch.manual_seed(0)
-    model = pno.ProbabilisticNeuralOperator(3, 256, 4, 20, engine=engine)
+    with torch.device(device):                 # config 5 has 14.5 GB of parameters: initialise on the GPU (same seed on every rank)
+        model = pno.ProbabilisticNeuralOperator(3, hid, layers, modes, engine=engine)
     if parallel == "mp":
         from pno_physics_bench_b200.mode_parallel import ModeParallelPNO
         model = ModeParallelPNO(model, engine=engine)
+        torch.cuda.empty_cache()
     trainer = PNOTrainer(model, ELBOLoss(kl_weight=1e-4), device=str(device), seed=1)
-    Bl = 32
     torch.manual_seed(1 + rank)
-    x_host, y_host = torch.randn(Bl, 3, 64, 64).pin_memory(), torch.randn(Bl, 1, 64, 64).pin_memory()
+    x_host, y_host = torch.randn(Bl, 3, hw, hw).pin_memory(), torch.randn(Bl, 1, hw, hw).pin_memory()
     x, y = x_host.to(device), y_host.to(device)
     loss_host = torch.empty(()).pin_memory()
 
@@ -692,19 +700,20 @@ def run_train(args, device, rank, world, local, timed):
     import torch.distributed as dist
     with ClockSampler(local) as clocks:
         clocks.mark("start")
-        leg = train_leg(args.engine, args.parallel, device, rank, world, timed, args.steps, args.warmup)
+        leg = train_leg(args.engine, args.parallel, device, rank, world, timed, args.steps, args.warmup, args.workload)
         clocks.mark("end")
     if rank == 0:
         how = ("data parallel: per-parameter NCCL all-reduce (AVG) of the 2.5 GB of gradients, launched from autograd hooks while backward "
                "continues" if args.parallel == "dp" else
                "mode parallel: spectral weights / gradients / AdamW state sharded by modes, two all-to-alls of the truncated spectrum per "
                "layer and direction")
-        line = {"metric": "PNOTrainer fields/sec at 64^2 hid256 modes20 (one ELBO step: fwd, bwd, clip, AdamW)", "value": leg["value"],
+        hid, layers, modes, hw, Bl = TRAIN_CFGS[args.workload]
+        line = {"metric": f"PNOTrainer fields/sec at {hw}^2 hid{hid} modes{modes} (one ELBO step: fwd, bwd, clip, AdamW)", "value": leg["value"],
                 "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.engine, "data": "synthetic",
-                "config": {"workload": f"cfg2: PNOTrainer.train_step 64x64 in3 hid256 L4 modes20, batch 32 per GPU (global {32 * world})",
+                "config": {"workload": f"{args.workload[6:]}: PNOTrainer.train_step {hw}x{hw} in3 hid{hid} L{layers} modes{modes}, batch {Bl} per GPU (global {Bl * world})",
                            "engine": args.engine, "parallelism": f"x{world}, {how}",
-                           "l2": "inputs larger than L2 (10 GB of parameters / gradients / AdamW state per step)"},
+                           "l2": "inputs larger than L2 (10 GB (cfg 2) / 58 GB (cfg 5) of parameters / gradients / AdamW state per step)"},
                 "clocks": clocks.summary("start", "end"), "gpu_launches": leg["gpu_launches"], "peak_mem_gib": leg["peak_mem_gib"],
                 "e2e": {"value": leg["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": leg["h2d_bytes_per_step"],
                         "d2h_bytes_per_step": leg["d2h_bytes_per_step"]}}
