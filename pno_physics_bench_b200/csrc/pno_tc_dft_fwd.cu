@@ -323,10 +323,10 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                     const uint32_t hi = smem_u32(smem + g.off_ring + (size_t)stage * g.stage_bytes), lo = hi + g.KPS * g.x_bytes;
 #pragma unroll 4
                     for (int i = t; i < g.KPS * g.x_bytes / 16; i += 128) {
+                        // split by truncation: kind::tf32 ignores the 13 low mantissa bits, so the staged tile itself is the hi
+                        // operand (no store) and lo = v - trunc(v)
                         const float4 v = lds128(hi + 16 * i);
-                        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                        sts128(hi + 16 * i, h);
-                        sts128(lo + 16 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+                        sts128(lo + 16 * i, make_float4(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y), v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w)));
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar_split[stage]);
