@@ -495,6 +495,14 @@ __host__ __device__ __forceinline__ uint32_t mnmajor16_sw128_off(int k, int n, i
 // i.e. ~1e-6), the last term (2^-22) is dropped.  Against three kind::tf32 MMAs on hi / lo fp32 copies this is 2/3 of the tensor
 // time and 2/3 of the operand bytes read from shared memory, for the same fp32-grade result.
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// lo part of a truncation split, itself ROUNDED to tf32: l(v) has up to 13 significant bits and kind::tf32 would truncate it again,
+// always towards zero and l(v) always has the sign of v, i.e. a systematic 2^-23-ish scale-down of every operand (seen as a
+// 5.6e-5 error on a cancellation-heavy bias gradient); rounded to nearest the lo operand is exact in tf32 and the split unbiased.
+__device__ __forceinline__ float tf32_lo_rn(float v) {
+    const float l = v - tf32_trunc(v);
+    return __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float4 tf32_lo_rn4(float4 v) { return make_float4(tf32_lo_rn(v.x), tf32_lo_rn(v.y), tf32_lo_rn(v.z), tf32_lo_rn(v.w)); }
 // bf16 pair (lo half = a, hi half = b), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     uint32_t r;

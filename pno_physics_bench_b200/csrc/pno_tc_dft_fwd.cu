@@ -326,7 +326,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         // split by truncation: kind::tf32 ignores the 13 low mantissa bits, so the staged tile itself is the hi
                         // operand (no store) and lo = v - trunc(v)
                         const float4 v = lds128(hi + 16 * i);
-                        sts128(lo + 16 * i, make_float4(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y), v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w)));
+                        sts128(lo + 16 * i, tf32_lo_rn4(v));
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar_split[stage]);

@@ -112,13 +112,8 @@ k_tc_local_dw(const DwArgs a, const __grid_constant__ CUtensorMap tmG, const __g
 #pragma unroll 4
                 for (int i = t; i < n16; i += kSplitWarps * 32) {
                     const float4 v = lds128(hi + 16 * i);
-                    float4 h;
-                    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-                    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-                    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-                    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-                    sts128(hi + 16 * i, h);
-                    sts128(lw + 16 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+                    // the tensor core drops the low 13 mantissa bits of the raw tile (the hi operand): only lo = v - trunc(v) is stored
+                    sts128(lw + 16 * i, tf32_lo_rn4(v));
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_split[stage]);
