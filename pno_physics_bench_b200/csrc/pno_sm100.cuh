@@ -281,6 +281,25 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t ta, int n, uint32_t (&r)[8
 #undef PNO_LD8
 #undef PNO_LD16
 }
+// Up to 16 consecutive columns (n a multiple of 4; more are ignored): x16, or x8 (+ x4), or x4.  No wait inside.
+__device__ __forceinline__ void tmem_ld_cols16(uint32_t ta, int n, uint32_t (&r)[4][4]) {
+    if (n >= 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0][0]), "=r"(r[0][1]), "=r"(r[0][2]), "=r"(r[0][3]), "=r"(r[1][0]), "=r"(r[1][1]), "=r"(r[1][2]), "=r"(r[1][3]),
+                       "=r"(r[2][0]), "=r"(r[2][1]), "=r"(r[2][2]), "=r"(r[2][3]), "=r"(r[3][0]), "=r"(r[3][1]), "=r"(r[3][2]), "=r"(r[3][3])
+                     : "r"(ta));
+    } else if (n >= 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0][0]), "=r"(r[0][1]), "=r"(r[0][2]), "=r"(r[0][3]), "=r"(r[1][0]), "=r"(r[1][1]), "=r"(r[1][2]), "=r"(r[1][3])
+                     : "r"(ta));
+        if (n >= 12)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[2][0]), "=r"(r[2][1]), "=r"(r[2][2]), "=r"(r[2][3]) : "r"(ta + 8));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0][0]), "=r"(r[0][1]), "=r"(r[0][2]), "=r"(r[0][3]) : "r"(ta));
+    }
+}
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) {
     return base + ((uint32_t)lane << 16) + (uint32_t)col;
 }

@@ -44,6 +44,9 @@ struct FwdGeom {
     int KPS;        // x k-blocks per ring stage (a whole tile when W <= 64: one barrier round trip per tile instead of per k-block)
     int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
     int swap13;               // physical warps 1 and 3 swap roles (see the kernel)
+    int ncat;                 // fp32-parity form with N-concatenated operands (see issue_stage1 / issue_stage2): 2 + 4 instead of 3 + 6 MMAs
+                              // per k-step; needs the stacked tables
+    int D1W;                  // columns of one stage-1 accumulator buffer: N1p, or 2*tw_rows (main | correction) with ncat
     int stack;                // stage 2 with the stacked table T = [S; C; -S] (see issue_stage2): half the MMAs, one accumulator
     int ablate;               // measurement only (PNO_FWD_ABLATE, wrong results): 1 = no correction MMAs in stage 1, 2 = none in stage 2
     int pf;                   // L2 prefetch distance of the x tiles, in 128-row tiles (0 = off)
@@ -83,7 +86,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
 
-template <int NSPLIT>
+template <int NSPLIT, bool NCAT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict__ xr, float* __restrict__ xi,
              const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTwHi,
@@ -132,14 +135,16 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
 
     constexpr int NT = NSPLIT == 3 ? 2 : 1;            // hi (+ lo) copies of every operand
     // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then nslot buffers of 2*N2p (re | im), one batch each
-    const int d2_base = 2 * g.N1p;
+    const int d2_base = 2 * g.D1W;
     // tables: (C hi, [C lo], S hi, [S lo]), each KB2 k-blocks of [R2 x 128 B]; TwT (hi, [lo]) each KB1 k-blocks of [N1p x 128 B]
     unsigned char* tab = smem + g.off_tab;
     unsigned char* twt = smem + g.off_tw;
     const int tab_kb = (g.stack ? 3 : 1) * g.R2 * 128;
-    const int tw_kb = g.tw_rows * 128;
+    const int tw_kb = (NCAT ? 2 : 1) * g.tw_rows * 128;      // ncat: [hi rows | lo rows] per k-block
     // B2 operands: (Rre hi, [Rre lo], Rim hi, [Rim lo]), each KB2 k-blocks of [N2p x 128 B]; rows = (tile in batch, image, ky)
-    const int b2_kb = g.N2p * 128;
+    // ncat: [hi rows | lo rows] per k-block, so that one N = 2*N2p MMA multiplies a table by both
+    const int b2_kb = (NCAT ? 2 : 1) * g.N2p * 128;
+    const int b2_lo = NCAT ? g.N2p * 128 : g.b2_one;          // lo copy of an element, relative to its hi copy
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -160,7 +165,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             }
             for (int kb = 0; kb < g.KB1; ++kb) {
                 tma_load_2d(twt + kb * tw_kb, &tmTwHi, &bar_tab, kb * 32, 0);
-                if (NSPLIT == 3) tma_load_2d(twt + g.tw_one + kb * tw_kb, &tmTwLo, &bar_tab, kb * 32, 0);
+                if (NSPLIT == 3) tma_load_2d(twt + (NCAT ? g.tw_rows * 128 : g.tw_one) + kb * tw_kb, &tmTwLo, &bar_tab, kb * 32, 0);
             }
             int stage = 0, phase = 0;
             // this CTA's tiles are TPS consecutive 128-row tiles per super tile, super tiles gridDim.x apart: pull the tile that is
@@ -194,6 +199,8 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             const uint32_t idesc1 = make_idesc(FMT_TF32, 128, g.N1p, MAJOR_K, MAJOR_K);
             const uint32_t idesc2 = make_idesc(FMT_TF32, 128, g.N2p, MAJOR_K, MAJOR_K);
             const uint32_t idesc2n = make_idesc(FMT_TF32, 128, g.N2p, MAJOR_K, MAJOR_K, 1, 0);
+            const uint32_t idesc1c = make_idesc(FMT_TF32, 128, 2 * g.tw_rows, MAJOR_K, MAJOR_K);      // ncat forms
+            const uint32_t idesc2c = make_idesc(FMT_TF32, 128, 2 * g.N2p, MAJOR_K, MAJOR_K);
             const uint32_t khi = sdesc_base(0, 16, 1024, SWIZZLE_128B).hi;     // all operands: K-major SW128
             const uint32_t tb = sdesc_base(smem_u32(tab), 16, 1024, SWIZZLE_128B).lo;
             const uint32_t twb = sdesc_base(smem_u32(twt), 16, 1024, SWIZZLE_128B).lo;
@@ -208,7 +215,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 const int buf = n1 & 1;
                 mbar_wait(&bar_d1_empty[buf], ((n1 >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
-                const uint32_t d1 = tmem + buf * g.N1p;
+                const uint32_t d1 = tmem + buf * g.D1W;
                 for (int kb0 = 0; kb0 < g.KB1; kb0 += g.KPS) {
                     mbar_wait(NSPLIT == 3 ? &bar_split[stage] : &bar_raw[stage], phase);
                     TRACE(0, 5);
@@ -223,6 +230,14 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t accf = (kb | ks) ? 1u : 0u;
                             const uint32_t o = ks * 2;
+                            if (NCAT) {
+                                // B = [TwT hi | TwT lo] (N = 2*tw_rows): accumulator columns [0, tw_rows) = x * hi, [tw_rows, ..) = x * lo,
+                                // for A = the raw x tile (the tensor core reads its tf32 truncation) and A = its lo part: all four
+                                // terms of the product in two MMAs instead of three terms in three.  The transposer adds the halves.
+                                mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1c, accf, el);
+                                mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1c, 1u, el);
+                                continue;
+                            }
                             mma_tf32(d1, x_hi + o, khi, tw_hi + o, khi, idesc1, accf, el);
                             if (NSPLIT == 3 && g.ablate != 1) {
                                 mma_tf32(d1, x_lo + o, khi, tw_hi + o, khi, idesc1, 1u, el);
@@ -254,6 +269,16 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         const uint32_t first = (kb | ks) ? 1u : 0u;
                         const uint32_t c = tb + ((kb * tab_kb) >> 4) + ks * 2, r = bbase + ((kb * b2_kb) >> 4) + ks * 2;
                         const uint32_t sn = c + NT * t1, ri = r + NT * bo1;
+                        if (NCAT) {
+                            // stacked tables (below) times B = [R | R lo] (N = 2*N2p): columns [0, N2p) main, [N2p, 2 N2p) correction;
+                            // the lo tables times R go to the correction columns.  4 MMAs per k-step instead of 6.
+                            const uint32_t a_cs = c + ((g.R2 * 128) >> 4), a_sc = c;
+                            mma_tf32(d_re, a_cs, khi, r, khi, idesc2c, first, el);
+                            mma_tf32(d_re, a_sc, khi, ri, khi, idesc2c, 1u, el);
+                            mma_tf32(d_im, a_cs + t1, khi, r, khi, idesc2, 1u, el);
+                            mma_tf32(d_im, a_sc + t1, khi, ri, khi, idesc2, 1u, el);
+                            continue;
+                        }
                         if (g.stack) {
                             // one accumulator, rows [0, R2) = Xre = C Rre + S Rim, rows [R2, 2 R2) = Xim = -S Rre + C Rim:
                             // A = [C; -S] (table rows R2 ..) with Rre, A = [S; C] (table rows 0 ..) with Rim
@@ -353,9 +378,32 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 tc_fence_after_sync();
                 if (tb_ == 0) mbar_wait(&bar_b2_empty[bb], bph ^ 1);   // stage 2 of the batch that used this buffer is done
                 if (warp == 8) TRACE(1, 2);
-                const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.N1p + im * g.m2);
+                const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.D1W + im * g.m2);
                 const uint32_t dst0 = smem_u32(smem + g.off_b2) + bb * g.b2_bytes + im * NT * g.b2_one + col_off;
                 const int r0 = (tb_ * g.IPT + img_l) * g.m2;
+                if (NCAT) {
+                    // main + correction halves of the stage-1 accumulator, 16 columns a pass (two 16-register loads in flight)
+                    for (int c0 = 0; c0 < g.m2; c0 += 16) {
+                        uint32_t ra[4][4], rb[4][4];
+                        tmem_ld_cols16(t1 + c0, g.m2 - c0, ra);
+                        tmem_ld_cols16(t1 + g.tw_rows + c0, g.m2 - c0, rb);
+                        tmem_ld_wait();
+                        if (warp == 8) TRACE(1, 3);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (c0 + 4 * u < g.m2) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int r = r0 + c0 + 4 * u + j;
+                                    const uint32_t dst = dst0 + r * 128 + ((chunk ^ (r & 7)) << 4);
+                                    const float v = __uint_as_float(ra[u][j]) + __uint_as_float(rb[u][j]);
+                                    sts32(dst, v);                       // raw: the tensor core truncates it
+                                    sts32(dst + b2_lo, tf32_lo_rn(v));
+                                }
+                            }
+                        }
+                    }
+                } else
                 for (int c0 = 0; c0 < g.m2; c0 += 32) {          // up to 32 columns with the widest loads (x16 / x8 / x4), one wait
                     uint32_t rv[8][4];
                     tmem_ld_cols(t1 + c0, g.m2 - c0, rv);
@@ -425,6 +473,40 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                     const int b = sb, c0 = sc0 + k * GB;         // a super tile never straddles a batch item (C % (bps*GB) == 0)
                     const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + (g.stack ? 0 : part * g.N2p));
                     for (int ky0 = ky_first; ky0 < g.m2; ky0 += ky_step) {
+                        if (NCAT) {
+                            // main + correction columns (N2p apart), four images a pass
+                            for (int g0 = 0; g0 < GB; g0 += 4) {
+                                float va[4][4], vb[4][4];
+#pragma unroll
+                                for (int gi = 0; gi < 4; ++gi) {
+                                    if (g0 + gi < GB) {
+                                        tmem_ld4(tb0 + (g0 + gi) * g.m2 + ky0, va[gi]);
+                                        tmem_ld4(tb0 + g.N2p + (g0 + gi) * g.m2 + ky0, vb[gi]);
+                                    } else {
+                                        va[gi][0] = va[gi][1] = va[gi][2] = va[gi][3] = 0.f;
+                                        vb[gi][0] = vb[gi][1] = vb[gi][2] = vb[gi][3] = 0.f;
+                                    }
+                                }
+                                tmem_ld_wait();
+                                if (active) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const int mode = row * g.m2 + ky0 + j;
+                                        const float cf = g.grad_scale ? coef[mode] : 1.f;
+                                        float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0 + g0;
+                                        if (GB - g0 >= 4) {
+                                            reinterpret_cast<float4*>(dst)[0] = make_float4((va[0][j] + vb[0][j]) * cf, (va[1][j] + vb[1][j]) * cf,
+                                                                                            (va[2][j] + vb[2][j]) * cf, (va[3][j] + vb[3][j]) * cf);
+                                        } else {
+#pragma unroll
+                                            for (int gi = 0; gi < 4; ++gi)
+                                                if (g0 + gi < GB) dst[gi] = (va[gi][j] + vb[gi][j]) * cf;
+                                        }
+                                    }
+                                }
+                            }
+                            continue;
+                        }
                         float vals[8][4];
 #pragma unroll
                         for (int gi = 0; gi < 8; ++gi) {
@@ -558,6 +640,8 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     // un-stacked form is tried next.
     int want_stack = getenv("PNO_FWD_STACK") ? atoi(getenv("PNO_FWD_STACK")) : (x3 ? 1 : 0);
     if (2 * g.R2 > 128 || 3 * g.R2 > 256) want_stack = 0;      // accumulator lanes; TMA box rows
+    // N-concatenated operands (see the issuers): fp32-parity engine with the stacked tables; PNO_FWD_NCAT=0 switches back (tuning)
+    const int want_ncat = x3 && !(getenv("PNO_FWD_NCAT") && atoi(getenv("PNO_FWD_NCAT")) == 0);
     bool fits = false;
     int best = -1;
     FwdGeom bg = g;
@@ -567,6 +651,8 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     // the padding rows [2 m2, N1p) of a TwT k-block are not stored when the stacked tables need the room: the MMA reads the rows
     // that follow instead, and the accumulator columns they feed are never read
     g.tw_rows = g.stack ? pad_to(2 * m2, 8) : g.N1p;
+    g.ncat = want_ncat && g.stack;
+    g.D1W = g.ncat ? 2 * g.tw_rows : g.N1p;
     g.tw_one = g.KB1 * g.tw_rows * 128;
     g.off_tab = 0;
     g.off_tw = pad_to((g.stack ? 1 : 2) * NT * g.tab_one, 1024);
@@ -587,7 +673,7 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
                 c.TPS = ns; c.TPB = tpb; c.nb2 = nb2; c.KPS = kps;
                 c.stage_bytes = NT * kps * g.x_bytes;
                 c.N2p = pad_to(tpb * g.IPT * m2, 16);
-                c.nslot = 2 * g.N1p + 4 * c.N2p <= 512 ? 2 : 1;
+                c.nslot = 2 * g.D1W + 4 * c.N2p <= 512 ? 2 : 1;
                 c.b2_one = g.KB2 * c.N2p * 128;
                 c.b2_bytes = pad_to(2 * NT * c.b2_one, 1024);
                 c.off_ring = g.off_b2 + nb2 * c.b2_bytes;
@@ -595,7 +681,8 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
                 if (c.stages > 8) c.stages = 8;
                 if (getenv("PNO_FWD_STAGES") && atoi(getenv("PNO_FWD_STAGES")) < c.stages) c.stages = atoi(getenv("PNO_FWD_STAGES"));   // diagnostics
                 if (getenv("PNO_FWD_KPS") && atoi(getenv("PNO_FWD_KPS")) != kps) continue;
-                if (c.N2p > 256 || g.N1p > 256 || 2 * g.N1p + c.nslot * 2 * c.N2p > 512 || c.stages < 2) continue;
+                if (c.N2p > 256 || g.N1p > 256 || 2 * g.D1W + c.nslot * 2 * c.N2p > 512 || c.stages < 2) continue;
+                if (g.ncat && (c.N2p > 128 || g.tw_rows > 128)) continue;        // N = 2*N2p / 2*tw_rows <= 256
                 // prefer >= 16-byte output runs, then overlap (two accumulator / operand buffers), then ring depth
                 const int gb = tpb * g.IPT;
                 const int score = (gb >= 4 ? 1000 : 0) + (ns * g.IPT >= 8 ? 500 : 0) + c.nslot * 100 + nb2 * 10 + (kps > 1 ? 5 : 0) + (c.stages < 4 ? c.stages : 4);   // measured: whole-tile stages 130 us vs 142 us
@@ -657,11 +744,12 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     sms = pno_usable_sms(sms);
     const int grid = g.n_super < sms ? g.n_super : sms;
     if (x3) {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        PNO_CUDA(pno_launch(k_tc_dft_fwd<3>, grid, kThreads, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
+        auto kern = g.ncat ? k_tc_dft_fwd<3, true> : k_tc_dft_fwd<3, false>;
+        PNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PNO_CUDA(pno_launch(kern, grid, kThreads, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
     } else {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        PNO_CUDA(pno_launch(k_tc_dft_fwd<1>, grid, kThreads - 32, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
+        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PNO_CUDA(pno_launch(k_tc_dft_fwd<1, false>, grid, kThreads - 32, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
     }
     PNO_LAUNCH_CHECK();
     return PNO_OK;
