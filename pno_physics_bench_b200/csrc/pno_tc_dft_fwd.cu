@@ -49,6 +49,7 @@ struct FwdGeom {
     int D1W;                  // columns of one stage-1 accumulator buffer: N1p, or 2*tw_rows (main | correction) with ncat
     int stack;                // stage 2 with the stacked table T = [S; C; -S] (see issue_stage2): half the MMAs, one accumulator
     int ablate;               // measurement only (PNO_FWD_ABLATE, wrong results): 1 = no correction MMAs in stage 1, 2 = none in stage 2
+    int epace;                // fp32-parity form: nanoseconds an epilogue warp sleeps after each of its scattered 16-byte stores (see there)
     int pf;                   // L2 prefetch distance of the x tiles, in 128-row tiles (0 = off)
     int tw_rows;              // rows of one TwT k-block in shared memory (N1p, or 2*m2 rounded to 8 when the padding rows are not stored)
     // shared-memory byte offsets (from the 1024-aligned base)
@@ -380,7 +381,12 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (warp == 8) TRACE(1, 2);
                 const uint32_t t1 = tmem_addr(tmem, q * 32, buf * g.D1W + im * g.m2);
                 const uint32_t dst0 = smem_u32(smem + g.off_b2) + bb * g.b2_bytes + im * NT * g.b2_one + col_off;
-                const int r0 = (tb_ * g.IPT + img_l) * g.m2;
+                // row of the B2 operand = stage-2 accumulator column: ky * GB + image of the batch, so that the GB images (consecutive
+                // channels) of one ky are adjacent columns and the epilogue reads whole 16-column runs (4 ky x 4 images = four
+                // 16-byte stores) with one wide tensor-memory load instead of one narrow load per image
+                // (fp32-parity form; the single-pass kernel keeps image-major columns and its narrow loads: 128 vs 136 us)
+                const int GBt = NCAT ? g.TPB * g.IPT : 1;
+                const int r0 = NCAT ? tb_ * g.IPT + img_l : (tb_ * g.IPT + img_l) * g.m2;
                 if (NCAT) {
                     // main + correction halves of the stage-1 accumulator, 16 columns a pass (two 16-register loads in flight)
                     for (int c0 = 0; c0 < g.m2; c0 += 16) {
@@ -394,7 +400,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                             if (c0 + 4 * u < g.m2) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const int r = r0 + c0 + 4 * u + j;
+                                    const int r = r0 + (c0 + 4 * u + j) * GBt;
                                     const uint32_t dst = dst0 + r * 128 + ((chunk ^ (r & 7)) << 4);
                                     const float v = __uint_as_float(ra[u][j]) + __uint_as_float(rb[u][j]);
                                     sts32(dst, v);                       // raw: the tensor core truncates it
@@ -419,7 +425,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         if (c0 + 4 * u < g.m2) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const int r = r0 + c0 + 4 * u + j;
+                                const int r = r0 + (c0 + 4 * u + j) * GBt;
                                 const uint32_t dst = dst0 + r * 128 + ((chunk ^ (r & 7)) << 4);
                                 if (NSPLIT == 3) {
                                     const float h = tf32_rn(v[u][j]);
@@ -459,6 +465,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
         float* dst_plane = half ? xi : xr;
         // (x8 loads of 8 ky per image were tried here: 64 values in flight spill at the 80-register cap of this 22-23 warp CTA:
         //  128 -> 193 us)
+        const int ch_first = g.stack ? part : 0, ch_step = g.stack ? 2 : 1;      // NCAT: 16-column passes of this warp
         const int ky_first = g.stack ? part * 4 : 0, ky_step = g.stack ? 8 : 4;
         const int bps = g.TPS / g.TPB;                   // batches per super tile
         int slot = 0, sph = 0;
@@ -472,41 +479,72 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (warp_active) {
                     const int b = sb, c0 = sc0 + k * GB;         // a super tile never straddles a batch item (C % (bps*GB) == 0)
                     const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + (g.stack ? 0 : part * g.N2p));
-                    for (int ky0 = ky_first; ky0 < g.m2; ky0 += ky_step) {
-                        if (NCAT) {
-                            // main + correction columns (N2p apart), four images a pass
-                            for (int g0 = 0; g0 < GB; g0 += 4) {
-                                float va[4][4], vb[4][4];
+                    if (NCAT) {
+                    // accumulator columns = ky * GB + image: 16 columns a pass = 16 / GB values of ky x GB consecutive channels
+                    const int ncols = g.m2 * GB;
+                    for (int cc = ch_first; cc * 16 < ncols; cc += ch_step) {
+                        uint32_t ra[4][4];
+                        float v[4][4];
+                        tmem_ld_cols16(tb0 + cc * 16, 16, ra);
+                        if (NCAT) {                                 // main + correction columns (N2p apart)
+                            uint32_t rb[4][4];
+                            tmem_ld_cols16(tb0 + g.N2p + cc * 16, 16, rb);
+                            tmem_ld_wait();
 #pragma unroll
-                                for (int gi = 0; gi < 4; ++gi) {
-                                    if (g0 + gi < GB) {
-                                        tmem_ld4(tb0 + (g0 + gi) * g.m2 + ky0, va[gi]);
-                                        tmem_ld4(tb0 + g.N2p + (g0 + gi) * g.m2 + ky0, vb[gi]);
-                                    } else {
-                                        va[gi][0] = va[gi][1] = va[gi][2] = va[gi][3] = 0.f;
-                                        vb[gi][0] = vb[gi][1] = vb[gi][2] = vb[gi][3] = 0.f;
-                                    }
-                                }
-                                tmem_ld_wait();
-                                if (active) {
+                            for (int u = 0; u < 4; ++u)
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const int mode = row * g.m2 + ky0 + j;
-                                        const float cf = g.grad_scale ? coef[mode] : 1.f;
-                                        float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0 + g0;
-                                        if (GB - g0 >= 4) {
-                                            reinterpret_cast<float4*>(dst)[0] = make_float4((va[0][j] + vb[0][j]) * cf, (va[1][j] + vb[1][j]) * cf,
-                                                                                            (va[2][j] + vb[2][j]) * cf, (va[3][j] + vb[3][j]) * cf);
-                                        } else {
+                                for (int j = 0; j < 4; ++j) v[u][j] = __uint_as_float(ra[u][j]) + __uint_as_float(rb[u][j]);
+                        } else {
+                            tmem_ld_wait();
 #pragma unroll
-                                            for (int gi = 0; gi < 4; ++gi)
-                                                if (g0 + gi < GB) dst[gi] = (va[gi][j] + vb[gi][j]) * cf;
-                                        }
-                                    }
-                                }
-                            }
-                            continue;
+                            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[u][j] = __uint_as_float(ra[u][j]);
                         }
+                        if (!active) continue;
+                        if (GB == 4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int mode = row * g.m2 + cc * 4 + u;
+                                const float cf = g.grad_scale ? coef[mode] : 1.f;
+                                float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0;
+                                *reinterpret_cast<float4*>(dst) = make_float4(v[u][0] * cf, v[u][1] * cf, v[u][2] * cf, v[u][3] * cf);
+                                // Pacing.  Every lane of such a store hits its own 128-byte line (modes are B*C*4 bytes apart), i.e. 32
+                                // LSU passes per instruction; issued back to back by six warps they fill the load / store queue for
+                                // ~3.5 k cycles per batch and the transposer's shared-memory stores of the NEXT batch -- the critical
+                                // chain transposer -> stage 2 -> transposer -- queue behind them (its 16-column pass took 3.7 k cycles
+                                // under the epilogue, 0.8 k alone: tools/trace_fwd.py).  The epilogue has a whole batch period to
+                                // spare (two accumulator slots), so it spreads its stores: 169 -> 159 us at 150 ns (100: 162, 200:
+                                // 161, 300: 197 = the epilogue becomes the bound).  The single-pass kernel has four active epilogue
+                                // warps and no slack: paced the same way it goes from 127 to 202 us, so it is not.
+                                if (g.epace) __nanosleep(g.epace);
+                            }
+                        } else if (GB == 8) {
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int mode = row * g.m2 + cc * 2 + u;
+                                const float cf = g.grad_scale ? coef[mode] : 1.f;
+                                float* dst = dst_plane + ((size_t)mode * g.B + b) * g.C + c0;
+                                reinterpret_cast<float4*>(dst)[0] = make_float4(v[2 * u][0] * cf, v[2 * u][1] * cf, v[2 * u][2] * cf, v[2 * u][3] * cf);
+                                reinterpret_cast<float4*>(dst)[1] = make_float4(v[2 * u + 1][0] * cf, v[2 * u + 1][1] * cf, v[2 * u + 1][2] * cf, v[2 * u + 1][3] * cf);
+                            }
+                        } else {                                    // GB = 1 or 2
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int col = cc * 16 + 4 * u + j;
+                                    if (col < ncols) {
+                                        const int ky = GB == 2 ? col >> 1 : col, gi = GB == 2 ? col & 1 : 0;
+                                        const int mode = row * g.m2 + ky;
+                                        const float cf = g.grad_scale ? coef[mode] : 1.f;
+                                        dst_plane[((size_t)mode * g.B + b) * g.C + c0 + gi] = v[u][j] * cf;
+                                    }
+                                }
+                        }
+                    }
+                    } else {
+                    for (int ky0 = ky_first; ky0 < g.m2; ky0 += ky_step) {
                         float vals[8][4];
 #pragma unroll
                         for (int gi = 0; gi < 8; ++gi) {
@@ -532,6 +570,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                                 }
                             }
                         }
+                    }
                     }
                 }
                 tc_fence_before_sync();
@@ -697,6 +736,7 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     // measured at the headline shape: fp32-parity engine (2 ring stages) 191 -> 185 us with a distance of 1, single pass (3 stages)
     // 128 -> 131 / 136 us with 1 / 4: on for the former only
     g.ablate = getenv("PNO_FWD_ABLATE") ? atoi(getenv("PNO_FWD_ABLATE")) : 0;
+    g.epace = getenv("PNO_FWD_EPACE") ? atoi(getenv("PNO_FWD_EPACE")) : 150;
     g.pf = getenv("PNO_FWD_PF") ? atoi(getenv("PNO_FWD_PF")) : (x3 ? 1 : 0);
     g.swap13 = !(getenv("PNO_FWD_SWAP13") && atoi(getenv("PNO_FWD_SWAP13")) == 0);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
