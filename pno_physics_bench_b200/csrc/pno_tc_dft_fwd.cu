@@ -44,6 +44,8 @@ struct FwdGeom {
     int KPS;        // x k-blocks per ring stage (a whole tile when W <= 64: one barrier round trip per tile instead of per k-block)
     int stages, nslot, nb2;   // ring depth, stage-2 accumulator buffers, B2 operand buffers
     int swap13;               // physical warps 1 and 3 swap roles (see the kernel)
+    int kym;                  // single pass with stacked tables: ky-major accumulator columns and 16-column epilogue loads (the
+                              // fp32-parity form with N-concatenated operands always has them)
     int ncat;                 // fp32-parity form with N-concatenated operands (see issue_stage1 / issue_stage2): 2 + 4 instead of 3 + 6 MMAs
                               // per k-step; needs the stacked tables
     int D1W;                  // columns of one stage-1 accumulator buffer: N1p, or 2*tw_rows (main | correction) with ncat
@@ -135,17 +137,19 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
     pdl_wait();                                        // x (the previous kernel's output) is complete from here on
 
     constexpr int NT = NSPLIT == 3 ? 2 : 1;            // hi (+ lo) copies of every operand
+    constexpr bool KYM = NCAT;                         // ky-major stage-2 accumulator columns + 16-column epilogue loads
+    constexpr bool CAT = NCAT && NSPLIT == 3;          // N-concatenated hi / lo operands (fp32-parity form)
     // TMEM columns: [0, 2*N1p) stage-1 accumulators (double buffered); then nslot buffers of 2*N2p (re | im), one batch each
     const int d2_base = 2 * g.D1W;
     // tables: (C hi, [C lo], S hi, [S lo]), each KB2 k-blocks of [R2 x 128 B]; TwT (hi, [lo]) each KB1 k-blocks of [N1p x 128 B]
     unsigned char* tab = smem + g.off_tab;
     unsigned char* twt = smem + g.off_tw;
     const int tab_kb = (g.stack ? 3 : 1) * g.R2 * 128;
-    const int tw_kb = (NCAT ? 2 : 1) * g.tw_rows * 128;      // ncat: [hi rows | lo rows] per k-block
+    const int tw_kb = (CAT ? 2 : 1) * g.tw_rows * 128;      // ncat: [hi rows | lo rows] per k-block
     // B2 operands: (Rre hi, [Rre lo], Rim hi, [Rim lo]), each KB2 k-blocks of [N2p x 128 B]; rows = (tile in batch, image, ky)
     // ncat: [hi rows | lo rows] per k-block, so that one N = 2*N2p MMA multiplies a table by both
-    const int b2_kb = (NCAT ? 2 : 1) * g.N2p * 128;
-    const int b2_lo = NCAT ? g.N2p * 128 : g.b2_one;          // lo copy of an element, relative to its hi copy
+    const int b2_kb = (CAT ? 2 : 1) * g.N2p * 128;
+    const int b2_lo = CAT ? g.N2p * 128 : g.b2_one;          // lo copy of an element, relative to its hi copy
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -166,7 +170,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
             }
             for (int kb = 0; kb < g.KB1; ++kb) {
                 tma_load_2d(twt + kb * tw_kb, &tmTwHi, &bar_tab, kb * 32, 0);
-                if (NSPLIT == 3) tma_load_2d(twt + (NCAT ? g.tw_rows * 128 : g.tw_one) + kb * tw_kb, &tmTwLo, &bar_tab, kb * 32, 0);
+                if (NSPLIT == 3) tma_load_2d(twt + (CAT ? g.tw_rows * 128 : g.tw_one) + kb * tw_kb, &tmTwLo, &bar_tab, kb * 32, 0);
             }
             int stage = 0, phase = 0;
             // this CTA's tiles are TPS consecutive 128-row tiles per super tile, super tiles gridDim.x apart: pull the tile that is
@@ -231,7 +235,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t accf = (kb | ks) ? 1u : 0u;
                             const uint32_t o = ks * 2;
-                            if (NCAT) {
+                            if (CAT) {
                                 // B = [TwT hi | TwT lo] (N = 2*tw_rows): accumulator columns [0, tw_rows) = x * hi, [tw_rows, ..) = x * lo,
                                 // for A = the raw x tile (the tensor core reads its tf32 truncation) and A = its lo part: all four
                                 // terms of the product in two MMAs instead of three terms in three.  The transposer adds the halves.
@@ -270,7 +274,7 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                         const uint32_t first = (kb | ks) ? 1u : 0u;
                         const uint32_t c = tb + ((kb * tab_kb) >> 4) + ks * 2, r = bbase + ((kb * b2_kb) >> 4) + ks * 2;
                         const uint32_t sn = c + NT * t1, ri = r + NT * bo1;
-                        if (NCAT) {
+                        if (CAT) {
                             // stacked tables (below) times B = [R | R lo] (N = 2*N2p): columns [0, N2p) main, [N2p, 2 N2p) correction;
                             // the lo tables times R go to the correction columns.  4 MMAs per k-step instead of 6.
                             const uint32_t a_cs = c + ((g.R2 * 128) >> 4), a_sc = c;
@@ -385,9 +389,9 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 // channels) of one ky are adjacent columns and the epilogue reads whole 16-column runs (4 ky x 4 images = four
                 // 16-byte stores) with one wide tensor-memory load instead of one narrow load per image
                 // (fp32-parity form; the single-pass kernel keeps image-major columns and its narrow loads: 128 vs 136 us)
-                const int GBt = NCAT ? g.TPB * g.IPT : 1;
-                const int r0 = NCAT ? tb_ * g.IPT + img_l : (tb_ * g.IPT + img_l) * g.m2;
-                if (NCAT) {
+                const int GBt = KYM ? g.TPB * g.IPT : 1;
+                const int r0 = KYM ? tb_ * g.IPT + img_l : (tb_ * g.IPT + img_l) * g.m2;
+                if (CAT) {
                     // main + correction halves of the stage-1 accumulator, 16 columns a pass (two 16-register loads in flight)
                     for (int c0 = 0; c0 < g.m2; c0 += 16) {
                         uint32_t ra[4][4], rb[4][4];
@@ -479,14 +483,14 @@ k_tc_dft_fwd(const FwdGeom g, const float* __restrict__ coef, float* __restrict_
                 if (warp_active) {
                     const int b = sb, c0 = sc0 + k * GB;         // a super tile never straddles a batch item (C % (bps*GB) == 0)
                     const uint32_t tb0 = tmem_addr(tmem, q * 32, d2_base + slot * 2 * g.N2p + (g.stack ? 0 : part * g.N2p));
-                    if (NCAT) {
+                    if (KYM) {
                     // accumulator columns = ky * GB + image: 16 columns a pass = 16 / GB values of ky x GB consecutive channels
                     const int ncols = g.m2 * GB;
                     for (int cc = ch_first; cc * 16 < ncols; cc += ch_step) {
                         uint32_t ra[4][4];
                         float v[4][4];
                         tmem_ld_cols16(tb0 + cc * 16, 16, ra);
-                        if (NCAT) {                                 // main + correction columns (N2p apart)
+                        if (CAT) {                                 // main + correction columns (N2p apart)
                             uint32_t rb[4][4];
                             tmem_ld_cols16(tb0 + g.N2p + cc * 16, 16, rb);
                             tmem_ld_wait();
@@ -673,11 +677,14 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     g.x_bytes = 128 * 128;                        // [128 rows][32 floats]
     g.KPS = 1;
     g.stage_bytes = NT * g.x_bytes;
-    // stacked stage-2 tables (see the kernel): on for the fp32-parity engine, where stage 2 is 96 MMAs per batch on one issuer and
-    // serialises with the transposer (one B2 operand buffer); PNO_FWD_STACK=0 / 1 forces the choice (tuning)
-    // (measured at the headline shape: fp32-parity 202 -> 192 us, single pass 121 -> 137 us).  If the larger tables do not fit, the
-    // un-stacked form is tried next.
-    int want_stack = getenv("PNO_FWD_STACK") ? atoi(getenv("PNO_FWD_STACK")) : (x3 ? 1 : 0);
+    // stacked stage-2 tables (see the kernel): half the stage-2 MMAs, one accumulator, epilogue work on three lane quarters instead
+    // of one and a quarter.  With image-major accumulator columns and one narrow tensor-memory load per image it measured
+    // 202 -> 192 us (fp32 parity) but 121 -> 137 us (single pass); with ky-major columns (one 16-column load per four stores,
+    // `kym`) the single-pass kernel gains too: 127 -> 114 us.  Single pass: only while the stacked table stays small (<= 32 KB:
+    // 64-row images), larger ones cost ring stages and the second B2 buffer.  PNO_FWD_STACK / PNO_FWD_KYM = 0 / 1 force the choice.
+    // If the larger tables do not fit, the un-stacked form is tried next.
+    const int kym_env = getenv("PNO_FWD_KYM") ? atoi(getenv("PNO_FWD_KYM")) : 1;
+    int want_stack = getenv("PNO_FWD_STACK") ? atoi(getenv("PNO_FWD_STACK")) : (x3 ? 1 : (kym_env && g.KB2 * 3 * g.R2 * 128 <= 32 * 1024));
     if (2 * g.R2 > 128 || 3 * g.R2 > 256) want_stack = 0;      // accumulator lanes; TMA box rows
     // N-concatenated operands (see the issuers): fp32-parity engine with the stacked tables; PNO_FWD_NCAT=0 switches back (tuning)
     const int want_ncat = x3 && !(getenv("PNO_FWD_NCAT") && atoi(getenv("PNO_FWD_NCAT")) == 0);
@@ -736,7 +743,8 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
     // measured at the headline shape: fp32-parity engine (2 ring stages) 191 -> 185 us with a distance of 1, single pass (3 stages)
     // 128 -> 131 / 136 us with 1 / 4: on for the former only
     g.ablate = getenv("PNO_FWD_ABLATE") ? atoi(getenv("PNO_FWD_ABLATE")) : 0;
-    g.epace = getenv("PNO_FWD_EPACE") ? atoi(getenv("PNO_FWD_EPACE")) : 150;
+    g.epace = getenv("PNO_FWD_EPACE") ? atoi(getenv("PNO_FWD_EPACE")) : (x3 ? 150 : 0);
+    g.kym = !x3 && g.stack && kym_env;
     g.pf = getenv("PNO_FWD_PF") ? atoi(getenv("PNO_FWD_PF")) : (x3 ? 1 : 0);
     g.swap13 = !(getenv("PNO_FWD_SWAP13") && atoi(getenv("PNO_FWD_SWAP13")) == 0);
     g.smem_bytes = g.off_ring + g.stages * g.stage_bytes + 1024;
@@ -788,8 +796,9 @@ int tc_dft_fwd_fused(const pno_plan* p, int engine, const float* x, int B, int C
         PNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         PNO_CUDA(pno_launch(kern, grid, kThreads, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
     } else {
-        PNO_CUDA(cudaFuncSetAttribute(k_tc_dft_fwd<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        PNO_CUDA(pno_launch(k_tc_dft_fwd<1, false>, grid, kThreads - 32, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
+        auto kern = g.kym ? k_tc_dft_fwd<1, true> : k_tc_dft_fwd<1, false>;
+        PNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PNO_CUDA(pno_launch(kern, grid, kThreads - 32, g.smem_bytes, st, g, (const float*)p->coef, xr, xi, tmX, tmTwHi, tmTwLo, tmCHi, tmCLo, tmSHi, tmSLo));
     }
     PNO_LAUNCH_CHECK();
     return PNO_OK;

@@ -1,4 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -k "dft_fwd or transform_pair or two_pass or full_size or model_tensor" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_baseline_shapes.py -x -q 2>&1 | tail -3
 timeout 120 python tools/kernel_times.py tf32 tf32x3 | python -c "
 import sys,json
 for l in sys.stdin:
