@@ -53,6 +53,7 @@ struct InvGeom {
     int nb1, nzt, nd2;            // buffer counts: B1 operand sets, Zt operand sets, stage-2 accumulators
     int b1_buf;                   // bytes of one B1 operand set
     int add_stages, off_add, add_bytes;   // TMA-staged addend tiles (0 stages: the epilogue loads the addend with LDG)
+    int ldg_t;                            // LDG addend: row-major loads transposed through the store scratch (PNO_INV_LDGT=0: lane-per-row loads)
     int tma_out;                          // the epilogue overwrites the staged addend tile with y and the tile leaves by TMA store
     int off_tabA, off_tabB, off_b1, off_zt, tabA_one, tabB_one, b1_one, b1_im, zt_one, zt_buf, smem_bytes;
     long long* dbg;   // optional per-CTA wait-cycle counters (pno_debug_set_buffer)
@@ -487,6 +488,26 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                         const int j0 = (c & 31) >> 2;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) a4[k] = lds128(blk + (((j0 + k) ^ (row & 7)) << 4));
+                    } else if (addend && g.ldg_t) {
+                        // row-major loads (8 rows x 64 B per instruction = 8 lines instead of 32: a lane-per-row load costs the
+                        // load / store unit 32 passes) turned into lane-per-row through this warp's store scratch: 256 -> 250 us
+                        // (fp32-parity engine, headline shape).  Staggering the store bursts of the four column chunks the way
+                        // the forward transform paces its epilogue does NOT pay here (100 / 250 / 500 ns: 256 / 265 / 292 us): this
+                        // epilogue is on the tile's critical path.
+                        const float* src = addend + wofs + c + (size_t)(lane >> 2) * g.W + 4 * (lane & 3);
+                        const uint32_t s0 = smem_u32(sc);
+                        float4 t[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)8 * i * g.W));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = 8 * i + (lane >> 2), ch = lane & 3;
+                            sts128(s0 + 16u * (rr * 4 + (ch ^ (rr & 3))), t[i]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) a4[k] = lds128(s0 + 16u * (lane * 4 + (k ^ (lane & 3))));
+                        __syncwarp();
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -792,6 +813,7 @@ int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_dft_inv needs 16-byte aligned tensors");
     if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     g.n_groups = B * C / g.G;
+    g.ldg_t = !g.tma_out && !(getenv("PNO_INV_LDGT") && atoi(getenv("PNO_INV_LDGT")) == 0);
     if (getenv("PNO_INV_PAD")) g.smem_bytes += atoi(getenv("PNO_INV_PAD")) * 1024;   // diagnostics: shrink the L1 carve-out
     g.dbg = g_pno_debug_buffer;
     g.dbg_mma = g_pno_debug_buffer != nullptr && getenv("PNO_DEBUG_MMA") != nullptr;
