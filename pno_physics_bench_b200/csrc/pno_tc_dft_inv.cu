@@ -360,8 +360,15 @@ k_tc_dft_inv(const InvGeom g, const float* __restrict__ tabA_g, const float* __r
                         int part, kx2, ky;
                         decode(w, part, kx2, ky);
                         const float* src = (part ? yi : yr) + (size_t)(kx2 * g.m2 + ky) * g.B * g.C + o_grp;
-                        va[u] = __ldg(reinterpret_cast<const float4*>(src));
-                        if (G == 8) vb[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                        if (G == 8) {          // one 256-bit load per 32-byte run: every lane hits its own line, so each load
+                                               // instruction costs the load / store unit 32 passes whatever its width
+                            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=f"(va[u].x), "=f"(va[u].y), "=f"(va[u].z), "=f"(va[u].w), "=f"(vb[u].x), "=f"(vb[u].y),
+                                           "=f"(vb[u].z), "=f"(vb[u].w)
+                                         : "l"(src));
+                        } else {
+                            va[u] = __ldg(reinterpret_cast<const float4*>(src));
+                        }
                     }
                 }
                 if (!waited) {
