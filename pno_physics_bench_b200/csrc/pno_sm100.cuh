@@ -510,13 +510,18 @@ __host__ __device__ __forceinline__ uint32_t mnmajor16_sw128_off(int k, int n, i
 // operand) and  l(v) = v - h(v)  (exact, <= 13 significant bits),
 //     a * b  =  h(a) h(b)  +  [ h(a) l(b) + l(a) h(b) ]  +  l(a) l(b)
 // the first term is ONE kind::tf32 MMA on the raw fp32 tiles (no hi copy needed), the bracket is TWO kind::f16 MMAs on bf16 copies
-// (bf16(a) x bf16(l(b)) and bf16(l(a)) x bf16(b): the 8-bit mantissas cost 2^-9 relative on terms that are 2^-11 of the product,
-// i.e. ~1e-6), the last term (2^-22) is dropped.  Against three kind::tf32 MMAs on hi / lo fp32 copies this is 2/3 of the tensor
-// time and 2/3 of the operand bytes read from shared memory, for the same fp32-grade result.
+// (bf16(h(a)) x bf16(l(b)) and bf16(l(a)) x bf16(b): the 8-bit mantissas cost 2^-9 relative on terms that are 2^-11 of the product,
+// i.e. ~1e-6; with the FULL b in the second one the last term l(a) l(b) is included as well -- and with the full a in the first it
+// would be included twice, a +1.2e-7 bias since truncation parts carry the sign of their value: k_split_weights copies h(W)).
+// Against three kind::tf32 MMAs on hi / lo fp32 copies this is 2/3 of the tensor time and 2/3 of the operand bytes read from shared
+// memory, for the same fp32-grade result.
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 // lo part of a truncation split, itself ROUNDED to tf32: l(v) has up to 13 significant bits and kind::tf32 would truncate it again,
-// always towards zero and l(v) always has the sign of v, i.e. a systematic 2^-23-ish scale-down of every operand (seen as a
-// 5.6e-5 error on a cancellation-heavy bias gradient); rounded to nearest the lo operand is exact in tf32 and the split unbiased.
+// always towards zero and l(v) always has the sign of v, i.e. a systematic scale-down of every operand by ~1.4e-7 (seen as a
+// 5.6e-5 error on a cancellation-heavy bias gradient); rounded to nearest the lo operand is exact in tf32.  What is left is the
+// round-half-up of a value with only 0-2 bits to drop (+3e-8 per operand split this way) and, where the l(a) l(b) term is dropped,
+// its mean (-1.2e-7 when BOTH operands are truncation-split; zero when one of them is split by rounding, as the host-made tables
+// and the mix weights are): tests/test_split_numerics.py models all the variants.
 __device__ __forceinline__ float tf32_lo_rn(float v) {
     const float l = v - tf32_trunc(v);
     return __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xFFFFE000u);

@@ -503,12 +503,15 @@ k_tc_local(const LocalArgs a, const __grid_constant__ CUtensorMap tmX, const __g
 }
 
 // bf16 copies of the two 1x1 weight matrices for the fp32-parity engine: out = rows [Wm][Wl][Wm lo][Wl lo], n bf16 each, where
-// lo = w - trunc_tf32(w) is what the kind::tf32 main term (run on the raw fp32 weights) leaves out
+// lo = w - trunc_tf32(w) is what the kind::tf32 main term (run on the raw fp32 weights) leaves out.  The first two are copies of
+// trunc_tf32(w), not of w: the cross terms are then  h(W) l(x) + l(W) x  =  h(W) l(x) + l(W) h(x) + l(W) l(x), all three terms
+// the main product misses; with bf16(w) there the l(W) l(x) term is counted twice, and because truncation parts carry the sign of
+// their value that is a +1.2e-7 scale bias of every output (tests/test_split_numerics.py).
 __global__ void k_split_weights(const float* __restrict__ wm, const float* __restrict__ wl, int n, uint16_t* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float a_ = wm[i], b_ = wl ? wl[i] : 0.f;
-    const uint32_t f = pack_bf16(a_, b_), l = pack_bf16(a_ - tf32_trunc(a_), b_ - tf32_trunc(b_));
+    const uint32_t f = pack_bf16(tf32_trunc(a_), tf32_trunc(b_)), l = pack_bf16(a_ - tf32_trunc(a_), b_ - tf32_trunc(b_));
     out[i] = (uint16_t)(f & 0xFFFF);
     out[n + i] = (uint16_t)(f >> 16);
     out[2 * n + i] = (uint16_t)(l & 0xFFFF);
