@@ -6,6 +6,14 @@
 //   stage 2 (columns): Xre[kx2][(img,ky)] = C Rre^T + S Rim^T ;  Xim = C Rim^T - S Rre^T        (A = twiddles, negate-A bit)
 // Stage-2 accumulators of a "super tile" (up to 8 consecutive channels) stay in TMEM so that the epilogue writes
 // [mode][b][c] with 32-byte contiguous channel runs.  All twiddle tables are shared-memory resident; the ring only carries x.
+// Forms of stage 2 (FwdGeom::stack / ncat / kym; the launcher picks, PNO_FWD_* override):
+//   * stacked table T = [S; C; -S]: one accumulator whose rows [0, R2) are Re and [R2, 2 R2) are Im, half the MMAs;
+//   * ky-major accumulator columns (ky * GB + image): the epilogue reads 4 ky x 4 channels with one 16-column TMEM load;
+//   * fp32 parity, N-concatenated operands: stage 1 = {x, lo(x)} x [TwT hi | TwT lo], stage 2 = T x [R | lo(R)] + lo(T) x R, the
+//     halves (main | correction columns) added by the transposer / epilogue; the raw fp32 tile is the hi operand (the tensor
+//     core truncates it), lo(v) = RN_tf32(v - trunc(v)).
+// In this kernel the MMAs are bound by the shared-memory reads of their own operands (an N = 80 MMA fetches 6.5 KB in the 53
+// cycles it lasts alone), so everything that enlarges N per MMA or takes other traffic off shared memory pays.
 //   warp 0        TMA producer (tables once, then x row tiles)
 //   warps 1, 22   MMA issuers (warp 22 only in 3xTF32 mode, where stage 2 gets its own issuer).  A tcgen05.mma costs >= ~53 cycles whatever its N
 //                 (tools/micro/mma_rate.cu), so stage 2 runs once per batch of TPB tiles with N = TPB*IPT*m2 (80 at the
