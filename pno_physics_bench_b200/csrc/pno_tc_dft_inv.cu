@@ -716,6 +716,7 @@ int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float
     g.IPT = 128 / H;
     const int nbuf = x3 ? 2 : 1;          // hi (+ lo)
     bool ok = false;
+    const bool spec32 = !((reinterpret_cast<uintptr_t>(yr) | reinterpret_cast<uintptr_t>(yi)) & 31);      // 32-byte aligned spectra
     const char* e_epi = getenv("PNO_INV_EPI");         // tuning override: 8 = narrow epilogue
     const int epi_max = (W % 64 == 0 && !(e_epi && atoi(e_epi) == 8)) ? 16 : 8;
     const int add_bytes = 128 * W * 4;                 // one 128-row tile of the addend
@@ -737,6 +738,7 @@ int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float
         for (int G = 8; G >= g.IPT && G >= 4; G >>= 1) {
             const int N1 = G * zs;
             if (C % G || N1 % 16 || N1 > 256) continue;
+            if (G == 8 && !spec32) continue;                 // the loaders fetch 8-channel runs with one 256-bit load
             if (getenv("PNO_INV_G") && atoi(getenv("PNO_INV_G")) != G) continue;      // tuning override
             int nd2 = (512 - 2 * N1) / (g.IPT * W);
             if (nd2 < 1) continue;
@@ -772,6 +774,7 @@ int tc_dft_inv_fused(const pno_plan* p, int engine, const float* yr, const float
     // ---- transposer path (3xTF32, or no tensor-memory geometry fits) ----
     for (int G = 8; G >= g.IPT && G >= 4 && !ok; G >>= 1) {
         if (C % G || (G * m2) % 16 || G * m2 > 256 || 2 * G * m2 + 2 * W > 512) continue;
+        if (G == 8 && !spec32) continue;                     // the loaders fetch 8-channel runs with one 256-bit load
         if (getenv("PNO_INV_G") && atoi(getenv("PNO_INV_G")) != G) continue;      // tuning override
         g.ts = 0; g.zs = m2; g.n_lw = 4; g.rowsA = H; g.d2_stride = W;
         g.G = G; g.N1 = G * m2; g.TPG = G / g.IPT;

@@ -579,6 +579,8 @@ int tc_local_fwd(int engine, const float* x, int B, int Ci, int Co, int HW, cons
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wm) | reinterpret_cast<uintptr_t>(Wl) |
          reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout_dlv)) & 15)
         PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_fwd needs 16-byte aligned tensors");
+    if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout_dlv)) & 31)      // 256-bit row stores
+        PNO_FAIL(PNO_E_UNSUPPORTED, "tc_local_fwd needs 32-byte aligned outputs");
     if (g_pno_dry_run) return PNO_OK;          // pno_engine_supports: the shape is tiled; nothing is launched
     LocalArgs a;
     a.B = B; a.Ci = Ci; a.Co = Co; a.HW = HW;
